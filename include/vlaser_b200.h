@@ -1,0 +1,160 @@
+/* vlaser_b200 — C ABI of the B200-native Vlaser-VLA `infer_action` hot path.
+ *
+ * Drop-in boundary: the reference exposes this path as a Python class,
+ * `PiZeroInference.forward -> PiZero.infer_action`
+ * (Vlaser_VLA/Simpler/src/model/vla/pizero_internvl.py:1286-1307, 798-936), constructed in
+ * `EvalAgent.__init__` (Vlaser_VLA/Simpler/src/agent/eval.py:33-56) and fed a checkpoint by
+ * `load_state_dict` (eval.py:196-212). The entry points below are exactly what a binding for that
+ * class needs: create from the cfg keys `PiZero.__init__` reads (:156-337), set weights by
+ * state-dict key, finalize (pack + build schedules), infer, destroy. `vlaser_b200/policy.py` is the
+ * ctypes binding that mirrors the reference class; INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions: plain pointers and sizes only; 0 = OK, negative = error (text via
+ * vlaser_last_error()); one handle per GPU (the current CUDA device at vlaser_create); calls on one
+ * handle are serialised by the caller; device entry points are asynchronous w.r.t. the host
+ * (stream-ordered on `stream`, a cudaStream_t passed as void*), borrow their pointers for the call
+ * only, and never synchronise. There is no CPU fallback: without a CUDA device every compute entry
+ * point fails with an error.
+ */
+#ifndef VLASER_B200_H
+#define VLASER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLASER_ABI_VERSION 1
+
+/* dtype codes for floating-point I/O tensors and weights */
+#define VLASER_F32 0
+#define VLASER_BF16 1
+
+typedef struct vlaser_handle vlaser_t;
+
+/* Mirrors the hydra cfg keys read by PiZero.__init__ (pizero_internvl.py:156-337) plus the
+ * InternVL3 / InternViT / Qwen2.5 dims the reference takes from the HF checkpoint config
+ * (get_internvl3, :32-152). */
+typedef struct vlaser_cfg {
+  /* InternViT (S/ivl/modeling_intern_vit.py) */
+  int32_t image_size, patch_size, vit_hidden, vit_layers, vit_heads, vit_mlp;
+  float vit_eps;  /* layer_norm_eps, 1e-6 */
+  float proj_eps; /* mlp1[0] nn.LayerNorm default eps, 1e-5 */
+  /* LLM ("vlm" mixture) */
+  int32_t hidden, layers, n_heads, n_kv_heads, head_dim, mlp;
+  float rms_eps, rope_theta;
+  /* action expert ("proprio"/"action" mixtures) */
+  int32_t hidden_e, mlp_e;
+  /* tokens */
+  int32_t embed_rows, image_token_index, pad_token_id, max_image_text_tokens;
+  /* action parameterisation */
+  int32_t cond_steps, horizon_steps, action_dim, proprio_dim, num_inference_steps;
+  int32_t clip_enabled;          /* final_action_clip_value is not None */
+  float final_action_clip_value;
+  float time_max_period;
+  /* capacity */
+  int32_t max_batch;             /* largest B any call will use on this handle */
+} vlaser_cfg;
+
+int32_t vlaser_abi_version(void);
+const char* vlaser_last_error(void);
+
+/* PiZeroInference(cfg)  — pizero_internvl.py:156-337 */
+int32_t vlaser_create(const vlaser_cfg* cfg, vlaser_t** out);
+/* load_state_dict, one tensor at a time — eval.py:196-212. `key` is the reference state-dict key
+ * (aliases `_orig_mod.`, `joint_model.mixtures.proprio.`, `internvl_model.*` accepted); `data` may
+ * be a host or device pointer; dtype VLASER_F32 or VLASER_BF16. Unknown keys return 1 (ignored). */
+int32_t vlaser_set_weight(vlaser_t* h, const char* key, const void* data, const int64_t* shape, int32_t ndim,
+                          int32_t dtype);
+/* .to(dtype).to(device).eval() + schedule construction — eval.py:43-56. Fails if a weight is missing. */
+int32_t vlaser_finalize(vlaser_t* h);
+/* forward == infer_action — pizero_internvl.py:1287-1307, 798-936. All pointers are DEVICE pointers.
+ *   input_ids    i64 [B, max_image_text_tokens]
+ *   pixel_values io_dtype [B*cond_steps, 3, image_size, image_size], already (x/255-mean)/std
+ *   valid_len    i32 [B] or NULL: number of valid prefix tokens per sample == number of zeros in
+ *                image_text_proprio_mask[b,0,0,:S]; NULL derives it as count(input_ids != pad_token_id)
+ *   proprios     io_dtype [B, 1, proprio_dim]
+ *   noise        io_dtype [B, H, action_dim], H = horizon_steps+cond_steps-1: the draw of
+ *                torch.randn at :879-881, made by the caller so results are reproducible
+ *   actions_out  io_dtype [B, horizon_steps, action_dim], normalised actions */
+int32_t vlaser_infer_action(vlaser_t* h, const int64_t* input_ids, const void* pixel_values, const int32_t* valid_len,
+                            const void* proprios, const void* noise, void* actions_out, int32_t B, int32_t io_dtype,
+                            void* stream);
+/* Same call with HOST buffers (what an evaluator holds before eval.py:130 / after :139): stages the
+ * inputs through pinned memory, runs on the handle's own stream, copies the actions back and
+ * synchronises. */
+int32_t vlaser_infer_action_host(vlaser_t* h, const int64_t* input_ids, const void* pixel_values,
+                                 const int32_t* valid_len, const void* proprios, const void* noise, void* actions_out,
+                                 int32_t B, int32_t io_dtype);
+void vlaser_destroy(vlaser_t* h);
+
+/* Options: "use_graph" (default 1: replay the whole call as one CUDA graph per batch size),
+ * "stop_after" (debug: 0 all, 1 ViT, 2 prefix embedding, 3 prefill, 4 first denoise step),
+ * "simt_gemm" (debug/tests: route GEMMs through the CUDA-core cross-check kernel). */
+int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value);
+/* Introspection for parity tests: copies the named internal device buffer to host memory.
+ * Returns the buffer size in bytes (>= 0) or a negative error; copies min(size, max_bytes). */
+int64_t vlaser_debug_copy(vlaser_t* h, const char* name, void* host_dst, int64_t max_bytes);
+/* Number of kernels launched by the last vlaser_infer_action* call on this handle. */
+int64_t vlaser_last_launch_count(vlaser_t* h);
+/* Algorithmic FLOPs of one call at batch B with the given valid lengths (SURVEY.md §8d formulae). */
+double vlaser_flops_per_call(vlaser_t* h, const int32_t* valid_len_host, int32_t B);
+
+/* ---- single-kernel entry points (used by the parity tests and micro-benchmarks) ---------- */
+typedef struct vlaser_gemm_args {
+  const void* A;        /* bf16 [M,K] */
+  const void* W;        /* bf16 [N,K] (nn.Linear layout) */
+  int32_t M, N, K;
+  const int32_t* M_dev; /* optional live row count on device */
+  int32_t epi;          /* see vlaser::Epi in csrc/gemm.cuh */
+  int32_t block_n;      /* 128 | 256 */
+  int32_t max_splits;
+  int32_t simt;         /* 1 = CUDA-core cross-check kernel */
+  void* out;
+  int32_t ldo;
+  const float* bias;
+  const float* scale;
+  const int32_t* row_map;
+  const int32_t* row_pos;
+  const int32_t* row_kvrow;
+  const float* cos_tab;
+  const float* sin_tab;
+  void* k_cache;
+  void* v_cache;
+  int64_t kv_head_stride;
+  int32_t n_q_heads, n_kv_heads;
+  const float* pos_emb;
+  int32_t patches;
+} vlaser_gemm_args;
+int32_t vlaser_op_gemm(const vlaser_gemm_args* a, void* stream);
+
+typedef struct vlaser_attn_args {
+  const void* q; int64_t q_row_stride;
+  const void* q2; int64_t q2_row_stride;
+  const void* k; const void* v; int64_t kv_row_stride; int64_t kv_head_stride;
+  void* out; int64_t out_row_stride;
+  void* out2; int64_t out2_row_stride;
+  const int32_t* q_start; const int32_t* q_len; const int32_t* kv_start; const int32_t* kv_len;
+  int32_t uni_q_len, uni_kv_len, max_q_len, group, n_kv_heads, batch, head_dim;
+  float scale;
+} vlaser_attn_args;
+int32_t vlaser_op_attention(const vlaser_attn_args* a, void* stream);
+
+int32_t vlaser_op_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, int32_t rows,
+                            int32_t width, float eps, int32_t shuffle_grid, int32_t shuffle_channels, void* stream);
+int32_t vlaser_op_rmsnorm(const float* x, const float* gamma, void* out_bf16, int32_t rows, int32_t width, float eps,
+                          void* stream);
+int32_t vlaser_op_pixel_shuffle(const void* in, void* out, int32_t n, int32_t grid, int32_t channels,
+                                int32_t elem_bytes, void* stream);
+int32_t vlaser_op_im2col(const void* pixel, int32_t pixel_dtype, void* cols_bf16, int32_t n, int32_t px, int32_t ps,
+                         int32_t kpad, void* stream);
+int32_t vlaser_op_euler_step(const float* x, const float* gamma, const float* Wdec, const float* bdec, float* action,
+                             void* out, int32_t out_dtype, int32_t rows, int32_t width, int32_t A, int32_t H,
+                             int32_t horizon, float dt, float eps, int32_t last_step, int32_t do_clip, float clip,
+                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLASER_B200_H */

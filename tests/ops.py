@@ -1,0 +1,128 @@
+"""Thin torch wrappers over the single-kernel C-ABI entry points + torch fp32 references.
+Used by the `-m gpu` kernel tests and by tools/gpu_diag.py."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from vlaser_b200 import _lib
+from vlaser_b200._lib import (AttnArgs, GemmArgs, EPI_GELU_BF16, EPI_PATCH_EMBED, EPI_QKV_ROPE, EPI_RESID_F32,
+                              EPI_SILU_BF16, EPI_STORE_BF16, EPI_STORE_F32, EPI_SWIGLU_BF16)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def gemm(A, W, epi, block_n=128, simt=False, out=None, ldo=None, bias=None, scale=None, M_dev=None, max_splits=1,
+         row_map=None, row_pos=None, row_kvrow=None, cos_tab=None, sin_tab=None, k_cache=None, v_cache=None,
+         kv_head_stride=0, n_q_heads=0, n_kv_heads=0, pos_emb=None, patches=0):
+    lib = _lib.load()
+    a = GemmArgs()
+    a.A, a.W = _p(A), _p(W)
+    a.M, a.K = A.shape
+    a.N = W.shape[0]
+    a.M_dev = _p(M_dev)
+    a.epi, a.block_n, a.max_splits, a.simt = epi, block_n, max_splits, int(simt)
+    a.out, a.ldo = _p(out), (ldo if ldo is not None else out.shape[-1])
+    a.bias, a.scale, a.row_map = _p(bias), _p(scale), _p(row_map)
+    a.row_pos, a.row_kvrow, a.cos_tab, a.sin_tab = _p(row_pos), _p(row_kvrow), _p(cos_tab), _p(sin_tab)
+    a.k_cache, a.v_cache, a.kv_head_stride = _p(k_cache), _p(v_cache), kv_head_stride
+    a.n_q_heads, a.n_kv_heads = n_q_heads, n_kv_heads
+    a.pos_emb, a.patches = _p(pos_emb), patches
+    _lib.check(lib.vlaser_op_gemm(C.byref(a), _stream()), "op_gemm")
+    return out
+
+
+def interleave_gate_up(gate, up):
+    """Row layout the SwiGLU epilogue expects: 32 gate rows, 32 up rows, ..."""
+    n, k = gate.shape
+    return torch.stack([gate.view(n // 32, 32, k), up.view(n // 32, 32, k)], dim=1).reshape(2 * n, k).contiguous()
+
+
+def rope_tables(max_pos, theta=1e6, device="cuda"):
+    inv = 1.0 / (theta ** (torch.arange(0, 128, 2, dtype=torch.float32) / 128))
+    ang = torch.arange(max_pos, dtype=torch.float32)[:, None] * inv[None, :]
+    return ang.cos().to(device).contiguous(), ang.sin().to(device).contiguous()
+
+
+def rope_ref(x, cos, sin):
+    """x [..., 128] fp32; cos/sin [..., 64] (rotate-half)."""
+    x1, x2 = x[..., :64], x[..., 64:]
+    return torch.cat([x1 * cos - x2 * sin, x2 * cos + x1 * sin], dim=-1)
+
+
+def attention(q, k, v, out, head_dim, group, n_kv_heads, batch, scale, q_row_stride, kv_row_stride, kv_head_stride,
+              out_row_stride, uni_q_len=0, uni_kv_len=0, max_q_len=0, q_start=None, q_len=None, kv_start=None,
+              kv_len=None, q2=None, q2_row_stride=0, out2=None, out2_row_stride=0):
+    lib = _lib.load()
+    a = AttnArgs()
+    a.q, a.q_row_stride, a.q2, a.q2_row_stride = _p(q), q_row_stride, _p(q2), q2_row_stride
+    a.k, a.v, a.kv_row_stride, a.kv_head_stride = _p(k), _p(v), kv_row_stride, kv_head_stride
+    a.out, a.out_row_stride, a.out2, a.out2_row_stride = _p(out), out_row_stride, _p(out2), out2_row_stride
+    a.q_start, a.q_len, a.kv_start, a.kv_len = _p(q_start), _p(q_len), _p(kv_start), _p(kv_len)
+    a.uni_q_len, a.uni_kv_len, a.max_q_len = uni_q_len, uni_kv_len, max_q_len
+    a.group, a.n_kv_heads, a.batch, a.head_dim, a.scale = group, n_kv_heads, batch, head_dim, scale
+    _lib.check(lib.vlaser_op_attention(C.byref(a), _stream()), "op_attention")
+    return out
+
+
+def layernorm(x, gamma, beta, eps, shuffle_grid=0, shuffle_channels=0, rows=None, width=None):
+    lib = _lib.load()
+    rows = x.shape[0] if rows is None else rows
+    width = x.shape[1] if width is None else width
+    out = torch.empty(rows, width, dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.vlaser_op_layernorm(_p(x), _p(gamma), _p(beta), _p(out), rows, width, eps, shuffle_grid,
+                                       shuffle_channels, _stream()), "op_layernorm")
+    return out
+
+
+def rmsnorm(x, gamma, eps):
+    lib = _lib.load()
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.vlaser_op_rmsnorm(_p(x), _p(gamma), _p(out), x.shape[0], x.shape[1], eps, _stream()), "op_rmsnorm")
+    return out
+
+
+def pixel_shuffle(x):
+    """x [n,g,g,C] fp32/bf16 -> [n,g/2,g/2,4C]"""
+    lib = _lib.load()
+    n, g, _, Cc = x.shape
+    out = torch.empty(n, g // 2, g // 2, 4 * Cc, dtype=x.dtype, device=x.device)
+    _lib.check(lib.vlaser_op_pixel_shuffle(_p(x), _p(out), n, g, Cc, x.element_size(), _stream()), "op_pixel_shuffle")
+    return out
+
+
+def im2col(pix, ps, kpad):
+    lib = _lib.load()
+    n, _, px, _ = pix.shape
+    g = px // ps
+    out = torch.empty(n * g * g, kpad, dtype=torch.bfloat16, device=pix.device)
+    dt = _lib.BF16 if pix.dtype == torch.bfloat16 else _lib.F32
+    _lib.check(lib.vlaser_op_im2col(_p(pix), dt, _p(out), n, px, ps, kpad, _stream()), "op_im2col")
+    return out
+
+
+def euler_step(x, gamma, Wdec, bdec, action, out, H, horizon, dt, eps, last_step, clip):
+    lib = _lib.load()
+    rows, width = x.shape
+    A = Wdec.shape[0]
+    odt = _lib.BF16 if out.dtype == torch.bfloat16 else _lib.F32
+    _lib.check(lib.vlaser_op_euler_step(_p(x), _p(gamma), _p(Wdec), _p(bdec), _p(action), _p(out), odt, rows, width, A,
+                                        H, horizon, dt, eps, int(last_step), int(clip is not None),
+                                        float(clip or 0.0), _stream()), "op_euler_step")
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def max_err(a, b):
+    return float((a.double() - b.double()).abs().max())

@@ -1,0 +1,288 @@
+"""-m gpu: every CUDA kernel behind the C ABI against a plain torch fp32 reference of the same op
+(bit-exact for the indexing kernels)."""
+from __future__ import annotations
+
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from tests import ops  # noqa: E402
+from tests.ops import (EPI_GELU_BF16, EPI_PATCH_EMBED, EPI_QKV_ROPE, EPI_RESID_F32, EPI_SILU_BF16,  # noqa: E402
+                       EPI_STORE_BF16, EPI_STORE_F32, EPI_SWIGLU_BF16)
+
+DEV = "cuda"
+BF16_TOL = 6e-3  # relative L2 of a bf16-rounded output vs the fp32 reference
+
+
+def _rand(*shape, scale=1.0, dtype=torch.bfloat16, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+def _ref_mm(A, W):
+    return A.float() @ W.float().t()
+
+
+VARIANTS = [("tcgen05", 128, False), ("tcgen05", 256, False), ("simt", 128, True)]
+
+
+@pytest.mark.parametrize("name,bn,simt", VARIANTS)
+@pytest.mark.parametrize("M,N,K", [(300, 256, 128), (1000, 1024, 512), (129, 768, 768), (4096, 2048, 1024)])
+def test_gemm_store_bias(name, bn, simt, M, N, K):
+    if N % bn:
+        pytest.skip("N not a multiple of block_n")
+    A, W = _rand(M, K), _rand(N, K, scale=0.05)
+    bias = _rand(N, dtype=torch.float32, seed=3)
+    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.gemm(A, W, EPI_STORE_BF16, bn, simt, out=out, bias=bias)
+    ref = _ref_mm(A, W) + bias
+    err = ops.rel_err(out, ref)
+    print(f"gemm_store {name} bn={bn} {M}x{N}x{K}: rel={err:.2e}")
+    assert err < BF16_TOL
+
+
+@pytest.mark.parametrize("name,bn,simt", VARIANTS)
+def test_gemm_gelu_silu(name, bn, simt):
+    M, N, K = 777, 512, 256
+    A, W = _rand(M, K), _rand(N, K, scale=0.1)
+    bias = _rand(N, dtype=torch.float32, seed=5)
+    for epi, fn in ((EPI_GELU_BF16, torch.nn.functional.gelu), (EPI_SILU_BF16, torch.nn.functional.silu)):
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        ops.gemm(A, W, epi, bn, simt, out=out, bias=bias)
+        ref = fn(_ref_mm(A, W) + bias)
+        err = ops.rel_err(out, ref)
+        print(f"gemm_act epi={epi} {name} bn={bn}: rel={err:.2e}")
+        assert err < BF16_TOL
+
+
+@pytest.mark.parametrize("name,bn,simt", VARIANTS)
+@pytest.mark.parametrize("splits", [1, 8])
+def test_gemm_resid(name, bn, simt, splits):
+    M, N, K = 256, 768, 2048
+    A, W = _rand(M, K), _rand(N, K, scale=0.05)
+    bias = _rand(N, dtype=torch.float32, seed=7)
+    scale = _rand(N, dtype=torch.float32, seed=8) * 0.1
+    x0 = _rand(M, N, dtype=torch.float32, seed=9)
+    out = x0.clone()
+    ops.gemm(A, W, EPI_RESID_F32, bn, simt, out=out, bias=bias, scale=scale, max_splits=splits)
+    ref = x0 + scale * (_ref_mm(A, W) + bias)
+    err = ops.rel_err(out, ref)
+    print(f"gemm_resid {name} bn={bn} splits={splits}: rel={err:.2e} max={ops.max_err(out, ref):.2e}")
+    assert err < 1e-5
+
+
+@pytest.mark.parametrize("name,bn,simt", VARIANTS)
+def test_gemm_dynamic_m(name, bn, simt):
+    """Live row count from device memory: rows >= M_dev must stay untouched."""
+    cap, M, N, K = 640, 333, 512, 256
+    A, W = _rand(cap, K), _rand(N, K, scale=0.1)
+    m_dev = torch.tensor([M], dtype=torch.int32, device=DEV)
+    out = torch.full((cap, N), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(A, W, EPI_STORE_BF16, bn, simt, out=out, M_dev=m_dev)
+    ref = _ref_mm(A[:M], W)
+    assert ops.rel_err(out[:M], ref) < BF16_TOL
+    assert torch.all(out[M:] == 7.0)
+
+
+@pytest.mark.parametrize("name,bn,simt", VARIANTS)
+def test_gemm_swiglu(name, bn, simt):
+    M, F, K = 500, 512, 256
+    A = _rand(M, K)
+    gate, up = _rand(F, K, scale=0.1, seed=1), _rand(F, K, scale=0.1, seed=2)
+    W = ops.interleave_gate_up(gate, up)
+    out = torch.empty(M, F, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(A, W, EPI_SWIGLU_BF16, bn, simt, out=out)
+    ref = torch.nn.functional.silu(_ref_mm(A, gate)) * _ref_mm(A, up)
+    err = ops.rel_err(out, ref)
+    print(f"gemm_swiglu {name} bn={bn}: rel={err:.2e}")
+    assert err < BF16_TOL
+
+
+@pytest.mark.parametrize("name,simt", [("tcgen05", False), ("simt", True)])
+def test_gemm_qkv_rope(name, simt):
+    M, K, nq, nkv = 200, 256, 6, 1
+    N = (nq + 2 * nkv) * 128
+    A, W = _rand(M, K), _rand(N, K, scale=0.1)
+    bias = _rand(N, dtype=torch.float32, seed=4)
+    cos, sin = ops.rope_tables(512)
+    g = torch.Generator().manual_seed(0)
+    pos = torch.randint(1, 400, (M,), generator=g, dtype=torch.int32).to(DEV)
+    kvrow = torch.randperm(300, generator=g)[:M].to(torch.int32).to(DEV)
+    rows_cap = 300
+    q = torch.zeros(M, nq * 128, dtype=torch.bfloat16, device=DEV)
+    kc = torch.zeros(nkv, rows_cap, 128, dtype=torch.bfloat16, device=DEV)
+    vc = torch.zeros(nkv, rows_cap, 128, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(A, W, EPI_QKV_ROPE, 128, simt, out=q, bias=bias, row_pos=pos, row_kvrow=kvrow, cos_tab=cos, sin_tab=sin,
+             k_cache=kc, v_cache=vc, kv_head_stride=rows_cap * 128, n_q_heads=nq, n_kv_heads=nkv)
+    y = (_ref_mm(A, W) + bias).view(M, nq + 2 * nkv, 128)
+    c, s = cos[pos.long()][:, None, :], sin[pos.long()][:, None, :]
+    q_ref = ops.rope_ref(y[:, :nq], c, s).reshape(M, -1)
+    k_ref = ops.rope_ref(y[:, nq:nq + nkv], c, s)
+    v_ref = y[:, nq + nkv:]
+    print(f"qkv_rope {name}: q={ops.rel_err(q, q_ref):.2e} k={ops.rel_err(kc[:, kvrow.long()].transpose(0, 1), k_ref):.2e}")
+    assert ops.rel_err(q, q_ref) < BF16_TOL
+    assert ops.rel_err(kc[:, kvrow.long()].transpose(0, 1), k_ref) < BF16_TOL
+    assert ops.rel_err(vc[:, kvrow.long()].transpose(0, 1), v_ref) < BF16_TOL
+
+
+@pytest.mark.parametrize("name,bn,simt", VARIANTS)
+def test_gemm_patch_embed_and_store_f32(name, bn, simt):
+    n_img, P, N, K = 3, 256, 256, 640
+    A, W = _rand(n_img * P, K), _rand(N, K, scale=0.05)
+    bias = _rand(N, dtype=torch.float32, seed=2)
+    pos = _rand(P + 1, N, dtype=torch.float32, seed=3)
+    out = torch.zeros(n_img * (P + 1), N, dtype=torch.float32, device=DEV)
+    ops.gemm(A, W, EPI_PATCH_EMBED, bn, simt, out=out, bias=bias, pos_emb=pos, patches=P)
+    ref = (_ref_mm(A, W) + bias).view(n_img, P, N) + pos[1:]
+    assert ops.rel_err(out.view(n_img, P + 1, N)[:, 1:], ref) < 1e-5
+    assert torch.all(out.view(n_img, P + 1, N)[:, 0] == 0)
+    # STORE_F32 with a scatter map (row -> packed row, -1 = drop)
+    M = n_img * P
+    g = torch.Generator().manual_seed(1)
+    rmap = torch.randperm(2 * M, generator=g)[:M].to(torch.int32)
+    rmap[::7] = -1
+    rmap = rmap.to(DEV)
+    out2 = torch.zeros(2 * M, N, dtype=torch.float32, device=DEV)
+    ops.gemm(A, W, EPI_STORE_F32, bn, simt, out=out2, bias=bias, row_map=rmap)
+    ref2 = torch.zeros_like(out2)
+    keep = rmap >= 0
+    ref2[rmap[keep].long()] = (_ref_mm(A, W) + bias)[keep]
+    assert ops.rel_err(out2, ref2) < 1e-5
+
+
+def _attn_ref(q, k, v, scale, kv_limit):
+    """q [Lq,hd] k,v [Lk,hd] fp32, keys < kv_limit visible."""
+    s = (q @ k.t()) * scale
+    s[:, kv_limit:] = float("-inf")
+    return torch.softmax(s, dim=-1) @ v
+
+
+def test_attention_vit():
+    B, heads, N, hd, d = 3, 4, 257, 64, 256
+    qkv = _rand(B * N, 3 * d)
+    out = torch.zeros(B * N, d, dtype=torch.bfloat16, device=DEV)
+    ops.attention(qkv, qkv[:, d:], qkv[:, 2 * d:], out, hd, 1, heads, B, hd ** -0.5, 3 * d, 3 * d, hd, d,
+                  uni_q_len=N, uni_kv_len=N, max_q_len=N)
+    x = qkv.float().view(B, N, 3, heads, hd)
+    ref = torch.empty(B, N, heads, hd, device=DEV)
+    for b in range(B):
+        for h in range(heads):
+            ref[b, :, h] = _attn_ref(x[b, :, 0, h], x[b, :, 1, h], x[b, :, 2, h], hd ** -0.5, N)
+    err = ops.rel_err(out.view(B, N, heads, hd), ref)
+    print(f"attention_vit rel={err:.2e}")
+    assert err < 1e-2
+
+
+def test_attention_prefill_and_denoise():
+    """GQA 6:1, ragged lengths, proprio extra row (prefill) then H action queries (denoise)."""
+    B, nkv, group, hd, H = 3, 2, 6, 128, 4
+    nq = nkv * group
+    lens = [85, 1, 130]
+    cu = [0]
+    for L in lens:
+        cu.append(cu[-1] + L)
+    kvoff = [cu[b] + b * (1 + H) for b in range(B)]
+    rows_cap = cu[-1] + B * (1 + H) + 3
+    q = _rand(cu[-1], nq * hd, seed=1)
+    q2 = _rand(B, nq * hd, seed=2)
+    kc = _rand(nkv, rows_cap, hd, seed=3)
+    vc = _rand(nkv, rows_cap, hd, seed=4)
+    i32 = lambda x: torch.tensor(x, dtype=torch.int32, device=DEV)
+    out = torch.zeros_like(q)
+    out2 = torch.zeros_like(q2)
+    scale = hd ** -0.5
+    ops.attention(q, kc, vc, out, hd, group, nkv, B, scale, nq * hd, hd, rows_cap * hd, nq * hd,
+                  max_q_len=max(lens) + 1, q_start=i32(cu[:-1]), q_len=i32(lens), kv_start=i32(kvoff), kv_len=i32(lens),
+                  q2=q2, q2_row_stride=nq * hd, out2=out2, out2_row_stride=nq * hd)
+    errs = []
+    for b in range(B):
+        L = lens[b]
+        for h in range(nq):
+            g = h // group
+            K = kc[g, kvoff[b]:kvoff[b] + L + 1].float()
+            V = vc[g, kvoff[b]:kvoff[b] + L + 1].float()
+            r = _attn_ref(q[cu[b]:cu[b] + L, h * hd:(h + 1) * hd].float(), K, V, scale, L)
+            errs.append(ops.rel_err(out[cu[b]:cu[b] + L, h * hd:(h + 1) * hd], r))
+            r2 = _attn_ref(q2[b:b + 1, h * hd:(h + 1) * hd].float(), K, V, scale, L + 1)
+            errs.append(ops.rel_err(out2[b:b + 1, h * hd:(h + 1) * hd], r2))
+    print(f"attention_prefill max rel={max(errs):.2e}")
+    assert max(errs) < 1e-2
+    # denoise: H queries per sample over prefix + proprio + H action keys
+    qa = _rand(B * H, nq * hd, seed=5)
+    outa = torch.zeros_like(qa)
+    ops.attention(qa, kc, vc, outa, hd, group, nkv, B, scale, nq * hd, hd, rows_cap * hd, nq * hd, max_q_len=H,
+                  q_start=i32([b * H for b in range(B)]), q_len=i32([H] * B), kv_start=i32(kvoff),
+                  kv_len=i32([L + 1 + H for L in lens]))
+    errs = []
+    for b in range(B):
+        Lk = lens[b] + 1 + H
+        for h in range(nq):
+            g = h // group
+            r = _attn_ref(qa[b * H:(b + 1) * H, h * hd:(h + 1) * hd].float(), kc[g, kvoff[b]:kvoff[b] + Lk].float(),
+                          vc[g, kvoff[b]:kvoff[b] + Lk].float(), scale, Lk)
+            errs.append(ops.rel_err(outa[b * H:(b + 1) * H, h * hd:(h + 1) * hd], r))
+    print(f"attention_denoise max rel={max(errs):.2e}")
+    assert max(errs) < 1e-2
+
+
+@pytest.mark.parametrize("width", [128, 768, 1024, 1536, 4096])
+def test_norms(width):
+    rows = 515
+    x = _rand(rows, width, dtype=torch.float32, seed=1) * 3 + 0.5
+    gamma = _rand(width, dtype=torch.float32, seed=2)
+    beta = _rand(width, dtype=torch.float32, seed=3)
+    ln = ops.layernorm(x, gamma, beta, 1e-6)
+    ref = torch.nn.functional.layer_norm(x, (width,), gamma, beta, 1e-6)
+    assert ops.rel_err(ln, ref) < 4e-3
+    rms = ops.rmsnorm(x, gamma, 1e-6)
+    ref = gamma * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6))
+    assert ops.rel_err(rms, ref) < 4e-3
+
+
+def test_pixel_shuffle_bit_exact():
+    """Integer/indexing work: bit-exact against the closed-form index map and the reference op."""
+    from oracle.vlaser_oracle import pixel_shuffle as ref_ps
+    for g, Cc, dtype in ((16, 1024, torch.float32), (32, 128, torch.float32), (16, 256, torch.bfloat16)):
+        n = 3
+        x = torch.arange(n * g * g * Cc, dtype=torch.float32).remainder(65521).to(dtype).view(n, g, g, Cc)
+        got = ops.pixel_shuffle(x.to(DEV)).cpu()
+        assert torch.equal(got, ref_ps(x))
+
+
+def test_pixel_shuffle_layernorm_gather():
+    from oracle.vlaser_oracle import pixel_shuffle as ref_ps
+    n, g, Cc = 2, 16, 256
+    x = _rand(n * (g * g + 1), Cc, dtype=torch.float32, seed=1)
+    gamma = _rand(4 * Cc, dtype=torch.float32, seed=2)
+    beta = _rand(4 * Cc, dtype=torch.float32, seed=3)
+    got = ops.layernorm(x, gamma, beta, 1e-5, g, Cc, rows=n * g * g // 4, width=4 * Cc)
+    feats = x.view(n, g * g + 1, Cc)[:, 1:].reshape(n, g, g, Cc).cpu()
+    sh = ref_ps(feats).reshape(-1, 4 * Cc).to(DEV)
+    ref = torch.nn.functional.layer_norm(sh, (4 * Cc,), gamma, beta, 1e-5)
+    assert ops.rel_err(got, ref) < 4e-3
+
+
+def test_im2col_exact():
+    n, px, ps = 2, 224, 14
+    pix = _rand(n, 3, px, px, dtype=torch.bfloat16, seed=1)
+    cols = ops.im2col(pix, ps, 640)
+    ref = torch.nn.functional.unfold(pix.float(), ps, stride=ps).transpose(1, 2).reshape(n * 256, 588)
+    assert torch.equal(cols[:, :588].float(), ref)
+    assert torch.all(cols[:, 588:] == 0)
+
+
+def test_euler_step():
+    B, H, A, width, horizon = 5, 4, 7, 768, 4
+    x = _rand(B * H, width, dtype=torch.float32, seed=1)
+    gamma = _rand(width, dtype=torch.float32, seed=2)
+    Wd = _rand(A, width, dtype=torch.float32, seed=3) * 0.1
+    bd = _rand(A, dtype=torch.float32, seed=4)
+    act = _rand(B * H, A, dtype=torch.float32, seed=5)
+    ref = act + 0.1 * ((gamma * x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6)) @ Wd.t() + bd)
+    out = torch.zeros(B, horizon, A, dtype=torch.float32, device=DEV)
+    ops.euler_step(x, gamma, Wd, bd, act, out, H, horizon, 0.1, 1e-6, True, 1.0)
+    assert ops.max_err(act, ref) < 1e-5
+    assert ops.max_err(out.view(-1, A), ref.clamp(-1, 1)) < 1e-5

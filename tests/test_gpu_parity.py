@@ -1,0 +1,179 @@
+"""-m gpu: end-to-end parity of the CUDA path (through the C ABI, via the PiZeroInference binding)
+against (a) the golden vectors produced by the unmodified reference and (b) the fp32 oracle, with
+per-stage hidden-state relative errors (SURVEY.md §8d "Correctness gates").
+
+Tolerances (stated by BASELINE.json north_star): normalised actions max-abs error <= 1e-2 vs the fp32
+reference on identical bf16-rounded weights/inputs and injected noise; per-layer hidden states are
+checked by relative L2 error; indexing work (token layout, pixel_shuffle, patch order) is bit-exact.
+"""
+from __future__ import annotations
+
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import vlaser_oracle as O  # noqa: E402  (checker only)
+from tests.golden_util import CASES, load_case  # noqa: E402
+from tests.ops import max_err, rel_err  # noqa: E402
+from vlaser_b200.config import tiny, vlaser_2b_bridge  # noqa: E402
+from vlaser_b200.policy import PiZeroInference  # noqa: E402
+from vlaser_b200.synth import make_inputs  # noqa: E402
+from vlaser_b200.weights import random_state_dict  # noqa: E402
+
+ACTION_TOL = 1e-2
+
+
+def _policy(cfg, sd, B, **opts):
+    pol = PiZeroInference(cfg, max_batch=B)
+    pol.load_state_dict(sd, strict=True)
+    for k, v in opts.items():
+        pol.set_option(k, v)
+    return pol
+
+
+def _run(pol, inp, dtype=torch.float32, masks=False):
+    ids = inp["input_ids"].cuda()
+    pix = inp["pixel_values"].to(dtype).cuda()
+    prop = inp["proprios"].to(dtype).cuda()
+    noise = inp["noise"].to(dtype).cuda()
+    if masks:
+        am = (inp["input_ids"] != pol.pad_token_id).to(torch.int64)
+        m, vp, pp, ap = pol.build_causal_mask_and_position_ids(am, dtype)
+        itp, amask = pol.split_full_mask_into_submasks(m)
+        return pol(ids, pix, itp.cuda(), amask.cuda(), vp.cuda(), pp.cuda(), ap.cuda(), prop, noise=noise).float().cpu()
+    return pol.infer_action(ids, pix, proprios=prop, noise=noise).float().cpu()
+
+
+def _stage_report(cfg, sd, inp, pol, B, log):
+    """Per-stage relative errors of the CUDA path vs the fp32 oracle. Returns dict of errors."""
+    tr = {}
+    O.infer_action(cfg.with_(final_action_clip_value=None), sd, inp["input_ids"], inp["pixel_values"], inp["proprios"],
+                   inp["noise"], trace=tr)
+    errs = {}
+    S, H, A = cfg.max_image_text_tokens, cfg.num_action_tokens, cfg.action_dim
+    Ni = B * cfg.num_images
+    valid = (inp["input_ids"] != cfg.pad_token_id).sum(-1).tolist()
+    # ---- ViT
+    pol.set_option("stop_after", 1)
+    _run(pol, inp)
+    vit = pol.debug_buffer("vit_x", torch.float32)[: Ni * cfg.vit_tokens * cfg.vit_hidden].view(Ni, cfg.vit_tokens, -1)
+    errs["vit_embed"] = None
+    errs["vit_out"] = rel_err(vit, tr["vit_out"])
+    # ---- prefix embedding (packed rows)
+    pol.set_option("stop_after", 2)
+    _run(pol, inp)
+    assert pol.debug_buffer("valid_len", torch.int32)[:B].tolist() == valid
+    cu = pol.debug_buffer("cu", torch.int32)[: B + 1].tolist()
+    px = pol.debug_buffer("prefix_x", torch.float32)[: cu[-1] * cfg.hidden].view(cu[-1], cfg.hidden)
+    ref = torch.cat([tr["prefix_embeds"][b, : valid[b]] for b in range(B)])
+    errs["prefix_embeds"] = rel_err(px, ref)
+    # text rows are a pure gather of bf16-exact embeddings: bit exact
+    is_text = torch.cat([(inp["input_ids"][b, : valid[b]] != cfg.image_token_index) for b in range(B)])
+    assert torch.equal(px[is_text], ref[is_text]), "text-token rows of the prefix must be bit-exact"
+    xp = pol.debug_buffer("proprio_x", torch.float32)[: B * cfg.hidden_e].view(B, 1, -1)
+    errs["proprio_embeds"] = rel_err(xp, tr["proprio_embeds"])
+    # ---- prefill: KV caches
+    pol.set_option("stop_after", 3)
+    _run(pol, inp)
+    kv_rows = int(pol.debug_buffer("kv_rows", torch.int64)[0])
+    kvoff = pol.debug_buffer("kvoff", torch.int32)[:B].tolist()
+    kc = pol.debug_buffer("k_cache", torch.bfloat16).view(cfg.layers, cfg.n_kv_heads, kv_rows, 128).float()
+    vc = pol.debug_buffer("v_cache", torch.bfloat16).view(cfg.layers, cfg.n_kv_heads, kv_rows, 128).float()
+    for li in (0, cfg.layers - 1):
+        for nm, cache in (("k", kc), ("v", vc)):
+            got = torch.cat([cache[li, :, kvoff[b]: kvoff[b] + valid[b]] for b in range(B)], dim=1)
+            want = torch.cat([tr[f"{nm}_vlm_layer{li}"][b, :, : valid[b]] for b in range(B)], dim=1)
+            errs[f"{nm}_vlm_layer{li}"] = rel_err(got, want)
+            gotp = torch.stack([cache[li, :, kvoff[b] + valid[b]] for b in range(B)])
+            errs[f"{nm}_proprio_layer{li}"] = rel_err(gotp, tr[f"{nm}_proprio_layer{li}"][:, :, 0])
+    # ---- first denoise step
+    pol.set_option("stop_after", 4)
+    _run(pol, inp)
+    act = pol.debug_buffer("action", torch.float32)[: B * H * A].view(B, H, A)
+    errs["action_step0_maxabs"] = max_err(act, tr["action_step0"])
+    pol.set_option("stop_after", 0)
+    for k, v in errs.items():
+        if v is not None:
+            log(f"    {k:28s} {v:.3e}")
+    return errs, tr
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("simt", [0, 1])
+def test_golden_parity(name, simt, capsys):
+    """CUDA path vs the reference's golden vectors (tiny configs: bridge / fractal / 3-camera RoboTwin)."""
+    cfg, sd, inp, gold = load_case(name)
+    B = inp["input_ids"].shape[0]
+    pol = _policy(cfg, sd, B, simt_gemm=simt)
+    act = _run(pol, inp)
+    e_post = max_err(act, gold["actions"])
+    pol_pre = _policy(cfg.with_(final_action_clip_value=None), sd, B, simt_gemm=simt)
+    pre = _run(pol_pre, inp)
+    e_pre = max_err(pre, gold["trace_actions_preclamp_sliced"])
+    with capsys.disabled():
+        print(f"\n[{name} simt={simt}] actions max-abs vs reference golden: post-clamp {e_post:.3e}  pre-clamp {e_pre:.3e}")
+        errs, _ = _stage_report(cfg, sd, inp, pol, B, print)
+    assert e_post <= ACTION_TOL and e_pre <= ACTION_TOL
+    assert errs["vit_out"] < 1e-2 and errs["prefix_embeds"] < 1e-2
+    assert errs["k_vlm_layer0"] < 1e-2 and errs[f"k_vlm_layer{cfg.layers - 1}"] < 3e-2
+    assert errs["action_step0_maxabs"] < ACTION_TOL
+
+
+def test_graph_equals_direct_and_mask_api():
+    cfg, sd, inp, gold = load_case("tiny_bridge")
+    B = inp["input_ids"].shape[0]
+    pol = _policy(cfg, sd, B, use_graph=1)
+    a1 = _run(pol, inp)
+    a2 = _run(pol, inp)            # graph replay
+    a3 = _run(pol, inp, masks=True)  # reference-style call with dense masks / position ids
+    pol2 = _policy(cfg, sd, B, use_graph=0)
+    a4 = _run(pol2, inp)
+    a5 = _run(pol2, inp, dtype=torch.bfloat16)
+    # split-K accumulates with fp32 atomics, so runs agree to rounding, not bitwise
+    assert max_err(a1, a2) < 1e-4 and max_err(a1, a3) < 1e-4 and max_err(a1, a4) < 1e-4
+    assert max_err(a5, gold["actions"]) < 2e-2  # bf16 I/O rounds the returned actions
+    assert pol.last_launch_count() > 100
+
+
+def test_batch_row_independence_and_ragged():
+    cfg = tiny()
+    sd = random_state_dict(cfg, 3)
+    inp = make_inputs(cfg, 5, 21, [3, 14, 7, 1, 9])
+    pol = _policy(cfg, sd, 5)
+    full = _run(pol, inp)
+    for b in (0, 3):
+        one = {k: v[b:b + 1] for k, v in inp.items() if k in ("input_ids", "pixel_values", "proprios", "noise")}
+        assert max_err(_run(pol, one), full[b:b + 1]) < 1e-4
+    ref = O.infer_action(cfg, sd, inp["input_ids"], inp["pixel_values"], inp["proprios"], inp["noise"])
+    assert max_err(full, ref) <= ACTION_TOL
+
+
+def test_host_entry_point():
+    cfg, sd, inp, gold = load_case("tiny_bridge")
+    B = inp["input_ids"].shape[0]
+    pol = _policy(cfg, sd, B)
+    out = pol.infer_action_host(inp["input_ids"], inp["pixel_values"], inp["proprios"], inp["noise"])
+    assert max_err(out, gold["actions"]) <= ACTION_TOL
+
+
+@pytest.mark.skipif(os.environ.get("VLASER_SKIP_FULL", "0") == "1", reason="full-size parity skipped by env")
+def test_full_size_2b_parity(capsys):
+    """BASELINE config 1 shapes (Vlaser-2B-VLA, 1x224 px, S=384, 10 steps), B=2, vs the fp32 oracle."""
+    cfg = vlaser_2b_bridge()
+    sd = random_state_dict(cfg, 0)
+    B = 2
+    inp = make_inputs(cfg, B, 1)
+    pol = _policy(cfg.with_(final_action_clip_value=None), sd, B)
+    pre = _run(pol, inp)
+    with capsys.disabled():
+        print("\n[vlaser_2b_bridge B=2] per-stage relative errors vs fp32 oracle:")
+        errs, tr = _stage_report(cfg, sd, inp, pol, B, print)
+        ref_pre = tr["actions_preclamp"][:, -cfg.horizon_steps:]
+        e_pre = max_err(pre, ref_pre)
+        e_post = max_err(pre.clamp(-1, 1), ref_pre.clamp(-1, 1))
+        print(f"    actions max-abs: pre-clamp {e_pre:.3e} post-clamp {e_post:.3e} (mean-abs pre {float((pre - ref_pre).abs().mean()):.3e})")
+    assert errs["vit_out"] < 2e-2 and errs["prefix_embeds"] < 2e-2
+    assert e_post <= ACTION_TOL

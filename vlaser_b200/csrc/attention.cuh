@@ -1,0 +1,43 @@
+// Fused (flash-style, online-softmax) attention used at the three sites of the hot path:
+//   * InternViT self-attention    (head_dim 64, no mask, N = P+1 tokens per image)       -- _naive_attn
+//   * prefix prefill              (head_dim 128, GQA, bidirectional over the valid prefix; the
+//                                  proprio token is an extra query row that also sees its own key)
+//   * denoise step                (head_dim 128, GQA, H action queries over cached prefix + proprio
+//                                  + H fresh action keys)
+// No mask tensor is read: the block-attention rule of build_causal_mask_and_position_ids
+// (pizero_internvl.py:517-587) is encoded as per-sample (q_len, kv_len) plus the extra-row rule.
+#pragma once
+#include "common.cuh"
+
+namespace vlaser {
+
+struct AttnParams {
+  const __nv_bfloat16* q = nullptr;   // row r, head h at q + r*q_row_stride + h*HD
+  long long q_row_stride = 0;
+  const __nv_bfloat16* q2 = nullptr;  // optional extra query row per sample (proprio): q2 + b*q2_row_stride + h*HD
+  long long q2_row_stride = 0;
+  const __nv_bfloat16* k = nullptr;   // kv row r, kv head g at k + g*kv_head_stride + r*kv_row_stride
+  const __nv_bfloat16* v = nullptr;
+  long long kv_row_stride = 0;
+  long long kv_head_stride = 0;
+  __nv_bfloat16* out = nullptr;       // same addressing as q
+  long long out_row_stride = 0;
+  __nv_bfloat16* out2 = nullptr;      // same addressing as q2
+  long long out2_row_stride = 0;
+  // per-sample segments; when q_len == nullptr the uniform values are used (start = b * uni_*)
+  const int* q_start = nullptr;
+  const int* q_len = nullptr;
+  const int* kv_start = nullptr;
+  const int* kv_len = nullptr;
+  int uni_q_len = 0;
+  int uni_kv_len = 0;
+  int max_q_len = 0;    // upper bound on q_len (+1 if q2) for grid sizing
+  int group = 1;        // query heads per kv head
+  int n_kv_heads = 1;
+  int batch = 0;
+  float scale = 1.f;
+};
+
+int attention_launch(const AttnParams& p, int head_dim, cudaStream_t stream);
+
+}  // namespace vlaser

@@ -1,0 +1,439 @@
+// Memory-bound kernels (see elementwise.cuh). All of them are one pass over their operands with
+// 16-byte vector accesses; norms keep the row in registers (one warp per row).
+#include "elementwise.cuh"
+
+namespace vlaser {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// norms
+// ------------------------------------------------------------------------------------------
+template <int VPL, bool RMS, bool GATHER>
+__global__ void __launch_bounds__(128) norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                                                   int rows, const int* __restrict__ rows_dev, float eps, int g,
+                                                   int C) {
+  constexpr int W = VPL * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + warp;
+  const int nrows = rows_dev ? min(*rows_dev, rows) : rows;
+  if (row >= nrows) return;
+  float4 v[VPL];
+  if constexpr (GATHER) {
+    // row = (img, r2, c2) of the pixel-shuffled grid; source = 4 ViT tokens (CLS skipped)
+    const int hg = g >> 1, T = hg * hg, P = g * g;
+    const int img = row / T, t = row - img * T;
+    const int r2 = t / hg, c2 = t - r2 * hg;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int e = (i * 32 + lane) * 4;
+      const int seg = e / C, within = e - seg * C;
+      const int tok = (2 * r2 + (seg >> 1)) * g + 2 * c2 + (seg & 1);
+      v[i] = *reinterpret_cast<const float4*>(x + (size_t)(img * (P + 1) + 1 + tok) * C + within);
+    }
+  } else {
+    const float4* src = reinterpret_cast<const float4*>(x + (size_t)row * W);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) v[i] = src[i * 32 + lane];
+  }
+  float mean = 0.f;
+  if constexpr (!RMS) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    mean = warp_sum(s) * (1.0f / W);
+  }
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / W) + eps);
+  uint2* dst = reinterpret_cast<uint2*>(out + (size_t)row * W);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int e4 = i * 32 + lane;
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + e4);
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * gm.x;
+    y.y = (v[i].y - mean) * rstd * gm.y;
+    y.z = (v[i].z - mean) * rstd * gm.z;
+    y.w = (v[i].w - mean) * rstd * gm.w;
+    if constexpr (!RMS) {
+      const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + e4);
+      y.x += bt.x;
+      y.y += bt.y;
+      y.z += bt.z;
+      y.w += bt.w;
+    }
+    uint2 u;
+    u.x = pack_bf16(y.x, y.y);
+    u.y = pack_bf16(y.z, y.w);
+    dst[e4] = u;
+  }
+}
+
+template <bool RMS, bool GATHER>
+int norm_dispatch(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows,
+                  const int* rows_dev, int width, float eps, int g, int C, cudaStream_t stream) {
+  VL_CHECK(width % 128 == 0 && width >= 128 && width <= 4096, "norm: width must be a multiple of 128, <= 4096");
+  if (rows <= 0) return 0;
+  const int grid = (rows + 3) / 4;
+#define VL_NORM_CASE(V)                                                                                          \
+  case V:                                                                                                        \
+    norm_kernel<V, RMS, GATHER><<<grid, 128, 0, stream>>>(x, gamma, beta, out, rows, rows_dev, eps, g, C);       \
+    break;
+  switch (width / 128) {
+    VL_NORM_CASE(1) VL_NORM_CASE(2) VL_NORM_CASE(3) VL_NORM_CASE(4) VL_NORM_CASE(6) VL_NORM_CASE(8)
+    VL_NORM_CASE(12) VL_NORM_CASE(16) VL_NORM_CASE(28) VL_NORM_CASE(32)
+    default:
+      set_last_error("norm: unsupported width " + std::to_string(width));
+      return -2;
+  }
+#undef VL_NORM_CASE
+  VL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// pixel_shuffle (standalone, bit exact)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pixel_shuffle_kernel(const T* __restrict__ in, T* __restrict__ out, int n, int g, int C) {
+  // out[img, r2, c2, b*2C + a*C + c] = in[img, 2*r2+b, 2*c2+a, c]
+  const int hg = g >> 1;
+  const long long total = (long long)n * hg * hg * 4 * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int seg = (int)(r & 3);
+    r >>= 2;
+    const int c2 = (int)(r % hg);
+    r /= hg;
+    const int r2 = (int)(r % hg);
+    const int img = (int)(r / hg);
+    const long long src = (((long long)img * g + (2 * r2 + (seg >> 1))) * g + (2 * c2 + (seg & 1))) * C + c;
+    out[i] = in[src];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// im2col / cls rows
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void im2col_kernel(const T* __restrict__ pix, __nv_bfloat16* __restrict__ cols, int n, int px, int ps,
+                              int kpad) {
+  const int g = px / ps;
+  const int kreal = 3 * ps * ps;
+  const long long total = (long long)n * g * g * kpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % kpad);
+    const long long row = i / kpad;
+    float val = 0.f;
+    if (k < kreal) {
+      const int p = (int)(row % (g * g));
+      const int img = (int)(row / (g * g));
+      const int pr = p / g, pc = p - pr * g;
+      const int ch = k / (ps * ps), rem = k - ch * ps * ps;
+      const int ky = rem / ps, kx = rem - ky * ps;
+      val = static_cast<float>(pix[(((long long)img * 3 + ch) * px + pr * ps + ky) * px + pc * ps + kx]);
+    }
+    cols[i] = __float2bfloat16(val);
+  }
+}
+
+__global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
+                                int n, int tokens, int width) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * width) return;
+  const int img = i / width, c = i - img * width;
+  x[(size_t)img * tokens * width + c] = cls[c] + pos[c];
+}
+
+// ------------------------------------------------------------------------------------------
+// planning
+// ------------------------------------------------------------------------------------------
+__global__ void plan_lengths_kernel(const long long* __restrict__ ids, const int* __restrict__ valid_in, PlanBuffers pb,
+                                    int B, int S, int H, int pad_token) {
+  // one warp per sample counts non-pad ids
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  int cnt = 0;
+  if (valid_in) {
+    cnt = valid_in[warp];
+  } else {
+    for (int j = lane; j < S; j += 32) cnt += ids[(size_t)warp * S + j] != pad_token;
+    cnt = (int)warp_sum((float)cnt);
+  }
+  if (lane == 0) pb.valid_len[warp] = min(max(cnt, 0), S);
+}
+
+__global__ void plan_scan_kernel(PlanBuffers pb, int B, int H) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int acc = 0;
+    for (int b = 0; b < B; ++b) {
+      pb.cu[b] = acc;
+      pb.kvoff[b] = acc + b * (1 + H);
+      acc += pb.valid_len[b];
+    }
+    pb.cu[B] = acc;
+    *pb.m_tot = acc;
+  }
+}
+
+__global__ void plan_rows_kernel(const long long* __restrict__ ids, PlanBuffers pb, int B, int S, int H,
+                                 int img_tokens, int image_token, int pad_token) {
+  // one warp per sample
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int vl = pb.valid_len[b], base = pb.cu[b], kvo = pb.kvoff[b];
+  int seen = 0;
+  for (int j0 = 0; j0 < S; j0 += 32) {
+    const int j = j0 + lane;
+    const bool valid = j < vl;
+    const long long id = (j < S) ? ids[(size_t)b * S + j] : pad_token;
+    const bool is_img = valid && id == image_token;
+    const unsigned mask = __ballot_sync(0xffffffffu, is_img);
+    if (valid) {
+      const int m = base + j;
+      pb.row_pos[m] = j + 1;
+      pb.row_kvrow[m] = kvo + j;
+      int src;
+      if (is_img) {
+        const int k = seen + __popc(mask & ((1u << lane) - 1u));
+        if (k < img_tokens) {
+          pb.img_row_map[b * img_tokens + k] = m;
+          src = -2;
+        } else {
+          src = -1;
+        }
+      } else {
+        src = (id == pad_token) ? -1 : (int)id;
+      }
+      pb.row_src[m] = src;
+    }
+    seen += __popc(mask);
+  }
+  if (lane == 0) {
+    pb.prop_pos[b] = 1;
+    pb.prop_kvrow[b] = kvo + vl;
+    pb.pre_kv_len[b] = vl;
+    pb.den_q_start[b] = b * H;
+    pb.den_q_len[b] = H;
+    pb.den_kv_len[b] = vl + 1 + H;
+  }
+  for (int i = lane; i < H; i += 32) {
+    pb.act_pos[b * H + i] = 2 + i;
+    pb.act_kvrow[b * H + i] = kvo + vl + 1 + i;
+  }
+}
+
+__global__ void assemble_text_kernel(const __nv_bfloat16* __restrict__ embed, const int* __restrict__ row_src,
+                                     const int* __restrict__ m_tot, float* __restrict__ x, int rows_cap, int width) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= min(*m_tot, rows_cap)) return;
+  const int src = row_src[row];
+  if (src == -2) return;
+  float* dst = x + (size_t)row * width;
+  if (src < 0) {
+    for (int c = lane * 4; c < width; c += 128) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const __nv_bfloat16* s = embed + (size_t)src * width;
+  for (int c = lane * 8; c < width; c += 256) {
+    const uint4 u = *reinterpret_cast<const uint4*>(s + c);
+    *reinterpret_cast<float4*>(dst + c) = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+    *reinterpret_cast<float4*>(dst + c + 4) = make_float4(bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// small heads
+// ------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void small_linear_kernel(const TI* __restrict__ in, const float* __restrict__ W,
+                                    const float* __restrict__ bias, TO* __restrict__ out, int rows, int K, int N) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * N) return;
+  const int r = (int)(i / N), n = (int)(i - (long long)r * N);
+  float acc = bias ? bias[n] : 0.f;
+  for (int k = 0; k < K; ++k) acc += W[(size_t)n * K + k] * static_cast<float>(in[(size_t)r * K + k]);
+  out[i] = static_cast<TO>(acc);
+}
+
+template <typename TI, typename TO>
+__global__ void convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = static_cast<TO>(static_cast<float>(in[i]));
+}
+
+// ------------------------------------------------------------------------------------------
+// final norm + decoder + Euler
+// ------------------------------------------------------------------------------------------
+template <typename TO>
+__global__ void __launch_bounds__(128) euler_step_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ Wdec,
+                                                         const float* __restrict__ bdec, float* __restrict__ action,
+                                                         TO* __restrict__ out, int rows, int width, int A, int H,
+                                                         int horizon, float dt, float eps, int last_step, int do_clip,
+                                                         float clip) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + warp;
+  if (r >= rows) return;
+  const float* xr = x + (size_t)r * width;
+  float q = 0.f;
+  for (int c = lane; c < width; c += 32) {
+    const float v = xr[c];
+    q += v * v;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / width + eps);
+  for (int a = 0; a < A; ++a) {
+    float acc = 0.f;
+    for (int c = lane; c < width; c += 32) acc += xr[c] * rstd * gamma[c] * Wdec[(size_t)a * width + c];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float val = action[(size_t)r * A + a] + dt * (acc + bdec[a]);
+      action[(size_t)r * A + a] = val;
+      if (last_step) {
+        const int b = r / H, i = r - b * H;
+        if (i >= H - horizon) {
+          if (do_clip) val = fminf(fmaxf(val, -clip), clip);
+          out[((size_t)b * horizon + (i - (H - horizon))) * A + a] = static_cast<TO>(val);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// ==========================================================================================
+int layernorm_launch(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows, int width,
+                     float eps, ShuffleGather sg, cudaStream_t stream) {
+  if (sg.grid > 0) {
+    VL_CHECK(width == 4 * sg.channels && sg.channels % 4 == 0 && sg.grid % 2 == 0, "layernorm gather: bad shape");
+    return norm_dispatch<false, true>(x, gamma, beta, out, rows, nullptr, width, eps, sg.grid, sg.channels, stream);
+  }
+  return norm_dispatch<false, false>(x, gamma, beta, out, rows, nullptr, width, eps, 0, 0, stream);
+}
+
+int rmsnorm_launch(const float* x, const float* gamma, __nv_bfloat16* out, int rows, const int* rows_dev, int width,
+                   float eps, cudaStream_t stream) {
+  return norm_dispatch<true, false>(x, gamma, nullptr, out, rows, rows_dev, width, eps, 0, 0, stream);
+}
+
+int pixel_shuffle_launch(const void* in, void* out, int n, int grid, int channels, int elem_bytes,
+                         cudaStream_t stream) {
+  VL_CHECK(grid % 2 == 0 && grid > 0, "pixel_shuffle: grid must be even");
+  const long long total = (long long)n * grid * grid * channels;
+  if (total == 0) return 0;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+  if (elem_bytes == 4)
+    pixel_shuffle_kernel<uint32_t><<<blocks, 256, 0, stream>>>((const uint32_t*)in, (uint32_t*)out, n, grid, channels);
+  else if (elem_bytes == 2)
+    pixel_shuffle_kernel<uint16_t><<<blocks, 256, 0, stream>>>((const uint16_t*)in, (uint16_t*)out, n, grid, channels);
+  else {
+    set_last_error("pixel_shuffle: elem_bytes must be 2 or 4");
+    return -2;
+  }
+  VL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int im2col_launch(const void* pixel, int pixel_dtype, __nv_bfloat16* cols, int n, int px, int ps, int kpad,
+                  cudaStream_t stream) {
+  VL_CHECK(px % ps == 0 && kpad >= 3 * ps * ps, "im2col: bad shape");
+  const long long total = (long long)n * (px / ps) * (px / ps) * kpad;
+  if (total == 0) return 0;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 32);
+  if (pixel_dtype == DT_F32)
+    im2col_kernel<float><<<blocks, 256, 0, stream>>>((const float*)pixel, cols, n, px, ps, kpad);
+  else
+    im2col_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)pixel, cols, n, px, ps, kpad);
+  VL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int cls_rows_launch(float* x, const float* cls, const float* pos, int n, int tokens, int width, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  cls_rows_kernel<<<(n * width + 255) / 256, 256, 0, stream>>>(x, cls, pos, n, tokens, width);
+  VL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int plan_launch(const long long* input_ids, const int* valid_len_in, PlanBuffers pb, int B, int S, int H,
+                int img_tokens_per_sample, int image_token, int pad_token, cudaStream_t stream) {
+  VL_CHECK(B > 0, "plan: empty batch");
+  VL_CUDA_CHECK(cudaMemsetAsync(pb.img_row_map, 0xFF, sizeof(int) * (size_t)B * img_tokens_per_sample, stream));
+  plan_lengths_kernel<<<(B * 32 + 127) / 128, 128, 0, stream>>>(input_ids, valid_len_in, pb, B, S, H, pad_token);
+  plan_scan_kernel<<<1, 32, 0, stream>>>(pb, B, H);
+  plan_rows_kernel<<<B, 32, 0, stream>>>(input_ids, pb, B, S, H, img_tokens_per_sample, image_token, pad_token);
+  VL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int assemble_text_launch(const __nv_bfloat16* embed, const int* row_src, const int* m_tot, float* x, int rows_cap,
+                         int width, cudaStream_t stream) {
+  VL_CHECK(width % 8 == 0, "assemble: width % 8");
+  if (rows_cap <= 0) return 0;
+  assemble_text_kernel<<<(rows_cap + 3) / 4, 128, 0, stream>>>(embed, row_src, m_tot, x, rows_cap, width);
+  VL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int small_linear_launch(const void* in, int in_dtype, const float* W, const float* bias, void* out, int out_dtype,
+                        int rows, int K, int N, cudaStream_t stream) {
+  const long long total = (long long)rows * N;
+  if (total <= 0) return 0;
+  const int blocks = (int)((total + 255) / 256);
+  if (in_dtype == DT_F32 && out_dtype == DT_F32)
+    small_linear_kernel<float, float><<<blocks, 256, 0, stream>>>((const float*)in, W, bias, (float*)out, rows, K, N);
+  else if (in_dtype == DT_F32 && out_dtype == DT_BF16)
+    small_linear_kernel<float, __nv_bfloat16>
+        <<<blocks, 256, 0, stream>>>((const float*)in, W, bias, (__nv_bfloat16*)out, rows, K, N);
+  else if (in_dtype == DT_BF16 && out_dtype == DT_F32)
+    small_linear_kernel<__nv_bfloat16, float>
+        <<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)in, W, bias, (float*)out, rows, K, N);
+  else
+    small_linear_kernel<__nv_bfloat16, __nv_bfloat16>
+        <<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)in, W, bias, (__nv_bfloat16*)out, rows, K, N);
+  VL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int convert_launch(const void* in, int in_dtype, void* out, int out_dtype, long long n, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  if (in_dtype == DT_F32 && out_dtype == DT_F32)
+    convert_kernel<float, float><<<blocks, 256, 0, stream>>>((const float*)in, (float*)out, n);
+  else if (in_dtype == DT_BF16 && out_dtype == DT_F32)
+    convert_kernel<__nv_bfloat16, float><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)in, (float*)out, n);
+  else if (in_dtype == DT_F32 && out_dtype == DT_BF16)
+    convert_kernel<float, __nv_bfloat16><<<blocks, 256, 0, stream>>>((const float*)in, (__nv_bfloat16*)out, n);
+  else
+    convert_kernel<__nv_bfloat16, __nv_bfloat16>
+        <<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, n);
+  VL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int euler_step_launch(const float* x, const float* gamma, const float* Wdec, const float* bdec, float* action,
+                      void* out, int out_dtype, int rows, int width, int A, int H, int horizon, float dt, float eps,
+                      int last_step, int do_clip, float clip, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  const int grid = (rows + 3) / 4;
+  if (out_dtype == DT_F32)
+    euler_step_kernel<float><<<grid, 128, 0, stream>>>(x, gamma, Wdec, bdec, action, (float*)out, rows, width, A, H,
+                                                       horizon, dt, eps, last_step, do_clip, clip);
+  else
+    euler_step_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(x, gamma, Wdec, bdec, action, (__nv_bfloat16*)out, rows,
+                                                               width, A, H, horizon, dt, eps, last_step, do_clip, clip);
+  VL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vlaser

@@ -1,0 +1,72 @@
+// Memory-bound kernels of the hot path (HBM roofline): norms, pixel-shuffle gather, im2col,
+// token planning / embedding assembly, the action encoder head and the fused
+// final-norm + action decoder + Euler update.
+#pragma once
+#include "common.cuh"
+
+namespace vlaser {
+
+enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
+
+// ---- norms: fp32 residual stream in, bf16 GEMM operand out. width % 128 == 0, width <= 4096.
+// LayerNorm (nn.LayerNorm, two-pass statistics) and HF Qwen2RMSNorm.
+struct ShuffleGather {   // pixel_shuffle(0.5) gather fused into the projector's LayerNorm
+  int grid = 0;          // g (patch grid side); 0 = no gather
+  int channels = 0;      // C (ViT hidden)
+};
+int layernorm_launch(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows, int width,
+                     float eps, ShuffleGather sg, cudaStream_t stream);
+int rmsnorm_launch(const float* x, const float* gamma, __nv_bfloat16* out, int rows, const int* rows_dev, int width,
+                   float eps, cudaStream_t stream);
+
+// ---- pixel_shuffle (pizero_internvl.py:706-716), pure re-index, bit exact. elem_bytes in {2,4}.
+int pixel_shuffle_launch(const void* in, void* out, int n, int grid, int channels, int elem_bytes, cudaStream_t stream);
+
+// ---- patch embedding support (modeling_intern_vit.py:162-174)
+// pixel [n,3,px,px] (f32|bf16) -> cols bf16 [n*P, kpad], column = ch*ps*ps + ky*ps + kx, zero padded.
+int im2col_launch(const void* pixel, int pixel_dtype, __nv_bfloat16* cols, int n, int px, int ps, int kpad,
+                  cudaStream_t stream);
+// x[img*(P+1), :] = cls + pos[0]
+int cls_rows_launch(float* x, const float* cls, const float* pos, int n, int tokens, int width, cudaStream_t stream);
+
+// ---- prefix planning (valid lengths, packed offsets, row tables) — replaces the dense mask /
+// position-id tensors of build_causal_mask_and_position_ids (pizero_internvl.py:517-587)
+struct PlanBuffers {
+  int* valid_len;     // [B]
+  int* cu;            // [B+1] packed-row offsets
+  int* kvoff;         // [B]   KV-cache row offsets: cu[b] + b*(1+H)
+  int* m_tot;         // [1]
+  int* row_pos;       // [B*S] RoPE position per packed row (j+1)
+  int* row_kvrow;     // [B*S]
+  int* row_src;       // [B*S] >=0 embed row, -1 zeros, -2 image row (written by the projector epilogue)
+  int* img_row_map;   // [B*n_img*T] projector output row -> packed row (or -1)
+  int* prop_pos;      // [B] == 1
+  int* prop_kvrow;    // [B]
+  int* act_pos;       // [B*H] 2..H+1
+  int* act_kvrow;     // [B*H]
+  int* pre_kv_len;    // [B]  == valid_len
+  int* den_q_start;   // [B]
+  int* den_q_len;     // [B]
+  int* den_kv_len;    // [B]  valid_len + 1 + H
+};
+int plan_launch(const long long* input_ids, const int* valid_len_in, PlanBuffers pb, int B, int S, int H,
+                int img_tokens_per_sample, int image_token, int pad_token, cudaStream_t stream);
+// text rows of the packed prefix: x[m,:] = embed[row_src[m],:] (bf16 -> fp32) or zeros
+int assemble_text_launch(const __nv_bfloat16* embed, const int* row_src, const int* m_tot, float* x, int rows_cap,
+                         int width, cudaStream_t stream);
+
+// ---- small dense heads on CUDA cores (K = action/proprio dim <= 32)
+// out[r,n] = bias[n] + sum_k W[n,k] * in[r,k]   (in f32|bf16; out fp32 or bf16)
+int small_linear_launch(const void* in, int in_dtype, const float* W, const float* bias, void* out, int out_dtype,
+                        int rows, int K, int N, cudaStream_t stream);
+// convert/copy a [n] vector between dtypes (noise ingest)
+int convert_launch(const void* in, int in_dtype, void* out, int out_dtype, long long n, cudaStream_t stream);
+
+// ---- final RMSNorm + action decoder + Euler step (pizero_internvl.py:911-912, 927-934)
+// action[r,:] += dt * (Wdec * RMS(x[r,:], gamma) + bdec); on the last step also writes
+// out[b, i-(H-horizon), :] = clamp(action) for the last `horizon` tokens.
+int euler_step_launch(const float* x, const float* gamma, const float* Wdec, const float* bdec, float* action,
+                      void* out, int out_dtype, int rows, int width, int A, int H, int horizon, float dt, float eps,
+                      int last_step, int do_clip, float clip, cudaStream_t stream);
+
+}  // namespace vlaser

@@ -1,0 +1,1114 @@
+// Engine behind the C ABI (include/vlaser_b200.h): weight packing, HBM-resident buffers, the
+// launch schedule of PiZero.infer_action (pizero_internvl.py:798-936) and its CUDA-graph replay.
+//
+// Data layout in HBM (all sized for cfg.max_batch at create):
+//   weights      bf16 [N,K] row-major (nn.Linear layout == K-major UMMA operand), q|k|v fused,
+//                gate/up interleaved in 32-row groups; norm gains, biases, layer-scales, RoPE
+//                tables, time-embedding biases in fp32
+//   residuals    fp32  ViT [imgs*(P+1), d], prefix [sum valid_len, h] PACKED (no padding rows),
+//                proprio [B, he], action [B*H, he]
+//   GEMM inputs  bf16 activations written by the norm kernels / epilogues
+//   KV cache     bf16 [layer][K|V][kv_head][rows][128], sample b owns rows kvoff[b].. :
+//                valid prefix tokens, then the proprio token, then the H action tokens
+// The valid lengths live on the device (plan kernels), every launch configuration depends on B
+// only, so one CUDA graph per batch size replays the whole call.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/vlaser_b200.h"
+#include "attention.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+
+namespace vlaser {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+// ------------------------------------------------------------------------------------------
+// weight ingest
+// ------------------------------------------------------------------------------------------
+enum PackMode : int { PK_PLAIN = 0, PK_GATE = 1, PK_UP = 2 };
+
+struct Slot {
+  void* dst = nullptr;
+  int dst_dtype = DT_F32;
+  long long rows = 1, cols = 1;       // expected source view [rows, cols]
+  long long src_col0 = 0, ncols = 0;  // copied column range (ncols==0 -> all)
+  long long dst_ld = 0, dst_row_off = 0;
+  int mode = PK_PLAIN;
+  bool filled = false;
+};
+
+template <typename TS, typename TD>
+__global__ void pack_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long rows, long long src_ld,
+                            long long src_col0, long long ncols, long long dst_ld, long long dst_row_off, int mode) {
+  const long long total = rows * ncols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ncols, c = i - r * ncols;
+    long long dr = r;
+    if (mode == PK_GATE) dr = (r >> 5) * 64 + (r & 31);
+    if (mode == PK_UP) dr = (r >> 5) * 64 + 32 + (r & 31);
+    dst[(dst_row_off + dr) * dst_ld + c] = static_cast<TD>(static_cast<float>(src[r * src_ld + src_col0 + c]));
+  }
+}
+
+struct Lin {            // one packed projection weight
+  bf16* w = nullptr;
+  int N = 0, K = 0;
+  CUtensorMap tm128, tm256;
+  bool has256 = false;
+};
+struct Act {            // one bf16 activation buffer usable as GEMM A operand
+  bf16* p = nullptr;
+  int rows = 0, K = 0;
+  CUtensorMap tm;
+};
+
+struct VitLayer {
+  float *n1w, *n1b, *n2w, *n2b, *bqkv, *bproj, *ls1, *bfc1, *bfc2, *ls2;
+  Lin qkv, proj, fc1, fc2;
+};
+struct LlmLayer {
+  float *ln_in, *ln_post, *bqkv;
+  Lin qkv, o, gu, down;
+};
+
+struct Engine {
+  vlaser_cfg c{};
+  int device = 0;
+  int P = 0, T = 0, G = 0, H = 0, S = 0, Bc = 0, kpad = 0, n_img = 0;
+  int qdim = 0, kvdim = 0, qkvN = 0;
+  long long kv_rows = 0;
+  bool finalized = false;
+  std::vector<void*> allocs;
+  std::multimap<std::string, Slot> slots;
+
+  // weights
+  Lin patch;
+  float *patch_b = nullptr, *cls = nullptr, *pos = nullptr;
+  std::vector<VitLayer> vit;
+  float *pj_lnw = nullptr, *pj_lnb = nullptr, *pj_b1 = nullptr, *pj_b2 = nullptr;
+  Lin pj1, pj2;
+  bf16* embed = nullptr;
+  std::vector<LlmLayer> llm, exp;
+  float* final_norm = nullptr;
+  float *ae_w1 = nullptr, *ae_b1 = nullptr, *ae_w2a = nullptr, *ae_b2 = nullptr, *ae_b3 = nullptr;
+  Lin ae_w2b, ae_w3;
+  float *pe_w = nullptr, *pe_b = nullptr, *dec_w = nullptr, *dec_b = nullptr;
+  float *cos_tab = nullptr, *sin_tab = nullptr, *time_bias = nullptr;  // [steps][he]
+
+  // activations
+  Act cols, vn, vattn, vmlp, ps, pa, xn, ao, act, xpn, aop, actp, xan, aoa, acta, e1, h2;
+  float *vx = nullptr, *xv = nullptr, *xp = nullptr, *xa = nullptr, *action = nullptr;
+  bf16 *vqkv = nullptr, *q = nullptr, *qp = nullptr, *qa = nullptr;
+  bf16 *kc = nullptr, *vc = nullptr;  // [layers][kv_heads][kv_rows][128]
+  PlanBuffers pb{};
+  // static I/O staging (graph operands)
+  long long* in_ids = nullptr;
+  void *in_pix = nullptr, *in_prop = nullptr, *in_noise = nullptr, *out_act = nullptr;
+  int* in_valid = nullptr;
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+
+  // options / state
+  int use_graph = 1, stop_after = 0, simt = 0;
+  long long launches = 0, last_launches = 0;
+  cudaStream_t own_stream = nullptr;
+  struct GraphKey {
+    int B, io, stop, simt, has_valid;
+    bool operator<(const GraphKey& o) const {
+      return std::tie(B, io, stop, simt, has_valid) < std::tie(o.B, o.io, o.stop, o.simt, o.has_valid);
+    }
+  };
+  struct GraphVal {
+    cudaGraphExec_t exec;
+    long long launches;
+  };
+  std::map<GraphKey, GraphVal> graphs;
+
+  ~Engine() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
+    for (void* p : allocs) cudaFree(p);
+    if (pinned) cudaFreeHost(pinned);
+    if (own_stream) cudaStreamDestroy(own_stream);
+  }
+
+  template <typename Tp>
+  int alloc(Tp** out, size_t count) {
+    void* p = nullptr;
+    const size_t bytes = std::max<size_t>(count * sizeof(Tp), 256);
+    VL_CUDA_CHECK(cudaMalloc(&p, bytes));
+    VL_CUDA_CHECK(cudaMemset(p, 0, bytes));
+    allocs.push_back(p);
+    *out = reinterpret_cast<Tp*>(p);
+    return 0;
+  }
+
+  // ---- slot helpers
+  void add_slot(const std::string& key, void* dst, int dtype, long long rows, long long cols, long long dst_ld = 0,
+                long long dst_row_off = 0, int mode = PK_PLAIN, long long src_col0 = 0, long long ncols = 0) {
+    Slot s;
+    s.dst = dst;
+    s.dst_dtype = dtype;
+    s.rows = rows;
+    s.cols = cols;
+    s.src_col0 = src_col0;
+    s.ncols = ncols ? ncols : cols;
+    s.dst_ld = dst_ld ? dst_ld : s.ncols;
+    s.dst_row_off = dst_row_off;
+    s.mode = mode;
+    slots.emplace(key, s);
+  }
+  int add_vec(const std::string& key, float** dst, long long n) {
+    if (alloc(dst, (size_t)n)) return -1;
+    add_slot(key, *dst, DT_F32, 1, n);
+    return 0;
+  }
+  int add_lin(const std::string& key, Lin* l, int N, int K) {
+    l->N = N;
+    l->K = K;
+    if (alloc(&l->w, (size_t)N * K)) return -1;
+    if (!key.empty()) add_slot(key, l->w, DT_BF16, N, K);
+    return 0;
+  }
+  int make_lin_maps(Lin* l) {
+    if (make_tmap_bf16(&l->tm128, l->w, l->N, l->K, 128)) return -1;
+    l->has256 = (l->N % 256 == 0);
+    if (l->has256 && make_tmap_bf16(&l->tm256, l->w, l->N, l->K, 256)) return -1;
+    return 0;
+  }
+  int add_act(Act* a, int rows, int K) {
+    a->rows = rows;
+    a->K = K;
+    // pad the row count to a multiple of 128 so that TMA boxes never start out of bounds
+    const int rows_alloc = (rows + 127) / 128 * 128;
+    if (alloc(&a->p, (size_t)rows_alloc * K)) return -1;
+    return make_tmap_bf16(&a->tm, a->p, rows_alloc, K, 128);
+  }
+};
+
+#define VL_TRY(expr)          \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != 0) return _r;   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// construction
+// ------------------------------------------------------------------------------------------
+int engine_build(Engine& e) {
+  const vlaser_cfg& c = e.c;
+  VL_CHECK(c.head_dim == 128, "head_dim must be 128 (joint_model.py:437)");
+  VL_CHECK(c.vit_hidden == c.vit_heads * 64, "InternViT head dim must be 64");
+  VL_CHECK(c.image_size % c.patch_size == 0, "image_size % patch_size");
+  VL_CHECK(c.n_heads % c.n_kv_heads == 0, "n_heads % n_kv_heads");
+  VL_CHECK(c.max_batch > 0, "max_batch > 0");
+  VL_CHECK(c.mlp % 32 == 0 && c.mlp_e % 32 == 0, "mlp sizes must be multiples of 32");
+  VL_CHECK(c.hidden % 128 == 0 && c.hidden_e % 128 == 0 && c.vit_hidden % 128 == 0 && c.vit_mlp % 128 == 0,
+           "hidden sizes must be multiples of 128");
+  VL_CHECK(c.action_dim <= 32 && c.proprio_dim <= 64, "action/proprio dims too large");
+  e.G = c.image_size / c.patch_size;
+  VL_CHECK(e.G % 2 == 0, "patch grid must be even for pixel_shuffle(0.5)");
+  e.P = e.G * e.G;
+  e.T = e.P / 4;
+  e.n_img = c.cond_steps;
+  e.H = c.horizon_steps + c.cond_steps - 1;
+  e.S = c.max_image_text_tokens;
+  e.Bc = c.max_batch;
+  e.kpad = (3 * c.patch_size * c.patch_size + 63) / 64 * 64;
+  e.qdim = c.n_heads * 128;
+  e.kvdim = c.n_kv_heads * 128;
+  e.qkvN = e.qdim + 2 * e.kvdim;
+  e.kv_rows = (long long)e.Bc * (e.S + 1 + e.H);
+  VL_CHECK(e.n_img * e.T <= e.S, "image tokens exceed max_image_text_tokens");
+  VL_CUDA_CHECK(cudaGetDevice(&e.device));
+  VL_CUDA_CHECK(cudaStreamCreateWithFlags(&e.own_stream, cudaStreamNonBlocking));
+
+  const int d = c.vit_hidden, f = c.vit_mlp, h = c.hidden, he = c.hidden_e;
+  const std::string v = "vision_tower.vision_model.";
+  // --- ViT
+  VL_TRY(e.add_lin("", &e.patch, d, e.kpad));
+  e.add_slot(v + "embeddings.patch_embedding.weight", e.patch.w, DT_BF16, d, 3 * c.patch_size * c.patch_size, e.kpad);
+  VL_TRY(e.add_vec(v + "embeddings.patch_embedding.bias", &e.patch_b, d));
+  VL_TRY(e.add_vec(v + "embeddings.class_embedding", &e.cls, d));
+  VL_TRY(e.add_vec(v + "embeddings.position_embedding", &e.pos, (long long)(e.P + 1) * d));
+  e.vit.resize(c.vit_layers);
+  for (int i = 0; i < c.vit_layers; ++i) {
+    VitLayer& L = e.vit[i];
+    const std::string p = v + "encoder.layers." + std::to_string(i) + ".";
+    VL_TRY(e.add_vec(p + "norm1.weight", &L.n1w, d));
+    VL_TRY(e.add_vec(p + "norm1.bias", &L.n1b, d));
+    VL_TRY(e.add_lin(p + "attn.qkv.weight", &L.qkv, 3 * d, d));
+    VL_TRY(e.add_vec(p + "attn.qkv.bias", &L.bqkv, 3 * d));
+    VL_TRY(e.add_lin(p + "attn.proj.weight", &L.proj, d, d));
+    VL_TRY(e.add_vec(p + "attn.proj.bias", &L.bproj, d));
+    VL_TRY(e.add_vec(p + "ls1", &L.ls1, d));
+    VL_TRY(e.add_vec(p + "norm2.weight", &L.n2w, d));
+    VL_TRY(e.add_vec(p + "norm2.bias", &L.n2b, d));
+    VL_TRY(e.add_lin(p + "mlp.fc1.weight", &L.fc1, f, d));
+    VL_TRY(e.add_vec(p + "mlp.fc1.bias", &L.bfc1, f));
+    VL_TRY(e.add_lin(p + "mlp.fc2.weight", &L.fc2, d, f));
+    VL_TRY(e.add_vec(p + "mlp.fc2.bias", &L.bfc2, d));
+    VL_TRY(e.add_vec(p + "ls2", &L.ls2, d));
+  }
+  // --- projector
+  VL_TRY(e.add_vec("multi_modal_projector.0.weight", &e.pj_lnw, 4 * d));
+  VL_TRY(e.add_vec("multi_modal_projector.0.bias", &e.pj_lnb, 4 * d));
+  VL_TRY(e.add_lin("multi_modal_projector.1.weight", &e.pj1, h, 4 * d));
+  VL_TRY(e.add_vec("multi_modal_projector.1.bias", &e.pj_b1, h));
+  VL_TRY(e.add_lin("multi_modal_projector.3.weight", &e.pj2, h, h));
+  VL_TRY(e.add_vec("multi_modal_projector.3.bias", &e.pj_b2, h));
+  VL_TRY(e.alloc(&e.embed, (size_t)c.embed_rows * h));
+  e.add_slot("embed_tokens.weight", e.embed, DT_BF16, c.embed_rows, h);
+  // --- LLM + expert
+  auto add_llm = [&](std::vector<LlmLayer>& Ls, const std::string& prefix, int hid, int mlp) -> int {
+    Ls.resize(c.layers);
+    for (int i = 0; i < c.layers; ++i) {
+      LlmLayer& L = Ls[i];
+      const std::string p = prefix + "layers." + std::to_string(i) + ".";
+      VL_TRY(e.add_vec(p + "input_layernorm.weight", &L.ln_in, hid));
+      VL_TRY(e.add_vec(p + "post_attention_layernorm.weight", &L.ln_post, hid));
+      VL_TRY(e.add_lin("", &L.qkv, e.qkvN, hid));
+      e.add_slot(p + "self_attn.q_proj.weight", L.qkv.w, DT_BF16, e.qdim, hid, hid, 0);
+      e.add_slot(p + "self_attn.k_proj.weight", L.qkv.w, DT_BF16, e.kvdim, hid, hid, e.qdim);
+      e.add_slot(p + "self_attn.v_proj.weight", L.qkv.w, DT_BF16, e.kvdim, hid, hid, e.qdim + e.kvdim);
+      VL_TRY(e.alloc(&L.bqkv, (size_t)e.qkvN));
+      e.add_slot(p + "self_attn.q_proj.bias", L.bqkv, DT_F32, 1, e.qdim);
+      e.add_slot(p + "self_attn.k_proj.bias", L.bqkv + e.qdim, DT_F32, 1, e.kvdim);
+      e.add_slot(p + "self_attn.v_proj.bias", L.bqkv + e.qdim + e.kvdim, DT_F32, 1, e.kvdim);
+      VL_TRY(e.add_lin(p + "self_attn.o_proj.weight", &L.o, hid, e.qdim));
+      VL_TRY(e.add_lin("", &L.gu, 2 * mlp, hid));
+      e.add_slot(p + "mlp.gate_proj.weight", L.gu.w, DT_BF16, mlp, hid, hid, 0, PK_GATE);
+      e.add_slot(p + "mlp.up_proj.weight", L.gu.w, DT_BF16, mlp, hid, hid, 0, PK_UP);
+      VL_TRY(e.add_lin(p + "mlp.down_proj.weight", &L.down, hid, mlp));
+    }
+    return 0;
+  };
+  VL_TRY(add_llm(e.llm, "joint_model.mixtures.vlm.", h, c.mlp));
+  VL_TRY(add_llm(e.exp, "joint_model.mixtures.action.", he, c.mlp_e));
+  VL_TRY(e.add_vec("joint_model.mixtures.action.norm.weight", &e.final_norm, he));
+  // --- heads
+  VL_TRY(e.add_vec("action_encoder.linear_1.weight", &e.ae_w1, (long long)he * c.action_dim));
+  VL_TRY(e.add_vec("action_encoder.linear_1.bias", &e.ae_b1, he));
+  VL_TRY(e.alloc(&e.ae_w2a, (size_t)he * he));
+  VL_TRY(e.add_lin("", &e.ae_w2b, he, he));
+  e.add_slot("action_encoder.linear_2.weight", e.ae_w2a, DT_F32, he, 2 * he, he, 0, PK_PLAIN, 0, he);
+  e.add_slot("action_encoder.linear_2.weight", e.ae_w2b.w, DT_BF16, he, 2 * he, he, 0, PK_PLAIN, he, he);
+  VL_TRY(e.add_vec("action_encoder.linear_2.bias", &e.ae_b2, he));
+  VL_TRY(e.add_lin("action_encoder.linear_3.weight", &e.ae_w3, he, he));
+  VL_TRY(e.add_vec("action_encoder.linear_3.bias", &e.ae_b3, he));
+  VL_TRY(e.add_vec("proprio_encoder.weight", &e.pe_w, (long long)he * c.proprio_dim));
+  VL_TRY(e.add_vec("proprio_encoder.bias", &e.pe_b, he));
+  VL_TRY(e.add_vec("action_decoder.weight", &e.dec_w, (long long)c.action_dim * he));
+  VL_TRY(e.add_vec("action_decoder.bias", &e.dec_b, c.action_dim));
+
+  // --- activations
+  const int Ni = e.Bc * e.n_img;
+  const int vrows = Ni * (e.P + 1);
+  const int prow = e.Bc * e.S;
+  const int arow = e.Bc * e.H;
+  VL_TRY(e.add_act(&e.cols, Ni * e.P, e.kpad));
+  VL_TRY(e.alloc(&e.vx, (size_t)vrows * d));
+  VL_TRY(e.add_act(&e.vn, vrows, d));
+  VL_TRY(e.alloc(&e.vqkv, (size_t)vrows * 3 * d));
+  VL_TRY(e.add_act(&e.vattn, vrows, d));
+  VL_TRY(e.add_act(&e.vmlp, vrows, f));
+  VL_TRY(e.add_act(&e.ps, Ni * e.T, 4 * d));
+  VL_TRY(e.add_act(&e.pa, Ni * e.T, h));
+  VL_TRY(e.alloc(&e.xv, (size_t)prow * h));
+  VL_TRY(e.add_act(&e.xn, prow, h));
+  VL_TRY(e.alloc(&e.q, (size_t)prow * e.qdim));
+  VL_TRY(e.add_act(&e.ao, prow, e.qdim));
+  VL_TRY(e.add_act(&e.act, prow, c.mlp));
+  VL_TRY(e.alloc(&e.xp, (size_t)e.Bc * he));
+  VL_TRY(e.add_act(&e.xpn, e.Bc, he));
+  VL_TRY(e.alloc(&e.qp, (size_t)e.Bc * e.qdim));
+  VL_TRY(e.add_act(&e.aop, e.Bc, e.qdim));
+  VL_TRY(e.add_act(&e.actp, e.Bc, c.mlp_e));
+  VL_TRY(e.alloc(&e.xa, (size_t)arow * he));
+  VL_TRY(e.add_act(&e.xan, arow, he));
+  VL_TRY(e.alloc(&e.qa, (size_t)arow * e.qdim));
+  VL_TRY(e.add_act(&e.aoa, arow, e.qdim));
+  VL_TRY(e.add_act(&e.acta, arow, c.mlp_e));
+  VL_TRY(e.add_act(&e.e1, arow, he));
+  VL_TRY(e.add_act(&e.h2, arow, he));
+  VL_TRY(e.alloc(&e.action, (size_t)arow * c.action_dim));
+  const size_t kv_elems = (size_t)c.layers * c.n_kv_heads * e.kv_rows * 128;
+  VL_TRY(e.alloc(&e.kc, kv_elems));
+  VL_TRY(e.alloc(&e.vc, kv_elems));
+  // --- plan buffers
+  PlanBuffers& pb = e.pb;
+  VL_TRY(e.alloc(&pb.valid_len, e.Bc));
+  VL_TRY(e.alloc(&pb.cu, e.Bc + 1));
+  VL_TRY(e.alloc(&pb.kvoff, e.Bc));
+  VL_TRY(e.alloc(&pb.m_tot, 1));
+  VL_TRY(e.alloc(&pb.row_pos, prow));
+  VL_TRY(e.alloc(&pb.row_kvrow, prow));
+  VL_TRY(e.alloc(&pb.row_src, prow));
+  VL_TRY(e.alloc(&pb.img_row_map, e.Bc * e.n_img * e.T));
+  VL_TRY(e.alloc(&pb.prop_pos, e.Bc));
+  VL_TRY(e.alloc(&pb.prop_kvrow, e.Bc));
+  VL_TRY(e.alloc(&pb.act_pos, arow));
+  VL_TRY(e.alloc(&pb.act_kvrow, arow));
+  VL_TRY(e.alloc(&pb.pre_kv_len, e.Bc));
+  VL_TRY(e.alloc(&pb.den_q_start, e.Bc));
+  VL_TRY(e.alloc(&pb.den_q_len, e.Bc));
+  VL_TRY(e.alloc(&pb.den_kv_len, e.Bc));
+  // --- I/O staging
+  VL_TRY(e.alloc(&e.in_ids, (size_t)e.Bc * e.S));
+  VL_TRY(e.alloc(&e.in_valid, e.Bc));
+  const size_t pix_elems = (size_t)Ni * 3 * c.image_size * c.image_size;
+  VL_TRY(e.alloc((float**)&e.in_pix, pix_elems));
+  VL_TRY(e.alloc((float**)&e.in_prop, (size_t)e.Bc * c.proprio_dim));
+  VL_TRY(e.alloc((float**)&e.in_noise, (size_t)arow * c.action_dim));
+  VL_TRY(e.alloc((float**)&e.out_act, (size_t)e.Bc * c.horizon_steps * c.action_dim));
+  e.pinned_bytes = (size_t)e.Bc * e.S * 8 + pix_elems * 4 + (size_t)e.Bc * 4 + (size_t)e.Bc * c.proprio_dim * 4 +
+                   (size_t)arow * c.action_dim * 4 + (size_t)e.Bc * c.horizon_steps * c.action_dim * 4 + 4096;
+  VL_CUDA_CHECK(cudaMallocHost(&e.pinned, e.pinned_bytes));
+  return 0;
+}
+
+int engine_set_weight(Engine& e, std::string key, const void* data, const int64_t* shape, int ndim, int dtype) {
+  VL_CHECK(!e.finalized, "set_weight after finalize");
+  VL_CHECK(dtype == DT_F32 || dtype == DT_BF16, "weight dtype must be f32 or bf16");
+  static const std::pair<const char*, const char*> aliases[] = {
+      {"_orig_mod.", ""},
+      {"joint_model.mixtures.proprio.", "joint_model.mixtures.action."},
+      {"internvl_model.vision_model.", "vision_tower.vision_model."},
+      {"internvl_model.mlp1.", "multi_modal_projector."},
+      {"internvl_model.language_model.model.embed_tokens.", "embed_tokens."},
+      {"internvl_model.language_model.model.layers.", "joint_model.mixtures.vlm.layers."},
+      {"internvl_model.action_expert.model.layers.", "joint_model.mixtures.action.layers."},
+      {"internvl_model.action_expert.model.norm.", "joint_model.mixtures.action.norm."},
+  };
+  for (auto& a : aliases) {
+    const size_t n = strlen(a.first);
+    if (key.compare(0, n, a.first) == 0) key = std::string(a.second) + key.substr(n);
+  }
+  auto range = e.slots.equal_range(key);
+  if (range.first == range.second) return 1;  // not a tensor of this path
+  long long numel = 1;
+  for (int i = 0; i < ndim; ++i) numel *= shape[i];
+  const size_t esz = dtype == DT_F32 ? 4 : 2;
+  // stage host data on the device
+  cudaPointerAttributes attr{};
+  const void* src = data;
+  void* tmp = nullptr;
+  cudaError_t pe = cudaPointerGetAttributes(&attr, data);
+  if (pe != cudaSuccess) cudaGetLastError();
+  if (pe != cudaSuccess || attr.type == cudaMemoryTypeUnregistered || attr.type == cudaMemoryTypeHost) {
+    VL_CUDA_CHECK(cudaMalloc(&tmp, (size_t)numel * esz));
+    VL_CUDA_CHECK(cudaMemcpy(tmp, data, (size_t)numel * esz, cudaMemcpyHostToDevice));
+    src = tmp;
+  }
+  int rc = 0;
+  for (auto it = range.first; it != range.second && rc == 0; ++it) {
+    Slot& s = it->second;
+    if (numel != s.rows * s.cols) {
+      set_last_error("set_weight: " + key + " has " + std::to_string(numel) + " elements, expected " +
+                     std::to_string(s.rows * s.cols));
+      rc = -2;
+      break;
+    }
+    const long long total = s.rows * s.ncols;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+#define VL_PACK(TS, TD)                                                                                       \
+  pack_kernel<TS, TD><<<blocks, 256>>>((const TS*)src, (TD*)s.dst, s.rows, s.cols, s.src_col0, s.ncols,       \
+                                       s.dst_ld, s.dst_row_off, s.mode)
+    if (dtype == DT_F32 && s.dst_dtype == DT_F32) VL_PACK(float, float);
+    else if (dtype == DT_F32 && s.dst_dtype == DT_BF16) VL_PACK(float, bf16);
+    else if (dtype == DT_BF16 && s.dst_dtype == DT_F32) VL_PACK(bf16, float);
+    else VL_PACK(bf16, bf16);
+#undef VL_PACK
+    if (cudaGetLastError() != cudaSuccess) {
+      set_last_error("set_weight: pack kernel launch failed for " + key);
+      rc = -1;
+    }
+    s.filled = true;
+  }
+  if (tmp) {
+    cudaDeviceSynchronize();
+    cudaFree(tmp);
+  }
+  return rc;
+}
+
+int engine_finalize(Engine& e) {
+  const vlaser_cfg& c = e.c;
+  for (auto& kv : e.slots) {
+    if (!kv.second.filled) {
+      set_last_error("finalize: missing weight " + kv.first);
+      return -3;
+    }
+  }
+  VL_CUDA_CHECK(cudaDeviceSynchronize());
+  // tensor maps for every packed weight
+  VL_TRY(e.make_lin_maps(&e.patch));
+  for (auto& L : e.vit) {
+    VL_TRY(e.make_lin_maps(&L.qkv));
+    VL_TRY(e.make_lin_maps(&L.proj));
+    VL_TRY(e.make_lin_maps(&L.fc1));
+    VL_TRY(e.make_lin_maps(&L.fc2));
+  }
+  VL_TRY(e.make_lin_maps(&e.pj1));
+  VL_TRY(e.make_lin_maps(&e.pj2));
+  for (auto* Ls : {&e.llm, &e.exp})
+    for (auto& L : *Ls) {
+      VL_TRY(e.make_lin_maps(&L.qkv));
+      VL_TRY(e.make_lin_maps(&L.o));
+      VL_TRY(e.make_lin_maps(&L.gu));
+      VL_TRY(e.make_lin_maps(&L.down));
+    }
+  VL_TRY(e.make_lin_maps(&e.ae_w2b));
+  VL_TRY(e.make_lin_maps(&e.ae_w3));
+  // RoPE tables (HF Qwen2RotaryEmbedding, default rope): cos/sin(pos * theta^(-2i/128)), i < 64
+  const int max_pos = std::max(e.S, e.H + 1) + 1;
+  std::vector<float> ct((size_t)max_pos * 64), st((size_t)max_pos * 64);
+  for (int p = 0; p < max_pos; ++p)
+    for (int i = 0; i < 64; ++i) {
+      const float inv = 1.0f / std::pow((float)c.rope_theta, (float)(2 * i) / 128.0f);
+      const float ang = (float)p * inv;  // fp32 product as in the reference
+      ct[(size_t)p * 64 + i] = (float)std::cos((double)ang);
+      st[(size_t)p * 64 + i] = (float)std::sin((double)ang);
+    }
+  VL_TRY(e.alloc(&e.cos_tab, ct.size()));
+  VL_TRY(e.alloc(&e.sin_tab, st.size()));
+  VL_CUDA_CHECK(cudaMemcpy(e.cos_tab, ct.data(), ct.size() * 4, cudaMemcpyHostToDevice));
+  VL_CUDA_CHECK(cudaMemcpy(e.sin_tab, st.data(), st.size() * 4, cudaMemcpyHostToDevice));
+  // time-embedding contribution of ActionEncoder.linear_2 for each Euler step:
+  //   tb[k] = b2 + W2[:, :he] * cat(sin(t_k w), cos(t_k w))   (modules.py:15-22, 39-53)
+  const int he = c.hidden_e, half = he / 2, steps = c.num_inference_steps;
+  std::vector<float> w2a((size_t)he * he), b2(he), tb((size_t)steps * he);
+  VL_CUDA_CHECK(cudaMemcpy(w2a.data(), e.ae_w2a, w2a.size() * 4, cudaMemcpyDeviceToHost));
+  VL_CUDA_CHECK(cudaMemcpy(b2.data(), e.ae_b2, b2.size() * 4, cudaMemcpyDeviceToHost));
+  float t = 0.f;
+  const float dtf = (float)(1.0 / steps);
+  const float emb = (float)(std::log((double)c.time_max_period) / (half - 1));
+  std::vector<double> tau(he);
+  for (int k = 0; k < steps; ++k) {
+    for (int i = 0; i < half; ++i) {
+      const float w = std::exp((float)i * -emb);
+      const float a = t * w;
+      tau[i] = std::sin((double)a);
+      tau[half + i] = std::cos((double)a);
+    }
+    for (int n = 0; n < he; ++n) {
+      double acc = b2[n];
+      for (int j = 0; j < he; ++j) acc += (double)w2a[(size_t)n * he + j] * tau[j];
+      tb[(size_t)k * he + n] = (float)acc;
+    }
+    t += dtf;
+  }
+  VL_TRY(e.alloc(&e.time_bias, tb.size()));
+  VL_CUDA_CHECK(cudaMemcpy(e.time_bias, tb.data(), tb.size() * 4, cudaMemcpyHostToDevice));
+  e.finalized = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// schedule
+// ------------------------------------------------------------------------------------------
+struct Run {
+  Engine& e;
+  cudaStream_t st;
+  int B;
+  int io;
+  int rc = 0;
+
+  int gemm(const Act& a, const Lin& w, int M, const int* M_dev, int epi, EpiParams ep, int max_splits = 1) {
+    GemmDims d;
+    d.M = M;
+    d.N = w.N;
+    d.K = w.K;
+    d.M_dev = M_dev;
+    d.max_splits = max_splits;
+    e.launches++;
+    if (e.simt) return gemm_launch_simt(a.p, w.w, d, ep, epi, st);
+    int bn = 128;
+    if (epi != EPI_QKV_ROPE && w.has256) {
+      const long long tiles256 = (long long)((M + 127) / 128) * (w.N / 256);
+      if (tiles256 >= gemm_num_sms()) bn = 256;
+    }
+    return gemm_launch(a.tm, bn == 256 ? w.tm256 : w.tm128, d, ep, bn, epi, st);
+  }
+
+  EpiParams rope_ep(bf16* qout, const float* bias, const int* pos, const int* kvrow, int layer) {
+    EpiParams ep;
+    ep.out = qout;
+    ep.ldo = e.qdim;
+    ep.bias = bias;
+    ep.row_pos = pos;
+    ep.row_kvrow = kvrow;
+    ep.cos_tab = e.cos_tab;
+    ep.sin_tab = e.sin_tab;
+    const size_t off = (size_t)layer * e.c.n_kv_heads * e.kv_rows * 128;
+    ep.k_cache = e.kc + off;
+    ep.v_cache = e.vc + off;
+    ep.kv_head_stride = e.kv_rows * 128;
+    ep.n_q_heads = e.c.n_heads;
+    ep.n_kv_heads = e.c.n_kv_heads;
+    return ep;
+  }
+
+  int vit() {
+    const vlaser_cfg& c = e.c;
+    const int d = c.vit_hidden, f = c.vit_mlp;
+    const int Ni = B * e.n_img, rows = Ni * (e.P + 1);
+    VL_TRY(im2col_launch(e.in_pix, io, e.cols.p, Ni, c.image_size, c.patch_size, e.kpad, st));
+    VL_TRY(cls_rows_launch(e.vx, e.cls, e.pos, Ni, e.P + 1, d, st));
+    e.launches += 2;
+    EpiParams ep;
+    ep.out = e.vx;
+    ep.ldo = d;
+    ep.bias = e.patch_b;
+    ep.pos_emb = e.pos;
+    ep.patches = e.P;
+    VL_TRY(gemm(e.cols, e.patch, Ni * e.P, nullptr, EPI_PATCH_EMBED, ep));
+    for (int i = 0; i < c.vit_layers; ++i) {
+      VitLayer& L = e.vit[i];
+      VL_TRY(layernorm_launch(e.vx, L.n1w, L.n1b, e.vn.p, rows, d, c.vit_eps, ShuffleGather{}, st));
+      EpiParams e1;
+      e1.out = e.vqkv;
+      e1.ldo = 3 * d;
+      e1.bias = L.bqkv;
+      VL_TRY(gemm(e.vn, L.qkv, rows, nullptr, EPI_STORE_BF16, e1));
+      AttnParams ap;
+      ap.q = e.vqkv;
+      ap.k = e.vqkv + d;
+      ap.v = e.vqkv + 2 * d;
+      ap.q_row_stride = ap.kv_row_stride = 3 * d;
+      ap.kv_head_stride = 64;
+      ap.out = e.vattn.p;
+      ap.out_row_stride = d;
+      ap.uni_q_len = ap.uni_kv_len = ap.max_q_len = e.P + 1;
+      ap.group = 1;
+      ap.n_kv_heads = c.vit_heads;
+      ap.batch = Ni;
+      ap.scale = 0.125f;
+      VL_TRY(attention_launch(ap, 64, st));
+      EpiParams e2;
+      e2.out = e.vx;
+      e2.ldo = d;
+      e2.bias = L.bproj;
+      e2.scale = L.ls1;
+      VL_TRY(gemm(e.vattn, L.proj, rows, nullptr, EPI_RESID_F32, e2));
+      VL_TRY(layernorm_launch(e.vx, L.n2w, L.n2b, e.vn.p, rows, d, c.vit_eps, ShuffleGather{}, st));
+      EpiParams e3;
+      e3.out = e.vmlp.p;
+      e3.ldo = f;
+      e3.bias = L.bfc1;
+      VL_TRY(gemm(e.vn, L.fc1, rows, nullptr, EPI_GELU_BF16, e3));
+      EpiParams e4;
+      e4.out = e.vx;
+      e4.ldo = d;
+      e4.bias = L.bfc2;
+      e4.scale = L.ls2;
+      VL_TRY(gemm(e.vmlp, L.fc2, rows, nullptr, EPI_RESID_F32, e4));
+      e.launches += 3;
+    }
+    return 0;
+  }
+
+  int embed() {
+    const vlaser_cfg& c = e.c;
+    const int d = c.vit_hidden, h = c.hidden;
+    const int Ni = B * e.n_img, prows = Ni * e.T;
+    ShuffleGather sg;
+    sg.grid = e.G;
+    sg.channels = d;
+    VL_TRY(layernorm_launch(e.vx, e.pj_lnw, e.pj_lnb, e.ps.p, prows, 4 * d, c.proj_eps, sg, st));
+    EpiParams e1;
+    e1.out = e.pa.p;
+    e1.ldo = h;
+    e1.bias = e.pj_b1;
+    VL_TRY(gemm(e.ps, e.pj1, prows, nullptr, EPI_GELU_BF16, e1));
+    EpiParams e2;
+    e2.out = e.xv;
+    e2.ldo = h;
+    e2.bias = e.pj_b2;
+    e2.row_map = e.pb.img_row_map;
+    VL_TRY(gemm(e.pa, e.pj2, prows, nullptr, EPI_STORE_F32, e2));
+    VL_TRY(assemble_text_launch(e.embed, e.pb.row_src, e.pb.m_tot, e.xv, B * e.S, h, st));
+    VL_TRY(small_linear_launch(e.in_prop, io, e.pe_w, e.pe_b, e.xp, DT_F32, B, c.proprio_dim, c.hidden_e, st));
+    e.launches += 3;
+    return 0;
+  }
+
+  // one transformer block of a stream (residual x fp32, expert or LLM weights)
+  int block_pre(LlmLayer& L, float* x, Act& xn, bf16* qout, int M, const int* M_dev, int hid, const int* pos,
+                const int* kvrow, int layer) {
+    VL_TRY(rmsnorm_launch(x, L.ln_in, xn.p, M, M_dev, hid, e.c.rms_eps, st));
+    e.launches++;
+    return gemm(xn, L.qkv, M, M_dev, EPI_QKV_ROPE, rope_ep(qout, L.bqkv, pos, kvrow, layer));
+  }
+  int block_post(LlmLayer& L, float* x, Act& xn, Act& ao, Act& act, int M, const int* M_dev, int hid, int mlp,
+                 int splits) {
+    EpiParams eo;
+    eo.out = x;
+    eo.ldo = hid;
+    VL_TRY(gemm(ao, L.o, M, M_dev, EPI_RESID_F32, eo, splits));
+    VL_TRY(rmsnorm_launch(x, L.ln_post, xn.p, M, M_dev, hid, e.c.rms_eps, st));
+    e.launches++;
+    EpiParams eg;
+    eg.out = act.p;
+    eg.ldo = mlp;
+    VL_TRY(gemm(xn, L.gu, M, M_dev, EPI_SWIGLU_BF16, eg));
+    return gemm(act, L.down, M, M_dev, EPI_RESID_F32, eo, splits);
+  }
+
+  int prefill() {
+    const vlaser_cfg& c = e.c;
+    const int cap = B * e.S;
+    for (int li = 0; li < c.layers; ++li) {
+      VL_TRY(block_pre(e.llm[li], e.xv, e.xn, e.q, cap, e.pb.m_tot, c.hidden, e.pb.row_pos, e.pb.row_kvrow, li));
+      VL_TRY(block_pre(e.exp[li], e.xp, e.xpn, e.qp, B, nullptr, c.hidden_e, e.pb.prop_pos, e.pb.prop_kvrow, li));
+      if (li == c.layers - 1) break;  // last layer: only K/V are needed (joint_model.py:192-193, 690-691)
+      AttnParams ap;
+      const size_t off = (size_t)li * c.n_kv_heads * e.kv_rows * 128;
+      ap.q = e.q;
+      ap.q_row_stride = e.qdim;
+      ap.q2 = e.qp;
+      ap.q2_row_stride = e.qdim;
+      ap.k = e.kc + off;
+      ap.v = e.vc + off;
+      ap.kv_row_stride = 128;
+      ap.kv_head_stride = e.kv_rows * 128;
+      ap.out = e.ao.p;
+      ap.out_row_stride = e.qdim;
+      ap.out2 = e.aop.p;
+      ap.out2_row_stride = e.qdim;
+      ap.q_start = e.pb.cu;
+      ap.q_len = e.pb.valid_len;
+      ap.kv_start = e.pb.kvoff;
+      ap.kv_len = e.pb.pre_kv_len;
+      ap.max_q_len = e.S + 1;
+      ap.group = c.n_heads / c.n_kv_heads;
+      ap.n_kv_heads = c.n_kv_heads;
+      ap.batch = B;
+      ap.scale = 0.08838834764831845f;  // 128^-0.5
+      VL_TRY(attention_launch(ap, 128, st));
+      e.launches++;
+      VL_TRY(block_post(e.llm[li], e.xv, e.xn, e.ao, e.act, cap, e.pb.m_tot, c.hidden, c.mlp, 1));
+      VL_TRY(block_post(e.exp[li], e.xp, e.xpn, e.aop, e.actp, B, nullptr, c.hidden_e, c.mlp_e, 32));
+    }
+    return 0;
+  }
+
+  int denoise(int step) {
+    const vlaser_cfg& c = e.c;
+    const int M = B * e.H, he = c.hidden_e;
+    // action encoder (modules.py:39-53) with the time term pre-reduced into a per-step bias
+    VL_TRY(small_linear_launch(e.action, DT_F32, e.ae_w1, e.ae_b1, e.e1.p, DT_BF16, M, c.action_dim, he, st));
+    e.launches++;
+    EpiParams e2;
+    e2.out = e.h2.p;
+    e2.ldo = he;
+    e2.bias = e.time_bias + (size_t)step * he;
+    VL_TRY(gemm(e.e1, e.ae_w2b, M, nullptr, EPI_SILU_BF16, e2));
+    EpiParams e3;
+    e3.out = e.xa;
+    e3.ldo = he;
+    e3.bias = e.ae_b3;
+    VL_TRY(gemm(e.h2, e.ae_w3, M, nullptr, EPI_STORE_F32, e3));
+    for (int li = 0; li < c.layers; ++li) {
+      VL_TRY(block_pre(e.exp[li], e.xa, e.xan, e.qa, M, nullptr, he, e.pb.act_pos, e.pb.act_kvrow, li));
+      AttnParams ap;
+      const size_t off = (size_t)li * c.n_kv_heads * e.kv_rows * 128;
+      ap.q = e.qa;
+      ap.q_row_stride = e.qdim;
+      ap.k = e.kc + off;
+      ap.v = e.vc + off;
+      ap.kv_row_stride = 128;
+      ap.kv_head_stride = e.kv_rows * 128;
+      ap.out = e.aoa.p;
+      ap.out_row_stride = e.qdim;
+      ap.q_start = e.pb.den_q_start;
+      ap.q_len = e.pb.den_q_len;
+      ap.kv_start = e.pb.kvoff;
+      ap.kv_len = e.pb.den_kv_len;
+      ap.max_q_len = e.H;
+      ap.group = c.n_heads / c.n_kv_heads;
+      ap.n_kv_heads = c.n_kv_heads;
+      ap.batch = B;
+      ap.scale = 0.08838834764831845f;
+      VL_TRY(attention_launch(ap, 128, st));
+      e.launches++;
+      VL_TRY(block_post(e.exp[li], e.xa, e.xan, e.aoa, e.acta, M, nullptr, he, c.mlp_e, 32));
+    }
+    const int last = step == c.num_inference_steps - 1;
+    VL_TRY(euler_step_launch(e.xa, e.final_norm, e.dec_w, e.dec_b, e.action, e.out_act, io, M, he, c.action_dim, e.H,
+                             c.horizon_steps, (float)(1.0 / c.num_inference_steps), c.rms_eps, last, c.clip_enabled,
+                             c.final_action_clip_value, st));
+    e.launches++;
+    return 0;
+  }
+
+  int all(bool has_valid) {
+    const vlaser_cfg& c = e.c;
+    VL_TRY(plan_launch(e.in_ids, has_valid ? e.in_valid : nullptr, e.pb, B, e.S, e.H, e.n_img * e.T,
+                       c.image_token_index, c.pad_token_id, st));
+    VL_TRY(convert_launch(e.in_noise, io, e.action, DT_F32, (long long)B * e.H * c.action_dim, st));
+    e.launches += 5;
+    VL_TRY(vit());
+    if (e.stop_after == 1) return 0;
+    VL_TRY(embed());
+    if (e.stop_after == 2) return 0;
+    VL_TRY(prefill());
+    if (e.stop_after == 3) return 0;
+    for (int k = 0; k < c.num_inference_steps; ++k) {
+      VL_TRY(denoise(k));
+      if (e.stop_after == 4) return 0;
+    }
+    return 0;
+  }
+};
+
+int engine_execute(Engine& e, int B, int io, bool has_valid, cudaStream_t st) {
+  e.launches = 0;
+  if (!e.use_graph) {
+    Run r{e, st, B, io};
+    const int rc = r.all(has_valid);
+    e.last_launches = e.launches;
+    return rc;
+  }
+  Engine::GraphKey key{B, io, e.stop_after, e.simt, has_valid ? 1 : 0};
+  auto it = e.graphs.find(key);
+  if (it == e.graphs.end()) {
+    // Build on the handle's own stream (the caller's may be the legacy default stream, which cannot
+    // be captured). A warm, non-captured pass first sets the per-kernel attributes outside capture.
+    VL_CUDA_CHECK(cudaStreamSynchronize(st));  // staged inputs have landed
+    cudaStream_t cs = e.own_stream;
+    {
+      Run r{e, cs, B, io};
+      VL_TRY(r.all(has_valid));
+      VL_CUDA_CHECK(cudaStreamSynchronize(cs));
+    }
+    e.launches = 0;
+    cudaGraph_t graph = nullptr;
+    VL_CUDA_CHECK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    Run r{e, cs, B, io};
+    const int rc = r.all(has_valid);
+    cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    if (rc != 0) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    VL_CUDA_CHECK(ce);
+    cudaGraphExec_t exec = nullptr;
+    VL_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    it = e.graphs.emplace(key, Engine::GraphVal{exec, e.launches}).first;
+  }
+  VL_CUDA_CHECK(cudaGraphLaunch(it->second.exec, st));
+  e.last_launches = it->second.launches;
+  return 0;
+}
+
+size_t io_size(int io) { return io == DT_F32 ? 4 : 2; }
+
+}  // namespace
+}  // namespace vlaser
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+using namespace vlaser;
+
+struct vlaser_handle {
+  Engine e;
+};
+
+extern "C" {
+
+int32_t vlaser_abi_version(void) { return VLASER_ABI_VERSION; }
+const char* vlaser_last_error(void) { return g_last_error.c_str(); }
+
+int32_t vlaser_create(const vlaser_cfg* cfg, vlaser_t** out) {
+  VL_CHECK(cfg && out, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_last_error("vlaser_create: no CUDA device (this library has no CPU fallback)");
+    return -10;
+  }
+  auto* h = new vlaser_handle();
+  h->e.c = *cfg;
+  const int rc = engine_build(h->e);
+  if (rc != 0) {
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+int32_t vlaser_set_weight(vlaser_t* h, const char* key, const void* data, const int64_t* shape, int32_t ndim,
+                          int32_t dtype) {
+  VL_CHECK(h && key && data && shape, "null argument");
+  return engine_set_weight(h->e, key, data, shape, ndim, dtype);
+}
+
+int32_t vlaser_finalize(vlaser_t* h) {
+  VL_CHECK(h, "null handle");
+  return engine_finalize(h->e);
+}
+
+int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
+  VL_CHECK(h && key, "null argument");
+  const std::string k(key);
+  if (k == "use_graph") h->e.use_graph = (int)value;
+  else if (k == "stop_after") h->e.stop_after = (int)value;
+  else if (k == "simt_gemm") h->e.simt = (int)value;
+  else {
+    set_last_error("unknown option " + k);
+    return -2;
+  }
+  return 0;
+}
+
+int32_t vlaser_infer_action(vlaser_t* h, const int64_t* input_ids, const void* pixel_values, const int32_t* valid_len,
+                            const void* proprios, const void* noise, void* actions_out, int32_t B, int32_t io_dtype,
+                            void* stream) {
+  VL_CHECK(h, "null handle");
+  Engine& e = h->e;
+  VL_CHECK(e.finalized, "infer_action before finalize");
+  VL_CHECK(B > 0 && B <= e.Bc, "batch exceeds max_batch");
+  VL_CHECK(io_dtype == DT_F32 || io_dtype == DT_BF16, "io_dtype must be f32 or bf16");
+  VL_CHECK(input_ids && pixel_values && proprios && noise && actions_out, "null tensor");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const vlaser_cfg& c = e.c;
+  const size_t es = io_size(io_dtype);
+  const size_t pix = (size_t)B * e.n_img * 3 * c.image_size * c.image_size;
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_ids, input_ids, (size_t)B * e.S * 8, cudaMemcpyDeviceToDevice, st));
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_pix, pixel_values, pix * es, cudaMemcpyDeviceToDevice, st));
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_prop, proprios, (size_t)B * c.proprio_dim * es, cudaMemcpyDeviceToDevice, st));
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_noise, noise, (size_t)B * e.H * c.action_dim * es, cudaMemcpyDeviceToDevice, st));
+  if (valid_len) VL_CUDA_CHECK(cudaMemcpyAsync(e.in_valid, valid_len, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  VL_TRY(engine_execute(e, B, io_dtype, valid_len != nullptr, st));
+  VL_CUDA_CHECK(cudaMemcpyAsync(actions_out, e.out_act, (size_t)B * c.horizon_steps * c.action_dim * es,
+                                cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int32_t vlaser_infer_action_host(vlaser_t* h, const int64_t* input_ids, const void* pixel_values,
+                                 const int32_t* valid_len, const void* proprios, const void* noise, void* actions_out,
+                                 int32_t B, int32_t io_dtype) {
+  VL_CHECK(h, "null handle");
+  Engine& e = h->e;
+  VL_CHECK(e.finalized, "infer_action before finalize");
+  VL_CHECK(B > 0 && B <= e.Bc, "batch exceeds max_batch");
+  VL_CHECK(io_dtype == DT_F32 || io_dtype == DT_BF16, "io_dtype must be f32 or bf16");
+  VL_CHECK(input_ids && pixel_values && proprios && noise && actions_out, "null tensor");
+  cudaStream_t st = e.own_stream;
+  const vlaser_cfg& c = e.c;
+  const size_t es = io_size(io_dtype);
+  const size_t n_ids = (size_t)B * e.S * 8;
+  const size_t n_pix = (size_t)B * e.n_img * 3 * c.image_size * c.image_size * es;
+  const size_t n_prop = (size_t)B * c.proprio_dim * es;
+  const size_t n_noise = (size_t)B * e.H * c.action_dim * es;
+  const size_t n_out = (size_t)B * c.horizon_steps * c.action_dim * es;
+  // stage through the handle's pinned buffer so the H2D copies are truly asynchronous
+  uint8_t* pin = reinterpret_cast<uint8_t*>(e.pinned);
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  uint8_t* p_ids = pin;
+  uint8_t* p_pix = p_ids + up(n_ids);
+  uint8_t* p_prop = p_pix + up(n_pix);
+  uint8_t* p_noise = p_prop + up(n_prop);
+  uint8_t* p_valid = p_noise + up(n_noise);
+  uint8_t* p_out = p_valid + up((size_t)B * 4);
+  VL_CHECK((size_t)(p_out + n_out - pin) <= e.pinned_bytes, "pinned staging buffer too small");
+  memcpy(p_ids, input_ids, n_ids);
+  memcpy(p_pix, pixel_values, n_pix);
+  memcpy(p_prop, proprios, n_prop);
+  memcpy(p_noise, noise, n_noise);
+  if (valid_len) memcpy(p_valid, valid_len, (size_t)B * 4);
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_ids, p_ids, n_ids, cudaMemcpyHostToDevice, st));
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_pix, p_pix, n_pix, cudaMemcpyHostToDevice, st));
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_prop, p_prop, n_prop, cudaMemcpyHostToDevice, st));
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_noise, p_noise, n_noise, cudaMemcpyHostToDevice, st));
+  if (valid_len) VL_CUDA_CHECK(cudaMemcpyAsync(e.in_valid, p_valid, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  VL_TRY(engine_execute(e, B, io_dtype, valid_len != nullptr, st));
+  VL_CUDA_CHECK(cudaMemcpyAsync(p_out, e.out_act, n_out, cudaMemcpyDeviceToHost, st));
+  VL_CUDA_CHECK(cudaStreamSynchronize(st));
+  memcpy(actions_out, p_out, n_out);
+  return 0;
+}
+
+void vlaser_destroy(vlaser_t* h) {
+  if (!h) return;
+  cudaDeviceSynchronize();
+  delete h;
+}
+
+int64_t vlaser_last_launch_count(vlaser_t* h) { return h ? h->e.last_launches : -1; }
+
+int64_t vlaser_debug_copy(vlaser_t* h, const char* name, void* host_dst, int64_t max_bytes) {
+  VL_CHECK(h && name, "null argument");
+  Engine& e = h->e;
+  const vlaser_cfg& c = e.c;
+  const std::string n(name);
+  const void* src = nullptr;
+  size_t bytes = 0;
+  const size_t Ni = (size_t)e.Bc * e.n_img;
+  const size_t kvb = (size_t)c.layers * c.n_kv_heads * e.kv_rows * 128 * 2;
+  if (n == "vit_x") src = e.vx, bytes = Ni * (e.P + 1) * c.vit_hidden * 4;
+  else if (n == "prefix_x") src = e.xv, bytes = (size_t)e.Bc * e.S * c.hidden * 4;
+  else if (n == "proprio_x") src = e.xp, bytes = (size_t)e.Bc * c.hidden_e * 4;
+  else if (n == "action_x") src = e.xa, bytes = (size_t)e.Bc * e.H * c.hidden_e * 4;
+  else if (n == "action") src = e.action, bytes = (size_t)e.Bc * e.H * c.action_dim * 4;
+  else if (n == "k_cache") src = e.kc, bytes = kvb;
+  else if (n == "v_cache") src = e.vc, bytes = kvb;
+  else if (n == "valid_len") src = e.pb.valid_len, bytes = (size_t)e.Bc * 4;
+  else if (n == "cu") src = e.pb.cu, bytes = (size_t)(e.Bc + 1) * 4;
+  else if (n == "kvoff") src = e.pb.kvoff, bytes = (size_t)e.Bc * 4;
+  else if (n == "img_row_map") src = e.pb.img_row_map, bytes = Ni * e.T * 4;
+  else if (n == "row_src") src = e.pb.row_src, bytes = (size_t)e.Bc * e.S * 4;
+  else if (n == "kv_rows") {
+    const int64_t v = e.kv_rows;
+    if (host_dst && max_bytes >= 8) memcpy(host_dst, &v, 8);
+    return 8;
+  } else {
+    set_last_error("debug_copy: unknown buffer " + n);
+    return -2;
+  }
+  if (host_dst && max_bytes > 0) {
+    VL_CUDA_CHECK(cudaDeviceSynchronize());
+    VL_CUDA_CHECK(cudaMemcpy(host_dst, src, std::min<size_t>(bytes, (size_t)max_bytes), cudaMemcpyDeviceToHost));
+  }
+  return (int64_t)bytes;
+}
+
+double vlaser_flops_per_call(vlaser_t* h, const int32_t* valid_len_host, int32_t B) {
+  if (!h || !valid_len_host) return -1.0;
+  const vlaser_cfg& c = h->e.c;
+  const Engine& e = h->e;
+  // W(h,f) = h*nh*hd + 2*h*nkv*hd + nh*hd*h + 3*h*f
+  auto W = [&](double hid, double f) { return hid * e.qdim + 2 * hid * e.kvdim + e.qdim * hid + 3 * hid * f; };
+  const double N = e.P + 1, dv = c.vit_hidden, fv = c.vit_mlp, L = c.layers, hh = c.hidden, he = c.hidden_e;
+  const double nhd = e.qdim, H = e.H, A = c.action_dim;
+  const double k_patch = 3.0 * c.patch_size * c.patch_size;
+  const double F_vit =
+      e.n_img * (c.vit_layers * (2 * N * dv * 3 * dv + 2 * N * dv * dv + 4 * N * dv * fv + 4 * N * N * dv) +
+                 2 * e.P * k_patch * dv);
+  const double F_proj = e.n_img * e.T * (2 * 4 * dv * hh + 2 * hh * hh);
+  double total = 0;
+  for (int b = 0; b < B; ++b) {
+    const double Sx = valid_len_host[b];
+    const double F_prefill = L * (2 * Sx * W(hh, c.mlp) + 2 * W(he, c.mlp_e) + 4 * (Sx * Sx + Sx + 1) * nhd) -
+                             2 * Sx * (nhd * hh + 3 * hh * c.mlp) - 2 * (nhd * he + 3 * he * c.mlp_e);
+    const double F_step = L * (2 * H * W(he, c.mlp_e) + 4 * H * (Sx + 1 + H) * nhd) + 2 * H * (A * he + 3 * he * he) +
+                          2 * H * he * A;
+    total += F_vit + F_proj + F_prefill + c.num_inference_steps * F_step;
+  }
+  return total;
+}
+
+// ---- single-kernel entry points ---------------------------------------------------------------
+int32_t vlaser_op_gemm(const vlaser_gemm_args* a, void* stream) {
+  VL_CHECK(a, "null args");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GemmDims d;
+  d.M = a->M;
+  d.N = a->N;
+  d.K = a->K;
+  d.M_dev = a->M_dev;
+  d.max_splits = a->max_splits > 0 ? a->max_splits : 1;
+  EpiParams ep;
+  ep.out = a->out;
+  ep.ldo = a->ldo;
+  ep.bias = a->bias;
+  ep.scale = a->scale;
+  ep.row_map = a->row_map;
+  ep.row_pos = a->row_pos;
+  ep.row_kvrow = a->row_kvrow;
+  ep.cos_tab = a->cos_tab;
+  ep.sin_tab = a->sin_tab;
+  ep.k_cache = reinterpret_cast<__nv_bfloat16*>(a->k_cache);
+  ep.v_cache = reinterpret_cast<__nv_bfloat16*>(a->v_cache);
+  ep.kv_head_stride = a->kv_head_stride;
+  ep.n_q_heads = a->n_q_heads;
+  ep.n_kv_heads = a->n_kv_heads;
+  ep.pos_emb = a->pos_emb;
+  ep.patches = a->patches;
+  if (a->simt)
+    return gemm_launch_simt(reinterpret_cast<const __nv_bfloat16*>(a->A), reinterpret_cast<const __nv_bfloat16*>(a->W),
+                            d, ep, a->epi, st);
+  CUtensorMap tmA, tmB;
+  // rows of A beyond M are zero-filled by TMA (the map's row extent is the true M)
+  VL_TRY(make_tmap_bf16(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, 128));
+  VL_TRY(make_tmap_bf16(&tmB, a->W, (uint64_t)a->N, (uint64_t)a->K, (uint32_t)a->block_n));
+  return gemm_launch(tmA, tmB, d, ep, a->block_n, a->epi, st);
+}
+
+int32_t vlaser_op_attention(const vlaser_attn_args* a, void* stream) {
+  VL_CHECK(a, "null args");
+  AttnParams p;
+  p.q = reinterpret_cast<const __nv_bfloat16*>(a->q);
+  p.q_row_stride = a->q_row_stride;
+  p.q2 = reinterpret_cast<const __nv_bfloat16*>(a->q2);
+  p.q2_row_stride = a->q2_row_stride;
+  p.k = reinterpret_cast<const __nv_bfloat16*>(a->k);
+  p.v = reinterpret_cast<const __nv_bfloat16*>(a->v);
+  p.kv_row_stride = a->kv_row_stride;
+  p.kv_head_stride = a->kv_head_stride;
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  p.out_row_stride = a->out_row_stride;
+  p.out2 = reinterpret_cast<__nv_bfloat16*>(a->out2);
+  p.out2_row_stride = a->out2_row_stride;
+  p.q_start = a->q_start;
+  p.q_len = a->q_len;
+  p.kv_start = a->kv_start;
+  p.kv_len = a->kv_len;
+  p.uni_q_len = a->uni_q_len;
+  p.uni_kv_len = a->uni_kv_len;
+  p.max_q_len = a->max_q_len;
+  p.group = a->group;
+  p.n_kv_heads = a->n_kv_heads;
+  p.batch = a->batch;
+  p.scale = a->scale;
+  return attention_launch(p, a->head_dim, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t vlaser_op_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, int32_t rows,
+                            int32_t width, float eps, int32_t shuffle_grid, int32_t shuffle_channels, void* stream) {
+  ShuffleGather sg;
+  sg.grid = shuffle_grid;
+  sg.channels = shuffle_channels;
+  return layernorm_launch(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, width, eps, sg,
+                          reinterpret_cast<cudaStream_t>(stream));
+}
+int32_t vlaser_op_rmsnorm(const float* x, const float* gamma, void* out_bf16, int32_t rows, int32_t width, float eps,
+                          void* stream) {
+  return rmsnorm_launch(x, gamma, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, nullptr, width, eps,
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+int32_t vlaser_op_pixel_shuffle(const void* in, void* out, int32_t n, int32_t grid, int32_t channels,
+                                int32_t elem_bytes, void* stream) {
+  return pixel_shuffle_launch(in, out, n, grid, channels, elem_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+int32_t vlaser_op_im2col(const void* pixel, int32_t pixel_dtype, void* cols_bf16, int32_t n, int32_t px, int32_t ps,
+                         int32_t kpad, void* stream) {
+  return im2col_launch(pixel, pixel_dtype, reinterpret_cast<__nv_bfloat16*>(cols_bf16), n, px, ps, kpad,
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+int32_t vlaser_op_euler_step(const float* x, const float* gamma, const float* Wdec, const float* bdec, float* action,
+                             void* out, int32_t out_dtype, int32_t rows, int32_t width, int32_t A, int32_t H,
+                             int32_t horizon, float dt, float eps, int32_t last_step, int32_t do_clip, float clip,
+                             void* stream) {
+  return euler_step_launch(x, gamma, Wdec, bdec, action, out, out_dtype, rows, width, A, H, horizon, dt, eps, last_step,
+                           do_clip, clip, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,61 @@
+// bf16 GEMM  C[M,N] = A[M,K] * W[N,K]^T  (nn.Linear layout, both operands K-major) on the
+// sm_100a 5th-gen tensor cores: TMA (cp.async.bulk.tensor, 128B swizzle) -> shared-memory ring ->
+// tcgen05.mma (single issuing thread, fp32 accumulators in TMEM, double buffered) ->
+// tcgen05.ld epilogue fused with the op that follows the projection in the reference
+// (bias / GELU / SiLU / SwiGLU / layer-scale + residual / RoPE + KV-cache write / patch-embed).
+#pragma once
+#include "common.cuh"
+
+namespace vlaser {
+
+enum Epi : int {
+  EPI_STORE_BF16 = 0,   // out_bf16[m,n] = acc + bias[n]
+  EPI_GELU_BF16 = 1,    // out_bf16[m,n] = gelu_erf(acc + bias[n])                (InternMLP fc1, mlp1[1..2])
+  EPI_SILU_BF16 = 2,    // out_bf16[m,n] = silu(acc + bias[n])                    (ActionEncoder linear_2)
+  EPI_RESID_F32 = 3,    // out_f32[m,n] += scale[n] * (acc + bias[n])             (o_proj/down_proj/proj/fc2 + residual)
+  EPI_SWIGLU_BF16 = 4,  // out_bf16[m,j] = silu(gate_j) * up_j, W rows interleaved in 32-row gate/up groups
+  EPI_QKV_ROPE = 5,     // fused q|k|v projection: +bias, rotate-half RoPE on q,k; q -> out, k,v -> KV cache rows
+  EPI_PATCH_EMBED = 6,  // out_f32[img*(P+1)+1+p, n] = acc + bias[n] + pos[1+p, n]  (InternVisionEmbeddings)
+  EPI_STORE_F32 = 7,    // out_f32[row_map[m], n] = acc + bias[n]
+  EPI_COUNT = 8
+};
+
+struct EpiParams {
+  void* out = nullptr;        // primary output (bf16 or f32, see Epi)
+  int ldo = 0;                // leading dimension of out, in elements
+  const float* bias = nullptr;
+  const float* scale = nullptr;
+  const int* row_map = nullptr;
+  // EPI_QKV_ROPE
+  const int* row_pos = nullptr;     // RoPE position id per row
+  const int* row_kvrow = nullptr;   // KV-cache row per row
+  const float* cos_tab = nullptr;   // [pos][64]
+  const float* sin_tab = nullptr;
+  __nv_bfloat16* k_cache = nullptr; // [kv_head][rows][128]
+  __nv_bfloat16* v_cache = nullptr;
+  long long kv_head_stride = 0;     // elements between kv heads
+  int n_q_heads = 0;
+  int n_kv_heads = 0;
+  // EPI_PATCH_EMBED
+  const float* pos_emb = nullptr;   // [(P+1), N]
+  int patches = 0;
+};
+
+struct GemmDims {
+  int M = 0, N = 0, K = 0;       // K % 64 == 0, N % block_n == 0
+  const int* M_dev = nullptr;    // optional: live row count in device memory (M is then the capacity)
+  int max_splits = 1;            // split-K cap (EPI_RESID_F32 only)
+};
+
+// Host API -------------------------------------------------------------------------------
+// Encodes a 2-D bf16 row-major [rows, cols] tensor map with a [box_rows x 64] box, 128B swizzle.
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
+// Launches the tcgen05 kernel (block_n in {128,256}); `simt` launches the CUDA-core cross-check kernel
+// (debug / tests only) that shares the epilogue code but reads A and W through plain pointers.
+int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDims& d, const EpiParams& ep, int block_n,
+                int epi, cudaStream_t stream);
+int gemm_launch_simt(const __nv_bfloat16* A, const __nv_bfloat16* W, const GemmDims& d, const EpiParams& ep, int epi,
+                     cudaStream_t stream);
+int gemm_num_sms();
+
+}  // namespace vlaser

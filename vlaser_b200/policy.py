@@ -1,0 +1,287 @@
+"""Drop-in policy object for the reference's `PiZeroInference`
+(`Vlaser_VLA/Simpler/src/model/vla/pizero_internvl.py:1286-1307`), backed by the sm_100a library
+through the C ABI (include/vlaser_b200.h). Same call surface as the reference class as used by
+`EvalAgent` (`Vlaser_VLA/Simpler/src/agent/eval.py:33-56, 111-139`):
+
+    model = PiZeroInference(cfg)                       # cfg: hydra-style cfg of the reference or VlaserConfig
+    model.load_state_dict(sd, strict=False); model.freeze_all_weights()
+    model.to(dtype); model.to(device); model.eval()
+    mask, vp, pp, ap = model.build_causal_mask_and_position_ids(attention_mask, dtype)
+    itp_mask, action_mask = model.split_full_mask_into_submasks(mask)
+    actions = model(input_ids, pixel_values, itp_mask, action_mask, vp, pp, ap, proprios)   # [B, horizon, A]
+
+PyTorch is used only for device memory / streams of the caller's tensors; there is no PyTorch
+compute path and no fallback: a missing library or GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from collections import namedtuple
+from typing import Dict, Iterable, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .config import VlaserConfig
+from .weights import canonical_key, state_dict_spec
+
+_IncompatibleKeys = namedtuple("IncompatibleKeys", ["missing_keys", "unexpected_keys"])
+
+
+def _cfg_get(cfg, name, default=None):
+    if hasattr(cfg, "get"):
+        try:
+            v = cfg.get(name, default)
+            return default if v is None else v
+        except TypeError:
+            pass
+    return getattr(cfg, name, default)
+
+
+def config_from_reference_cfg(cfg) -> VlaserConfig:
+    """Maps the hydra cfg keys `PiZero.__init__` reads (pizero_internvl.py:156-337) plus the
+    `IMAGE_448` env switch (:180-183) and `model_size` (:116-135) onto a VlaserConfig."""
+    if isinstance(cfg, VlaserConfig):
+        return cfg
+    model_size = str(_cfg_get(cfg, "model_size", "2B"))
+    kw = {}
+    if model_size == "8B":  # InternVL3-8B: Qwen2.5-7B LLM, expert MLP 5600 (pizero_internvl.py:128-131)
+        kw.update(hidden=3584, n_heads=28, n_kv_heads=4, mlp=18944, mlp_e=5600)
+    clip = _cfg_get(cfg, "final_action_clip_value", None)
+    return VlaserConfig(
+        image_size=448 if "IMAGE_448" in os.environ else 224,
+        max_image_text_tokens=int(_cfg_get(cfg, "max_image_text_tokens")),
+        cond_steps=int(_cfg_get(cfg, "cond_steps")),
+        horizon_steps=int(_cfg_get(cfg, "horizon_steps")),
+        action_dim=int(_cfg_get(cfg, "action_dim")),
+        proprio_dim=int(_cfg_get(cfg, "proprio_dim")),
+        num_inference_steps=int(_cfg_get(cfg, "num_inference_steps")),
+        final_action_clip_value=None if clip is None else float(clip),
+        time_max_period=float(_cfg_get(cfg, "time_max_period", 10000.0)),
+        image_token_index=int(_cfg_get(cfg, "image_token_index", 151667)),
+        pad_token_id=int(_cfg_get(cfg, "pad_token_id", 151643)),
+        **kw,
+    )
+
+
+def _to_c_cfg(cfg: VlaserConfig, max_batch: int) -> _lib.VlaserCfg:
+    c = _lib.VlaserCfg()
+    for name, _ in _lib.VlaserCfg._fields_:
+        if name in ("clip_enabled", "final_action_clip_value", "max_batch"):
+            continue
+        setattr(c, name, getattr(cfg, name))
+    c.clip_enabled = 0 if cfg.final_action_clip_value is None else 1
+    c.final_action_clip_value = 0.0 if cfg.final_action_clip_value is None else float(cfg.final_action_clip_value)
+    c.max_batch = int(max_batch)
+    return c
+
+
+class PiZeroInference:
+    """B200-native `PiZeroInference` (inference only)."""
+
+    def __init__(self, cfg, use_ddp: bool = False, max_batch: Optional[int] = None, device: Optional[int] = None):
+        self.cfg = cfg
+        self.vcfg = config_from_reference_cfg(cfg)
+        self.use_ddp = use_ddp
+        v = self.vcfg
+        # attributes the reference exposes and callers read (pizero_internvl.py:207-224, 336)
+        self.max_image_text_tokens = v.max_image_text_tokens
+        self.num_proprio_tokens = 1
+        self.num_action_tokens = v.num_action_tokens
+        self.horizon_steps = v.num_action_tokens
+        self.action_dim = v.action_dim
+        self.proprio_dim = v.proprio_dim
+        self.num_inference_steps = v.num_inference_steps
+        self.final_action_clip_value = v.final_action_clip_value
+        self.image_token_index = v.image_token_index
+        self.pad_token_id = v.pad_token_id
+        self.num_images = v.num_images
+        self.training = False
+
+        self._lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("vlaser_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.max_batch = int(max_batch if max_batch is not None else _cfg_get(cfg, "max_batch", 64))
+        self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            ccfg = _to_c_cfg(v, self.max_batch)
+            _lib.check(self._lib.vlaser_create(C.byref(ccfg), C.byref(self._handle)), "vlaser_create")
+        self._finalized = False
+        self._loaded = set()
+        self.dtype = torch.bfloat16
+
+    # ---- nn.Module-like surface used by EvalAgent ------------------------------------------------
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
+        """eval.py:196-212 — feeds every tensor of the path to the library by its state-dict key."""
+        if self._finalized:
+            raise RuntimeError("weights are frozen after the first forward")
+        unexpected = []
+        with torch.cuda.device(self.device):
+            for key, t in state_dict.items():
+                if not torch.is_tensor(t):
+                    continue
+                t = t.detach()
+                if t.dtype not in (torch.float32, torch.bfloat16):
+                    t = t.to(torch.float32)
+                t = t.contiguous()
+                shape = (C.c_int64 * max(t.dim(), 1))(*(list(t.shape) or [1]))
+                rc = self._lib.vlaser_set_weight(self._handle, key.encode(), C.c_void_p(t.data_ptr()), shape,
+                                                 max(t.dim(), 1), _lib.BF16 if t.dtype == torch.bfloat16 else _lib.F32)
+                _lib.check(rc, f"vlaser_set_weight({key})")
+                if rc == 1:
+                    unexpected.append(key)
+                else:
+                    self._loaded.add(canonical_key(key))
+            torch.cuda.synchronize(self.device)
+        missing = [k for k in state_dict_spec(self.vcfg) if k not in self._loaded]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"load_state_dict: missing={missing[:5]} unexpected={unexpected[:5]}")
+        return _IncompatibleKeys(missing, unexpected)
+
+    def finalize(self):
+        if not self._finalized:
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.vlaser_finalize(self._handle), "vlaser_finalize")
+            self._finalized = True
+        return self
+
+    def freeze_all_weights(self):
+        return self
+
+    def tie_action_proprio_weights(self):
+        return self
+
+    def to(self, *args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.dtype):
+                self.dtype = a
+        return self
+
+    def eval(self):
+        return self
+
+    def parameters(self) -> Iterable[torch.Tensor]:
+        return iter(())
+
+    def set_option(self, key: str, value: int):
+        _lib.check(self._lib.vlaser_set_option(self._handle, key.encode(), int(value)), f"set_option({key})")
+        return self
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None and self._handle.value:
+                self._lib.vlaser_destroy(self._handle)
+                self._handle = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- input preparation (kept for API compatibility; the kernels never read the dense mask) ----
+    def build_causal_mask_and_position_ids(self, attention_mask: torch.Tensor, dtype: torch.dtype):
+        """pizero_internvl.py:517-587 (block attention mask + per-block position ids starting at 1).
+        Vectorised; same values as the reference's per-sample loop."""
+        bsz, S = attention_mask.shape
+        H = self.num_action_tokens
+        L = S + H + 1
+        cnt = attention_mask.sum(dim=1).view(bsz, 1, 1)
+        dev = attention_mask.device
+        r = torch.arange(L, device=dev).view(1, L, 1)
+        c = torch.arange(L, device=dev).view(1, 1, L)
+        allowed = ((r < cnt) & (c < cnt)) | ((r >= S) & (c < cnt)) | ((r == S) & (c == S)) | ((r > S) & (c >= S))
+        mask = torch.full((bsz, L, L), torch.finfo(dtype).min, dtype=dtype, device=dev)
+        mask.masked_fill_(allowed, 0)
+        mask = mask.unsqueeze(1)
+        vlm_position_ids = torch.arange(1, S + 1).repeat(bsz, 1)
+        proprio_position_ids = torch.arange(1, 2).repeat(bsz, 1)
+        action_position_ids = torch.arange(2, H + 2).repeat(bsz, 1)
+        return mask, vlm_position_ids, proprio_position_ids, action_position_ids
+
+    def split_full_mask_into_submasks(self, causal_mask: torch.Tensor):
+        """pizero_internvl.py:589-603 (4-D branch)."""
+        n = self.max_image_text_tokens + self.num_proprio_tokens
+        return causal_mask[..., :n, :n], causal_mask[..., -self.num_action_tokens:, :]
+
+    # ---- the hot path ------------------------------------------------------------------------------
+    def forward(self, input_ids, pixel_values, image_text_proprio_mask=None, action_mask=None,
+                vlm_position_ids=None, proprio_position_ids=None, action_position_ids=None, proprios=None,
+                noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.infer_action(input_ids, pixel_values, image_text_proprio_mask, action_mask, vlm_position_ids,
+                                 proprio_position_ids, action_position_ids, proprios, noise=noise)
+
+    __call__ = forward
+
+    def infer_action(self, input_ids, pixel_values, image_text_proprio_mask=None, action_mask=None,
+                     vlm_position_ids=None, proprio_position_ids=None, action_position_ids=None, proprios=None,
+                     noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """pizero_internvl.py:798-936. Position ids are the ones `build_causal_mask_and_position_ids`
+        produces (vlm 1..S, proprio 1, action 2..H+1); the id tensors are accepted for signature
+        compatibility. `noise` (optional, [B,H,A]) replaces the internal `torch.randn` draw."""
+        v = self.vcfg
+        self.finalize()
+        dev = self.device
+        dtype = pixel_values.dtype
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("pixel_values must be float32 or bfloat16")
+        io = _lib.BF16 if dtype == torch.bfloat16 else _lib.F32
+        B = pixel_values.size(0) // v.num_images
+        S, H, A = v.max_image_text_tokens, v.num_action_tokens, v.action_dim
+        input_ids = input_ids.to(dev, torch.int64).contiguous()
+        pixel_values = pixel_values.to(dev).contiguous()
+        proprios = proprios.to(dev, dtype).contiguous()
+        assert input_ids.shape == (B, S), f"input_ids must be [B,{S}]"
+        valid_len = None
+        if image_text_proprio_mask is not None:
+            # number of keys the first prefix row may attend to == valid prefix length
+            valid_len = (image_text_proprio_mask[:, 0, 0, :S] == 0).sum(-1).to(dev, torch.int32).contiguous()
+        if noise is None:
+            noise = torch.randn((B, H, A), device=dev, dtype=dtype)  # pizero_internvl.py:879-881
+        noise = noise.to(dev, dtype).contiguous()
+        assert noise.shape == (B, H, A)
+        out = torch.empty((B, v.horizon_steps, A), device=dev, dtype=dtype)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = self._lib.vlaser_infer_action(
+                self._handle, C.c_void_p(input_ids.data_ptr()), C.c_void_p(pixel_values.data_ptr()),
+                C.c_void_p(valid_len.data_ptr()) if valid_len is not None else None,
+                C.c_void_p(proprios.data_ptr()), C.c_void_p(noise.data_ptr()), C.c_void_p(out.data_ptr()),
+                B, io, C.c_void_p(stream))
+        _lib.check(rc, "vlaser_infer_action")
+        return out
+
+    def infer_action_host(self, input_ids, pixel_values, proprios, noise, valid_len=None) -> torch.Tensor:
+        """Same call on HOST tensors (CPU torch tensors): H2D staging, compute, D2H, synchronise."""
+        v = self.vcfg
+        self.finalize()
+        dtype = pixel_values.dtype
+        io = _lib.BF16 if dtype == torch.bfloat16 else _lib.F32
+        B = pixel_values.size(0) // v.num_images
+        input_ids = input_ids.to(torch.int64).contiguous()
+        pixel_values = pixel_values.contiguous()
+        proprios = proprios.to(dtype).contiguous()
+        noise = noise.to(dtype).contiguous()
+        out = torch.empty((B, v.horizon_steps, v.action_dim), dtype=dtype)
+        vl = valid_len.to(torch.int32).contiguous() if valid_len is not None else None
+        with torch.cuda.device(self.device):
+            rc = self._lib.vlaser_infer_action_host(
+                self._handle, C.c_void_p(input_ids.data_ptr()), C.c_void_p(pixel_values.data_ptr()),
+                C.c_void_p(vl.data_ptr()) if vl is not None else None, C.c_void_p(proprios.data_ptr()),
+                C.c_void_p(noise.data_ptr()), C.c_void_p(out.data_ptr()), B, io)
+        _lib.check(rc, "vlaser_infer_action_host")
+        return out
+
+    # ---- introspection (tests, bench) --------------------------------------------------------------
+    def debug_buffer(self, name: str, dtype: torch.dtype) -> torch.Tensor:
+        n = self._lib.vlaser_debug_copy(self._handle, name.encode(), None, 0)
+        _lib.check(int(n), f"debug_copy({name})")
+        buf = torch.empty(int(n), dtype=torch.uint8)
+        _lib.check(int(self._lib.vlaser_debug_copy(self._handle, name.encode(), C.c_void_p(buf.data_ptr()), int(n))),
+                   f"debug_copy({name})")
+        return buf.view(dtype)
+
+    def last_launch_count(self) -> int:
+        return int(self._lib.vlaser_last_launch_count(self._handle))
+
+    def flops_per_call(self, valid_len) -> float:
+        vl = torch.as_tensor(valid_len, dtype=torch.int32).contiguous()
+        return float(self._lib.vlaser_flops_per_call(self._handle, C.c_void_p(vl.data_ptr()), vl.numel()))

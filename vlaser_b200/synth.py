@@ -56,11 +56,14 @@ def make_inputs(cfg: VlaserConfig, batch: int, seed: int = 1,
         ids[b, n_pre:n_pre + n_img * T] = cfg.image_token_index
         ids[b, n_pre + n_img * T:total] = txt[n_pre:]
         valid.append(total)
-    proprios = torch.rand(batch, 1, cfg.proprio_dim, generator=g) * 2 - 1
-    noise = torch.randn(batch, cfg.num_action_tokens, cfg.action_dim, generator=g)
+    # Values are rounded to the bf16 grid (and kept as fp32): the bf16 device path and the fp32 oracle
+    # then see IDENTICAL inputs, so parity measures compute error only (SURVEY.md §7 hard parts).
+    r16 = lambda t: t.to(torch.bfloat16).to(torch.float32)
+    proprios = r16(torch.rand(batch, 1, cfg.proprio_dim, generator=g) * 2 - 1)
+    noise = r16(torch.randn(batch, cfg.num_action_tokens, cfg.action_dim, generator=g))
     return {
         "images_u8": images,
-        "pixel_values": process_images(images),
+        "pixel_values": r16(process_images(images)),
         "input_ids": ids,
         "attention_mask": (ids != cfg.pad_token_id).to(torch.int64),
         "proprios": proprios,
@@ -75,3 +78,8 @@ def weights_checksum(sd: Dict[str, torch.Tensor]) -> float:
     for i, (k, v) in enumerate(sd.items()):
         acc += float(v.double().sum()) * (1.0 + (i % 7)) + float(v.double().abs().sum())
     return acc
+
+
+def pixel_values_from_u8(images_u8: torch.Tensor) -> torch.Tensor:
+    """uint8 frames -> normalised pixel values on the bf16 grid (fp32 tensor), as `make_inputs` does."""
+    return process_images(images_u8).to(torch.bfloat16).to(torch.float32)
