@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Benchmark of the Vlaser-VLA `infer_action` hot path (BASELINE.json metric: policy actions/s,
+Vlaser-2B-VLA, bs=64 per GPU, bf16, 10 flow steps; configs[1] at N=1, data-parallel weak scaling at N>1).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --steps K --warmup W    # reference algorithm on the host cores (oracle port)
+
+One "step" = one policy call on one batch of synthetic observations (64 per GPU). `value` is timed with
+CUDA events around K calls whose inputs are already resident in HBM; `e2e` is the same call through
+the host-buffer C-ABI entry (H2D of the inputs from pinned memory and D2H of the actions inside the
+timed region). Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from vlaser_b200.config import PRESETS  # noqa: E402
+from vlaser_b200.synth import make_inputs  # noqa: E402
+from vlaser_b200.weights import random_state_dict, state_dict_spec  # noqa: E402
+
+WORKLOAD = "Vlaser-2B-VLA WidowX/Bridge bs=64 bf16, 10 flow steps, single B200 (BASELINE configs[1])"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"tflops": float(d["bf16_tflops_sustained"]), "tflops_burst": float(d["bf16_tflops"]),
+                "hbm_gbs": float(d["hbm_gbs"]), "which": "measured (MEASURED_PEAKS.json, sustained)"}
+    return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "which": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons while the timed region runs (NVML)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def _cpu_oracle_timing(cfg, sd, steps: int, warmup: int):
+    """Times the reference algorithm (oracle port, fp32, all host threads) on B=1 observations of the workload."""
+    from oracle import vlaser_oracle as O  # bench.py's cpu_baseline / --impl reference legs only
+    torch.set_num_threads(os.cpu_count() or 1)
+    times = []
+    with torch.inference_mode():
+        for i in range(warmup + steps):
+            inp = make_inputs(cfg, 1, 100 + i)
+            t0 = time.perf_counter()
+            O.infer_action(cfg, sd, inp["input_ids"], inp["pixel_values"], inp["proprios"], inp["noise"])
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return times, torch.get_num_threads()
+
+
+def _device_state_dict_stream(cfg, seed: int, device):
+    """Random-init weights generated directly on the GPU (bench only; shapes/architecture as the model)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    for key, (shape, kind) in state_dict_spec(cfg).items():
+        if kind == "n02":
+            t = torch.randn(shape, generator=g, device=device) * 0.02
+        elif kind == "randn":
+            t = torch.randn(shape, generator=g, device=device)
+        elif kind == "one":
+            t = 1.0 + torch.randn(shape, generator=g, device=device) * 0.02
+        elif kind == "ls":
+            t = 0.1 + torch.randn(shape, generator=g, device=device) * 0.002
+        else:
+            bound = 1.0 / float(kind[3:]) ** 0.5
+            t = (torch.rand(shape, generator=g, device=device) * 2 - 1) * bound
+        yield key, t.to(torch.bfloat16)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = PRESETS[args.config]()
+    sd = random_state_dict(cfg, 0)
+    times, cores = _cpu_oracle_timing(cfg, sd, args.steps, args.warmup)
+    per_obs = sum(times) / len(times)
+    value = cfg.horizon_steps / per_obs
+    line = {
+        "impl": "reference", "metric": "policy actions/s", "value": value, "unit": "actions/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_obs * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": "each step = 1 observation (B=1) of the workload, fp32, padded S=384"},
+        "cpu_baseline": {"value": value, "unit": "actions/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} single-observation calls of the oracle port (reference algorithm, fp32)"},
+        "e2e": {"value": value, "unit": "actions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from vlaser_b200.dp import gather_actions
+    from vlaser_b200.policy import PiZeroInference
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = PRESETS[args.config]()
+    Bg = args.batch_per_gpu
+    peaks = _peaks()
+
+    # ---- weights (random-init, bf16). N=1 rank 0 builds them on the CPU so the cpu_baseline leg can share them.
+    want_cpu = (world == 1 and not args.no_cpu_baseline)
+    pol = PiZeroInference(cfg, max_batch=Bg, device=local)
+    sd_cpu = None
+    if want_cpu:
+        sd_cpu = random_state_dict(cfg, 0)
+        pol.load_state_dict(sd_cpu, strict=True)
+    else:
+        for k, t in _device_state_dict_stream(cfg, 0, dev):
+            pol.load_state_dict({k: t}, strict=False)
+    pol.finalize()
+
+    inp = make_inputs(cfg, Bg, 1 + rank)
+    valid = inp["valid_len"]
+    ids_h = inp["input_ids"]
+    pix_h = inp["pixel_values"].to(torch.bfloat16).pin_memory()
+    prop_h = inp["proprios"].to(torch.bfloat16).pin_memory()
+    noise_h = inp["noise"].to(torch.bfloat16).pin_memory()
+    ids_d, pix_d, prop_d, noise_d = ids_h.to(dev), pix_h.to(dev), prop_h.to(dev), noise_h.to(dev)
+    vl_d = valid.to(dev)
+    global_B = Bg * world
+
+    def step_device():
+        out = pol.infer_action(ids_d, pix_d, proprios=prop_d, noise=noise_d)
+        return gather_actions(out, global_B)
+
+    def step_host():
+        out = pol.infer_action_host(ids_h, pix_h, prop_h, noise_h)
+        if world > 1:
+            return gather_actions(out.to(dev), global_B).cpu()
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (builds the CUDA graph)
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- timed region: K calls, inputs resident in HBM, CUDA events on the launch stream
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = pol.last_launch_count() * args.steps
+    # ---- e2e: host buffers through the C ABI
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join()
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+
+    # ---- in-situ GEMM timing for the roofline figure (rank 0; direct launches, events around every GEMM)
+    roof = None
+    if rank == 0 and not args.no_profile:
+        pol.set_option("use_graph", 0)
+        pol.infer_action(ids_d, pix_d, proprios=prop_d, noise=noise_d)  # warm direct path
+        torch.cuda.synchronize()
+        pol.set_option("profile_mtot", int(valid.sum()))
+        pol.set_option("profile_gemm", 1)
+        for _ in range(3):
+            pol.infer_action(ids_d, pix_d, proprios=prop_d, noise=noise_d)
+        gms, gfl, gn = pol.profile_read()
+        pol.set_option("profile_gemm", 0)
+        pol.set_option("use_graph", 1)
+        achieved = gfl / (gms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all projection GEMMs of one call)",
+                "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                "traffic": None, "peak_source": peaks["which"], "gemm_launches_per_call": gn // 3,
+                "gemm_ms_per_call": gms / 3, "gemm_share_of_step": (gms / 3) / (ms / args.steps)}
+    if world > 1:
+        dist.barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    obs_per_s = global_B * args.steps / (ms * 1e-3)
+    value = obs_per_s * cfg.horizon_steps
+    e2e_value = global_B * args.steps / (e2e_ms * 1e-3) * cfg.horizon_steps
+    flops_call = pol.flops_per_call(valid)
+    es = 2
+    h2d = ids_h.numel() * 8 + (pix_h.numel() + prop_h.numel() + noise_h.numel()) * es
+    d2h = Bg * cfg.horizon_steps * cfg.action_dim * es
+    line = {
+        "metric": "policy actions/s", "value": value, "unit": "actions/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD if args.config == "vlaser_2b_bridge" else args.config,
+                   "batch_per_gpu": Bg, "global_batch": global_B, "parallelism": f"dp{world}",
+                   "valid_len": f"{int(valid.min())}-{int(valid.max())} of {cfg.max_image_text_tokens} (var-len packed prefix)",
+                   "obs_per_s": obs_per_s, "actions_per_obs": cfg.horizon_steps,
+                   "l2": "no explicit flush: weights (5 GB) + activations per call >> 126 MB L2",
+                   "algorithmic_gflop_per_obs": flops_call / Bg / 1e9,
+                   "frac_of_bf16_roofline_whole_call": (flops_call / (ms / args.steps * 1e-3) / 1e12) / peaks["tflops"]},
+        "clocks": sampler.result(),
+        "e2e": {"value": e2e_value, "unit": "actions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
+    }
+    if roof is not None:
+        line["roofline"] = roof
+    if want_cpu:
+        times, cores = _cpu_oracle_timing(cfg, sd_cpu, 3, 1)
+        per_obs = statistics.median(times)
+        line["cpu_baseline"] = {"value": cfg.horizon_steps / per_obs, "unit": "actions/s", "cores": cores, "kind": "port",
+                                "sample": "3 single-observation calls (B=1, fp32, padded S=384) of the oracle port after 1 warm-up"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="vlaser_2b_bridge", choices=sorted(PRESETS))
+    ap.add_argument("--batch-per-gpu", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

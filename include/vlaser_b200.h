@@ -91,13 +91,19 @@ void vlaser_destroy(vlaser_t* h);
 
 /* Options: "use_graph" (default 1: replay the whole call as one CUDA graph per batch size),
  * "stop_after" (debug: 0 all, 1 ViT, 2 prefix embedding, 3 prefill, 4 first denoise step),
- * "simt_gemm" (debug/tests: route GEMMs through the CUDA-core cross-check kernel). */
+ * "simt_gemm" (debug/tests: route GEMMs through the CUDA-core cross-check kernel),
+ * "profile_gemm" / "profile_mtot" (see vlaser_profile_read). */
 int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value);
 /* Introspection for parity tests: copies the named internal device buffer to host memory.
  * Returns the buffer size in bytes (>= 0) or a negative error; copies min(size, max_bytes). */
 int64_t vlaser_debug_copy(vlaser_t* h, const char* name, void* host_dst, int64_t max_bytes);
 /* Number of kernels launched by the last vlaser_infer_action* call on this handle. */
 int64_t vlaser_last_launch_count(vlaser_t* h);
+/* In-situ GEMM timing for the roofline figure: with options "use_graph"=0, "profile_gemm"=1 and
+ * "profile_mtot"=<sum of valid lengths> every tcgen05 GEMM launch of the following calls is bracketed by
+ * CUDA events on its launch stream; this returns (and resets) the summed device time, the summed
+ * algorithmic FLOPs (2*M*N*K with the live M) and the number of GEMM launches. */
+int32_t vlaser_profile_read(vlaser_t* h, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
 /* Algorithmic FLOPs of one call at batch B with the given valid lengths (SURVEY.md §8d formulae). */
 double vlaser_flops_per_call(vlaser_t* h, const int32_t* valid_len_host, int32_t B);
 

@@ -133,7 +133,7 @@ def test_graph_equals_direct_and_mask_api():
     a4 = _run(pol2, inp)
     a5 = _run(pol2, inp, dtype=torch.bfloat16)
     # split-K accumulates with fp32 atomics, so runs agree to rounding, not bitwise
-    assert max_err(a1, a2) < 1e-4 and max_err(a1, a3) < 1e-4 and max_err(a1, a4) < 1e-4
+    assert max_err(a1, a2) < 1e-3 and max_err(a1, a3) < 1e-3 and max_err(a1, a4) < 1e-3
     assert max_err(a5, gold["actions"]) < 2e-2  # bf16 I/O rounds the returned actions
     assert pol.last_launch_count() > 100
 

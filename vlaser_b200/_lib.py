@@ -58,7 +58,7 @@ class AttnArgs(C.Structure):
 EXPORTS = [
     "vlaser_abi_version", "vlaser_last_error", "vlaser_create", "vlaser_set_weight", "vlaser_finalize",
     "vlaser_infer_action", "vlaser_infer_action_host", "vlaser_destroy", "vlaser_set_option", "vlaser_debug_copy",
-    "vlaser_last_launch_count", "vlaser_flops_per_call", "vlaser_op_gemm", "vlaser_op_attention",
+    "vlaser_last_launch_count", "vlaser_flops_per_call", "vlaser_profile_read", "vlaser_op_gemm", "vlaser_op_attention",
     "vlaser_op_layernorm", "vlaser_op_rmsnorm", "vlaser_op_pixel_shuffle", "vlaser_op_im2col", "vlaser_op_euler_step",
 ]
 
@@ -98,6 +98,8 @@ def load() -> C.CDLL:
     lib.vlaser_last_launch_count.restype = i64
     lib.vlaser_flops_per_call.argtypes = [vp, vp, i32]
     lib.vlaser_flops_per_call.restype = C.c_double
+    lib.vlaser_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
+    lib.vlaser_profile_read.restype = i32
     lib.vlaser_op_gemm.argtypes = [C.POINTER(GemmArgs), vp]
     lib.vlaser_op_gemm.restype = i32
     lib.vlaser_op_attention.argtypes = [C.POINTER(AttnArgs), vp]

@@ -124,6 +124,11 @@ struct Engine {
 
   // options / state
   int use_graph = 1, stop_after = 0, simt = 0;
+  int profile_gemm = 0;        // bracket every GEMM launch with CUDA events (non-graph runs only)
+  long long profile_mtot = 0;  // live packed-row count used for the FLOP accounting of var-len GEMMs
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<double> prof_flops;
+  size_t prof_used = 0;
   long long launches = 0, last_launches = 0;
   cudaStream_t own_stream = nullptr;
   struct GraphKey {
@@ -140,6 +145,7 @@ struct Engine {
 
   ~Engine() {
     for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
+    for (auto ev : prof_events) cudaEventDestroy(ev);
     for (void* p : allocs) cudaFree(p);
     if (pinned) cudaFreeHost(pinned);
     if (own_stream) cudaStreamDestroy(own_stream);
@@ -541,7 +547,23 @@ struct Run {
       const long long tiles256 = (long long)((M + 127) / 128) * (w.N / 256);
       if (tiles256 >= gemm_num_sms()) bn = 256;
     }
-    return gemm_launch(a.tm, bn == 256 ? w.tm256 : w.tm128, d, ep, bn, epi, st);
+    const bool prof = e.profile_gemm && !e.use_graph;
+    if (prof) {
+      while (e.prof_events.size() < e.prof_used + 2) {
+        cudaEvent_t ev;
+        VL_CUDA_CHECK(cudaEventCreate(&ev));
+        e.prof_events.push_back(ev);
+      }
+      const double rows = M_dev ? (double)e.profile_mtot : (double)M;
+      e.prof_flops.push_back(2.0 * rows * (double)w.N * (double)w.K);
+      VL_CUDA_CHECK(cudaEventRecord(e.prof_events[e.prof_used], st));
+    }
+    const int rc = gemm_launch(a.tm, bn == 256 ? w.tm256 : w.tm128, d, ep, bn, epi, st);
+    if (prof) {
+      VL_CUDA_CHECK(cudaEventRecord(e.prof_events[e.prof_used + 1], st));
+      e.prof_used += 2;
+    }
+    return rc;
   }
 
   EpiParams rope_ep(bf16* qout, const float* bias, const int* pos, const int* kvrow, int layer) {
@@ -871,6 +893,11 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   if (k == "use_graph") h->e.use_graph = (int)value;
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
+  else if (k == "profile_gemm") {
+    h->e.profile_gemm = (int)value;
+    h->e.prof_used = 0;
+    h->e.prof_flops.clear();
+  } else if (k == "profile_mtot") h->e.profile_mtot = value;
   else {
     set_last_error("unknown option " + k);
     return -2;
@@ -929,16 +956,21 @@ int32_t vlaser_infer_action_host(vlaser_t* h, const int64_t* input_ids, const vo
   uint8_t* p_valid = p_noise + up(n_noise);
   uint8_t* p_out = p_valid + up((size_t)B * 4);
   VL_CHECK((size_t)(p_out + n_out - pin) <= e.pinned_bytes, "pinned staging buffer too small");
-  memcpy(p_ids, input_ids, n_ids);
-  memcpy(p_pix, pixel_values, n_pix);
-  memcpy(p_prop, proprios, n_prop);
-  memcpy(p_noise, noise, n_noise);
-  if (valid_len) memcpy(p_valid, valid_len, (size_t)B * 4);
-  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_ids, p_ids, n_ids, cudaMemcpyHostToDevice, st));
-  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_pix, p_pix, n_pix, cudaMemcpyHostToDevice, st));
-  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_prop, p_prop, n_prop, cudaMemcpyHostToDevice, st));
-  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_noise, p_noise, n_noise, cudaMemcpyHostToDevice, st));
-  if (valid_len) VL_CUDA_CHECK(cudaMemcpyAsync(e.in_valid, p_valid, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  // page-locked caller buffers are copied from directly; pageable ones are staged through the pinned buffer
+  auto stage = [&](uint8_t* pin_dst, const void* src, size_t n) -> const void* {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost) return src;
+    cudaGetLastError();
+    memcpy(pin_dst, src, n);
+    return pin_dst;
+  };
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_ids, stage(p_ids, input_ids, n_ids), n_ids, cudaMemcpyHostToDevice, st));
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_pix, stage(p_pix, pixel_values, n_pix), n_pix, cudaMemcpyHostToDevice, st));
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_prop, stage(p_prop, proprios, n_prop), n_prop, cudaMemcpyHostToDevice, st));
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_noise, stage(p_noise, noise, n_noise), n_noise, cudaMemcpyHostToDevice, st));
+  if (valid_len)
+    VL_CUDA_CHECK(cudaMemcpyAsync(e.in_valid, stage(p_valid, valid_len, (size_t)B * 4), (size_t)B * 4,
+                                  cudaMemcpyHostToDevice, st));
   VL_TRY(engine_execute(e, B, io_dtype, valid_len != nullptr, st));
   VL_CUDA_CHECK(cudaMemcpyAsync(p_out, e.out_act, n_out, cudaMemcpyDeviceToHost, st));
   VL_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -988,6 +1020,25 @@ int64_t vlaser_debug_copy(vlaser_t* h, const char* name, void* host_dst, int64_t
     VL_CUDA_CHECK(cudaMemcpy(host_dst, src, std::min<size_t>(bytes, (size_t)max_bytes), cudaMemcpyDeviceToHost));
   }
   return (int64_t)bytes;
+}
+
+int32_t vlaser_profile_read(vlaser_t* h, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches) {
+  VL_CHECK(h && gemm_ms && gemm_flops && gemm_launches, "null argument");
+  Engine& e = h->e;
+  VL_CUDA_CHECK(cudaDeviceSynchronize());
+  double ms = 0, fl = 0;
+  for (size_t i = 0; i + 1 < e.prof_used; i += 2) {
+    float t = 0;
+    VL_CUDA_CHECK(cudaEventElapsedTime(&t, e.prof_events[i], e.prof_events[i + 1]));
+    ms += t;
+    fl += e.prof_flops[i / 2];
+  }
+  *gemm_ms = ms;
+  *gemm_flops = fl;
+  *gemm_launches = (int64_t)(e.prof_used / 2);
+  e.prof_used = 0;
+  e.prof_flops.clear();
+  return 0;
 }
 
 double vlaser_flops_per_call(vlaser_t* h, const int32_t* valid_len_host, int32_t B) {

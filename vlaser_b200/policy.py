@@ -279,6 +279,12 @@ class PiZeroInference:
                    f"debug_copy({name})")
         return buf.view(dtype)
 
+    def profile_read(self):
+        """(gemm_ms, gemm_flops, gemm_launches) accumulated since "profile_gemm" was switched on."""
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
+        _lib.check(self._lib.vlaser_profile_read(self._handle, C.byref(ms), C.byref(fl), C.byref(n)), "profile_read")
+        return ms.value, fl.value, n.value
+
     def last_launch_count(self) -> int:
         return int(self._lib.vlaser_last_launch_count(self._handle))
 
