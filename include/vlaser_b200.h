@@ -89,7 +89,10 @@ int32_t vlaser_infer_action_host(vlaser_t* h, const int64_t* input_ids, const vo
                                  int32_t B, int32_t io_dtype);
 void vlaser_destroy(vlaser_t* h);
 
-/* Options: "use_graph" (default 1: replay the whole call as one CUDA graph per batch size),
+/* Options: "pdl" (process-wide; 0 off, 1 (default) programmatic dependent launch inside the denoise steps, 2 everywhere),
+ * "pair_gemm" (default 1: large-M GEMMs on the cta_group::2 kernel), "fuse_norm" (default 0; 1 fuses the expert streams' RMSNorm across the GEMM chain), "exp_stages" (smem ring depth
+ * of the expert GEMMs, 0 = default),
+ * "use_graph" (default 1: replay the whole call as one CUDA graph per batch size),
  * "stop_after" (debug: 0 all, 1 ViT, 2 prefix embedding, 3 prefill, 4 first denoise step),
  * "simt_gemm" (debug/tests: route GEMMs through the CUDA-core cross-check kernel),
  * "profile_gemm" / "profile_mtot" (see vlaser_profile_read). */
@@ -132,6 +135,16 @@ typedef struct vlaser_gemm_args {
   int32_t n_q_heads, n_kv_heads;
   const float* pos_emb;
   int32_t patches;
+  /* fused RMSNorm chain (see csrc/gemm.cuh): producer outputs and consumer row scale */
+  const float* gamma_next;
+  void* a_next;          /* bf16 [M, lda_next] */
+  int32_t lda_next;
+  float* ss_next;        /* f32 [M], caller-zeroed */
+  int32_t* tile_counters;/* i32, zero-initialised (split-K only) */
+  const float* row_ss;   /* f32 [M] */
+  float inv_width, eps;
+  int32_t stages;        /* smem ring depth, 0 = default */
+  int32_t pair;          /* 1 = CTA-pair kernel (cta_group::2, 256x256 tile per pair); block_n is ignored */
 } vlaser_gemm_args;
 int32_t vlaser_op_gemm(const vlaser_gemm_args* a, void* stream);
 

@@ -22,8 +22,11 @@ def _stream():
 
 def gemm(A, W, epi, block_n=128, simt=False, out=None, ldo=None, bias=None, scale=None, M_dev=None, max_splits=1,
          row_map=None, row_pos=None, row_kvrow=None, cos_tab=None, sin_tab=None, k_cache=None, v_cache=None,
-         kv_head_stride=0, n_q_heads=0, n_kv_heads=0, pos_emb=None, patches=0):
+         kv_head_stride=0, n_q_heads=0, n_kv_heads=0, pos_emb=None, patches=0, gamma_next=None, a_next=None,
+         ss_next=None, tile_counters=None, row_ss=None, inv_width=0.0, eps=0.0, stages=0, pair=False):
     lib = _lib.load()
+    if block_n == 512:  # test shorthand for the CTA-pair kernel (256x256 tile per pair)
+        block_n, pair = 256, True
     a = GemmArgs()
     a.A, a.W = _p(A), _p(W)
     a.M, a.K = A.shape
@@ -36,6 +39,10 @@ def gemm(A, W, epi, block_n=128, simt=False, out=None, ldo=None, bias=None, scal
     a.k_cache, a.v_cache, a.kv_head_stride = _p(k_cache), _p(v_cache), kv_head_stride
     a.n_q_heads, a.n_kv_heads = n_q_heads, n_kv_heads
     a.pos_emb, a.patches = _p(pos_emb), patches
+    a.gamma_next, a.a_next, a.ss_next, a.tile_counters = _p(gamma_next), _p(a_next), _p(ss_next), _p(tile_counters)
+    a.lda_next = a_next.shape[-1] if a_next is not None else 0
+    a.row_ss, a.inv_width, a.eps, a.stages = _p(row_ss), inv_width, eps, stages
+    a.pair = int(pair)
     _lib.check(lib.vlaser_op_gemm(C.byref(a), _stream()), "op_gemm")
     return out
 

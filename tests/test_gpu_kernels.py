@@ -26,13 +26,13 @@ def _ref_mm(A, W):
     return A.float() @ W.float().t()
 
 
-VARIANTS = [("tcgen05", 128, False), ("tcgen05", 256, False), ("simt", 128, True)]
+VARIANTS = [("tcgen05", 128, False), ("tcgen05", 256, False), ("pair", 512, False), ("simt", 128, True)]
 
 
 @pytest.mark.parametrize("name,bn,simt", VARIANTS)
 @pytest.mark.parametrize("M,N,K", [(300, 256, 128), (1000, 1024, 512), (129, 768, 768), (4096, 2048, 1024)])
 def test_gemm_store_bias(name, bn, simt, M, N, K):
-    if N % bn:
+    if N % min(bn, 256):
         pytest.skip("N not a multiple of block_n")
     A, W = _rand(M, K), _rand(N, K, scale=0.05)
     bias = _rand(N, dtype=torch.float32, seed=3)
@@ -61,6 +61,8 @@ def test_gemm_gelu_silu(name, bn, simt):
 @pytest.mark.parametrize("name,bn,simt", VARIANTS)
 @pytest.mark.parametrize("splits", [1, 8])
 def test_gemm_resid(name, bn, simt, splits):
+    if bn == 512 and splits > 1:
+        pytest.skip("the pair kernel has no split-K")
     M, N, K = 256, 768, 2048
     A, W = _rand(M, K), _rand(N, K, scale=0.05)
     bias = _rand(N, dtype=torch.float32, seed=7)
@@ -72,6 +74,44 @@ def test_gemm_resid(name, bn, simt, splits):
     err = ops.rel_err(out, ref)
     print(f"gemm_resid {name} bn={bn} splits={splits}: rel={err:.2e} max={ops.max_err(out, ref):.2e}")
     assert err < 1e-5
+
+
+@pytest.mark.parametrize("name,simt", [("tcgen05", False), ("simt", True)])
+@pytest.mark.parametrize("splits", [1, 32])
+@pytest.mark.parametrize("M", [64, 256])
+def test_gemm_fused_rmsnorm_chain(name, simt, splits, M):
+    """Producer (o/down-proj + residual) emits bf16(x*gamma) and row sums of squares; the consumer (gate/up with
+    SwiGLU) scales its accumulator by rsqrt(ss/width + eps): together == RMSNorm between the two GEMMs
+    (HF Qwen2RMSNorm as used at joint_model.py:166,209)."""
+    if simt and splits > 1:
+        pytest.skip("the cross-check kernel has no split-K")
+    N, K, F, eps = 768, 1536, 512, 1e-6
+    A, W = _rand(M, K), _rand(N, K, scale=0.05)
+    x0 = _rand(M, N, dtype=torch.float32, seed=9)
+    gamma = 1.0 + 0.1 * _rand(N, dtype=torch.float32, seed=10)
+    x = x0.clone()
+    a_next = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+    ss = torch.zeros(M, dtype=torch.float32, device=DEV)
+    ctr = torch.zeros(64, dtype=torch.int32, device=DEV)
+    for rep in range(2):  # second pass checks that the tile counters reset themselves
+        x.copy_(x0)
+        ss.zero_()
+        ops.gemm(A, W, EPI_RESID_F32, 128, simt, out=x, max_splits=splits, gamma_next=gamma, a_next=a_next, ss_next=ss,
+                 tile_counters=ctr, stages=3)
+        x_ref = x0 + _ref_mm(A, W)
+        assert ops.rel_err(x, x_ref) < 1e-5
+        assert ops.rel_err(ss, (x_ref * x_ref).sum(-1)) < 1e-5
+        assert ops.rel_err(a_next, x_ref * gamma) < BF16_TOL
+        assert int(ctr.abs().sum()) == 0
+    gate, up = _rand(F, N, scale=0.1, seed=1), _rand(F, N, scale=0.1, seed=2)
+    out = torch.empty(M, F, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(a_next, ops.interleave_gate_up(gate, up), EPI_SWIGLU_BF16, 128, simt, out=out, row_ss=ss,
+             inv_width=1.0 / N, eps=eps, stages=3)
+    xn = x_ref * torch.rsqrt((x_ref * x_ref).mean(-1, keepdim=True) + eps) * gamma
+    ref = torch.nn.functional.silu(xn @ gate.float().t()) * (xn @ up.float().t())
+    err = ops.rel_err(out, ref)
+    print(f"fused_rmsnorm_chain {name} M={M} splits={splits}: rel={err:.2e}")
+    assert err < 1.5 * BF16_TOL
 
 
 @pytest.mark.parametrize("name,bn,simt", VARIANTS)
@@ -101,7 +141,7 @@ def test_gemm_swiglu(name, bn, simt):
     assert err < BF16_TOL
 
 
-@pytest.mark.parametrize("name,simt", [("tcgen05", False), ("simt", True)])
+@pytest.mark.parametrize("name,simt", [("tcgen05", False), ("pair", False), ("simt", True)])
 def test_gemm_qkv_rope(name, simt):
     M, K, nq, nkv = 200, 256, 6, 1
     N = (nq + 2 * nkv) * 128
@@ -115,7 +155,7 @@ def test_gemm_qkv_rope(name, simt):
     q = torch.zeros(M, nq * 128, dtype=torch.bfloat16, device=DEV)
     kc = torch.zeros(nkv, rows_cap, 128, dtype=torch.bfloat16, device=DEV)
     vc = torch.zeros(nkv, rows_cap, 128, dtype=torch.bfloat16, device=DEV)
-    ops.gemm(A, W, EPI_QKV_ROPE, 128, simt, out=q, bias=bias, row_pos=pos, row_kvrow=kvrow, cos_tab=cos, sin_tab=sin,
+    ops.gemm(A, W, EPI_QKV_ROPE, 512 if name == "pair" else 128, simt, out=q, bias=bias, row_pos=pos, row_kvrow=kvrow, cos_tab=cos, sin_tab=sin,
              k_cache=kc, v_cache=vc, kv_head_stride=rows_cap * 128, n_q_heads=nq, n_kv_heads=nkv)
     y = (_ref_mm(A, W) + bias).view(M, nq + 2 * nkv, 128)
     c, s = cos[pos.long()][:, None, :], sin[pos.long()][:, None, :]

@@ -15,6 +15,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--only", default="")
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--batch", type=int, default=64)
+ap.add_argument("--bn", type=int, default=0, help="force block_n (0 = engine heuristic)")
+ap.add_argument("--pair", type=int, default=1, help="use the CTA-pair kernel where the engine would")
 a = ap.parse_args()
 B = a.batch
 MV, MP, MA = B * 257, B * 87, B * 4
@@ -43,6 +45,10 @@ for name, M, N, K, epi, cnt, splits in SHAPES:
     bn = 128
     if epi != EPI_QKV_ROPE and N % 256 == 0 and ((M + 127) // 128) * (N // 256) >= 148:
         bn = 256
+    if a.bn and epi != EPI_QKV_ROPE and N % a.bn == 0:
+        bn = a.bn
+    if a.pair and not a.bn and N % 256 == 0 and splits <= 1 and ((M + 255) // 256) * (N // 256) >= 74:
+        bn = 512
     if epi in (EPI_STORE_BF16, EPI_GELU_BF16, EPI_SILU_BF16):
         out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
     elif epi == EPI_SWIGLU_BF16:

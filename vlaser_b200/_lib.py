@@ -10,7 +10,7 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvlaser_b200.so")
+LIB_PATH = os.environ.get("VLASER_LIB") or os.path.join(HERE, "libvlaser_b200.so")  # env override: A/B of builds
 
 F32, BF16 = 0, 1
 
@@ -41,6 +41,9 @@ class GemmArgs(C.Structure):
         ("row_map", C.c_void_p), ("row_pos", C.c_void_p), ("row_kvrow", C.c_void_p), ("cos_tab", C.c_void_p),
         ("sin_tab", C.c_void_p), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p), ("kv_head_stride", C.c_int64),
         ("n_q_heads", C.c_int32), ("n_kv_heads", C.c_int32), ("pos_emb", C.c_void_p), ("patches", C.c_int32),
+        ("gamma_next", C.c_void_p), ("a_next", C.c_void_p), ("lda_next", C.c_int32), ("ss_next", C.c_void_p),
+        ("tile_counters", C.c_void_p), ("row_ss", C.c_void_p), ("inv_width", C.c_float), ("eps", C.c_float),
+        ("stages", C.c_int32), ("pair", C.c_int32),
     ]
 
 

@@ -23,6 +23,8 @@ __device__ __forceinline__ uint32_t swz(int row, int chunk) {
 
 template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(AttnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int CH = HD / 8;  // 16-byte chunks per row
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* Qs = smem;                                  // [64][HD]
@@ -231,7 +233,7 @@ int launch_hd(const AttnParams& p, cudaStream_t stream) {
   }
   const int rows_max = p.group * p.max_q_len;
   dim3 grid((rows_max + ATT_BM - 1) / ATT_BM, p.n_kv_heads, p.batch);
-  attention_kernel<HD><<<grid, ATT_THREADS, SMEM, stream>>>(p);
+  VL_CUDA_CHECK(launch_kernel(attention_kernel<HD>, dim3(grid), dim3(ATT_THREADS), SMEM, stream, p));
   VL_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

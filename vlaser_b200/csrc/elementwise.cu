@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(128) norm_kernel(const float* __restrict__ x, 
                                                    const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                                    int rows, const int* __restrict__ rows_dev, float eps, int g,
                                                    int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int W = VPL * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + warp;
@@ -83,7 +85,7 @@ int norm_dispatch(const float* x, const float* gamma, const float* beta, __nv_bf
   const int grid = (rows + 3) / 4;
 #define VL_NORM_CASE(V)                                                                                          \
   case V:                                                                                                        \
-    norm_kernel<V, RMS, GATHER><<<grid, 128, 0, stream>>>(x, gamma, beta, out, rows, rows_dev, eps, g, C);       \
+    VL_CUDA_CHECK(launch_kernel(norm_kernel<V, RMS, GATHER>, dim3(grid), dim3(128), 0, stream, x, gamma, beta, out, rows, rows_dev, eps, g, C));       \
     break;
   switch (width / 128) {
     VL_NORM_CASE(1) VL_NORM_CASE(2) VL_NORM_CASE(3) VL_NORM_CASE(4) VL_NORM_CASE(6) VL_NORM_CASE(8)
@@ -102,6 +104,8 @@ int norm_dispatch(const float* x, const float* gamma, const float* beta, __nv_bf
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void pixel_shuffle_kernel(const T* __restrict__ in, T* __restrict__ out, int n, int g, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   // out[img, r2, c2, b*2C + a*C + c] = in[img, 2*r2+b, 2*c2+a, c]
   const int hg = g >> 1;
   const long long total = (long long)n * hg * hg * 4 * C;
@@ -126,6 +130,8 @@ __global__ void pixel_shuffle_kernel(const T* __restrict__ in, T* __restrict__ o
 template <typename T>
 __global__ void im2col_kernel(const T* __restrict__ pix, __nv_bfloat16* __restrict__ cols, int n, int px, int ps,
                               int kpad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int g = px / ps;
   const int kreal = 3 * ps * ps;
   const long long total = (long long)n * g * g * kpad;
@@ -148,6 +154,8 @@ __global__ void im2col_kernel(const T* __restrict__ pix, __nv_bfloat16* __restri
 
 __global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
                                 int n, int tokens, int width) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * width) return;
   const int img = i / width, c = i - img * width;
@@ -159,6 +167,8 @@ __global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__
 // ------------------------------------------------------------------------------------------
 __global__ void plan_lengths_kernel(const long long* __restrict__ ids, const int* __restrict__ valid_in, PlanBuffers pb,
                                     int B, int S, int H, int pad_token) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one warp per sample counts non-pad ids
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B) return;
@@ -173,6 +183,8 @@ __global__ void plan_lengths_kernel(const long long* __restrict__ ids, const int
 }
 
 __global__ void plan_scan_kernel(PlanBuffers pb, int B, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     int acc = 0;
     for (int b = 0; b < B; ++b) {
@@ -187,6 +199,8 @@ __global__ void plan_scan_kernel(PlanBuffers pb, int B, int H) {
 
 __global__ void plan_rows_kernel(const long long* __restrict__ ids, PlanBuffers pb, int B, int S, int H,
                                  int img_tokens, int image_token, int pad_token) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one warp per sample
   const int b = blockIdx.x, lane = threadIdx.x;
   const int vl = pb.valid_len[b], base = pb.cu[b], kvo = pb.kvoff[b];
@@ -233,6 +247,8 @@ __global__ void plan_rows_kernel(const long long* __restrict__ ids, PlanBuffers 
 
 __global__ void assemble_text_kernel(const __nv_bfloat16* __restrict__ embed, const int* __restrict__ row_src,
                                      const int* __restrict__ m_tot, float* __restrict__ x, int rows_cap, int width) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + warp;
   if (row >= min(*m_tot, rows_cap)) return;
@@ -257,6 +273,8 @@ __global__ void assemble_text_kernel(const __nv_bfloat16* __restrict__ embed, co
 template <typename TI, typename TO>
 __global__ void small_linear_kernel(const TI* __restrict__ in, const float* __restrict__ W,
                                     const float* __restrict__ bias, TO* __restrict__ out, int rows, int K, int N) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)rows * N) return;
   const int r = (int)(i / N), n = (int)(i - (long long)r * N);
@@ -267,6 +285,8 @@ __global__ void small_linear_kernel(const TI* __restrict__ in, const float* __re
 
 template <typename TI, typename TO>
 __global__ void convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = static_cast<TO>(static_cast<float>(in[i]));
 }
@@ -281,6 +301,8 @@ __global__ void __launch_bounds__(128) euler_step_kernel(const float* __restrict
                                                          TO* __restrict__ out, int rows, int width, int A, int H,
                                                          int horizon, float dt, float eps, int last_step, int do_clip,
                                                          float clip) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + warp;
   if (r >= rows) return;
@@ -333,9 +355,9 @@ int pixel_shuffle_launch(const void* in, void* out, int n, int grid, int channel
   if (total == 0) return 0;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
   if (elem_bytes == 4)
-    pixel_shuffle_kernel<uint32_t><<<blocks, 256, 0, stream>>>((const uint32_t*)in, (uint32_t*)out, n, grid, channels);
+    VL_CUDA_CHECK(launch_kernel(pixel_shuffle_kernel<uint32_t>, dim3(blocks), dim3(256), 0, stream, (const uint32_t*)in, (uint32_t*)out, n, grid, channels));
   else if (elem_bytes == 2)
-    pixel_shuffle_kernel<uint16_t><<<blocks, 256, 0, stream>>>((const uint16_t*)in, (uint16_t*)out, n, grid, channels);
+    VL_CUDA_CHECK(launch_kernel(pixel_shuffle_kernel<uint16_t>, dim3(blocks), dim3(256), 0, stream, (const uint16_t*)in, (uint16_t*)out, n, grid, channels));
   else {
     set_last_error("pixel_shuffle: elem_bytes must be 2 or 4");
     return -2;
@@ -351,16 +373,16 @@ int im2col_launch(const void* pixel, int pixel_dtype, __nv_bfloat16* cols, int n
   if (total == 0) return 0;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 32);
   if (pixel_dtype == DT_F32)
-    im2col_kernel<float><<<blocks, 256, 0, stream>>>((const float*)pixel, cols, n, px, ps, kpad);
+    VL_CUDA_CHECK(launch_kernel(im2col_kernel<float>, dim3(blocks), dim3(256), 0, stream, (const float*)pixel, cols, n, px, ps, kpad));
   else
-    im2col_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)pixel, cols, n, px, ps, kpad);
+    VL_CUDA_CHECK(launch_kernel(im2col_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, stream, (const __nv_bfloat16*)pixel, cols, n, px, ps, kpad));
   VL_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 int cls_rows_launch(float* x, const float* cls, const float* pos, int n, int tokens, int width, cudaStream_t stream) {
   if (n <= 0) return 0;
-  cls_rows_kernel<<<(n * width + 255) / 256, 256, 0, stream>>>(x, cls, pos, n, tokens, width);
+  VL_CUDA_CHECK(launch_kernel(cls_rows_kernel, dim3((n * width + 255) / 256), dim3(256), 0, stream, x, cls, pos, n, tokens, width));
   VL_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -369,9 +391,9 @@ int plan_launch(const long long* input_ids, const int* valid_len_in, PlanBuffers
                 int img_tokens_per_sample, int image_token, int pad_token, cudaStream_t stream) {
   VL_CHECK(B > 0, "plan: empty batch");
   VL_CUDA_CHECK(cudaMemsetAsync(pb.img_row_map, 0xFF, sizeof(int) * (size_t)B * img_tokens_per_sample, stream));
-  plan_lengths_kernel<<<(B * 32 + 127) / 128, 128, 0, stream>>>(input_ids, valid_len_in, pb, B, S, H, pad_token);
-  plan_scan_kernel<<<1, 32, 0, stream>>>(pb, B, H);
-  plan_rows_kernel<<<B, 32, 0, stream>>>(input_ids, pb, B, S, H, img_tokens_per_sample, image_token, pad_token);
+  VL_CUDA_CHECK(launch_kernel(plan_lengths_kernel, dim3((B * 32 + 127) / 128), dim3(128), 0, stream, input_ids, valid_len_in, pb, B, S, H, pad_token));
+  VL_CUDA_CHECK(launch_kernel(plan_scan_kernel, dim3(1), dim3(32), 0, stream, pb, B, H));
+  VL_CUDA_CHECK(launch_kernel(plan_rows_kernel, dim3(B), dim3(32), 0, stream, input_ids, pb, B, S, H, img_tokens_per_sample, image_token, pad_token));
   VL_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -380,7 +402,7 @@ int assemble_text_launch(const __nv_bfloat16* embed, const int* row_src, const i
                          int width, cudaStream_t stream) {
   VL_CHECK(width % 8 == 0, "assemble: width % 8");
   if (rows_cap <= 0) return 0;
-  assemble_text_kernel<<<(rows_cap + 3) / 4, 128, 0, stream>>>(embed, row_src, m_tot, x, rows_cap, width);
+  VL_CUDA_CHECK(launch_kernel(assemble_text_kernel, dim3((rows_cap + 3) / 4), dim3(128), 0, stream, embed, row_src, m_tot, x, rows_cap, width));
   VL_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -391,16 +413,13 @@ int small_linear_launch(const void* in, int in_dtype, const float* W, const floa
   if (total <= 0) return 0;
   const int blocks = (int)((total + 255) / 256);
   if (in_dtype == DT_F32 && out_dtype == DT_F32)
-    small_linear_kernel<float, float><<<blocks, 256, 0, stream>>>((const float*)in, W, bias, (float*)out, rows, K, N);
+    VL_CUDA_CHECK(launch_kernel(small_linear_kernel<float, float>, dim3(blocks), dim3(256), 0, stream, (const float*)in, W, bias, (float*)out, rows, K, N));
   else if (in_dtype == DT_F32 && out_dtype == DT_BF16)
-    small_linear_kernel<float, __nv_bfloat16>
-        <<<blocks, 256, 0, stream>>>((const float*)in, W, bias, (__nv_bfloat16*)out, rows, K, N);
+    VL_CUDA_CHECK(launch_kernel(small_linear_kernel<float, __nv_bfloat16>, dim3(blocks), dim3(256), 0, stream, (const float*)in, W, bias, (__nv_bfloat16*)out, rows, K, N));
   else if (in_dtype == DT_BF16 && out_dtype == DT_F32)
-    small_linear_kernel<__nv_bfloat16, float>
-        <<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)in, W, bias, (float*)out, rows, K, N);
+    VL_CUDA_CHECK(launch_kernel(small_linear_kernel<__nv_bfloat16, float>, dim3(blocks), dim3(256), 0, stream, (const __nv_bfloat16*)in, W, bias, (float*)out, rows, K, N));
   else
-    small_linear_kernel<__nv_bfloat16, __nv_bfloat16>
-        <<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)in, W, bias, (__nv_bfloat16*)out, rows, K, N);
+    VL_CUDA_CHECK(launch_kernel(small_linear_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(blocks), dim3(256), 0, stream, (const __nv_bfloat16*)in, W, bias, (__nv_bfloat16*)out, rows, K, N));
   VL_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -409,14 +428,13 @@ int convert_launch(const void* in, int in_dtype, void* out, int out_dtype, long 
   if (n <= 0) return 0;
   const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
   if (in_dtype == DT_F32 && out_dtype == DT_F32)
-    convert_kernel<float, float><<<blocks, 256, 0, stream>>>((const float*)in, (float*)out, n);
+    VL_CUDA_CHECK(launch_kernel(convert_kernel<float, float>, dim3(blocks), dim3(256), 0, stream, (const float*)in, (float*)out, n));
   else if (in_dtype == DT_BF16 && out_dtype == DT_F32)
-    convert_kernel<__nv_bfloat16, float><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)in, (float*)out, n);
+    VL_CUDA_CHECK(launch_kernel(convert_kernel<__nv_bfloat16, float>, dim3(blocks), dim3(256), 0, stream, (const __nv_bfloat16*)in, (float*)out, n));
   else if (in_dtype == DT_F32 && out_dtype == DT_BF16)
-    convert_kernel<float, __nv_bfloat16><<<blocks, 256, 0, stream>>>((const float*)in, (__nv_bfloat16*)out, n);
+    VL_CUDA_CHECK(launch_kernel(convert_kernel<float, __nv_bfloat16>, dim3(blocks), dim3(256), 0, stream, (const float*)in, (__nv_bfloat16*)out, n));
   else
-    convert_kernel<__nv_bfloat16, __nv_bfloat16>
-        <<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, n);
+    VL_CUDA_CHECK(launch_kernel(convert_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(blocks), dim3(256), 0, stream, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, n));
   VL_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -427,11 +445,11 @@ int euler_step_launch(const float* x, const float* gamma, const float* Wdec, con
   if (rows <= 0) return 0;
   const int grid = (rows + 3) / 4;
   if (out_dtype == DT_F32)
-    euler_step_kernel<float><<<grid, 128, 0, stream>>>(x, gamma, Wdec, bdec, action, (float*)out, rows, width, A, H,
-                                                       horizon, dt, eps, last_step, do_clip, clip);
+    VL_CUDA_CHECK(launch_kernel(euler_step_kernel<float>, dim3(grid), dim3(128), 0, stream, x, gamma, Wdec, bdec, action, (float*)out, rows, width, A, H,
+                                                       horizon, dt, eps, last_step, do_clip, clip));
   else
-    euler_step_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(x, gamma, Wdec, bdec, action, (__nv_bfloat16*)out, rows,
-                                                               width, A, H, horizon, dt, eps, last_step, do_clip, clip);
+    VL_CUDA_CHECK(launch_kernel(euler_step_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, stream, x, gamma, Wdec, bdec, action, (__nv_bfloat16*)out, rows,
+                                                               width, A, H, horizon, dt, eps, last_step, do_clip, clip));
   VL_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -30,6 +30,11 @@ namespace vlaser {
 
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
+// PDL policy: 0 = off, 1 = only inside the latency-bound expert chain of the denoise steps, 2 = every kernel.
+static int g_pdl_mode = 1;
+static bool g_pdl_scope = false;  // set by the schedule while it enqueues a latency-bound section
+bool pdl_enabled() { return g_pdl_mode == 2 || (g_pdl_mode == 1 && g_pdl_scope); }
+void set_pdl_enabled(bool on) { g_pdl_scope = on; }
 
 namespace {
 
@@ -114,6 +119,12 @@ struct Engine {
   float *vx = nullptr, *xv = nullptr, *xp = nullptr, *xa = nullptr, *action = nullptr;
   bf16 *vqkv = nullptr, *q = nullptr, *qp = nullptr, *qa = nullptr;
   bf16 *kc = nullptr, *vc = nullptr;  // [layers][kv_heads][kv_rows][128]
+  // fused RMSNorm chain of the expert streams: per pass (prefill proprio, then each denoise step) one row-sum-of-
+  // squares slot per norm site [(steps+1)][2*layers+1][ss_rows], zeroed once per call; split-K tile counters
+  float* ss = nullptr;
+  int ss_rows = 0;
+  size_t ss_floats = 0;
+  int* tile_ctr = nullptr;
   PlanBuffers pb{};
   // static I/O staging (graph operands)
   long long* in_ids = nullptr;
@@ -124,6 +135,9 @@ struct Engine {
 
   // options / state
   int use_graph = 1, stop_after = 0, simt = 0;
+  int exp_stages = 0;          // smem ring depth of the expert-stream GEMMs (0 = kernel default)
+  int pair_gemm = 1;           // 1: large-M GEMMs run on the CTA-pair (cta_group::2) kernel
+  int fuse_norm = 0;           // 1: RMSNorm of the expert streams fused across the GEMM chain (see exp_pre/exp_post)
   int profile_gemm = 0;        // bracket every GEMM launch with CUDA events (non-graph runs only)
   long long profile_mtot = 0;  // live packed-row count used for the FLOP accounting of var-len GEMMs
   std::vector<cudaEvent_t> prof_events;
@@ -198,8 +212,8 @@ struct Engine {
   int add_act(Act* a, int rows, int K) {
     a->rows = rows;
     a->K = K;
-    // pad the row count to a multiple of 128 so that TMA boxes never start out of bounds
-    const int rows_alloc = (rows + 127) / 128 * 128;
+    // pad the row count to a multiple of 256 (one CTA-pair tile) so that TMA boxes never start out of bounds
+    const int rows_alloc = (rows + 255) / 256 * 256;
     if (alloc(&a->p, (size_t)rows_alloc * K)) return -1;
     return make_tmap_bf16(&a->tm, a->p, rows_alloc, K, 128);
   }
@@ -351,6 +365,10 @@ int engine_build(Engine& e) {
   VL_TRY(e.add_act(&e.e1, arow, he));
   VL_TRY(e.add_act(&e.h2, arow, he));
   VL_TRY(e.alloc(&e.action, (size_t)arow * c.action_dim));
+  e.ss_rows = std::max(arow, e.Bc);
+  e.ss_floats = (size_t)(c.num_inference_steps + 1) * (2 * c.layers + 1) * e.ss_rows;
+  VL_TRY(e.alloc(&e.ss, e.ss_floats));
+  VL_TRY(e.alloc(&e.tile_ctr, 4096));
   const size_t kv_elems = (size_t)c.layers * c.n_kv_heads * e.kv_rows * 128;
   VL_TRY(e.alloc(&e.kc, kv_elems));
   VL_TRY(e.alloc(&e.vc, kv_elems));
@@ -533,17 +551,22 @@ struct Run {
   int io;
   int rc = 0;
 
-  int gemm(const Act& a, const Lin& w, int M, const int* M_dev, int epi, EpiParams ep, int max_splits = 1) {
+  int gemm(const Act& a, const Lin& w, int M, const int* M_dev, int epi, EpiParams ep, int max_splits = 1,
+           int stages = 0) {
     GemmDims d;
     d.M = M;
     d.N = w.N;
     d.K = w.K;
     d.M_dev = M_dev;
     d.max_splits = max_splits;
+    d.stages = stages;
     e.launches++;
     if (e.simt) return gemm_launch_simt(a.p, w.w, d, ep, epi, st);
     int bn = 128;
-    if (epi != EPI_QKV_ROPE && w.has256) {
+    // large-M GEMMs: CTA-pair kernel (256x256 tile per pair) when there is at least one tile per pair
+    const long long pair_tiles = (long long)((M + 255) / 256) * (w.N / 256);
+    if (e.pair_gemm && w.N % 256 == 0 && max_splits <= 1 && pair_tiles >= gemm_num_sms() / 2) d.pair = 1;
+    if (!d.pair && epi != EPI_QKV_ROPE && w.has256) {
       const long long tiles256 = (long long)((M + 127) / 128) * (w.N / 256);
       if (tiles256 >= gemm_num_sms()) bn = 256;
     }
@@ -690,12 +713,57 @@ struct Run {
     return gemm(act, L.down, M, M_dev, EPI_RESID_F32, eo, splits);
   }
 
+  // ---- expert streams (proprio token in the prefill, action tokens in the denoise steps): RMSNorm is fused across
+  // the GEMM chain. `xn` always holds bf16(x * gamma) for the NEXT norm site and ss slot `site` its row sums of
+  // squares; the consuming GEMM scales its accumulator rows by rsqrt(ss/he + eps).
+  float* ss_slot(int pass, int site) { return e.ss + ((size_t)pass * (2 * e.c.layers + 1) + site) * e.ss_rows; }
+  void norm_consumer(EpiParams& ep, int pass, int site) {
+    ep.row_ss = ss_slot(pass, site);
+    ep.inv_width = 1.0f / (float)e.c.hidden_e;
+    ep.eps = e.c.rms_eps;
+  }
+  void norm_producer(EpiParams& ep, Act& xn, const float* gamma, int pass, int site) {
+    ep.a_next = xn.p;
+    ep.lda_next = e.c.hidden_e;
+    ep.gamma_next = gamma;
+    ep.ss_next = ss_slot(pass, site);
+    ep.tile_counters = e.tile_ctr;
+  }
+  int exp_pre(int li, Act& xn, bf16* qout, int M, const int* pos, const int* kvrow, int pass) {
+    EpiParams ep = rope_ep(qout, e.exp[li].bqkv, pos, kvrow, li);
+    norm_consumer(ep, pass, 2 * li);
+    return gemm(xn, e.exp[li].qkv, M, nullptr, EPI_QKV_ROPE, ep, 1, e.exp_stages);
+  }
+  int exp_post(int li, float* x, Act& xn, Act& ao, Act& act, int M, int pass, bool last_needs_norm) {
+    const vlaser_cfg& c = e.c;
+    LlmLayer& L = e.exp[li];
+    EpiParams eo;
+    eo.out = x;
+    eo.ldo = c.hidden_e;
+    norm_producer(eo, xn, L.ln_post, pass, 2 * li + 1);
+    VL_TRY(gemm(ao, L.o, M, nullptr, EPI_RESID_F32, eo, 32, e.exp_stages));
+    EpiParams eg;
+    eg.out = act.p;
+    eg.ldo = c.mlp_e;
+    norm_consumer(eg, pass, 2 * li + 1);
+    VL_TRY(gemm(xn, L.gu, M, nullptr, EPI_SWIGLU_BF16, eg, 1, e.exp_stages));
+    EpiParams ed;
+    ed.out = x;
+    ed.ldo = c.hidden_e;
+    if (li + 1 < c.layers) norm_producer(ed, xn, e.exp[li + 1].ln_in, pass, 2 * li + 2);
+    else if (last_needs_norm) norm_producer(ed, xn, e.final_norm, pass, 2 * li + 2);
+    return gemm(act, L.down, M, nullptr, EPI_RESID_F32, ed, 32, e.exp_stages);
+  }
+
   int prefill() {
     const vlaser_cfg& c = e.c;
     const int cap = B * e.S;
     for (int li = 0; li < c.layers; ++li) {
       VL_TRY(block_pre(e.llm[li], e.xv, e.xn, e.q, cap, e.pb.m_tot, c.hidden, e.pb.row_pos, e.pb.row_kvrow, li));
-      VL_TRY(block_pre(e.exp[li], e.xp, e.xpn, e.qp, B, nullptr, c.hidden_e, e.pb.prop_pos, e.pb.prop_kvrow, li));
+      if (li == 0 || !e.fuse_norm)  // (fused: the proprio encoder output has no producer epilogue -> plain RMSNorm)
+        VL_TRY(block_pre(e.exp[li], e.xp, e.xpn, e.qp, B, nullptr, c.hidden_e, e.pb.prop_pos, e.pb.prop_kvrow, li));
+      else
+        VL_TRY(exp_pre(li, e.xpn, e.qp, B, e.pb.prop_pos, e.pb.prop_kvrow, 0));
       if (li == c.layers - 1) break;  // last layer: only K/V are needed (joint_model.py:192-193, 690-691)
       AttnParams ap;
       const size_t off = (size_t)li * c.n_kv_heads * e.kv_rows * 128;
@@ -723,7 +791,8 @@ struct Run {
       VL_TRY(attention_launch(ap, 128, st));
       e.launches++;
       VL_TRY(block_post(e.llm[li], e.xv, e.xn, e.ao, e.act, cap, e.pb.m_tot, c.hidden, c.mlp, 1));
-      VL_TRY(block_post(e.exp[li], e.xp, e.xpn, e.aop, e.actp, B, nullptr, c.hidden_e, c.mlp_e, 32));
+      if (e.fuse_norm) VL_TRY(exp_post(li, e.xp, e.xpn, e.aop, e.actp, B, 0, false));
+      else VL_TRY(block_post(e.exp[li], e.xp, e.xpn, e.aop, e.actp, B, nullptr, c.hidden_e, c.mlp_e, 32));
     }
     return 0;
   }
@@ -743,9 +812,11 @@ struct Run {
     e3.out = e.xa;
     e3.ldo = he;
     e3.bias = e.ae_b3;
+    if (e.fuse_norm) norm_producer(e3, e.xan, e.exp[0].ln_in, step + 1, 0);
     VL_TRY(gemm(e.h2, e.ae_w3, M, nullptr, EPI_STORE_F32, e3));
     for (int li = 0; li < c.layers; ++li) {
-      VL_TRY(block_pre(e.exp[li], e.xa, e.xan, e.qa, M, nullptr, he, e.pb.act_pos, e.pb.act_kvrow, li));
+      if (e.fuse_norm) VL_TRY(exp_pre(li, e.xan, e.qa, M, e.pb.act_pos, e.pb.act_kvrow, step + 1));
+      else VL_TRY(block_pre(e.exp[li], e.xa, e.xan, e.qa, M, nullptr, he, e.pb.act_pos, e.pb.act_kvrow, li));
       AttnParams ap;
       const size_t off = (size_t)li * c.n_kv_heads * e.kv_rows * 128;
       ap.q = e.qa;
@@ -767,7 +838,8 @@ struct Run {
       ap.scale = 0.08838834764831845f;
       VL_TRY(attention_launch(ap, 128, st));
       e.launches++;
-      VL_TRY(block_post(e.exp[li], e.xa, e.xan, e.aoa, e.acta, M, nullptr, he, c.mlp_e, 32));
+      if (e.fuse_norm) VL_TRY(exp_post(li, e.xa, e.xan, e.aoa, e.acta, M, step + 1, false));
+      else VL_TRY(block_post(e.exp[li], e.xa, e.xan, e.aoa, e.acta, M, nullptr, he, c.mlp_e, 32));
     }
     const int last = step == c.num_inference_steps - 1;
     VL_TRY(euler_step_launch(e.xa, e.final_norm, e.dec_w, e.dec_b, e.action, e.out_act, io, M, he, c.action_dim, e.H,
@@ -782,6 +854,7 @@ struct Run {
     VL_TRY(plan_launch(e.in_ids, has_valid ? e.in_valid : nullptr, e.pb, B, e.S, e.H, e.n_img * e.T,
                        c.image_token_index, c.pad_token_id, st));
     VL_TRY(convert_launch(e.in_noise, io, e.action, DT_F32, (long long)B * e.H * c.action_dim, st));
+    if (e.fuse_norm) VL_CUDA_CHECK(cudaMemsetAsync(e.ss, 0, e.ss_floats * sizeof(float), st));
     e.launches += 5;
     VL_TRY(vit());
     if (e.stop_after == 1) return 0;
@@ -789,10 +862,15 @@ struct Run {
     if (e.stop_after == 2) return 0;
     VL_TRY(prefill());
     if (e.stop_after == 3) return 0;
+    set_pdl_enabled(true);
     for (int k = 0; k < c.num_inference_steps; ++k) {
-      VL_TRY(denoise(k));
-      if (e.stop_after == 4) return 0;
+      const int rc = denoise(k);
+      if (rc != 0 || e.stop_after == 4) {
+        set_pdl_enabled(false);
+        return rc;
+      }
     }
+    set_pdl_enabled(false);
     return 0;
   }
 };
@@ -893,6 +971,16 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   if (k == "use_graph") h->e.use_graph = (int)value;
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
+  else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm") {
+    // schedule-shaping options: captured graphs are stale afterwards
+    if (k == "pdl") g_pdl_mode = (int)value;
+    else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
+    else if (k == "pair_gemm") h->e.pair_gemm = (int)value;
+    else h->e.exp_stages = (int)value;
+    cudaDeviceSynchronize();
+    for (auto& g : h->e.graphs) cudaGraphExecDestroy(g.second.exec);
+    h->e.graphs.clear();
+  }
   else if (k == "profile_gemm") {
     h->e.profile_gemm = (int)value;
     h->e.prof_used = 0;
@@ -1093,14 +1181,24 @@ int32_t vlaser_op_gemm(const vlaser_gemm_args* a, void* stream) {
   ep.n_kv_heads = a->n_kv_heads;
   ep.pos_emb = a->pos_emb;
   ep.patches = a->patches;
+  ep.gamma_next = a->gamma_next;
+  ep.a_next = reinterpret_cast<__nv_bfloat16*>(a->a_next);
+  ep.lda_next = a->lda_next;
+  ep.ss_next = a->ss_next;
+  ep.tile_counters = a->tile_counters;
+  ep.row_ss = a->row_ss;
+  ep.inv_width = a->inv_width;
+  ep.eps = a->eps;
+  d.stages = a->stages;
+  d.pair = a->pair;
   if (a->simt)
     return gemm_launch_simt(reinterpret_cast<const __nv_bfloat16*>(a->A), reinterpret_cast<const __nv_bfloat16*>(a->W),
                             d, ep, a->epi, st);
   CUtensorMap tmA, tmB;
   // rows of A beyond M are zero-filled by TMA (the map's row extent is the true M)
   VL_TRY(make_tmap_bf16(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, 128));
-  VL_TRY(make_tmap_bf16(&tmB, a->W, (uint64_t)a->N, (uint64_t)a->K, (uint32_t)a->block_n));
-  return gemm_launch(tmA, tmB, d, ep, a->block_n, a->epi, st);
+  VL_TRY(make_tmap_bf16(&tmB, a->W, (uint64_t)a->N, (uint64_t)a->K, a->pair ? 128u : (uint32_t)a->block_n));
+  return gemm_launch(tmA, tmB, d, ep, a->pair ? 128 : a->block_n, a->epi, st);
 }
 
 int32_t vlaser_op_attention(const vlaser_attn_args* a, void* stream) {

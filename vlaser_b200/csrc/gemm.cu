@@ -18,16 +18,21 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                        // two warps per TMEM lane quarter, each drains half the columns
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
+
+constexpr int MAX_STAGES = 8;
 
 template <int BLOCK_N>
 struct GemmCfg {
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int DEFAULT_STAGES = (BLOCK_N == 256) ? 4 : 6;
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t smem_bytes(int stages) {
+    return stages * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  }
 };
 
 struct TileSched {
@@ -84,9 +89,37 @@ __device__ __forceinline__ void add_vec32(float (&v)[32], const float* __restric
   }
 }
 
+// a_next[row, col0..col0+31] = bf16(v * gamma_next), returns sum v^2 (fused RMSNorm producer side)
+__device__ __forceinline__ float norm_out_chunk(const EpiParams& ep, int row, int col0, const float (&v)[32]) {
+  float ss = 0.f;
+  float y[32];
+  const float4* g4 = reinterpret_cast<const float4*>(ep.gamma_next + col0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 g = __ldg(g4 + i);
+    ss += (v[4 * i] * v[4 * i] + v[4 * i + 1] * v[4 * i + 1]) + (v[4 * i + 2] * v[4 * i + 2] + v[4 * i + 3] * v[4 * i + 3]);
+    y[4 * i + 0] = v[4 * i + 0] * g.x;
+    y[4 * i + 1] = v[4 * i + 1] * g.y;
+    y[4 * i + 2] = v[4 * i + 2] * g.z;
+    y[4 * i + 3] = v[4 * i + 3] * g.w;
+  }
+  store_bf16x32(ep.a_next + (size_t)row * ep.lda_next + col0, y);
+  return ss;
+}
+
+// `rstd`: per-row scale of the accumulator (fused RMSNorm consumer side, 1 when unused);
+// `ss`: per-thread running sum of squares of the produced row (producer side).
 template <int EPI>
 __device__ __forceinline__ void epi_chunk(const EpiParams& ep, int N, int row, bool row_ok, int col0, float (&v)[32],
-                                          float (&w)[32], bool first_split, bool atomic) {
+                                          float (&w)[32], bool first_split, bool atomic, float rstd, float& ss) {
+  if (ep.row_ss) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= rstd;
+    if constexpr (EPI == EPI_SWIGLU_BF16 || EPI == EPI_QKV_ROPE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) w[j] *= rstd;
+    }
+  }
   if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_SILU_BF16) {
     if (ep.bias) add_vec32(v, ep.bias + col0);
     if constexpr (EPI == EPI_GELU_BF16) {
@@ -129,7 +162,12 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& ep, int N, int row, b
           x.z += v[4 * i + 2];
           x.w += v[4 * i + 3];
           o4[i] = x;
+          v[4 * i + 0] = x.x;
+          v[4 * i + 1] = x.y;
+          v[4 * i + 2] = x.z;
+          v[4 * i + 3] = x.w;
         }
+        if (ep.a_next) ss += norm_out_chunk(ep, row, col0, v);
       }
     }
   } else if constexpr (EPI == EPI_SWIGLU_BF16) {
@@ -194,7 +232,63 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& ep, int N, int row, b
         float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)dr * ep.ldo + col0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        if (ep.a_next) ss += norm_out_chunk(ep, dr, col0, v);
       }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// One epilogue warp's share of an accumulator tile: TMEM lane quarter `taddr` (32 rows, one per lane), column
+// half `half` of the BN-wide tile. Units of 32 (plain), 64 (SwiGLU gate|up) or 2x32 (RoPE x[i], x[i+64]) columns.
+// ------------------------------------------------------------------------------------------
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& ep, int N, uint32_t taddr, int half, int row, bool row_ok,
+                                              int n0, bool first_split, bool atomic, float rstd, float& ss) {
+  if constexpr (EPI == EPI_SWIGLU_BF16) {
+    constexpr int U = BN / 64 / 2;
+#pragma unroll 1
+    for (int c = half * U; c < (half + 1) * U; ++c) {
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(taddr + c * 64, r0);
+      tmem_ld_32x32(taddr + c * 64 + 32, r1);
+      tmem_ld_wait();
+      float v[32], w[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = __uint_as_float(r0[j]);
+        w[j] = __uint_as_float(r1[j]);
+      }
+      epi_chunk<EPI>(ep, N, row, row_ok, n0 + c * 64, v, w, first_split, atomic, rstd, ss);
+    }
+  } else if constexpr (EPI == EPI_QKV_ROPE) {
+    constexpr int U = BN / 64 / 2;  // unit u: head u>>1, half-head chunk u&1
+#pragma unroll 1
+    for (int u = half * U; u < (half + 1) * U; ++u) {
+      const int off = (u >> 1) * 128 + (u & 1) * 32;
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(taddr + off, r0);
+      tmem_ld_32x32(taddr + off + 64, r1);
+      tmem_ld_wait();
+      float v[32], w[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = __uint_as_float(r0[j]);
+        w[j] = __uint_as_float(r1[j]);
+      }
+      epi_chunk<EPI>(ep, N, row, row_ok, n0 + off, v, w, first_split, atomic, rstd, ss);
+    }
+  } else {
+    constexpr int U = BN / 32 / 2;
+#pragma unroll 1
+    for (int c = half * U; c < (half + 1) * U; ++c) {
+      uint32_t r0[32];
+      tmem_ld_32x32(taddr + c * 32, r0);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
+      epi_chunk<EPI>(ep, N, row, row_ok, n0 + c * 32, v, v, first_split, atomic, rstd, ss);
     }
   }
 }
@@ -202,25 +296,38 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& ep, int N, int row, b
 // ------------------------------------------------------------------------------------------
 // tcgen05 kernel
 // ------------------------------------------------------------------------------------------
+struct TileCoord {
+  int split, n_idx, m_idx, kb0, kb1, rem;
+};
+__device__ __forceinline__ TileCoord tile_coord(const TileSched& sc, int t) {
+  TileCoord c;
+  c.split = t / sc.base;
+  c.rem = t - c.split * sc.base;
+  c.n_idx = c.rem / sc.m_tiles;
+  c.m_idx = c.rem - c.n_idx * sc.m_tiles;
+  c.kb0 = c.split * sc.kb_per_split;
+  c.kb1 = min(sc.k_blocks, c.kb0 + sc.kb_per_split);
+  return c;
+}
+
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmDims d,
                     EpiParams ep) {
   using Cfg = GemmCfg<BLOCK_N>;
-  constexpr int STAGES = Cfg::STAGES;
+  const int STAGES = d.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full_bar = bars;                  // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;        // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* full_bar = bars;                          // [MAX_STAGES]
+  uint64_t* empty_bar = bars + MAX_STAGES;            // [MAX_STAGES]
+  uint64_t* tfull_bar = bars + 2 * MAX_STAGES;        // [2]
+  uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  volatile int* fin_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int M = d.M_dev ? min(*d.M_dev, d.M) : d.M;
-  const TileSched sc = make_sched<BLOCK_N, EPI>(d, M);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -231,7 +338,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -243,28 +350,76 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // The next kernel of the chain may start its own prologue now (its CTAs find TMEM/smem as ours retire).
+  pdl_launch_dependents();
+
+  // Live row count: a device-resident M belongs to this call's plan, so it is read after the PDL wait.
+  int M = d.M;
+  if (d.M_dev) {
+    pdl_wait();
+    M = min(*d.M_dev, d.M);
+  }
+  const TileSched sc = make_sched<BLOCK_N, EPI>(d, M);
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < sc.total; t += gridDim.x) {
-        const int split = t / sc.base, rem = t - split * sc.base;
-        const int n_idx = rem / sc.m_tiles, m_idx = rem - n_idx * sc.m_tiles;
-        const int kb0 = split * sc.kb_per_split;
-        const int kb1 = min(sc.k_blocks, kb0 + sc.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_idx * BLOCK_M);
-          tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, n_idx * BLOCK_N);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
+      int t = blockIdx.x;
+      int kb = 0;
+      TileCoord tc{};
+      bool have = t < sc.total;
+      if (have) {
+        tc = tile_coord(sc, t);
+        kb = tc.kb0;
+      }
+      auto advance = [&]() {
+        if (++kb >= tc.kb1) {
+          t += gridDim.x;
+          have = t < sc.total;
+          if (have) {
+            tc = tile_coord(sc, t);
+            kb = tc.kb0;
           }
         }
+      };
+      if (!d.M_dev) {
+        // Weights do not depend on the previous kernel: fill the ring's B halves before the PDL wait,
+        // then add the A halves (activations written by the previous kernel) after it.
+        int pre_n[MAX_STAGES], pre_m[MAX_STAGES], pre_kb[MAX_STAGES];
+        int npre = 0;
+        while (have && npre < STAGES) {
+          pre_n[npre] = tc.n_idx;
+          pre_m[npre] = tc.m_idx;
+          pre_kb[npre] = kb;
+          uint8_t* sa = smem + npre * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[npre], Cfg::STAGE_BYTES);
+          tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[npre], kb * BLOCK_K, tc.n_idx * BLOCK_N);
+          ++npre;
+          advance();
+        }
+        pdl_wait();
+        for (int i = 0; i < npre; ++i)
+          tma_load_2d(smem + i * Cfg::STAGE_BYTES, &tmA, &full_bar[i], pre_kb[i] * BLOCK_K, pre_m[i] * BLOCK_M);
+        (void)pre_n;
+        stage = npre;
+        if (stage == STAGES) {
+          stage = 0;
+          phase = 1;
+        }
+      }
+      while (have) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, tc.m_idx * BLOCK_M);
+        tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, tc.n_idx * BLOCK_N);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+        advance();
       }
     }
   } else if (warp == 1) {
@@ -276,13 +431,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int as = 0;
       uint32_t aphase = 0;
       for (int t = blockIdx.x; t < sc.total; t += gridDim.x) {
-        const int split = t / sc.base;
-        const int kb0 = split * sc.kb_per_split;
-        const int kb1 = min(sc.k_blocks, kb0 + sc.kb_per_split);
+        const TileCoord tc = tile_coord(sc, t);
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -291,7 +444,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in the (addr>>4) field
-            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == STAGES) {
@@ -306,70 +459,89 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ================================ epilogue warps ================================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    pdl_wait();
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;    // which half of the tile's columns it drains
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < sc.total; t += gridDim.x) {
-      const int split = t / sc.base, rem = t - split * sc.base;
-      const int n_idx = rem / sc.m_tiles, m_idx = rem - n_idx * sc.m_tiles;
+      const TileCoord tc = tile_coord(sc, t);
+      const int n_idx = tc.n_idx, m_idx = tc.m_idx;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const int row = m_idx * BLOCK_M + quarter * 32 + lane;
       const bool row_ok = row < M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
       const int n0 = n_idx * BLOCK_N;
-      const bool first_split = split == 0;
+      const bool first_split = tc.split == 0;
       const bool atomic = sc.splits > 1;
-      if constexpr (EPI == EPI_SWIGLU_BF16) {
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 64; ++c) {
-          uint32_t r0[32], r1[32];
-          tmem_ld_32x32(taddr + c * 64, r0);
-          tmem_ld_32x32(taddr + c * 64 + 32, r1);
-          tmem_ld_wait();
-          float v[32], w[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = __uint_as_float(r0[j]);
-            w[j] = __uint_as_float(r1[j]);
-          }
-          epi_chunk<EPI>(ep, d.N, row, row_ok, n0 + c * 64, v, w, first_split, atomic);
-        }
-      } else if constexpr (EPI == EPI_QKV_ROPE) {
-#pragma unroll 1
-        for (int hh = 0; hh < BLOCK_N / 128; ++hh) {
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t r0[32], r1[32];
-            tmem_ld_32x32(taddr + hh * 128 + c * 32, r0);
-            tmem_ld_32x32(taddr + hh * 128 + c * 32 + 64, r1);
-            tmem_ld_wait();
-            float v[32], w[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              v[j] = __uint_as_float(r0[j]);
-              w[j] = __uint_as_float(r1[j]);
-            }
-            epi_chunk<EPI>(ep, d.N, row, row_ok, n0 + hh * 128 + c * 32, v, w, first_split, atomic);
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
-          uint32_t r0[32];
-          tmem_ld_32x32(taddr + c * 32, r0);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
-          epi_chunk<EPI>(ep, d.N, row, row_ok, n0 + c * 32, v, v, first_split, atomic);
-        }
-      }
+      float rstd = 1.f;
+      if (ep.row_ss && row_ok) rstd = rsqrtf(__ldcg(ep.row_ss + row) * ep.inv_width + ep.eps);
+      float ss = 0.f;
+      epilogue_tile<BLOCK_N, EPI>(ep, d.N, taddr, half, row, row_ok, n0, first_split, atomic, rstd, ss);
+      // accumulator drained: hand the TMEM stage back before any slow tail work
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
       as ^= 1;
       if (as == 0) aphase ^= 1;
+
+      if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32) {
+        if (ep.a_next) {
+          if (!atomic) {
+            const int dr = (EPI == EPI_STORE_F32 && ep.row_map && row_ok) ? ep.row_map[row] : row;
+            if (row_ok && dr >= 0) atomicAdd(ep.ss_next + dr, ss);
+          } else {
+            // split-K: the CTA that retires the last split of this tile finishes the row statistics
+            __threadfence();
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+            if (threadIdx.x == 64) {
+              const int old = atomicAdd(ep.tile_counters + tc.rem, 1);
+              const int last = (old == sc.splits - 1);
+              if (last) ep.tile_counters[tc.rem] = 0;
+              *fin_flag = last;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+            const bool last = *fin_flag != 0;
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");  // flag consumed before the next tile may rewrite it
+            if (last) {
+              // coalesced pass over the finished tile: one warp per row, 8 rows in flight per warp
+              __threadfence();
+              const int m0 = m_idx * BLOCK_M + quarter * 32;
+#pragma unroll 1
+              for (int cb = 0; cb < BLOCK_N / 128; ++cb) {
+                const int col = n0 + cb * 128 + lane * 4;
+                const float4 g = __ldg(reinterpret_cast<const float4*>(ep.gamma_next + col));
+#pragma unroll 1
+                for (int rb = half * 16; rb < half * 16 + 16; rb += 8) {
+                  float4 xv[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const int r = m0 + rb + i;
+                    xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < M)
+                      xv[i] = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.out) +
+                                                                     (size_t)r * ep.ldo + col));
+                  }
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const int r = m0 + rb + i;
+                    const float q = warp_sum((xv[i].x * xv[i].x + xv[i].y * xv[i].y) +
+                                             (xv[i].z * xv[i].z + xv[i].w * xv[i].w));
+                    if (r < M) {
+                      uint2 u;
+                      u.x = pack_bf16(xv[i].x * g.x, xv[i].y * g.y);
+                      u.y = pack_bf16(xv[i].z * g.z, xv[i].w * g.w);
+                      *reinterpret_cast<uint2*>(ep.a_next + (size_t)r * ep.lda_next + col) = u;
+                      if (lane == 0) atomicAdd(ep.ss_next + r, q);
+                    }
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
     }
   }
 
@@ -379,12 +551,174 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
+// tcgen05 kernel, CTA pairs (cta_group::2): one 256(M) x 256(N) tile per pair. Each CTA stages its own
+// 128 rows of A and HALF of the W tile (128 of the 256 N rows); the pair's tensor cores read both halves, so
+// the L2->SM operand traffic per FLOP is 2/3 of the single-CTA 128x256 tile (L2 bandwidth, not the tensor
+// pipe, bounds the large-M GEMMs of this path). The leader CTA (rank 0) issues the MMAs; its full barriers
+// collect the TMA bytes of both CTAs; tcgen05.commit multicasts to the empty / accumulator-full barriers of both.
+// ------------------------------------------------------------------------------------------
+constexpr int PAIR_BLOCK_N = 256;
+constexpr int PAIR_STAGES = 6;
+constexpr uint32_t PAIR_A_BYTES = BLOCK_M * BLOCK_K * 2;           // this CTA's 128 rows of A
+constexpr uint32_t PAIR_B_BYTES = (PAIR_BLOCK_N / 2) * BLOCK_K * 2;  // this CTA's half of the W tile
+constexpr uint32_t PAIR_STAGE_BYTES = PAIR_A_BYTES + PAIR_B_BYTES;
+constexpr uint32_t PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 1024 + 256;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmDims d,
+                         EpiParams ep) {
+  constexpr int STAGES = PAIR_STAGES;
+  constexpr int BN = PAIR_BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * PAIR_STAGE_BYTES);
+  uint64_t* full_bar = bars;                          // [STAGES]   used in the leader only
+  uint64_t* empty_bar = bars + MAX_STAGES;            // [STAGES]   one set per CTA
+  uint64_t* tfull_bar = bars + 2 * MAX_STAGES;        // [2]        one set per CTA
+  uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 2;   // [2]        used in the leader only (8 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 2 * EPI_WARPS);  // epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, 2 * BN);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  const int M = d.M_dev ? min(*d.M_dev, d.M) : d.M;
+  const int m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int n_tiles = d.N / BN;
+  const int k_blocks = d.K / BLOCK_K;
+  const int total = m_tiles * n_tiles;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    if (lane == 0) {
+      const uint32_t full0 = mapa_u32(smem_u32(full_bar), 0);  // the leader's full barriers
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < total; t += n_pairs) {
+        const int n_idx = t / m_tiles, m_idx = t - n_idx * m_tiles;
+        const int row_a = (m_idx * 2 + (int)rank) * BLOCK_M;
+        const int row_b = n_idx * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * PAIR_STAGE_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * PAIR_STAGE_BYTES);
+          tma_load_2d_pair(sa, &tmA, full0 + stage * 8, kb * BLOCK_K, row_a);
+          tma_load_2d_pair(sa + PAIR_A_BYTES, &tmB, full0 + stage * 8, kb * BLOCK_K, row_b);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA only) ================================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = pair; t < total; t += n_pairs) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * PAIR_STAGE_BYTES);
+          const uint64_t da = make_umma_desc_sw128(sa);
+          const uint64_t db = make_umma_desc_sw128(sa + PAIR_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_pair(&empty_bar[stage], 0x3);  // frees this smem slot in both CTAs
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_pair(&tfull_bar[as], 0x3);  // accumulators (both CTAs' TMEM) ready
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else {
+    // ================================ epilogue warps (both CTAs) ================================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const uint32_t tempty0 = mapa_u32(smem_u32(tempty_bar), 0);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = pair; t < total; t += n_pairs) {
+      const int n_idx = t / m_tiles, m_idx = t - n_idx * m_tiles;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int row = (m_idx * 2 + (int)rank) * BLOCK_M + quarter * 32 + lane;
+      const bool row_ok = row < M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+      const int n0 = n_idx * BN;
+      float rstd = 1.f;
+      if (ep.row_ss && row_ok) rstd = rsqrtf(__ldcg(ep.row_ss + row) * ep.inv_width + ep.eps);
+      float ss = 0.f;
+      epilogue_tile<BN, EPI>(ep, d.N, taddr, half, row, row_ok, n0, true, false, rstd, ss);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty0 + as * 8);  // the leader's MMA thread owns both accumulators
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+      if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32) {
+        if (ep.a_next) {
+          const int dr = (EPI == EPI_STORE_F32 && ep.row_map && row_ok) ? ep.row_map[row] : row;
+          if (row_ok && dr >= 0) atomicAdd(ep.ss_next + dr, ss);
+        }
+      }
+    }
+  }
+
+  // neither CTA may exit (or free TMEM) while its peer can still signal its barriers or read its smem
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 2 * BN);
+}
+
+// ------------------------------------------------------------------------------------------
 // CUDA-core cross-check kernel (tests / bring-up only): same epilogue code, plain pointers.
 // One thread = one row x one 32-column chunk (plus its partner chunk where the epilogue needs one).
 // ------------------------------------------------------------------------------------------
 template <int EPI>
 __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ W, GemmDims d,
                                  EpiParams ep) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int M = d.M_dev ? min(*d.M_dev, d.M) : d.M;
   const int row = blockIdx.y * blockDim.y + threadIdx.y;
   const int unit = blockIdx.x * blockDim.x + threadIdx.x;
@@ -416,7 +750,15 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, const __nv
       }
     }
   }
-  epi_chunk<EPI>(ep, d.N, row, row_ok, col0, v, w, true, false);
+  float rstd = 1.f, ss = 0.f;
+  if (ep.row_ss && row_ok) rstd = rsqrtf(ep.row_ss[row] * ep.inv_width + ep.eps);
+  epi_chunk<EPI>(ep, d.N, row, row_ok, col0, v, w, true, false, rstd, ss);
+  if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32) {
+    if (ep.a_next && row_ok) {
+      const int dr = (EPI == EPI_STORE_F32 && ep.row_map) ? ep.row_map[row] : row;
+      if (dr >= 0) atomicAdd(ep.ss_next + dr, ss);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -440,23 +782,42 @@ PFN_encodeTiled get_encode_fn() {
 }
 
 template <int BLOCK_N, int EPI>
-int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDims& d, const EpiParams& ep, int grid,
+int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDims d, const EpiParams& ep, int grid,
                cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   static bool attr_set = false;
   auto kern = gemm_tcgen05_kernel<BLOCK_N, EPI>;
   if (!attr_set) {
-    VL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+    VL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Cfg::smem_bytes(Cfg::DEFAULT_STAGES)));
     attr_set = true;
   }
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, d, ep);
-  VL_CUDA_CHECK(cudaGetLastError());
+  if (d.stages <= 0 || d.stages > Cfg::DEFAULT_STAGES) d.stages = Cfg::DEFAULT_STAGES;
+  if (d.stages < 2) d.stages = 2;
+  VL_CUDA_CHECK(launch_kernel(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::smem_bytes(d.stages), stream, tmA, tmB, d, ep));
+  return 0;
+}
+
+template <int EPI>
+int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDims& d, const EpiParams& ep,
+                cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kern = gemm_tcgen05_pair_kernel<EPI>;
+  if (!attr_set) {
+    VL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM_BYTES));
+    attr_set = true;
+  }
+  const long long tiles = (long long)((d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (d.N / PAIR_BLOCK_N);
+  const int pairs = (int)std::min<long long>(tiles, gemm_num_sms() / 2);
+  // __cluster_dims__(2,1,1) is part of the kernel: a plain launch (with the optional PDL attribute) suffices
+  VL_CUDA_CHECK(launch_kernel(kern, dim3(2 * pairs), dim3(GEMM_THREADS), PAIR_SMEM_BYTES, stream, tmA, tmB, d, ep));
   return 0;
 }
 
 template <int EPI>
 int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDims& d, const EpiParams& ep, int block_n,
               int grid, cudaStream_t stream) {
+  if (d.pair) return launch_pair<EPI>(tmA, tmB, d, ep, stream);
   if (block_n == 128) return launch_one<128, EPI>(tmA, tmB, d, ep, grid, stream);
   if constexpr (EPI != EPI_QKV_ROPE) {
     if (block_n == 256) return launch_one<256, EPI>(tmA, tmB, d, ep, grid, stream);
@@ -502,8 +863,13 @@ int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDims& 
                 int epi, cudaStream_t stream) {
   VL_CHECK(d.K % BLOCK_K == 0 && d.K > 0, "gemm: K must be a positive multiple of 64");
   VL_CHECK(block_n == 128 || block_n == 256, "gemm: block_n must be 128 or 256");
+  VL_CHECK(!d.pair || (block_n == 128 && d.N % PAIR_BLOCK_N == 0 && !(epi == EPI_RESID_F32 && d.max_splits > 1)),
+           "gemm: pair mode needs the 128-row W map, N % 256 == 0 and no split-K");
   VL_CHECK(d.N % block_n == 0, "gemm: N must be a multiple of block_n");
   VL_CHECK(ep.out != nullptr, "gemm: null output");
+  VL_CHECK(!ep.a_next || (ep.gamma_next && ep.ss_next && ep.lda_next > 0), "gemm: incomplete fused-norm outputs");
+  VL_CHECK(!(ep.a_next && epi == EPI_RESID_F32 && d.max_splits > 1) || ep.tile_counters,
+           "gemm: split-K with fused-norm outputs needs tile counters");
   if (d.M <= 0) return 0;
   const int m_tiles = (d.M + BLOCK_M - 1) / BLOCK_M;
   long long tiles = (long long)m_tiles * (d.N / block_n);
@@ -530,8 +896,7 @@ static int launch_simt_one(const __nv_bfloat16* A, const __nv_bfloat16* W, const
   if (EPI == EPI_QKV_ROPE) units = d.N / 64;
   dim3 block(32, 4);
   dim3 grid((units + 31) / 32, (d.M + 3) / 4);
-  gemm_simt_kernel<EPI><<<grid, block, 0, stream>>>(A, W, d, ep);
-  VL_CUDA_CHECK(cudaGetLastError());
+  VL_CUDA_CHECK(launch_kernel(gemm_simt_kernel<EPI>, grid, block, 0, stream, A, W, d, ep));
   return 0;
 }
 

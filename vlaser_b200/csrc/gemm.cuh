@@ -39,12 +39,29 @@ struct EpiParams {
   // EPI_PATCH_EMBED
   const float* pos_emb = nullptr;   // [(P+1), N]
   int patches = 0;
+  // ---- RMSNorm fused across the GEMM chain (expert streams, HF Qwen2RMSNorm):
+  //   y = (x * rstd * gamma) W^T  ==  rstd[m] * ((x * gamma) W^T),  rstd[m] = rsqrt(ss[m]/width + eps)
+  // producer side (EPI_RESID_F32 / EPI_STORE_F32): besides the fp32 residual row x_new the epilogue writes the NEXT
+  // GEMM's A operand a_next[m,n] = bf16(x_new[m,n] * gamma_next[n]) and accumulates ss_next[m] += sum_n x_new[m,n]^2.
+  // With split-K (fp32 atomics into x) the CTA that retires the last split of a tile (tile_counters) re-reads the
+  // finished tile and does that work.
+  const float* gamma_next = nullptr;   // [N]
+  __nv_bfloat16* a_next = nullptr;     // [M, lda_next]
+  int lda_next = 0;
+  float* ss_next = nullptr;            // [M], zeroed by the caller
+  int* tile_counters = nullptr;        // [m_tiles*n_tiles] zero-initialised, self-resetting (split-K only)
+  // consumer side (any epilogue): acc is multiplied by rstd[m] before bias / activation.
+  const float* row_ss = nullptr;       // [M] sum of squares of the un-normalised row
+  float inv_width = 0.f;               // 1 / hidden width of the normalised row
+  float eps = 0.f;
 };
 
 struct GemmDims {
   int M = 0, N = 0, K = 0;       // K % 64 == 0, N % block_n == 0
   const int* M_dev = nullptr;    // optional: live row count in device memory (M is then the capacity)
   int max_splits = 1;            // split-K cap (EPI_RESID_F32 only)
+  int stages = 0;                // smem ring depth; 0 = default for the tile shape
+  int pair = 0;                  // 1: CTA-pair kernel (cta_group::2, 256x256 tile per pair; W map with 128-row boxes)
 };
 
 // Host API -------------------------------------------------------------------------------

@@ -111,6 +111,10 @@ class PiZeroInference:
         self._finalized = False
         self._loaded = set()
         self.dtype = torch.bfloat16
+        for env, opt in (("VLASER_PDL", "pdl"), ("VLASER_EXP_STAGES", "exp_stages"), ("VLASER_FUSE_NORM", "fuse_norm"),
+                         ("VLASER_PAIR_GEMM", "pair_gemm")):  # measurement switches
+            if env in os.environ:
+                self.set_option(opt, int(os.environ[env]))
 
     # ---- nn.Module-like surface used by EvalAgent ------------------------------------------------
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
