@@ -145,6 +145,7 @@ typedef struct vlaser_gemm_args {
   float inv_width, eps;
   int32_t stages;        /* smem ring depth, 0 = default */
   int32_t pair;          /* 1 = CTA-pair kernel (cta_group::2, 256x256 tile per pair); block_n is ignored */
+  int32_t tma_out;       /* pair kernel: epilogue through TMA store / reduce-add (bf16 and residual epilogues) */
 } vlaser_gemm_args;
 int32_t vlaser_op_gemm(const vlaser_gemm_args* a, void* stream);
 
@@ -159,6 +160,10 @@ typedef struct vlaser_attn_args {
   float scale;
 } vlaser_attn_args;
 int32_t vlaser_op_attention(const vlaser_attn_args* a, void* stream);
+/* InternViT self-attention fast path (_naive_attn, modeling_intern_vit.py:210-227): qkv bf16 [images*tokens, 3*heads*64]
+ * as written by the fused qkv projection, out bf16 [images*tokens, heads*64]; 128 <= tokens <= 320. */
+int32_t vlaser_op_vit_attention(const void* qkv, void* out, int32_t images, int32_t tokens, int32_t heads, float scale,
+                                void* stream);
 
 int32_t vlaser_op_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, int32_t rows,
                             int32_t width, float eps, int32_t shuffle_grid, int32_t shuffle_channels, void* stream);

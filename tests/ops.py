@@ -25,8 +25,9 @@ def gemm(A, W, epi, block_n=128, simt=False, out=None, ldo=None, bias=None, scal
          kv_head_stride=0, n_q_heads=0, n_kv_heads=0, pos_emb=None, patches=0, gamma_next=None, a_next=None,
          ss_next=None, tile_counters=None, row_ss=None, inv_width=0.0, eps=0.0, stages=0, pair=False):
     lib = _lib.load()
-    if block_n == 512:  # test shorthand for the CTA-pair kernel (256x256 tile per pair)
-        block_n, pair = 256, True
+    tma_out = False
+    if block_n in (512, 513, 515):  # test shorthand for the CTA-pair kernel; 513 = TMA epilogue, 515 = + n-fastest tiles
+        block_n, pair, tma_out = 256, (3 if block_n == 515 else 1), block_n >= 513
     a = GemmArgs()
     a.A, a.W = _p(A), _p(W)
     a.M, a.K = A.shape
@@ -42,7 +43,7 @@ def gemm(A, W, epi, block_n=128, simt=False, out=None, ldo=None, bias=None, scal
     a.gamma_next, a.a_next, a.ss_next, a.tile_counters = _p(gamma_next), _p(a_next), _p(ss_next), _p(tile_counters)
     a.lda_next = a_next.shape[-1] if a_next is not None else 0
     a.row_ss, a.inv_width, a.eps, a.stages = _p(row_ss), inv_width, eps, stages
-    a.pair = int(pair)
+    a.pair, a.tma_out = int(pair), int(tma_out)
     _lib.check(lib.vlaser_op_gemm(C.byref(a), _stream()), "op_gemm")
     return out
 
@@ -77,6 +78,14 @@ def attention(q, k, v, out, head_dim, group, n_kv_heads, batch, scale, q_row_str
     a.uni_q_len, a.uni_kv_len, a.max_q_len = uni_q_len, uni_kv_len, max_q_len
     a.group, a.n_kv_heads, a.batch, a.head_dim, a.scale = group, n_kv_heads, batch, head_dim, scale
     _lib.check(lib.vlaser_op_attention(C.byref(a), _stream()), "op_attention")
+    return out
+
+
+def vit_attention(qkv, images, tokens, heads, scale):
+    """qkv bf16 [images*tokens, 3*heads*64] -> out bf16 [images*tokens, heads*64] (InternViT fast path)."""
+    lib = _lib.load()
+    out = torch.zeros(images * tokens, heads * 64, dtype=torch.bfloat16, device=qkv.device)
+    _lib.check(lib.vlaser_op_vit_attention(_p(qkv), _p(out), images, tokens, heads, scale, _stream()), "op_vit_attention")
     return out
 
 

@@ -16,7 +16,7 @@ ap.add_argument("--only", default="")
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--bn", type=int, default=0, help="force block_n (0 = engine heuristic)")
-ap.add_argument("--pair", type=int, default=1, help="use the CTA-pair kernel where the engine would")
+ap.add_argument("--pair", type=int, default=1, help="0 single-CTA kernels, 1 CTA-pair kernel + TMA epilogue, 2 pair w/o TMA epilogue")
 a = ap.parse_args()
 B = a.batch
 MV, MP, MA = B * 257, B * 87, B * 4
@@ -48,7 +48,7 @@ for name, M, N, K, epi, cnt, splits in SHAPES:
     if a.bn and epi != EPI_QKV_ROPE and N % a.bn == 0:
         bn = a.bn
     if a.pair and not a.bn and N % 256 == 0 and splits <= 1 and ((M + 255) // 256) * (N // 256) >= 74:
-        bn = 512
+        bn = {1: 513, 2: 512, 3: 515}[a.pair]
     if epi in (EPI_STORE_BF16, EPI_GELU_BF16, EPI_SILU_BF16):
         out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
     elif epi == EPI_SWIGLU_BF16:

@@ -43,7 +43,7 @@ class GemmArgs(C.Structure):
         ("n_q_heads", C.c_int32), ("n_kv_heads", C.c_int32), ("pos_emb", C.c_void_p), ("patches", C.c_int32),
         ("gamma_next", C.c_void_p), ("a_next", C.c_void_p), ("lda_next", C.c_int32), ("ss_next", C.c_void_p),
         ("tile_counters", C.c_void_p), ("row_ss", C.c_void_p), ("inv_width", C.c_float), ("eps", C.c_float),
-        ("stages", C.c_int32), ("pair", C.c_int32),
+        ("stages", C.c_int32), ("pair", C.c_int32), ("tma_out", C.c_int32),
     ]
 
 
@@ -63,6 +63,7 @@ EXPORTS = [
     "vlaser_infer_action", "vlaser_infer_action_host", "vlaser_destroy", "vlaser_set_option", "vlaser_debug_copy",
     "vlaser_last_launch_count", "vlaser_flops_per_call", "vlaser_profile_read", "vlaser_op_gemm", "vlaser_op_attention",
     "vlaser_op_layernorm", "vlaser_op_rmsnorm", "vlaser_op_pixel_shuffle", "vlaser_op_im2col", "vlaser_op_euler_step",
+    "vlaser_op_vit_attention",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -107,6 +108,8 @@ def load() -> C.CDLL:
     lib.vlaser_op_gemm.restype = i32
     lib.vlaser_op_attention.argtypes = [C.POINTER(AttnArgs), vp]
     lib.vlaser_op_attention.restype = i32
+    lib.vlaser_op_vit_attention.argtypes = [vp, vp, i32, i32, i32, f32, vp]
+    lib.vlaser_op_vit_attention.restype = i32
     lib.vlaser_op_layernorm.argtypes = [vp, vp, vp, vp, i32, i32, f32, i32, i32, vp]
     lib.vlaser_op_layernorm.restype = i32
     lib.vlaser_op_rmsnorm.argtypes = [vp, vp, vp, i32, i32, f32, vp]

@@ -40,4 +40,9 @@ struct AttnParams {
 
 int attention_launch(const AttnParams& p, int head_dim, cudaStream_t stream);
 
+// InternViT self-attention fast path (head_dim 64, no mask, 128 <= tokens <= 320): qkv [images*tokens, 3*heads*64]
+// packed as the fused qkv projection writes it, out [images*tokens, heads*64]. One CTA per (image, head).
+int vit_attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int images, int tokens, int heads, float scale,
+                         cudaStream_t stream);
+
 }  // namespace vlaser

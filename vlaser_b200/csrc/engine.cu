@@ -75,10 +75,10 @@ struct Lin {            // one packed projection weight
   CUtensorMap tm128, tm256;
   bool has256 = false;
 };
-struct Act {            // one bf16 activation buffer usable as GEMM A operand
+struct Act {            // one bf16 activation buffer usable as GEMM A operand (tm) and as TMA-epilogue output (otm)
   bf16* p = nullptr;
   int rows = 0, K = 0;
-  CUtensorMap tm;
+  CUtensorMap tm, otm;
 };
 
 struct VitLayer {
@@ -117,6 +117,7 @@ struct Engine {
   // activations
   Act cols, vn, vattn, vmlp, ps, pa, xn, ao, act, xpn, aop, actp, xan, aoa, acta, e1, h2;
   float *vx = nullptr, *xv = nullptr, *xp = nullptr, *xa = nullptr, *action = nullptr;
+  CUtensorMap vx_otm, xv_otm, vqkv_otm;  // output maps of the fp32 residual streams / ViT qkv buffer
   bf16 *vqkv = nullptr, *q = nullptr, *qp = nullptr, *qa = nullptr;
   bf16 *kc = nullptr, *vc = nullptr;  // [layers][kv_heads][kv_rows][128]
   // fused RMSNorm chain of the expert streams: per pass (prefill proprio, then each denoise step) one row-sum-of-
@@ -136,6 +137,7 @@ struct Engine {
   // options / state
   int use_graph = 1, stop_after = 0, simt = 0;
   int exp_stages = 0;          // smem ring depth of the expert-stream GEMMs (0 = kernel default)
+  int tma_epi = 1;             // 1: pair-kernel epilogues leave through TMA stores / reduce-adds
   int pair_gemm = 1;           // 1: large-M GEMMs run on the CTA-pair (cta_group::2) kernel
   int fuse_norm = 0;           // 1: RMSNorm of the expert streams fused across the GEMM chain (see exp_pre/exp_post)
   int profile_gemm = 0;        // bracket every GEMM launch with CUDA events (non-graph runs only)
@@ -215,6 +217,7 @@ struct Engine {
     // pad the row count to a multiple of 256 (one CTA-pair tile) so that TMA boxes never start out of bounds
     const int rows_alloc = (rows + 255) / 256 * 256;
     if (alloc(&a->p, (size_t)rows_alloc * K)) return -1;
+    if (make_tmap_out(&a->otm, a->p, rows_alloc, K, 2)) return -1;
     return make_tmap_bf16(&a->tm, a->p, rows_alloc, K, 128);
   }
 };
@@ -341,13 +344,16 @@ int engine_build(Engine& e) {
   const int arow = e.Bc * e.H;
   VL_TRY(e.add_act(&e.cols, Ni * e.P, e.kpad));
   VL_TRY(e.alloc(&e.vx, (size_t)vrows * d));
+  VL_TRY(make_tmap_out(&e.vx_otm, e.vx, vrows, d, 4));
   VL_TRY(e.add_act(&e.vn, vrows, d));
   VL_TRY(e.alloc(&e.vqkv, (size_t)vrows * 3 * d));
+  VL_TRY(make_tmap_out(&e.vqkv_otm, e.vqkv, vrows, 3 * d, 2));
   VL_TRY(e.add_act(&e.vattn, vrows, d));
   VL_TRY(e.add_act(&e.vmlp, vrows, f));
   VL_TRY(e.add_act(&e.ps, Ni * e.T, 4 * d));
   VL_TRY(e.add_act(&e.pa, Ni * e.T, h));
   VL_TRY(e.alloc(&e.xv, (size_t)prow * h));
+  VL_TRY(make_tmap_out(&e.xv_otm, e.xv, prow, h, 4));
   VL_TRY(e.add_act(&e.xn, prow, h));
   VL_TRY(e.alloc(&e.q, (size_t)prow * e.qdim));
   VL_TRY(e.add_act(&e.ao, prow, e.qdim));
@@ -552,7 +558,7 @@ struct Run {
   int rc = 0;
 
   int gemm(const Act& a, const Lin& w, int M, const int* M_dev, int epi, EpiParams ep, int max_splits = 1,
-           int stages = 0) {
+           int stages = 0, const CUtensorMap* out_tm = nullptr) {
     GemmDims d;
     d.M = M;
     d.N = w.N;
@@ -566,6 +572,9 @@ struct Run {
     // large-M GEMMs: CTA-pair kernel (256x256 tile per pair) when there is at least one tile per pair
     const long long pair_tiles = (long long)((M + 255) / 256) * (w.N / 256);
     if (e.pair_gemm && w.N % 256 == 0 && max_splits <= 1 && pair_tiles >= gemm_num_sms() / 2) d.pair = 1;
+    // tile order: with many more rows than weight rows a wave of pairs should share A tiles (n fastest); measured on
+    // B200: ViT GEMMs and the LLM o/down projections gain, the wide-N LLM qkv/gate-up GEMMs prefer m fastest
+    d.n_fast = (M_dev == nullptr) ? (M > w.N) : (w.N <= 1536);
     if (!d.pair && epi != EPI_QKV_ROPE && w.has256) {
       const long long tiles256 = (long long)((M + 127) / 128) * (w.N / 256);
       if (tiles256 >= gemm_num_sms()) bn = 256;
@@ -581,7 +590,7 @@ struct Run {
       e.prof_flops.push_back(2.0 * rows * (double)w.N * (double)w.K);
       VL_CUDA_CHECK(cudaEventRecord(e.prof_events[e.prof_used], st));
     }
-    const int rc = gemm_launch(a.tm, bn == 256 ? w.tm256 : w.tm128, d, ep, bn, epi, st);
+    const int rc = gemm_launch(a.tm, bn == 256 ? w.tm256 : w.tm128, d, ep, bn, epi, st, e.tma_epi ? out_tm : nullptr);
     if (prof) {
       VL_CUDA_CHECK(cudaEventRecord(e.prof_events[e.prof_used + 1], st));
       e.prof_used += 2;
@@ -628,7 +637,10 @@ struct Run {
       e1.out = e.vqkv;
       e1.ldo = 3 * d;
       e1.bias = L.bqkv;
-      VL_TRY(gemm(e.vn, L.qkv, rows, nullptr, EPI_STORE_BF16, e1));
+      VL_TRY(gemm(e.vn, L.qkv, rows, nullptr, EPI_STORE_BF16, e1, 1, 0, &e.vqkv_otm));
+      if (e.P + 1 >= 128 && e.P + 1 <= 320) {
+        VL_TRY(vit_attention_launch(e.vqkv, e.vattn.p, Ni, e.P + 1, c.vit_heads, 0.125f, st));
+      } else {
       AttnParams ap;
       ap.q = e.vqkv;
       ap.k = e.vqkv + d;
@@ -643,24 +655,25 @@ struct Run {
       ap.batch = Ni;
       ap.scale = 0.125f;
       VL_TRY(attention_launch(ap, 64, st));
+      }
       EpiParams e2;
       e2.out = e.vx;
       e2.ldo = d;
       e2.bias = L.bproj;
       e2.scale = L.ls1;
-      VL_TRY(gemm(e.vattn, L.proj, rows, nullptr, EPI_RESID_F32, e2));
+      VL_TRY(gemm(e.vattn, L.proj, rows, nullptr, EPI_RESID_F32, e2, 1, 0, &e.vx_otm));
       VL_TRY(layernorm_launch(e.vx, L.n2w, L.n2b, e.vn.p, rows, d, c.vit_eps, ShuffleGather{}, st));
       EpiParams e3;
       e3.out = e.vmlp.p;
       e3.ldo = f;
       e3.bias = L.bfc1;
-      VL_TRY(gemm(e.vn, L.fc1, rows, nullptr, EPI_GELU_BF16, e3));
+      VL_TRY(gemm(e.vn, L.fc1, rows, nullptr, EPI_GELU_BF16, e3, 1, 0, &e.vmlp.otm));
       EpiParams e4;
       e4.out = e.vx;
       e4.ldo = d;
       e4.bias = L.bfc2;
       e4.scale = L.ls2;
-      VL_TRY(gemm(e.vmlp, L.fc2, rows, nullptr, EPI_RESID_F32, e4));
+      VL_TRY(gemm(e.vmlp, L.fc2, rows, nullptr, EPI_RESID_F32, e4, 1, 0, &e.vx_otm));
       e.launches += 3;
     }
     return 0;
@@ -678,7 +691,7 @@ struct Run {
     e1.out = e.pa.p;
     e1.ldo = h;
     e1.bias = e.pj_b1;
-    VL_TRY(gemm(e.ps, e.pj1, prows, nullptr, EPI_GELU_BF16, e1));
+    VL_TRY(gemm(e.ps, e.pj1, prows, nullptr, EPI_GELU_BF16, e1, 1, 0, &e.pa.otm));
     EpiParams e2;
     e2.out = e.xv;
     e2.ldo = h;
@@ -699,18 +712,18 @@ struct Run {
     return gemm(xn, L.qkv, M, M_dev, EPI_QKV_ROPE, rope_ep(qout, L.bqkv, pos, kvrow, layer));
   }
   int block_post(LlmLayer& L, float* x, Act& xn, Act& ao, Act& act, int M, const int* M_dev, int hid, int mlp,
-                 int splits) {
+                 int splits, const CUtensorMap* x_otm = nullptr) {
     EpiParams eo;
     eo.out = x;
     eo.ldo = hid;
-    VL_TRY(gemm(ao, L.o, M, M_dev, EPI_RESID_F32, eo, splits));
+    VL_TRY(gemm(ao, L.o, M, M_dev, EPI_RESID_F32, eo, splits, 0, x_otm));
     VL_TRY(rmsnorm_launch(x, L.ln_post, xn.p, M, M_dev, hid, e.c.rms_eps, st));
     e.launches++;
     EpiParams eg;
     eg.out = act.p;
     eg.ldo = mlp;
-    VL_TRY(gemm(xn, L.gu, M, M_dev, EPI_SWIGLU_BF16, eg));
-    return gemm(act, L.down, M, M_dev, EPI_RESID_F32, eo, splits);
+    VL_TRY(gemm(xn, L.gu, M, M_dev, EPI_SWIGLU_BF16, eg, 1, 0, &act.otm));
+    return gemm(act, L.down, M, M_dev, EPI_RESID_F32, eo, splits, 0, x_otm);
   }
 
   // ---- expert streams (proprio token in the prefill, action tokens in the denoise steps): RMSNorm is fused across
@@ -790,7 +803,7 @@ struct Run {
       ap.scale = 0.08838834764831845f;  // 128^-0.5
       VL_TRY(attention_launch(ap, 128, st));
       e.launches++;
-      VL_TRY(block_post(e.llm[li], e.xv, e.xn, e.ao, e.act, cap, e.pb.m_tot, c.hidden, c.mlp, 1));
+      VL_TRY(block_post(e.llm[li], e.xv, e.xn, e.ao, e.act, cap, e.pb.m_tot, c.hidden, c.mlp, 1, &e.xv_otm));
       if (e.fuse_norm) VL_TRY(exp_post(li, e.xp, e.xpn, e.aop, e.actp, B, 0, false));
       else VL_TRY(block_post(e.exp[li], e.xp, e.xpn, e.aop, e.actp, B, nullptr, c.hidden_e, c.mlp_e, 32));
     }
@@ -971,11 +984,12 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   if (k == "use_graph") h->e.use_graph = (int)value;
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
-  else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm") {
+  else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
     else if (k == "pair_gemm") h->e.pair_gemm = (int)value;
+    else if (k == "tma_epi") h->e.tma_epi = (int)value;
     else h->e.exp_stages = (int)value;
     cudaDeviceSynchronize();
     for (auto& g : h->e.graphs) cudaGraphExecDestroy(g.second.exec);
@@ -1190,7 +1204,8 @@ int32_t vlaser_op_gemm(const vlaser_gemm_args* a, void* stream) {
   ep.inv_width = a->inv_width;
   ep.eps = a->eps;
   d.stages = a->stages;
-  d.pair = a->pair;
+  d.pair = a->pair & 1;
+  d.n_fast = (a->pair >> 1) & 1;
   if (a->simt)
     return gemm_launch_simt(reinterpret_cast<const __nv_bfloat16*>(a->A), reinterpret_cast<const __nv_bfloat16*>(a->W),
                             d, ep, a->epi, st);
@@ -1198,7 +1213,10 @@ int32_t vlaser_op_gemm(const vlaser_gemm_args* a, void* stream) {
   // rows of A beyond M are zero-filled by TMA (the map's row extent is the true M)
   VL_TRY(make_tmap_bf16(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, 128));
   VL_TRY(make_tmap_bf16(&tmB, a->W, (uint64_t)a->N, (uint64_t)a->K, a->pair ? 128u : (uint32_t)a->block_n));
-  return gemm_launch(tmA, tmB, d, ep, a->pair ? 128 : a->block_n, a->epi, st);
+  CUtensorMap tmC;
+  const bool tma_out = a->pair && a->tma_out;
+  if (tma_out) VL_TRY(make_tmap_out(&tmC, a->out, (uint64_t)a->M, (uint64_t)a->ldo, a->epi == EPI_RESID_F32 ? 4 : 2));
+  return gemm_launch(tmA, tmB, d, ep, a->pair ? 128 : a->block_n, a->epi, st, tma_out ? &tmC : nullptr);
 }
 
 int32_t vlaser_op_attention(const vlaser_attn_args* a, void* stream) {
@@ -1228,6 +1246,12 @@ int32_t vlaser_op_attention(const vlaser_attn_args* a, void* stream) {
   p.batch = a->batch;
   p.scale = a->scale;
   return attention_launch(p, a->head_dim, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t vlaser_op_vit_attention(const void* qkv, void* out, int32_t images, int32_t tokens, int32_t heads, float scale,
+                                void* stream) {
+  return vit_attention_launch(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), images,
+                              tokens, heads, scale, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int32_t vlaser_op_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, int32_t rows,

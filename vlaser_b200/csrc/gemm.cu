@@ -124,7 +124,7 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& ep, int N, int row, b
     if (ep.bias) add_vec32(v, ep.bias + col0);
     if constexpr (EPI == EPI_GELU_BF16) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
     }
     if constexpr (EPI == EPI_SILU_BF16) {
 #pragma unroll
@@ -242,11 +242,11 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& ep, int N, int row, b
 // One epilogue warp's share of an accumulator tile: TMEM lane quarter `taddr` (32 rows, one per lane), column
 // half `half` of the BN-wide tile. Units of 32 (plain), 64 (SwiGLU gate|up) or 2x32 (RoPE x[i], x[i+64]) columns.
 // ------------------------------------------------------------------------------------------
-template <int BN, int EPI>
+template <int BN, int EPI, int PARTS = 2>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, int N, uint32_t taddr, int half, int row, bool row_ok,
                                               int n0, bool first_split, bool atomic, float rstd, float& ss) {
   if constexpr (EPI == EPI_SWIGLU_BF16) {
-    constexpr int U = BN / 64 / 2;
+    constexpr int U = BN / 64 / PARTS;
 #pragma unroll 1
     for (int c = half * U; c < (half + 1) * U; ++c) {
       uint32_t r0[32], r1[32];
@@ -262,7 +262,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, int N, uint32
       epi_chunk<EPI>(ep, N, row, row_ok, n0 + c * 64, v, w, first_split, atomic, rstd, ss);
     }
   } else if constexpr (EPI == EPI_QKV_ROPE) {
-    constexpr int U = BN / 64 / 2;  // unit u: head u>>1, half-head chunk u&1
+    constexpr int U = BN / 64 / PARTS;  // unit u: head u>>1, half-head chunk u&1
 #pragma unroll 1
     for (int u = half * U; u < (half + 1) * U; ++u) {
       const int off = (u >> 1) * 128 + (u & 1) * 32;
@@ -279,7 +279,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, int N, uint32
       epi_chunk<EPI>(ep, N, row, row_ok, n0 + off, v, w, first_split, atomic, rstd, ss);
     }
   } else {
-    constexpr int U = BN / 32 / 2;
+    constexpr int U = BN / 32 / PARTS;
 #pragma unroll 1
     for (int c = half * U; c < (half + 1) * U; ++c) {
       uint32_t r0[32];
@@ -551,6 +551,148 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
+// Coalesced epilogue of the pair kernel: accumulator rows are transposed through a 128B-swizzled smem tile
+// (conflict-free 16-byte stores, one row per lane) and leave the SM as ONE TMA transaction per 32 x 128-byte
+// tile: a bulk tensor store for bf16 outputs, a bulk tensor reduce-add (fp32 add at L2) for the residual
+// streams. Row-per-thread global accesses cost 32 L1 wavefronts per instruction and paced the tile loop.
+// Rows past the live M inside the last tile are written too (never read; TMA clips at the tensor bounds).
+// ------------------------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ constexpr bool epi_has_tma_out() {
+  return EPI == EPI_STORE_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_SILU_BF16 || EPI == EPI_RESID_F32 ||
+         EPI == EPI_SWIGLU_BF16;
+}
+
+__device__ __forceinline__ void stage_row_f32(uint8_t* buf, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+// 32 bf16 outputs = chunks [j0, j0+4) of the 128-byte row
+__device__ __forceinline__ void stage_row_bf16(uint8_t* buf, int lane, int j0, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 u;
+    u.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+    u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+    u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+    u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+    *reinterpret_cast<uint4*>(buf + lane * 128 + (((j0 + j) ^ (lane & 7)) << 4)) = u;
+  }
+}
+__device__ __forceinline__ void load_acc32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  tmem_ld_32x32(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+template <int BN, int EPI, int PARTS, int NBUF>
+__device__ __forceinline__ void epilogue_tile_tma(const EpiParams& ep, const CUtensorMap* tmC, uint8_t* wbuf,
+                                                  uint32_t& par, uint32_t taddr, int half, int lane, int row0, int n0,
+                                                  float rstd) {
+  auto acquire = [&]() -> uint8_t* {
+    // the staging tile about to be reused (two units ago with NBUF == 2, the previous one otherwise) has been read out
+    if (lane == 0) bulk_wait_read<NBUF - 1>();
+    __syncwarp();
+    uint8_t* b = wbuf + par * 4096;
+    if (NBUF == 2) par ^= 1;
+    return b;
+  };
+  auto scale_rows = [&](float (&v)[32]) {
+    if (ep.row_ss) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= rstd;
+    }
+  };
+  if constexpr (EPI == EPI_RESID_F32) {
+    constexpr int U = BN / 32 / PARTS;
+#pragma unroll 1
+    for (int c = half * U; c < (half + 1) * U; ++c) {
+      const int col0 = n0 + c * 32;
+      float v[32];
+      load_acc32(taddr + c * 32, v);
+      scale_rows(v);
+      if (ep.bias) add_vec32(v, ep.bias + col0);
+      if (ep.scale) {
+        const float4* sp = reinterpret_cast<const float4*>(ep.scale + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 sc = __ldg(sp + i);
+          v[4 * i + 0] *= sc.x;
+          v[4 * i + 1] *= sc.y;
+          v[4 * i + 2] *= sc.z;
+          v[4 * i + 3] *= sc.w;
+        }
+      }
+      uint8_t* b = acquire();
+      stage_row_f32(b, lane, v);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_2d(tmC, b, col0, row0);
+        bulk_commit();
+      }
+    }
+  } else if constexpr (EPI == EPI_SWIGLU_BF16) {
+    static_assert(PARTS == 2, "SwiGLU TMA epilogue: 8 epilogue warps");
+    constexpr int U = BN / 128 / PARTS;  // 128 accumulator columns -> 64 outputs -> one 128-byte row
+#pragma unroll 1
+    for (int u = half * U; u < (half + 1) * U; ++u) {
+      uint8_t* b = acquire();
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) {
+        float g[32], up[32];
+        load_acc32(taddr + u * 128 + q * 64, g);
+        load_acc32(taddr + u * 128 + q * 64 + 32, up);
+        scale_rows(g);
+        scale_rows(up);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) g[j] = silu(g[j]) * up[j];
+        stage_row_bf16(b, lane, q * 4, g);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmC, b, (n0 >> 1) + u * 64, row0);
+        bulk_commit();
+      }
+    }
+  } else {
+    constexpr int U = BN / 64 / PARTS;
+#pragma unroll 1
+    for (int u = half * U; u < (half + 1) * U; ++u) {
+      uint8_t* b = acquire();
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) {
+        const int col0 = n0 + u * 64 + q * 32;
+        float v[32];
+        load_acc32(taddr + u * 64 + q * 32, v);
+        scale_rows(v);
+        if (ep.bias) add_vec32(v, ep.bias + col0);
+        if constexpr (EPI == EPI_GELU_BF16) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+        }
+        if constexpr (EPI == EPI_SILU_BF16) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
+        }
+        stage_row_bf16(b, lane, q * 4, v);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmC, b, n0 + u * 64, row0);
+        bulk_commit();
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // tcgen05 kernel, CTA pairs (cta_group::2): one 256(M) x 256(N) tile per pair. Each CTA stages its own
 // 128 rows of A and HALF of the W tile (128 of the 256 N rows); the pair's tensor cores read both halves, so
 // the L2->SM operand traffic per FLOP is 2/3 of the single-CTA 128x256 tile (L2 bandwidth, not the tensor
@@ -558,21 +700,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // collect the TMA bytes of both CTAs; tcgen05.commit multicasts to the empty / accumulator-full barriers of both.
 // ------------------------------------------------------------------------------------------
 constexpr int PAIR_BLOCK_N = 256;
-constexpr int PAIR_STAGES = 6;
+constexpr int PAIR_MAX_STAGES = 6;
 constexpr uint32_t PAIR_A_BYTES = BLOCK_M * BLOCK_K * 2;           // this CTA's 128 rows of A
 constexpr uint32_t PAIR_B_BYTES = (PAIR_BLOCK_N / 2) * BLOCK_K * 2;  // this CTA's half of the W tile
 constexpr uint32_t PAIR_STAGE_BYTES = PAIR_A_BYTES + PAIR_B_BYTES;
-constexpr uint32_t PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 1024 + 256;
+// smem budget (227 KB): one 32-row x 128-byte output staging tile per epilogue warp + as many ring stages as fit
+constexpr int pair_stages(int nw) { return nw == 16 ? 5 : 6; }
+constexpr uint32_t pair_out_bytes(int nw) { return nw * 4096; }
+constexpr uint32_t pair_smem_bytes(int nw) { return pair_stages(nw) * PAIR_STAGE_BYTES + pair_out_bytes(nw) + 1024 + 256; }
+
+// tile order of the persistent loop: m fastest (the pairs of a wave share one W tile) or n fastest (share one A tile)
+__device__ __forceinline__ void pair_tile(int t, int m_tiles, int n_tiles, int n_fast, int& m_idx, int& n_idx) {
+  if (n_fast) {
+    m_idx = t / n_tiles;
+    n_idx = t - m_idx * n_tiles;
+  } else {
+    n_idx = t / m_tiles;
+    m_idx = t - n_idx * m_tiles;
+  }
+}
 
 template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmDims d,
-                         EpiParams ep) {
-  constexpr int STAGES = PAIR_STAGES;
+constexpr int pair_epi_warps() { return EPI == EPI_GELU_BF16 ? 16 : 8; }  // the exact-GELU epilogue is issue-bound at 8
+
+template <int EPI, int NW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * NW, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmC, GemmDims d, EpiParams ep) {
+  constexpr int STAGES = pair_stages(NW);
   constexpr int BN = PAIR_BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * PAIR_STAGE_BYTES);
+  uint8_t* out_stage = smem + STAGES * PAIR_STAGE_BYTES;  // [NW][NBUF][4096], 1024-byte aligned
+  constexpr int PARTS = NW / 4;                           // column parts per TMEM lane quarter
+  constexpr int NBUF = 1;                                 // staging tiles per epilogue warp
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + pair_out_bytes(NW));
   uint64_t* full_bar = bars;                          // [STAGES]   used in the leader only
   uint64_t* empty_bar = bars + MAX_STAGES;            // [STAGES]   one set per CTA
   uint64_t* tfull_bar = bars + 2 * MAX_STAGES;        // [2]        one set per CTA
@@ -589,13 +751,14 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (d.tma_out) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 2 * EPI_WARPS);  // epilogue warps of both CTAs
+      mbar_init(&tempty_bar[s], 2 * NW);  // epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
@@ -623,7 +786,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       for (int t = pair; t < total; t += n_pairs) {
-        const int n_idx = t / m_tiles, m_idx = t - n_idx * m_tiles;
+        int n_idx, m_idx;
+        pair_tile(t, m_tiles, n_tiles, d.n_fast, m_idx, n_idx);
         const int row_a = (m_idx * 2 + (int)rank) * BLOCK_M;
         const int row_b = n_idx * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < k_blocks; ++kb) {
@@ -676,10 +840,13 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const uint32_t tempty0 = mapa_u32(smem_u32(tempty_bar), 0);
+    uint8_t* wbuf = out_stage + (warp - 2) * (NBUF * 4096);
+    uint32_t out_par = 0;
     int as = 0;
     uint32_t aphase = 0;
     for (int t = pair; t < total; t += n_pairs) {
-      const int n_idx = t / m_tiles, m_idx = t - n_idx * m_tiles;
+      int n_idx, m_idx;
+      pair_tile(t, m_tiles, n_tiles, d.n_fast, m_idx, n_idx);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const int row = (m_idx * 2 + (int)rank) * BLOCK_M + quarter * 32 + lane;
@@ -689,7 +856,14 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       float rstd = 1.f;
       if (ep.row_ss && row_ok) rstd = rsqrtf(__ldcg(ep.row_ss + row) * ep.inv_width + ep.eps);
       float ss = 0.f;
-      epilogue_tile<BN, EPI>(ep, d.N, taddr, half, row, row_ok, n0, true, false, rstd, ss);
+      bool done = false;
+      if constexpr (epi_has_tma_out<EPI>()) {
+        if (d.tma_out) {
+          epilogue_tile_tma<BN, EPI, PARTS, NBUF>(ep, &tmC, wbuf, out_par, taddr, half, lane, row - lane, n0, rstd);
+          done = true;
+        }
+      }
+      if (!done) epilogue_tile<BN, EPI, PARTS>(ep, d.N, taddr, half, row, row_ok, n0, true, false, rstd, ss);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty0 + as * 8);  // the leader's MMA thread owns both accumulators
@@ -704,6 +878,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   }
 
+  if (warp >= 2 && lane == 0) bulk_wait<0>();  // this warp's TMA stores have landed
   // neither CTA may exit (or free TMEM) while its peer can still signal its barriers or read its smem
   tc_fence_before();
   cluster_sync_all();
@@ -799,25 +974,28 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDims d, const
 }
 
 template <int EPI>
-int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDims& d, const EpiParams& ep,
+int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, GemmDims d, const EpiParams& ep,
                 cudaStream_t stream) {
+  d.tma_out = (tmC != nullptr && epi_has_tma_out<EPI>() && !ep.a_next) ? 1 : 0;
+  const CUtensorMap& tc = d.tma_out ? *tmC : tmA;
   static bool attr_set = false;
-  auto kern = gemm_tcgen05_pair_kernel<EPI>;
+  constexpr int NW = pair_epi_warps<EPI>();
+  auto kern = gemm_tcgen05_pair_kernel<EPI, NW>;
   if (!attr_set) {
-    VL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM_BYTES));
+    VL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes(NW)));
     attr_set = true;
   }
   const long long tiles = (long long)((d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (d.N / PAIR_BLOCK_N);
   const int pairs = (int)std::min<long long>(tiles, gemm_num_sms() / 2);
   // __cluster_dims__(2,1,1) is part of the kernel: a plain launch (with the optional PDL attribute) suffices
-  VL_CUDA_CHECK(launch_kernel(kern, dim3(2 * pairs), dim3(GEMM_THREADS), PAIR_SMEM_BYTES, stream, tmA, tmB, d, ep));
+  VL_CUDA_CHECK(launch_kernel(kern, dim3(2 * pairs), dim3(64 + 32 * NW), pair_smem_bytes(NW), stream, tmA, tmB, tc, d, ep));
   return 0;
 }
 
 template <int EPI>
-int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDims& d, const EpiParams& ep, int block_n,
-              int grid, cudaStream_t stream) {
-  if (d.pair) return launch_pair<EPI>(tmA, tmB, d, ep, stream);
+int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, const GemmDims& d,
+              const EpiParams& ep, int block_n, int grid, cudaStream_t stream) {
+  if (d.pair) return launch_pair<EPI>(tmA, tmB, tmC, d, ep, stream);
   if (block_n == 128) return launch_one<128, EPI>(tmA, tmB, d, ep, grid, stream);
   if constexpr (EPI != EPI_QKV_ROPE) {
     if (block_n == 256) return launch_one<256, EPI>(tmA, tmB, d, ep, grid, stream);
@@ -859,8 +1037,27 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t co
   return 0;
 }
 
+int make_tmap_out(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, int elem_bytes) {
+  PFN_encodeTiled fn = get_encode_fn();
+  VL_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  VL_CHECK(elem_bytes == 2 || elem_bytes == 4, "output tensor map: bf16 or f32");
+  VL_CHECK((cols * elem_bytes) % 16 == 0 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA alignment");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), 32};  // 128-byte rows, 32 rows = one epilogue warp
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (output) failed with CUresult " + std::to_string((int)r));
+    return -1;
+  }
+  return 0;
+}
+
 int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDims& d, const EpiParams& ep, int block_n,
-                int epi, cudaStream_t stream) {
+                int epi, cudaStream_t stream, const CUtensorMap* tmC) {
   VL_CHECK(d.K % BLOCK_K == 0 && d.K > 0, "gemm: K must be a positive multiple of 64");
   VL_CHECK(block_n == 128 || block_n == 256, "gemm: block_n must be 128 or 256");
   VL_CHECK(!d.pair || (block_n == 128 && d.N % PAIR_BLOCK_N == 0 && !(epi == EPI_RESID_F32 && d.max_splits > 1)),
@@ -876,14 +1073,14 @@ int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDims& 
   if (epi == EPI_RESID_F32 && d.max_splits > 1) tiles *= d.max_splits;
   const int grid = (int)std::min<long long>(tiles, gemm_num_sms());
   switch (epi) {
-    case EPI_STORE_BF16: return launch_bn<EPI_STORE_BF16>(tmA, tmB, d, ep, block_n, grid, stream);
-    case EPI_GELU_BF16: return launch_bn<EPI_GELU_BF16>(tmA, tmB, d, ep, block_n, grid, stream);
-    case EPI_SILU_BF16: return launch_bn<EPI_SILU_BF16>(tmA, tmB, d, ep, block_n, grid, stream);
-    case EPI_RESID_F32: return launch_bn<EPI_RESID_F32>(tmA, tmB, d, ep, block_n, grid, stream);
-    case EPI_SWIGLU_BF16: return launch_bn<EPI_SWIGLU_BF16>(tmA, tmB, d, ep, block_n, grid, stream);
-    case EPI_QKV_ROPE: return launch_bn<EPI_QKV_ROPE>(tmA, tmB, d, ep, block_n, grid, stream);
-    case EPI_PATCH_EMBED: return launch_bn<EPI_PATCH_EMBED>(tmA, tmB, d, ep, block_n, grid, stream);
-    case EPI_STORE_F32: return launch_bn<EPI_STORE_F32>(tmA, tmB, d, ep, block_n, grid, stream);
+    case EPI_STORE_BF16: return launch_bn<EPI_STORE_BF16>(tmA, tmB, tmC, d, ep, block_n, grid, stream);
+    case EPI_GELU_BF16: return launch_bn<EPI_GELU_BF16>(tmA, tmB, tmC, d, ep, block_n, grid, stream);
+    case EPI_SILU_BF16: return launch_bn<EPI_SILU_BF16>(tmA, tmB, tmC, d, ep, block_n, grid, stream);
+    case EPI_RESID_F32: return launch_bn<EPI_RESID_F32>(tmA, tmB, tmC, d, ep, block_n, grid, stream);
+    case EPI_SWIGLU_BF16: return launch_bn<EPI_SWIGLU_BF16>(tmA, tmB, tmC, d, ep, block_n, grid, stream);
+    case EPI_QKV_ROPE: return launch_bn<EPI_QKV_ROPE>(tmA, tmB, tmC, d, ep, block_n, grid, stream);
+    case EPI_PATCH_EMBED: return launch_bn<EPI_PATCH_EMBED>(tmA, tmB, tmC, d, ep, block_n, grid, stream);
+    case EPI_STORE_F32: return launch_bn<EPI_STORE_F32>(tmA, tmB, tmC, d, ep, block_n, grid, stream);
     default: set_last_error("gemm_launch: unknown epilogue"); return -2;
   }
 }

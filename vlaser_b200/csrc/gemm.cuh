@@ -62,6 +62,8 @@ struct GemmDims {
   int max_splits = 1;            // split-K cap (EPI_RESID_F32 only)
   int stages = 0;                // smem ring depth; 0 = default for the tile shape
   int pair = 0;                  // 1: CTA-pair kernel (cta_group::2, 256x256 tile per pair; W map with 128-row boxes)
+  int n_fast = 0;                // pair kernel tile order: 0 = m fastest, 1 = n fastest
+  int tma_out = 0;               // set by the launcher: epilogue leaves through the output tensor map
 };
 
 // Host API -------------------------------------------------------------------------------
@@ -69,8 +71,12 @@ struct GemmDims {
 int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
 // Launches the tcgen05 kernel (block_n in {128,256}); `simt` launches the CUDA-core cross-check kernel
 // (debug / tests only) that shares the epilogue code but reads A and W through plain pointers.
+// Output tensor map for the pair kernel's TMA epilogue: row-major [rows, cols] bf16 (elem_bytes 2) or f32 (4), box =
+// 32 rows x 128 bytes, 128B swizzle. For EPI_SWIGLU_BF16 it describes the [M, N/2] result.
+int make_tmap_out(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, int elem_bytes);
+// `tmC` (optional, pair kernel + bf16/residual epilogues only): output tensor map; the epilogue then stores through TMA.
 int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDims& d, const EpiParams& ep, int block_n,
-                int epi, cudaStream_t stream);
+                int epi, cudaStream_t stream, const CUtensorMap* tmC = nullptr);
 int gemm_launch_simt(const __nv_bfloat16* A, const __nv_bfloat16* W, const GemmDims& d, const EpiParams& ep, int epi,
                      cudaStream_t stream);
 int gemm_num_sms();
