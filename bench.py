@@ -229,24 +229,57 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(t[0]), float(t[1])
 
-    # ---- in-situ GEMM timing for the roofline figure (rank 0; direct launches, events around every GEMM)
-    roof = None
+    # ---- in-situ kernel timing for the roofline figures (rank 0; direct launches, CUDA events on the launch stream
+    # around every GEMM launch). Dominant kernel = the CTA-pair tcgen05 GEMM (all large-M projections of ViT + prefill).
+    roof = roof_small = None
+    lat = None
     if rank == 0 and not args.no_profile:
         pol.set_option("use_graph", 0)
         pol.infer_action(ids_d, pix_d, proprios=prop_d, noise=noise_d)  # warm direct path
         torch.cuda.synchronize()
         pol.set_option("profile_mtot", int(valid.sum()))
         pol.set_option("profile_gemm", 1)
-        for _ in range(3):
+        reps = 3
+        for _ in range(reps):
             pol.infer_action(ids_d, pix_d, proprios=prop_d, noise=noise_d)
-        gms, gfl, gn = pol.profile_read()
+        cls = pol.profile_read_classes()
         pol.set_option("profile_gemm", 0)
         pol.set_option("use_graph", 1)
-        achieved = gfl / (gms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all projection GEMMs of one call)",
-                "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                "traffic": None, "peak_source": peaks["which"], "gemm_launches_per_call": gn // 3,
-                "gemm_ms_per_call": gms / 3, "gemm_share_of_step": (gms / 3) / (ms / args.steps)}
+        step_ms = ms / args.steps
+        pr, sg = cls["pair"], cls["single"]
+        if pr["launches"]:
+            ach = pr["flops"] / (pr["ms"] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "gemm_tcgen05_pair_kernel (cta_group::2 256x256 tiles: ViT + LLM-prefill projections)",
+                    "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
+                    "traffic": None, "peak_source": peaks["which"],
+                    "launches_per_call": int(pr["launches"] / reps), "avg_launch_us": 1e3 * pr["ms"] / pr["launches"],
+                    "algorithmic_gflop_per_launch": pr["flops"] / pr["launches"] / 1e9,
+                    "ms_per_call": pr["ms"] / reps, "share_of_step": (pr["ms"] / reps) / step_ms}
+        if sg["launches"]:
+            ach = sg["bytes"] / (sg["ms"] * 1e-3) / 1e9
+            roof_small = {"bound": "hbm", "kernel": "gemm_tcgen05_kernel (M<=256 expert / action-head GEMMs, weight streaming)",
+                          "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                          "traffic": None, "launches_per_call": int(sg["launches"] / reps),
+                          "avg_launch_us": 1e3 * sg["ms"] / sg["launches"], "ms_per_call": sg["ms"] / reps,
+                          "share_of_step": (sg["ms"] / reps) / step_ms,
+                          "achieved_tflops": sg["flops"] / (sg["ms"] * 1e-3) / 1e12}
+        # ---- p50 latency of a single-observation call (B=1), same handle, graph replay, CUDA events per call
+        one = make_inputs(cfg, 1, 999)
+        o_ids, o_pix = one["input_ids"].to(dev), one["pixel_values"].to(torch.bfloat16).to(dev)
+        o_prop, o_noise = one["proprios"].to(torch.bfloat16).to(dev), one["noise"].to(torch.bfloat16).to(dev)
+        for _ in range(3):
+            pol.infer_action(o_ids, o_pix, proprios=o_prop, noise=o_noise)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(21):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            pol.infer_action(o_ids, o_pix, proprios=o_prop, noise=o_noise)
+            a1.record()
+            torch.cuda.synchronize()
+            ts.append(a0.elapsed_time(a1))
+        lat = {"p50_ms": statistics.median(ts), "min_ms": min(ts), "calls": len(ts),
+               "hbm_floor_ms": 16.3e9 / (peaks["hbm_gbs"] * 1e9) * 1e3}
     if world > 1:
         dist.barrier()
 
@@ -279,6 +312,10 @@ def run_ours(args):
     }
     if roof is not None:
         line["roofline"] = roof
+    if roof_small is not None:
+        line["roofline_small_m"] = roof_small
+    if lat is not None:
+        line["latency_b1"] = lat
     if want_cpu:
         times, cores = _cpu_oracle_timing(cfg, sd_cpu, 3, 1)
         per_obs = statistics.median(times)

@@ -62,8 +62,8 @@ def test_gemm_gelu_silu(name, bn, simt):
 @pytest.mark.parametrize("name,bn,simt", VARIANTS)
 @pytest.mark.parametrize("splits", [1, 8])
 def test_gemm_resid(name, bn, simt, splits):
-    if bn >= 512 and splits > 1:
-        pytest.skip("the pair kernel has no split-K")
+    if bn == 512 and splits > 1:
+        pytest.skip("pair-kernel split-K needs the TMA reduce-add epilogue")
     M, N, K = 256, 768, 2048
     A, W = _rand(M, K), _rand(N, K, scale=0.05)
     bias = _rand(N, dtype=torch.float32, seed=7)

@@ -63,7 +63,7 @@ EXPORTS = [
     "vlaser_infer_action", "vlaser_infer_action_host", "vlaser_destroy", "vlaser_set_option", "vlaser_debug_copy",
     "vlaser_last_launch_count", "vlaser_flops_per_call", "vlaser_profile_read", "vlaser_op_gemm", "vlaser_op_attention",
     "vlaser_op_layernorm", "vlaser_op_rmsnorm", "vlaser_op_pixel_shuffle", "vlaser_op_im2col", "vlaser_op_euler_step",
-    "vlaser_op_vit_attention",
+    "vlaser_op_vit_attention", "vlaser_profile_read_classes",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -104,6 +104,8 @@ def load() -> C.CDLL:
     lib.vlaser_flops_per_call.restype = C.c_double
     lib.vlaser_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
     lib.vlaser_profile_read.restype = i32
+    lib.vlaser_profile_read_classes.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.vlaser_profile_read_classes.restype = i32
     lib.vlaser_op_gemm.argtypes = [C.POINTER(GemmArgs), vp]
     lib.vlaser_op_gemm.restype = i32
     lib.vlaser_op_attention.argtypes = [C.POINTER(AttnArgs), vp]

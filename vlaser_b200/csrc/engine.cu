@@ -117,7 +117,7 @@ struct Engine {
   // activations
   Act cols, vn, vattn, vmlp, ps, pa, xn, ao, act, xpn, aop, actp, xan, aoa, acta, e1, h2;
   float *vx = nullptr, *xv = nullptr, *xp = nullptr, *xa = nullptr, *action = nullptr;
-  CUtensorMap vx_otm, xv_otm, vqkv_otm;  // output maps of the fp32 residual streams / ViT qkv buffer
+  CUtensorMap vx_otm, xv_otm, vqkv_otm, xp_otm, xa_otm;  // output maps of the fp32 residual streams / ViT qkv buffer
   bf16 *vqkv = nullptr, *q = nullptr, *qp = nullptr, *qa = nullptr;
   bf16 *kc = nullptr, *vc = nullptr;  // [layers][kv_heads][kv_rows][128]
   // fused RMSNorm chain of the expert streams: per pass (prefill proprio, then each denoise step) one row-sum-of-
@@ -137,13 +137,16 @@ struct Engine {
   // options / state
   int use_graph = 1, stop_after = 0, simt = 0;
   int exp_stages = 0;          // smem ring depth of the expert-stream GEMMs (0 = kernel default)
+  int pair_min_tiles = 74;     // fewest pair tiles (x splits) for which the pair kernel is preferred: one per SM pair
+                               // (measured: the M<=256 expert GEMMs are latency-bound and do not gain from pairs)
   int tma_epi = 1;             // 1: pair-kernel epilogues leave through TMA stores / reduce-adds
   int pair_gemm = 1;           // 1: large-M GEMMs run on the CTA-pair (cta_group::2) kernel
   int fuse_norm = 0;           // 1: RMSNorm of the expert streams fused across the GEMM chain (see exp_pre/exp_post)
   int profile_gemm = 0;        // bracket every GEMM launch with CUDA events (non-graph runs only)
   long long profile_mtot = 0;  // live packed-row count used for the FLOP accounting of var-len GEMMs
   std::vector<cudaEvent_t> prof_events;
-  std::vector<double> prof_flops;
+  std::vector<double> prof_flops, prof_bytes;
+  std::vector<int> prof_class;  // 0 = single-CTA kernel (small-M / split-K), 1 = CTA-pair kernel (large-M)
   size_t prof_used = 0;
   long long launches = 0, last_launches = 0;
   cudaStream_t own_stream = nullptr;
@@ -359,11 +362,13 @@ int engine_build(Engine& e) {
   VL_TRY(e.add_act(&e.ao, prow, e.qdim));
   VL_TRY(e.add_act(&e.act, prow, c.mlp));
   VL_TRY(e.alloc(&e.xp, (size_t)e.Bc * he));
+  VL_TRY(make_tmap_out(&e.xp_otm, e.xp, e.Bc, he, 4));
   VL_TRY(e.add_act(&e.xpn, e.Bc, he));
   VL_TRY(e.alloc(&e.qp, (size_t)e.Bc * e.qdim));
   VL_TRY(e.add_act(&e.aop, e.Bc, e.qdim));
   VL_TRY(e.add_act(&e.actp, e.Bc, c.mlp_e));
   VL_TRY(e.alloc(&e.xa, (size_t)arow * he));
+  VL_TRY(make_tmap_out(&e.xa_otm, e.xa, arow, he, 4));
   VL_TRY(e.add_act(&e.xan, arow, he));
   VL_TRY(e.alloc(&e.qa, (size_t)arow * e.qdim));
   VL_TRY(e.add_act(&e.aoa, arow, e.qdim));
@@ -570,8 +575,11 @@ struct Run {
     if (e.simt) return gemm_launch_simt(a.p, w.w, d, ep, epi, st);
     int bn = 128;
     // large-M GEMMs: CTA-pair kernel (256x256 tile per pair) when there is at least one tile per pair
-    const long long pair_tiles = (long long)((M + 255) / 256) * (w.N / 256);
-    if (e.pair_gemm && w.N % 256 == 0 && max_splits <= 1 && pair_tiles >= gemm_num_sms() / 2) d.pair = 1;
+    // (with split-K through the TMA reduce-add epilogue the splits multiply the tile count)
+    long long pair_tiles = (long long)((M + 255) / 256) * (w.N / 256);
+    const bool pair_split = max_splits > 1 && epi == EPI_RESID_F32 && out_tm != nullptr && e.tma_epi && !ep.a_next;
+    if (pair_split) pair_tiles *= std::min(max_splits, std::max(1, w.K / 128));
+    if (e.pair_gemm && w.N % 256 == 0 && (max_splits <= 1 || pair_split) && pair_tiles >= e.pair_min_tiles) d.pair = 1;
     // tile order: with many more rows than weight rows a wave of pairs should share A tiles (n fastest); measured on
     // B200: ViT GEMMs and the LLM o/down projections gain, the wide-N LLM qkv/gate-up GEMMs prefer m fastest
     d.n_fast = (M_dev == nullptr) ? (M > w.N) : (w.N <= 1536);
@@ -588,6 +596,11 @@ struct Run {
       }
       const double rows = M_dev ? (double)e.profile_mtot : (double)M;
       e.prof_flops.push_back(2.0 * rows * (double)w.N * (double)w.K);
+      // algorithmic bytes: both operands once + the output once (residual epilogues: fp32 read-modify-write)
+      const double out_elems = rows * (double)(epi == EPI_SWIGLU_BF16 ? w.N / 2 : w.N);
+      const double out_bytes = (epi == EPI_RESID_F32) ? 8.0 * out_elems : ((epi == EPI_STORE_F32 || epi == EPI_PATCH_EMBED) ? 4.0 : 2.0) * out_elems;
+      e.prof_bytes.push_back(2.0 * (rows * (double)w.K + (double)w.N * (double)w.K) + out_bytes);
+      e.prof_class.push_back(d.pair);
       VL_CUDA_CHECK(cudaEventRecord(e.prof_events[e.prof_used], st));
     }
     const int rc = gemm_launch(a.tm, bn == 256 ? w.tm256 : w.tm128, d, ep, bn, epi, st, e.tma_epi ? out_tm : nullptr);
@@ -805,7 +818,7 @@ struct Run {
       e.launches++;
       VL_TRY(block_post(e.llm[li], e.xv, e.xn, e.ao, e.act, cap, e.pb.m_tot, c.hidden, c.mlp, 1, &e.xv_otm));
       if (e.fuse_norm) VL_TRY(exp_post(li, e.xp, e.xpn, e.aop, e.actp, B, 0, false));
-      else VL_TRY(block_post(e.exp[li], e.xp, e.xpn, e.aop, e.actp, B, nullptr, c.hidden_e, c.mlp_e, 32));
+      else VL_TRY(block_post(e.exp[li], e.xp, e.xpn, e.aop, e.actp, B, nullptr, c.hidden_e, c.mlp_e, 32, &e.xp_otm));
     }
     return 0;
   }
@@ -852,7 +865,7 @@ struct Run {
       VL_TRY(attention_launch(ap, 128, st));
       e.launches++;
       if (e.fuse_norm) VL_TRY(exp_post(li, e.xa, e.xan, e.aoa, e.acta, M, step + 1, false));
-      else VL_TRY(block_post(e.exp[li], e.xa, e.xan, e.aoa, e.acta, M, nullptr, he, c.mlp_e, 32));
+      else VL_TRY(block_post(e.exp[li], e.xa, e.xan, e.aoa, e.acta, M, nullptr, he, c.mlp_e, 32, &e.xa_otm));
     }
     const int last = step == c.num_inference_steps - 1;
     VL_TRY(euler_step_launch(e.xa, e.final_norm, e.dec_w, e.dec_b, e.action, e.out_act, io, M, he, c.action_dim, e.H,
@@ -984,12 +997,14 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   if (k == "use_graph") h->e.use_graph = (int)value;
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
-  else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi") {
+  else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
+           k == "pair_min_tiles") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
     else if (k == "pair_gemm") h->e.pair_gemm = (int)value;
     else if (k == "tma_epi") h->e.tma_epi = (int)value;
+    else if (k == "pair_min_tiles") h->e.pair_min_tiles = (int)value;
     else h->e.exp_stages = (int)value;
     cudaDeviceSynchronize();
     for (auto& g : h->e.graphs) cudaGraphExecDestroy(g.second.exec);
@@ -999,6 +1014,8 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
     h->e.profile_gemm = (int)value;
     h->e.prof_used = 0;
     h->e.prof_flops.clear();
+    h->e.prof_bytes.clear();
+    h->e.prof_class.clear();
   } else if (k == "profile_mtot") h->e.profile_mtot = value;
   else {
     set_last_error("unknown option " + k);
@@ -1140,6 +1157,29 @@ int32_t vlaser_profile_read(vlaser_t* h, double* gemm_ms, double* gemm_flops, in
   *gemm_launches = (int64_t)(e.prof_used / 2);
   e.prof_used = 0;
   e.prof_flops.clear();
+  e.prof_bytes.clear();
+  e.prof_class.clear();
+  return 0;
+}
+
+int32_t vlaser_profile_read_classes(vlaser_t* h, double* out8) {
+  VL_CHECK(h && out8, "null argument");
+  Engine& e = h->e;
+  VL_CUDA_CHECK(cudaDeviceSynchronize());
+  for (int i = 0; i < 8; ++i) out8[i] = 0.0;
+  for (size_t i = 0; i + 1 < e.prof_used; i += 2) {
+    float t = 0;
+    VL_CUDA_CHECK(cudaEventElapsedTime(&t, e.prof_events[i], e.prof_events[i + 1]));
+    const int c = e.prof_class[i / 2] ? 1 : 0;
+    out8[4 * c + 0] += t;
+    out8[4 * c + 1] += e.prof_flops[i / 2];
+    out8[4 * c + 2] += e.prof_bytes[i / 2];
+    out8[4 * c + 3] += 1.0;
+  }
+  e.prof_used = 0;
+  e.prof_flops.clear();
+  e.prof_bytes.clear();
+  e.prof_class.clear();
   return 0;
 }
 

@@ -592,7 +592,7 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, float (&v)[32]) {
 template <int BN, int EPI, int PARTS, int NBUF>
 __device__ __forceinline__ void epilogue_tile_tma(const EpiParams& ep, const CUtensorMap* tmC, uint8_t* wbuf,
                                                   uint32_t& par, uint32_t taddr, int half, int lane, int row0, int n0,
-                                                  float rstd) {
+                                                  float rstd, bool first_split) {
   auto acquire = [&]() -> uint8_t* {
     // the staging tile about to be reused (two units ago with NBUF == 2, the previous one otherwise) has been read out
     if (lane == 0) bulk_wait_read<NBUF - 1>();
@@ -615,7 +615,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiParams& ep, const CUt
       float v[32];
       load_acc32(taddr + c * 32, v);
       scale_rows(v);
-      if (ep.bias) add_vec32(v, ep.bias + col0);
+      if (ep.bias && first_split) add_vec32(v, ep.bias + col0);
       if (ep.scale) {
         const float4* sp = reinterpret_cast<const float4*>(ep.scale + col0);
 #pragma unroll
@@ -777,7 +777,16 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int n_tiles = d.N / BN;
   const int k_blocks = d.K / BLOCK_K;
-  const int total = m_tiles * n_tiles;
+  const int base = m_tiles * n_tiles;
+  // split-K (residual epilogue through TMA reduce-add only): partial sums meet in L2, no tile counters needed
+  int splits = 1;
+  if (EPI == EPI_RESID_F32 && d.max_splits > 1 && d.tma_out && base > 0) {
+    splits = min(min(d.max_splits, n_pairs / base), k_blocks / 2);
+    if (splits < 1) splits = 1;
+  }
+  const int kb_per_split = (k_blocks + splits - 1) / splits;
+  splits = (k_blocks + kb_per_split - 1) / kb_per_split;
+  const int total = base * splits;
 
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) ================================
@@ -787,10 +796,12 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       uint32_t phase = 0;
       for (int t = pair; t < total; t += n_pairs) {
         int n_idx, m_idx;
-        pair_tile(t, m_tiles, n_tiles, d.n_fast, m_idx, n_idx);
+        const int split = t / base;
+        pair_tile(t - split * base, m_tiles, n_tiles, d.n_fast, m_idx, n_idx);
         const int row_a = (m_idx * 2 + (int)rank) * BLOCK_M;
         const int row_b = n_idx * BN + (int)rank * (BN / 2);
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int kb0 = split * kb_per_split, kb1 = min(k_blocks, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * PAIR_STAGE_BYTES;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * PAIR_STAGE_BYTES);
@@ -815,7 +826,9 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int split = t / base;
+        const int kb0 = split * kb_per_split, kb1 = min(k_blocks, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * PAIR_STAGE_BYTES);
@@ -823,7 +836,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const uint64_t db = make_umma_desc_sw128(sa + PAIR_A_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k)
-            umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit_pair(&empty_bar[stage], 0x3);  // frees this smem slot in both CTAs
           if (++stage == STAGES) {
             stage = 0;
@@ -846,7 +859,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint32_t aphase = 0;
     for (int t = pair; t < total; t += n_pairs) {
       int n_idx, m_idx;
-      pair_tile(t, m_tiles, n_tiles, d.n_fast, m_idx, n_idx);
+      const int split = t / base;
+      pair_tile(t - split * base, m_tiles, n_tiles, d.n_fast, m_idx, n_idx);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const int row = (m_idx * 2 + (int)rank) * BLOCK_M + quarter * 32 + lane;
@@ -859,7 +873,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       bool done = false;
       if constexpr (epi_has_tma_out<EPI>()) {
         if (d.tma_out) {
-          epilogue_tile_tma<BN, EPI, PARTS, NBUF>(ep, &tmC, wbuf, out_par, taddr, half, lane, row - lane, n0, rstd);
+          epilogue_tile_tma<BN, EPI, PARTS, NBUF>(ep, &tmC, wbuf, out_par, taddr, half, lane, row - lane, n0, rstd,
+                                                  split == 0);
           done = true;
         }
       }
@@ -985,7 +1000,11 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     VL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes(NW)));
     attr_set = true;
   }
-  const long long tiles = (long long)((d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (d.N / PAIR_BLOCK_N);
+  long long tiles = (long long)((d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (d.N / PAIR_BLOCK_N);
+  if (EPI == EPI_RESID_F32 && d.max_splits > 1) {
+    VL_CHECK(d.tma_out, "gemm: split-K on the pair kernel needs the TMA reduce-add epilogue (output tensor map)");
+    tiles *= d.max_splits;
+  }
   const int pairs = (int)std::min<long long>(tiles, gemm_num_sms() / 2);
   // __cluster_dims__(2,1,1) is part of the kernel: a plain launch (with the optional PDL attribute) suffices
   VL_CUDA_CHECK(launch_kernel(kern, dim3(2 * pairs), dim3(64 + 32 * NW), pair_smem_bytes(NW), stream, tmA, tmB, tc, d, ep));
@@ -1060,8 +1079,7 @@ int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDims& 
                 int epi, cudaStream_t stream, const CUtensorMap* tmC) {
   VL_CHECK(d.K % BLOCK_K == 0 && d.K > 0, "gemm: K must be a positive multiple of 64");
   VL_CHECK(block_n == 128 || block_n == 256, "gemm: block_n must be 128 or 256");
-  VL_CHECK(!d.pair || (block_n == 128 && d.N % PAIR_BLOCK_N == 0 && !(epi == EPI_RESID_F32 && d.max_splits > 1)),
-           "gemm: pair mode needs the 128-row W map, N % 256 == 0 and no split-K");
+  VL_CHECK(!d.pair || (block_n == 128 && d.N % PAIR_BLOCK_N == 0), "gemm: pair mode needs the 128-row W map, N % 256 == 0");
   VL_CHECK(d.N % block_n == 0, "gemm: N must be a multiple of block_n");
   VL_CHECK(ep.out != nullptr, "gemm: null output");
   VL_CHECK(!ep.a_next || (ep.gamma_next && ep.ss_next && ep.lda_next > 0), "gemm: incomplete fused-norm outputs");

@@ -289,6 +289,13 @@ class PiZeroInference:
         _lib.check(self._lib.vlaser_profile_read(self._handle, C.byref(ms), C.byref(fl), C.byref(n)), "profile_read")
         return ms.value, fl.value, n.value
 
+    def profile_read_classes(self):
+        """{"single": {...}, "pair": {...}} with ms / flops / bytes / launches since "profile_gemm" was switched on."""
+        buf = (C.c_double * 8)()
+        _lib.check(self._lib.vlaser_profile_read_classes(self._handle, buf), "profile_read_classes")
+        keys = ("ms", "flops", "bytes", "launches")
+        return {"single": dict(zip(keys, buf[0:4])), "pair": dict(zip(keys, buf[4:8]))}
+
     def last_launch_count(self) -> int:
         return int(self._lib.vlaser_last_launch_count(self._handle))
 
