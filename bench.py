@@ -231,7 +231,7 @@ def run_ours(args):
 
     # ---- in-situ kernel timing for the roofline figures (rank 0; direct launches, CUDA events on the launch stream
     # around every GEMM launch). Dominant kernel = the CTA-pair tcgen05 GEMM (all large-M projections of ViT + prefill).
-    roof = roof_small = None
+    roof = roof_small = roof_expert = None
     lat = None
     if rank == 0 and not args.no_profile:
         pol.set_option("use_graph", 0)
@@ -263,6 +263,17 @@ def run_ours(args):
                           "avg_launch_us": 1e3 * sg["ms"] / sg["launches"], "ms_per_call": sg["ms"] / reps,
                           "share_of_step": (sg["ms"] / reps) / step_ms,
                           "achieved_tflops": sg["flops"] / (sg["ms"] * 1e-3) / 1e12}
+        xp = cls["expert"]
+        if xp["launches"]:
+            ach = xp["bytes"] / (xp["ms"] * 1e-3) / 1e9
+            roof_expert = {"bound": "hbm", "kernel": "expert_pass_kernel (persistent: 28 expert layers of one proprio / "
+                           "denoise pass per launch, weights streamed once per pass)",
+                           "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                           "traffic": None, "launches_per_call": int(xp["launches"] / reps),
+                           "avg_launch_us": 1e3 * xp["ms"] / xp["launches"], "ms_per_call": xp["ms"] / reps,
+                           "algorithmic_mbytes_per_launch": xp["bytes"] / xp["launches"] / 1e6,
+                           "share_of_step": (xp["ms"] / reps) / step_ms,
+                           "achieved_tflops": xp["flops"] / (xp["ms"] * 1e-3) / 1e12}
         # ---- p50 latency of a single-observation call (B=1), same handle, graph replay, CUDA events per call
         one = make_inputs(cfg, 1, 999)
         o_ids, o_pix = one["input_ids"].to(dev), one["pixel_values"].to(torch.bfloat16).to(dev)
@@ -314,6 +325,8 @@ def run_ours(args):
         line["roofline"] = roof
     if roof_small is not None:
         line["roofline_small_m"] = roof_small
+    if roof_expert is not None:
+        line["roofline_expert"] = roof_expert
     if lat is not None:
         line["latency_b1"] = lat
     if want_cpu:

@@ -238,6 +238,9 @@ __global__ void plan_rows_kernel(const long long* __restrict__ ids, PlanBuffers 
     pb.den_q_start[b] = b * H;
     pb.den_q_len[b] = H;
     pb.den_kv_len[b] = vl + 1 + H;
+    pb.prop_q_start[b] = b;
+    pb.prop_q_len[b] = 1;
+    pb.prop_kv_len[b] = vl + 1;
   }
   for (int i = lane; i < H; i += 32) {
     pb.act_pos[b * H + i] = 2 + i;

@@ -48,6 +48,9 @@ struct PlanBuffers {
   int* den_q_start;   // [B]
   int* den_q_len;     // [B]
   int* den_kv_len;    // [B]  valid_len + 1 + H
+  int* prop_q_start;  // [B]  == b   (proprio pass of the expert stream: one query row per sample)
+  int* prop_q_len;    // [B]  == 1
+  int* prop_kv_len;   // [B]  valid_len + 1 (prefix + the proprio token itself)
 };
 int plan_launch(const long long* input_ids, const int* valid_len_in, PlanBuffers pb, int B, int S, int H,
                 int img_tokens_per_sample, int image_token, int pad_token, cudaStream_t stream);

@@ -24,6 +24,7 @@
 #include "../../include/vlaser_b200.h"
 #include "attention.cuh"
 #include "elementwise.cuh"
+#include "expert.cuh"
 #include "gemm.cuh"
 
 namespace vlaser {
@@ -126,6 +127,11 @@ struct Engine {
   int ss_rows = 0;
   size_t ss_floats = 0;
   int* tile_ctr = nullptr;
+  // persistent expert-stream kernel (expert.cu): per-layer operand table and one grid-barrier counter per pass
+  ExpertLayerDev* xp_layers = nullptr;
+  unsigned int* xp_bar = nullptr;
+  long long* xp_timing = nullptr;  // [(steps+1)][7*layers] phase-completion timestamps, filled when xp_time is set
+  int xp_time = 0, xp_flags = 0;
   PlanBuffers pb{};
   // static I/O staging (graph operands)
   long long* in_ids = nullptr;
@@ -141,6 +147,8 @@ struct Engine {
                                // (measured: the M<=256 expert GEMMs are latency-bound and do not gain from pairs)
   int tma_epi = 1;             // 1: pair-kernel epilogues leave through TMA stores / reduce-adds
   int pair_gemm = 1;           // 1: large-M GEMMs run on the CTA-pair (cta_group::2) kernel
+  int mega = 1;                // 1: the expert streams (proprio pass of the prefill, every denoise step) run as ONE
+                               // persistent kernel per pass (expert.cu) instead of 7 kernels per layer
   int fuse_norm = 0;           // 1: RMSNorm of the expert streams fused across the GEMM chain (see exp_pre/exp_post)
   int profile_gemm = 0;        // bracket every GEMM launch with CUDA events (non-graph runs only)
   long long profile_mtot = 0;  // live packed-row count used for the FLOP accounting of var-len GEMMs
@@ -380,6 +388,9 @@ int engine_build(Engine& e) {
   e.ss_floats = (size_t)(c.num_inference_steps + 1) * (2 * c.layers + 1) * e.ss_rows;
   VL_TRY(e.alloc(&e.ss, e.ss_floats));
   VL_TRY(e.alloc(&e.tile_ctr, 4096));
+  VL_TRY(e.alloc(&e.xp_layers, (size_t)c.layers));
+  VL_TRY(e.alloc(&e.xp_bar, (size_t)(c.num_inference_steps + 1) * 7 * c.layers));
+  VL_TRY(e.alloc(&e.xp_timing, (size_t)(c.num_inference_steps + 1) * 7 * c.layers));
   const size_t kv_elems = (size_t)c.layers * c.n_kv_heads * e.kv_rows * 128;
   VL_TRY(e.alloc(&e.kc, kv_elems));
   VL_TRY(e.alloc(&e.vc, kv_elems));
@@ -401,6 +412,9 @@ int engine_build(Engine& e) {
   VL_TRY(e.alloc(&pb.den_q_start, e.Bc));
   VL_TRY(e.alloc(&pb.den_q_len, e.Bc));
   VL_TRY(e.alloc(&pb.den_kv_len, e.Bc));
+  VL_TRY(e.alloc(&pb.prop_q_start, e.Bc));
+  VL_TRY(e.alloc(&pb.prop_q_len, e.Bc));
+  VL_TRY(e.alloc(&pb.prop_kv_len, e.Bc));
   // --- I/O staging
   VL_TRY(e.alloc(&e.in_ids, (size_t)e.Bc * e.S));
   VL_TRY(e.alloc(&e.in_valid, e.Bc));
@@ -508,6 +522,21 @@ int engine_finalize(Engine& e) {
     }
   VL_TRY(e.make_lin_maps(&e.ae_w2b));
   VL_TRY(e.make_lin_maps(&e.ae_w3));
+  {
+    std::vector<ExpertLayerDev> tab(c.layers);
+    for (int i = 0; i < c.layers; ++i) {
+      const LlmLayer& L = e.exp[i];
+      memset(&tab[i], 0, sizeof(ExpertLayerDev));
+      tab[i].tm_qkv = L.qkv.tm128;
+      tab[i].tm_o = L.o.tm128;
+      tab[i].tm_gu = L.gu.tm128;
+      tab[i].tm_down = L.down.tm128;
+      tab[i].ln_in = L.ln_in;
+      tab[i].ln_post = L.ln_post;
+      tab[i].bqkv = L.bqkv;
+    }
+    VL_CUDA_CHECK(cudaMemcpy(e.xp_layers, tab.data(), tab.size() * sizeof(ExpertLayerDev), cudaMemcpyHostToDevice));
+  }
   // RoPE tables (HF Qwen2RotaryEmbedding, default rope): cos/sin(pos * theta^(-2i/128)), i < 64
   const int max_pos = std::max(e.S, e.H + 1) + 1;
   std::vector<float> ct((size_t)max_pos * 64), st((size_t)max_pos * 64);
@@ -781,12 +810,79 @@ struct Run {
     return gemm(act, L.down, M, nullptr, EPI_RESID_F32, ed, 32, e.exp_stages);
   }
 
+  bool mega() const { return e.mega && !e.simt; }
+
+  // One pass of the expert transformer over M rows as a single persistent kernel (expert.cu). pass 0 = the proprio
+  // token of the prefill (its K/V only in the last layer), pass k+1 = the action tokens of Euler step k.
+  int expert_pass(int pass, int M, float* x, const CUtensorMap& x_otm, Act& xn, bf16* q, Act& ao, Act& act, const int* pos, const int* kvrow,
+                  const int* q_start, const int* q_len, const int* kv_len, int max_q_len, bool last_kv_only) {
+    const vlaser_cfg& c = e.c;
+    ExpertPass p;
+    p.layers = e.xp_layers;
+    p.n_layers = c.layers;
+    p.last_kv_only = last_kv_only ? 1 : 0;
+    p.M = M;
+    p.he = c.hidden_e;
+    p.mlp = c.mlp_e;
+    p.n_q_heads = c.n_heads;
+    p.n_kv_heads = c.n_kv_heads;
+    p.eps = c.rms_eps;
+    p.x = x;
+    p.xn = xn.p;
+    p.q = q;
+    p.ao = ao.p;
+    p.act = act.p;
+    p.row_pos = pos;
+    p.row_kvrow = kvrow;
+    p.cos_tab = e.cos_tab;
+    p.sin_tab = e.sin_tab;
+    p.k_cache = e.kc;
+    p.v_cache = e.vc;
+    p.kv_layer_stride = (long long)c.n_kv_heads * e.kv_rows * 128;
+    p.kv_head_stride = e.kv_rows * 128;
+    p.q_start = q_start;
+    p.q_len = q_len;
+    p.kv_start = e.pb.kvoff;
+    p.kv_len = kv_len;
+    p.max_q_len = max_q_len;
+    p.batch = B;
+    p.scale = 0.08838834764831845f;  // 128^-0.5
+    p.barrier = e.xp_bar + (size_t)pass * 7 * c.layers;
+    p.flags = e.xp_flags;
+    p.timing = e.xp_time ? e.xp_timing + (size_t)pass * 7 * c.layers : nullptr;
+    e.launches++;
+    const bool prof = e.profile_gemm && !e.use_graph;
+    if (prof) {
+      while (e.prof_events.size() < e.prof_used + 2) {
+        cudaEvent_t ev;
+        VL_CUDA_CHECK(cudaEventCreate(&ev));
+        e.prof_events.push_back(ev);
+      }
+      // GEMM work of the pass: q|k|v, o, gate/up, down per layer (the last layer of a kv-only pass: q|k|v only)
+      const double he = c.hidden_e, f = c.mlp_e, rows = M;
+      const double w_full = he * e.qkvN + (double)e.qdim * he + 3.0 * he * f, w_kv = he * e.qkvN;
+      const double w = (c.layers - (last_kv_only ? 1 : 0)) * w_full + (last_kv_only ? w_kv : 0.0);
+      e.prof_flops.push_back(2.0 * rows * w);
+      e.prof_bytes.push_back(2.0 * w);  // algorithmic bytes: every expert weight streamed once from HBM
+      e.prof_class.push_back(2);
+      VL_CUDA_CHECK(cudaEventRecord(e.prof_events[e.prof_used], st));
+    }
+    const int rc = expert_pass_launch(p, xn.tm, ao.tm, act.tm, x_otm, st);
+    if (prof) {
+      VL_CUDA_CHECK(cudaEventRecord(e.prof_events[e.prof_used + 1], st));
+      e.prof_used += 2;
+    }
+    return rc;
+  }
+
   int prefill() {
     const vlaser_cfg& c = e.c;
     const int cap = B * e.S;
     for (int li = 0; li < c.layers; ++li) {
       VL_TRY(block_pre(e.llm[li], e.xv, e.xn, e.q, cap, e.pb.m_tot, c.hidden, e.pb.row_pos, e.pb.row_kvrow, li));
-      if (li == 0 || !e.fuse_norm)  // (fused: the proprio encoder output has no producer epilogue -> plain RMSNorm)
+      if (mega()) {
+        // the proprio token never feeds the prefix stream: its whole expert pass runs after the LLM prefill
+      } else if (li == 0 || !e.fuse_norm)  // (fused: the proprio encoder output has no producer epilogue -> plain RMSNorm)
         VL_TRY(block_pre(e.exp[li], e.xp, e.xpn, e.qp, B, nullptr, c.hidden_e, e.pb.prop_pos, e.pb.prop_kvrow, li));
       else
         VL_TRY(exp_pre(li, e.xpn, e.qp, B, e.pb.prop_pos, e.pb.prop_kvrow, 0));
@@ -795,7 +891,7 @@ struct Run {
       const size_t off = (size_t)li * c.n_kv_heads * e.kv_rows * 128;
       ap.q = e.q;
       ap.q_row_stride = e.qdim;
-      ap.q2 = e.qp;
+      ap.q2 = mega() ? nullptr : e.qp;
       ap.q2_row_stride = e.qdim;
       ap.k = e.kc + off;
       ap.v = e.vc + off;
@@ -809,7 +905,7 @@ struct Run {
       ap.q_len = e.pb.valid_len;
       ap.kv_start = e.pb.kvoff;
       ap.kv_len = e.pb.pre_kv_len;
-      ap.max_q_len = e.S + 1;
+      ap.max_q_len = e.S + (mega() ? 0 : 1);
       ap.group = c.n_heads / c.n_kv_heads;
       ap.n_kv_heads = c.n_kv_heads;
       ap.batch = B;
@@ -817,9 +913,13 @@ struct Run {
       VL_TRY(attention_launch(ap, 128, st));
       e.launches++;
       VL_TRY(block_post(e.llm[li], e.xv, e.xn, e.ao, e.act, cap, e.pb.m_tot, c.hidden, c.mlp, 1, &e.xv_otm));
+      if (mega()) continue;
       if (e.fuse_norm) VL_TRY(exp_post(li, e.xp, e.xpn, e.aop, e.actp, B, 0, false));
       else VL_TRY(block_post(e.exp[li], e.xp, e.xpn, e.aop, e.actp, B, nullptr, c.hidden_e, c.mlp_e, 32, &e.xp_otm));
     }
+    if (mega())
+      VL_TRY(expert_pass(0, B, e.xp, e.xp_otm, e.xpn, e.qp, e.aop, e.actp, e.pb.prop_pos, e.pb.prop_kvrow, e.pb.prop_q_start,
+                         e.pb.prop_q_len, e.pb.prop_kv_len, 1, true));
     return 0;
   }
 
@@ -838,9 +938,12 @@ struct Run {
     e3.out = e.xa;
     e3.ldo = he;
     e3.bias = e.ae_b3;
-    if (e.fuse_norm) norm_producer(e3, e.xan, e.exp[0].ln_in, step + 1, 0);
+    if (e.fuse_norm && !mega()) norm_producer(e3, e.xan, e.exp[0].ln_in, step + 1, 0);
     VL_TRY(gemm(e.h2, e.ae_w3, M, nullptr, EPI_STORE_F32, e3));
-    for (int li = 0; li < c.layers; ++li) {
+    if (mega())
+      VL_TRY(expert_pass(step + 1, M, e.xa, e.xa_otm, e.xan, e.qa, e.aoa, e.acta, e.pb.act_pos, e.pb.act_kvrow, e.pb.den_q_start,
+                         e.pb.den_q_len, e.pb.den_kv_len, e.H, false));
+    for (int li = 0; li < (mega() ? 0 : c.layers); ++li) {
       if (e.fuse_norm) VL_TRY(exp_pre(li, e.xan, e.qa, M, e.pb.act_pos, e.pb.act_kvrow, step + 1));
       else VL_TRY(block_pre(e.exp[li], e.xa, e.xan, e.qa, M, nullptr, he, e.pb.act_pos, e.pb.act_kvrow, li));
       AttnParams ap;
@@ -881,6 +984,7 @@ struct Run {
                        c.image_token_index, c.pad_token_id, st));
     VL_TRY(convert_launch(e.in_noise, io, e.action, DT_F32, (long long)B * e.H * c.action_dim, st));
     if (e.fuse_norm) VL_CUDA_CHECK(cudaMemsetAsync(e.ss, 0, e.ss_floats * sizeof(float), st));
+    VL_CUDA_CHECK(cudaMemsetAsync(e.xp_bar, 0, sizeof(unsigned int) * (size_t)(c.num_inference_steps + 1) * 7 * c.layers, st));
     e.launches += 5;
     VL_TRY(vit());
     if (e.stop_after == 1) return 0;
@@ -998,10 +1102,13 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_timing" || k == "expert_flags") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
+    else if (k == "expert_mega") h->e.mega = (int)value;
+    else if (k == "expert_timing") h->e.xp_time = (int)value;
+    else if (k == "expert_flags") h->e.xp_flags = (int)value;
     else if (k == "pair_gemm") h->e.pair_gemm = (int)value;
     else if (k == "tma_epi") h->e.tma_epi = (int)value;
     else if (k == "pair_min_tiles") h->e.pair_min_tiles = (int)value;
@@ -1126,6 +1233,7 @@ int64_t vlaser_debug_copy(vlaser_t* h, const char* name, void* host_dst, int64_t
   else if (n == "kvoff") src = e.pb.kvoff, bytes = (size_t)e.Bc * 4;
   else if (n == "img_row_map") src = e.pb.img_row_map, bytes = Ni * e.T * 4;
   else if (n == "row_src") src = e.pb.row_src, bytes = (size_t)e.Bc * e.S * 4;
+  else if (n == "expert_timing") src = e.xp_timing, bytes = (size_t)(c.num_inference_steps + 1) * 7 * c.layers * 8;
   else if (n == "kv_rows") {
     const int64_t v = e.kv_rows;
     if (host_dst && max_bytes >= 8) memcpy(host_dst, &v, 8);
@@ -1162,15 +1270,16 @@ int32_t vlaser_profile_read(vlaser_t* h, double* gemm_ms, double* gemm_flops, in
   return 0;
 }
 
-int32_t vlaser_profile_read_classes(vlaser_t* h, double* out8) {
-  VL_CHECK(h && out8, "null argument");
+int32_t vlaser_profile_read_classes(vlaser_t* h, double* out12) {
+  VL_CHECK(h && out12, "null argument");
   Engine& e = h->e;
   VL_CUDA_CHECK(cudaDeviceSynchronize());
-  for (int i = 0; i < 8; ++i) out8[i] = 0.0;
+  double* out8 = out12;
+  for (int i = 0; i < 12; ++i) out12[i] = 0.0;
   for (size_t i = 0; i + 1 < e.prof_used; i += 2) {
     float t = 0;
     VL_CUDA_CHECK(cudaEventElapsedTime(&t, e.prof_events[i], e.prof_events[i + 1]));
-    const int c = e.prof_class[i / 2] ? 1 : 0;
+    const int c = std::min(std::max(e.prof_class[i / 2], 0), 2);
     out8[4 * c + 0] += t;
     out8[4 * c + 1] += e.prof_flops[i / 2];
     out8[4 * c + 2] += e.prof_bytes[i / 2];

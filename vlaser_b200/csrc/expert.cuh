@@ -1,0 +1,68 @@
+// Persistent "expert stream" kernel: ONE launch runs a whole pass of the action-expert transformer
+// (joint_model.py:124-260 restricted to one mixture; pizero_internvl.py:884-912 calls it once per Euler step)
+// over a small row count M (B proprio tokens in the prefill, B*H action tokens in a denoise step):
+//
+//   for each layer:  RMSNorm -> q|k|v GEMM (+bias, RoPE, KV-cache write) -> attention over the cached prefix KV
+//                    -> o-proj (+residual) -> RMSNorm -> gate/up GEMM + SwiGLU -> down-proj (+residual)
+//
+// At M <= 512 every one of these is a few microseconds of work; launched as separate kernels the pass is bound
+// by launch / prologue / drain latency (7 kernels x 28 layers x 10 steps), not by HBM or the tensor pipe. Here the
+// 148 CTAs stay resident, keep their smem ring, mbarriers and TMEM allocation across phases, prefetch the next
+// phase's weight tiles while the grid barrier between two phases settles, and hand activations to each other
+// through L2.
+#pragma once
+#include "attention.cuh"
+#include "gemm.cuh"
+
+namespace vlaser {
+
+// Per-layer operands, resident in device memory (array of `layers` entries, 64-byte aligned for the tensor maps).
+struct alignas(64) ExpertLayerDev {
+  CUtensorMap tm_qkv, tm_o, tm_gu, tm_down;  // W operands, [N, K] bf16, box 128 rows x 64
+  const float* ln_in;
+  const float* ln_post;
+  const float* bqkv;
+  const void* pad_[5];
+};
+
+struct ExpertPass {
+  const ExpertLayerDev* layers = nullptr;
+  int n_layers = 0;
+  int last_kv_only = 0;  // 1: the last layer stops after its K/V are cached (joint_model.py:192-193, 690-691)
+  int M = 0;             // live rows
+  int he = 0, mlp = 0;   // hidden width / MLP width of the expert
+  int n_q_heads = 0, n_kv_heads = 0;  // head_dim is 128
+  float eps = 1e-6f;
+  float* x = nullptr;                 // [M, he] fp32 residual stream (in/out)
+  __nv_bfloat16* xn = nullptr;        // [Mpad, he]   normalised rows (GEMM A operand, tmXn)
+  __nv_bfloat16* q = nullptr;         // [M, n_q_heads*128]
+  __nv_bfloat16* ao = nullptr;        // [Mpad, n_q_heads*128] attention output (tmAo)
+  __nv_bfloat16* act = nullptr;       // [Mpad, mlp] SwiGLU output (tmAct)
+  // RoPE + KV cache of this pass' rows
+  const int* row_pos = nullptr;
+  const int* row_kvrow = nullptr;
+  const float* cos_tab = nullptr;
+  const float* sin_tab = nullptr;
+  __nv_bfloat16* k_cache = nullptr;   // layer 0; [layer][kv_head][rows][128]
+  __nv_bfloat16* v_cache = nullptr;
+  long long kv_layer_stride = 0;      // elements between layers
+  long long kv_head_stride = 0;       // elements between kv heads
+  // attention segments (per sample)
+  const int* q_start = nullptr;
+  const int* q_len = nullptr;
+  const int* kv_start = nullptr;
+  const int* kv_len = nullptr;
+  int max_q_len = 0;
+  int batch = 0;
+  float scale = 1.f;
+  int flags = 0;                      // profiling aids (wrong results!): 1 = drop the residual red.adds, 2 = skip attention
+  long long* timing = nullptr;        // optional [7 * n_layers]: globaltimer (ns) at which CTA 0 saw each phase complete
+  unsigned int* barrier = nullptr;    // grid-barrier arrival counters of this pass, [7 * n_layers], zero on entry
+};
+
+// tmXn / tmAo / tmAct: A-operand maps (box 128 rows x 64) of p.xn / p.ao / p.act; tmX: output map of the fp32 residual
+// stream p.x (make_tmap_out, box 32 rows x 32 columns) through which the split-K partial sums are reduce-added.
+int expert_pass_launch(const ExpertPass& p, const CUtensorMap& tmXn, const CUtensorMap& tmAo, const CUtensorMap& tmAct,
+                       const CUtensorMap& tmX, cudaStream_t stream);
+
+}  // namespace vlaser

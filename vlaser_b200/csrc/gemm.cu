@@ -9,6 +9,7 @@
 // The live row count M may come from device memory (var-len packed prefix), which keeps every
 // launch configuration static and the whole policy call CUDA-graph capturable.
 #include "gemm.cuh"
+#include "gemm_epilogue.cuh"
 
 #include <mutex>
 
@@ -16,8 +17,6 @@ namespace vlaser {
 
 namespace {
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;
 constexpr int EPI_WARPS = 8;                        // two warps per TMEM lane quarter, each drains half the columns
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
 
@@ -59,239 +58,6 @@ __device__ __forceinline__ TileSched make_sched(const GemmDims& d, int M) {
   return s;
 }
 
-// ------------------------------------------------------------------------------------------
-// Fused epilogue on one 32-column chunk `v` of one row (plus a partner chunk `w` for the
-// epilogues that combine two chunks: SwiGLU gate/up, RoPE x[i] / x[i+64]).
-//   col0  : global column of v[0];  for SWIGLU w starts at col0+32, for ROPE at col0+64.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
-  uint4* p = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 u;
-    u.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
-    u.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-    u.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
-    u.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
-    p[i] = u;
-  }
-}
-
-__device__ __forceinline__ void add_vec32(float (&v)[32], const float* __restrict__ src) {
-  const float4* p = reinterpret_cast<const float4*>(src);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float4 b = __ldg(p + i);
-    v[4 * i + 0] += b.x;
-    v[4 * i + 1] += b.y;
-    v[4 * i + 2] += b.z;
-    v[4 * i + 3] += b.w;
-  }
-}
-
-// a_next[row, col0..col0+31] = bf16(v * gamma_next), returns sum v^2 (fused RMSNorm producer side)
-__device__ __forceinline__ float norm_out_chunk(const EpiParams& ep, int row, int col0, const float (&v)[32]) {
-  float ss = 0.f;
-  float y[32];
-  const float4* g4 = reinterpret_cast<const float4*>(ep.gamma_next + col0);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float4 g = __ldg(g4 + i);
-    ss += (v[4 * i] * v[4 * i] + v[4 * i + 1] * v[4 * i + 1]) + (v[4 * i + 2] * v[4 * i + 2] + v[4 * i + 3] * v[4 * i + 3]);
-    y[4 * i + 0] = v[4 * i + 0] * g.x;
-    y[4 * i + 1] = v[4 * i + 1] * g.y;
-    y[4 * i + 2] = v[4 * i + 2] * g.z;
-    y[4 * i + 3] = v[4 * i + 3] * g.w;
-  }
-  store_bf16x32(ep.a_next + (size_t)row * ep.lda_next + col0, y);
-  return ss;
-}
-
-// `rstd`: per-row scale of the accumulator (fused RMSNorm consumer side, 1 when unused);
-// `ss`: per-thread running sum of squares of the produced row (producer side).
-template <int EPI>
-__device__ __forceinline__ void epi_chunk(const EpiParams& ep, int N, int row, bool row_ok, int col0, float (&v)[32],
-                                          float (&w)[32], bool first_split, bool atomic, float rstd, float& ss) {
-  if (ep.row_ss) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= rstd;
-    if constexpr (EPI == EPI_SWIGLU_BF16 || EPI == EPI_QKV_ROPE) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) w[j] *= rstd;
-    }
-  }
-  if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_SILU_BF16) {
-    if (ep.bias) add_vec32(v, ep.bias + col0);
-    if constexpr (EPI == EPI_GELU_BF16) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
-    }
-    if constexpr (EPI == EPI_SILU_BF16) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
-    }
-    if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + col0, v);
-  } else if constexpr (EPI == EPI_RESID_F32) {
-    if (ep.bias && first_split) add_vec32(v, ep.bias + col0);
-    if (ep.scale) {
-      const float4* sp = reinterpret_cast<const float4*>(ep.scale + col0);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 s = __ldg(sp + i);
-        v[4 * i + 0] *= s.x;
-        v[4 * i + 1] *= s.y;
-        v[4 * i + 2] *= s.z;
-        v[4 * i + 3] *= s.w;
-      }
-    }
-    if (row_ok) {
-      float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0;
-      if (atomic) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(v[4 * i]),
-                       "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
-                       : "memory");
-      } else {
-        float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 x = o4[i];
-          x.x += v[4 * i + 0];
-          x.y += v[4 * i + 1];
-          x.z += v[4 * i + 2];
-          x.w += v[4 * i + 3];
-          o4[i] = x;
-          v[4 * i + 0] = x.x;
-          v[4 * i + 1] = x.y;
-          v[4 * i + 2] = x.z;
-          v[4 * i + 3] = x.w;
-        }
-        if (ep.a_next) ss += norm_out_chunk(ep, row, col0, v);
-      }
-    }
-  } else if constexpr (EPI == EPI_SWIGLU_BF16) {
-    // v = gate chunk (cols col0..col0+31), w = up chunk (col0+32..); output column col0/2.
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = silu(v[j]) * w[j];
-    if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + (col0 >> 1), v);
-  } else if constexpr (EPI == EPI_QKV_ROPE) {
-    // one head = 128 columns; v = x[i0..i0+31], w = x[i0+64..i0+95] of that head, i0 in {0,32}.
-    const int head = col0 >> 7;
-    const int i0 = col0 & 127;
-    if (ep.bias) {
-      add_vec32(v, ep.bias + col0);
-      add_vec32(w, ep.bias + col0 + 64);
-    }
-    const bool is_q = head < ep.n_q_heads;
-    const bool is_k = !is_q && head < ep.n_q_heads + ep.n_kv_heads;
-    if (row_ok) {
-      if (is_q || is_k) {
-        const int pos = ep.row_pos[row];
-        const float4* c4 = reinterpret_cast<const float4*>(ep.cos_tab + (size_t)pos * 64 + i0);
-        const float4* s4 = reinterpret_cast<const float4*>(ep.sin_tab + (size_t)pos * 64 + i0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 c = __ldg(c4 + i), s = __ldg(s4 + i);
-          const float cc[4] = {c.x, c.y, c.z, c.w};
-          const float ss[4] = {s.x, s.y, s.z, s.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float a = v[4 * i + e], b = w[4 * i + e];
-            v[4 * i + e] = a * cc[e] - b * ss[e];   // x*cos + rot(x)*sin, rot(x)[i] = -x[i+64]
-            w[4 * i + e] = b * cc[e] + a * ss[e];   //                     rot(x)[i+64] = x[i]
-          }
-        }
-      }
-      __nv_bfloat16* dst;
-      if (is_q) {
-        dst = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + head * 128 + i0;
-      } else {
-        const int kvh = is_k ? head - ep.n_q_heads : head - ep.n_q_heads - ep.n_kv_heads;
-        __nv_bfloat16* base = is_k ? ep.k_cache : ep.v_cache;
-        dst = base + (size_t)kvh * ep.kv_head_stride + (size_t)ep.row_kvrow[row] * 128 + i0;
-      }
-      store_bf16x32(dst, v);
-      store_bf16x32(dst + 64, w);
-    }
-  } else if constexpr (EPI == EPI_PATCH_EMBED) {
-    if (ep.bias) add_vec32(v, ep.bias + col0);
-    const int img = row / ep.patches, p = row - img * ep.patches;
-    if (row_ok) {
-      add_vec32(v, ep.pos_emb + (size_t)(1 + p) * N + col0);
-      float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) +
-                                             (size_t)(img * (ep.patches + 1) + 1 + p) * ep.ldo + col0);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    }
-  } else if constexpr (EPI == EPI_STORE_F32) {
-    if (ep.bias) add_vec32(v, ep.bias + col0);
-    if (row_ok) {
-      const int dr = ep.row_map ? ep.row_map[row] : row;
-      if (dr >= 0) {
-        float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)dr * ep.ldo + col0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        if (ep.a_next) ss += norm_out_chunk(ep, dr, col0, v);
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// One epilogue warp's share of an accumulator tile: TMEM lane quarter `taddr` (32 rows, one per lane), column
-// half `half` of the BN-wide tile. Units of 32 (plain), 64 (SwiGLU gate|up) or 2x32 (RoPE x[i], x[i+64]) columns.
-// ------------------------------------------------------------------------------------------
-template <int BN, int EPI, int PARTS = 2>
-__device__ __forceinline__ void epilogue_tile(const EpiParams& ep, int N, uint32_t taddr, int half, int row, bool row_ok,
-                                              int n0, bool first_split, bool atomic, float rstd, float& ss) {
-  if constexpr (EPI == EPI_SWIGLU_BF16) {
-    constexpr int U = BN / 64 / PARTS;
-#pragma unroll 1
-    for (int c = half * U; c < (half + 1) * U; ++c) {
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32(taddr + c * 64, r0);
-      tmem_ld_32x32(taddr + c * 64 + 32, r1);
-      tmem_ld_wait();
-      float v[32], w[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] = __uint_as_float(r0[j]);
-        w[j] = __uint_as_float(r1[j]);
-      }
-      epi_chunk<EPI>(ep, N, row, row_ok, n0 + c * 64, v, w, first_split, atomic, rstd, ss);
-    }
-  } else if constexpr (EPI == EPI_QKV_ROPE) {
-    constexpr int U = BN / 64 / PARTS;  // unit u: head u>>1, half-head chunk u&1
-#pragma unroll 1
-    for (int u = half * U; u < (half + 1) * U; ++u) {
-      const int off = (u >> 1) * 128 + (u & 1) * 32;
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32(taddr + off, r0);
-      tmem_ld_32x32(taddr + off + 64, r1);
-      tmem_ld_wait();
-      float v[32], w[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] = __uint_as_float(r0[j]);
-        w[j] = __uint_as_float(r1[j]);
-      }
-      epi_chunk<EPI>(ep, N, row, row_ok, n0 + off, v, w, first_split, atomic, rstd, ss);
-    }
-  } else {
-    constexpr int U = BN / 32 / PARTS;
-#pragma unroll 1
-    for (int c = half * U; c < (half + 1) * U; ++c) {
-      uint32_t r0[32];
-      tmem_ld_32x32(taddr + c * 32, r0);
-      tmem_ld_wait();
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
-      epi_chunk<EPI>(ep, N, row, row_ok, n0 + c * 32, v, v, first_split, atomic, rstd, ss);
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------
 // tcgen05 kernel
@@ -561,32 +327,6 @@ template <int EPI>
 __device__ __forceinline__ constexpr bool epi_has_tma_out() {
   return EPI == EPI_STORE_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_SILU_BF16 || EPI == EPI_RESID_F32 ||
          EPI == EPI_SWIGLU_BF16;
-}
-
-__device__ __forceinline__ void stage_row_f32(uint8_t* buf, int lane, const float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-}
-// 32 bf16 outputs = chunks [j0, j0+4) of the 128-byte row
-__device__ __forceinline__ void stage_row_bf16(uint8_t* buf, int lane, int j0, const float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 u;
-    u.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-    u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-    u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-    u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-    *reinterpret_cast<uint4*>(buf + lane * 128 + (((j0 + j) ^ (lane & 7)) << 4)) = u;
-  }
-}
-__device__ __forceinline__ void load_acc32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  tmem_ld_32x32(taddr, r);
-  tmem_ld_wait();
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
 
 template <int BN, int EPI, int PARTS, int NBUF>

@@ -290,11 +290,12 @@ class PiZeroInference:
         return ms.value, fl.value, n.value
 
     def profile_read_classes(self):
-        """{"single": {...}, "pair": {...}} with ms / flops / bytes / launches since "profile_gemm" was switched on."""
-        buf = (C.c_double * 8)()
+        """{"single": {...}, "pair": {...}, "expert": {...}} with ms / flops / bytes / launches since "profile_gemm" was
+        switched on ("expert" = the persistent expert-stream kernel, one launch per pass)."""
+        buf = (C.c_double * 12)()
         _lib.check(self._lib.vlaser_profile_read_classes(self._handle, buf), "profile_read_classes")
         keys = ("ms", "flops", "bytes", "launches")
-        return {"single": dict(zip(keys, buf[0:4])), "pair": dict(zip(keys, buf[4:8]))}
+        return {"single": dict(zip(keys, buf[0:4])), "pair": dict(zip(keys, buf[4:8])), "expert": dict(zip(keys, buf[8:12]))}
 
     def last_launch_count(self) -> int:
         return int(self._lib.vlaser_last_launch_count(self._handle))
