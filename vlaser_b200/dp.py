@@ -57,10 +57,14 @@ def gather_actions(local_actions: torch.Tensor, batch: int, group=None) -> torch
                           device=local_actions.device)
         dist.all_gather_into_tensor(out, local_actions.contiguous(), group=group)
         return out
-    chunks = [torch.empty((hi - lo,) + tuple(local_actions.shape[1:]), dtype=local_actions.dtype,
-                          device=local_actions.device) for lo, hi in sizes]
-    dist.all_gather(chunks, local_actions.contiguous(), group=group)
-    return torch.cat(chunks, dim=0)
+    # ragged split: still ONE fixed-size collective -- pad every shard to the largest one, drop the pad rows after
+    rows = max(hi - lo for lo, hi in sizes)
+    tail = tuple(local_actions.shape[1:])
+    padded = local_actions.new_zeros((rows,) + tail)
+    padded[: local_actions.shape[0]] = local_actions
+    out = local_actions.new_empty((world * rows,) + tail)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * rows: r * rows + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], dim=0)
 
 
 def infer_action_dp(policy_fn: Callable[..., torch.Tensor], inputs: Dict[str, torch.Tensor], num_images: int,
