@@ -64,7 +64,7 @@ __device__ __forceinline__ GemmPhase gemm_phase(const ExpertPass& p, const CUten
 struct Sched {
   int m_groups, base, kb_per_split, k_blocks, total;
 };
-__device__ __forceinline__ Sched make_sched(const GemmPhase& g, int M) {
+__device__ __forceinline__ Sched make_sched(const GemmPhase& g, int M, int flags = 0) {
   Sched s;
   s.m_groups = (M + g.MT * BLOCK_M - 1) / (g.MT * BLOCK_M);
   s.k_blocks = g.K / BLOCK_K;
@@ -76,7 +76,7 @@ __device__ __forceinline__ Sched make_sched(const GemmPhase& g, int M) {
   }
   s.kb_per_split = (s.k_blocks + splits - 1) / splits;
   splits = (s.k_blocks + s.kb_per_split - 1) / s.kb_per_split;
-  s.total = s.base * splits;
+  s.total = (flags & 4) ? 0 : s.base * splits;  // flag 4 (profiling aid): barrier skeleton only
   return s;
 }
 struct Tile {
@@ -190,7 +190,7 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
           if (kv_only && j != PH_QKV) break;
           const unsigned int ph = (unsigned int)(layer * XP_PHASES + j);
           const GemmPhase g = gemm_phase(p, &tmXn, &tmAo, &tmAct, layer, j);
-          const Sched sc = make_sched(g, p.M);
+          const Sched sc = make_sched(g, p.M, p.flags);
           const uint32_t tx = (uint32_t)(g.MT + 1) * XP_SUB;
           bool open = false;
           int npend = 0;
@@ -252,7 +252,7 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
           const int j = jj == 0 ? PH_QKV : jj == 1 ? PH_O : jj == 2 ? PH_GU : PH_DOWN;
           if (kv_only && j != PH_QKV) break;
           const GemmPhase g = gemm_phase(p, &tmXn, &tmAo, &tmAct, layer, j);
-          const Sched sc = make_sched(g, p.M);
+          const Sched sc = make_sched(g, p.M, p.flags);
           for (int t = blockIdx.x; t < sc.total; t += (int)G) {
             const Tile tc = tile_of(sc, t);
             mbar_wait_guard(&tempty_bar[as], aphase ^ 1);
@@ -326,7 +326,7 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
           const float* gamma = j == PH_NORM1 ? L->ln_in : L->ln_post;
           const int nch = p.he >> 7;  // float4 chunks per lane
           const float inv_w = 1.0f / (float)p.he;
-          for (int r = (int)blockIdx.x + (int)G * wwarp; r < p.M; r += (int)G * XP_WORKER_WARPS) {
+          for (int r = (int)blockIdx.x + (int)G * wwarp; r < ((p.flags & 8) ? 0 : p.M); r += (int)G * XP_WORKER_WARPS) {
             const float4* src = reinterpret_cast<const float4*>(p.x + (size_t)r * p.he);
             float4 v[8];
             float qs = 0.f;
@@ -386,7 +386,7 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
         } else {
           // ---- GEMM epilogue
           const GemmPhase g = gemm_phase(p, &tmXn, &tmAo, &tmAct, layer, j);
-          const Sched sc = make_sched(g, p.M);
+          const Sched sc = make_sched(g, p.M, p.flags);
           EpiParams ep;
           if (j == PH_QKV) {
             ep.out = p.q;

@@ -55,7 +55,8 @@ struct ExpertPass {
   int max_q_len = 0;
   int batch = 0;
   float scale = 1.f;
-  int flags = 0;                      // profiling aids (wrong results!): 1 = drop the residual red.adds, 2 = skip attention
+  int flags = 0;                      // profiling aids (wrong results!): 1 = drop the residual red.adds, 2 = skip attention,
+                                      // 4 = no GEMM tiles, 8 = no norm rows (2|4|8 = the bare grid-barrier skeleton)
   long long* timing = nullptr;        // optional [7 * n_layers]: globaltimer (ns) at which CTA 0 saw each phase complete
   unsigned int* barrier = nullptr;    // grid-barrier arrival counters of this pass, [7 * n_layers], zero on entry
 };
