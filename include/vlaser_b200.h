@@ -92,6 +92,8 @@ void vlaser_destroy(vlaser_t* h);
 /* Options: "pdl" (process-wide; 0 off, 1 (default) programmatic dependent launch inside the denoise steps, 2 everywhere),
  * "pair_gemm" (default 1: large-M GEMMs on the cta_group::2 kernel), "fuse_norm" (default 0; 1 fuses the expert streams' RMSNorm across the GEMM chain), "exp_stages" (smem ring depth
  * of the expert GEMMs, 0 = default),
+ * "expert_mega" (default 1: each proprio / denoise pass of the action expert is ONE persistent kernel, csrc/expert.cu),
+ * "expert_streams" (default 2: independent sub-grids of that kernel, each owning a slice of the batch),
  * "use_graph" (default 1: replay the whole call as one CUDA graph per batch size),
  * "stop_after" (debug: 0 all, 1 ViT, 2 prefix embedding, 3 prefill, 4 first denoise step),
  * "simt_gemm" (debug/tests: route GEMMs through the CUDA-core cross-check kernel),
@@ -182,6 +184,32 @@ int32_t vlaser_op_euler_step(const float* x, const float* gamma, const float* Wd
                              void* out, int32_t out_dtype, int32_t rows, int32_t width, int32_t A, int32_t H,
                              int32_t horizon, float dt, float eps, int32_t last_step, int32_t do_clip, float clip,
                              void* stream);
+
+/* ---- either side of infer_action -------------------------------------------------
+ * Input staging — replaces, for a whole batch on the device, `cv2.resize(image, image_size, INTER_LANCZOS4)` +
+ * the optional centre crop (Vlaser_VLA/Simpler/src/agent/env_adapter/simpler.py:70-84) and `process_images`
+ * (src/model/vla/processing.py:27-63, mean/std :303-304).
+ *   frames        u8 device pointer, [n, src_h, src_w, 3] (layout 0, as the simulator returns them) or
+ *                 [n, 3, src_h, src_w] (layout 1)
+ *   center_crop   1 = the CENTER_CROP branch (crop to min(h, w) around the centre before the resize)
+ *   pixel_values  out_dtype [n, 3, px, px]: exactly what vlaser_infer_action takes
+ *   mean3/std3    HOST pointers to 3 floats, or NULL for the ImageNet constants of processing.py
+ * The 8-bit Lanczos4 resize is bit-exact with OpenCV's; the normalisation is bit-exact with the reference's float32
+ * arithmetic followed by the cast to out_dtype. */
+int32_t vlaser_op_stage_frames(const uint8_t* frames, int32_t n, int32_t src_h, int32_t src_w, int32_t layout,
+                               int32_t center_crop, void* pixel_values, int32_t out_dtype, int32_t px, const float* mean3,
+                               const float* std3, void* stream);
+/* Action post-processing — `SimplerAdapter.postprocess` for n_env environments at once (simpler.py:136-177;
+ * de-normalisation base.py:21-49; euler2axangle src/utils/geometry.py:261-434; gripper rules simpler.py:217-221
+ * (gripper 0, Bridge) and :259-286 (gripper 1, EDR sticky gripper)). All pointers are DEVICE pointers.
+ *   actions       dtype [n_env, T, 7] normalised action chunks (the output of vlaser_infer_action)
+ *   norm          0 = "bound": stat_a = p01, stat_b = p99; 1 = "gaussian": stat_a = mean, stat_b = std (f64 [7])
+ *   sticky_state  f64 [n_env, 3] = {sticky_action_is_on, gripper_action_repeat, sticky_gripper_action}, zero after
+ *                 reset(); read and updated (gripper 1 only; may be NULL otherwise)
+ *   out           f64 [n_env, T, 7] = (xyz, axis * angle, gripper), float64 like the reference's numpy */
+int32_t vlaser_op_postprocess_actions(const void* actions, int32_t dtype, int32_t n_env, int32_t T, int32_t A, int32_t norm,
+                                      const double* stat_a, const double* stat_b, int32_t gripper, int32_t sticky_repeat,
+                                      double* sticky_state, double* out, void* stream);
 
 #ifdef __cplusplus
 }

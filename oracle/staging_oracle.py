@@ -36,7 +36,7 @@ def lanczos4_coeffs(x: np.float32) -> np.ndarray:
     cs = ((1, 0), (-s45, -s45), (0, 1), (s45, -s45), (-1, 0), (s45, s45), (0, -1), (-s45, s45))
     x = np.float32(x)
     coeffs = np.zeros(8, np.float32)
-    y0 = -(float(x) + 3.0) * math.pi * 0.25
+    y0 = -float(np.float32(x + np.float32(3))) * math.pi * 0.25   # (x+3) is a float expression in OpenCV
     s0, c0 = math.sin(y0), math.cos(y0)
     total = np.float32(0)
     for i in range(8):

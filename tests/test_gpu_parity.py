@@ -214,5 +214,13 @@ def test_full_size_2b_bench_batch_expert_stream():
     pol.set_option("expert_mega", 1)
     assert torch.isfinite(a1).all()
     assert max_err(a1, a0) <= ACTION_TOL
-    one = {k: v[7:8] for k, v in inp.items() if k in ("input_ids", "pixel_values", "proprios", "noise")}
-    assert max_err(_run(pol, one, dtype=torch.bfloat16), a1[7:8]) <= ACTION_TOL
+    # independent sub-grids of the expert-stream kernel (1 = whole grid, 2 = 2 x 128 rows, 4 = 4 x 64 rows)
+    for streams in (1, 2, 4):
+        pol.set_option("expert_streams", streams)
+        a_s = _run(pol, inp, dtype=torch.bfloat16)
+        assert torch.isfinite(a_s).all()
+        assert max_err(a_s, a0) <= ACTION_TOL, streams
+    pol.set_option("expert_streams", 2)
+    for b in (7, 40, 63):   # one sample of each sub-grid (and the last row of the batch) run alone
+        one = {k: v[b:b + 1] for k, v in inp.items() if k in ("input_ids", "pixel_values", "proprios", "noise")}
+        assert max_err(_run(pol, one, dtype=torch.bfloat16), a1[b:b + 1]) <= ACTION_TOL

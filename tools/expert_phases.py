@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--config", default="vlaser_2b_bridge")
 ap.add_argument("--flags", default="0", help="comma list of expert_flags values to time (profiling aids)")
+ap.add_argument("--streams", default="", help="comma list of expert_streams values (sub-grids); stamps are those of sub-grid 0")
 a = ap.parse_args()
 cfg = PRESETS[a.config]()
 dev = torch.device("cuda", 0)
@@ -28,7 +29,12 @@ ids, pix = inp["input_ids"].to(dev), inp["pixel_values"].to(torch.bfloat16).to(d
 prop, noise = inp["proprios"].to(torch.bfloat16).to(dev), inp["noise"].to(torch.bfloat16).to(dev)
 L, P = cfg.layers, 7
 names = ["norm1", "qkv", "attn", "o", "norm2", "gate_up", "down"]
-for fl in [int(x) for x in a.flags.split(",")]:
+runs = [(int(f), None) for f in a.flags.split(",")] if not a.streams else \
+    [(int(f), int(st)) for st in a.streams.split(",") for f in a.flags.split(",")]
+for fl, st in runs:
+  if st is not None:
+      pol.set_option("expert_streams", st)
+      print(f"######## expert_streams = {st}")
   pol.set_option("expert_timing", 1)
   pol.set_option("expert_flags", fl)
   for _ in range(3):

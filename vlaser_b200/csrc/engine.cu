@@ -130,6 +130,8 @@ struct Engine {
   // persistent expert-stream kernel (expert.cu): per-layer operand table and one grid-barrier counter per pass
   ExpertLayerDev* xp_layers = nullptr;
   unsigned int* xp_bar = nullptr;
+  size_t xp_bar_words() const { return (size_t)EXPERT_MAX_STREAMS * 7 * c.layers; }  // barrier counters of one pass
+  int xp_streams = 2;              // sub-grids of the expert-stream kernel (option "expert_streams"), when the rows allow
   long long* xp_timing = nullptr;  // [(steps+1)][7*layers] phase-completion timestamps, filled when xp_time is set
   int xp_time = 0, xp_flags = 0;
   PlanBuffers pb{};
@@ -389,7 +391,7 @@ int engine_build(Engine& e) {
   VL_TRY(e.alloc(&e.ss, e.ss_floats));
   VL_TRY(e.alloc(&e.tile_ctr, 4096));
   VL_TRY(e.alloc(&e.xp_layers, (size_t)c.layers));
-  VL_TRY(e.alloc(&e.xp_bar, (size_t)(c.num_inference_steps + 1) * 7 * c.layers));
+  VL_TRY(e.alloc(&e.xp_bar, (size_t)(c.num_inference_steps + 1) * e.xp_bar_words()));
   VL_TRY(e.alloc(&e.xp_timing, (size_t)(c.num_inference_steps + 1) * 7 * c.layers));
   const size_t kv_elems = (size_t)c.layers * c.n_kv_heads * e.kv_rows * 128;
   VL_TRY(e.alloc(&e.kc, kv_elems));
@@ -811,6 +813,13 @@ struct Run {
   }
 
   bool mega() const { return e.mega && !e.simt; }
+  // largest power-of-two sub-grid count <= the option that keeps whole samples, a multiple of 32 rows and at least 64
+  // rows per sub-grid
+  int expert_streams(int M, int B) const {
+    int s = std::min(e.xp_streams, (int)EXPERT_MAX_STREAMS);
+    while (s > 1 && !(B % s == 0 && (M / s) % 32 == 0 && M % s == 0 && M / s >= 64)) s >>= 1;
+    return std::max(s, 1);
+  }
 
   // One pass of the expert transformer over M rows as a single persistent kernel (expert.cu). pass 0 = the proprio
   // token of the prefill (its K/V only in the last layer), pass k+1 = the action tokens of Euler step k.
@@ -847,7 +856,8 @@ struct Run {
     p.max_q_len = max_q_len;
     p.batch = B;
     p.scale = 0.08838834764831845f;  // 128^-0.5
-    p.barrier = e.xp_bar + (size_t)pass * 7 * c.layers;
+    p.barrier = e.xp_bar + (size_t)pass * e.xp_bar_words();
+    p.n_streams = expert_streams(M, B);
     p.flags = e.xp_flags;
     p.timing = e.xp_time ? e.xp_timing + (size_t)pass * 7 * c.layers : nullptr;
     e.launches++;
@@ -984,7 +994,7 @@ struct Run {
                        c.image_token_index, c.pad_token_id, st));
     VL_TRY(convert_launch(e.in_noise, io, e.action, DT_F32, (long long)B * e.H * c.action_dim, st));
     if (e.fuse_norm) VL_CUDA_CHECK(cudaMemsetAsync(e.ss, 0, e.ss_floats * sizeof(float), st));
-    VL_CUDA_CHECK(cudaMemsetAsync(e.xp_bar, 0, sizeof(unsigned int) * (size_t)(c.num_inference_steps + 1) * 7 * c.layers, st));
+    VL_CUDA_CHECK(cudaMemsetAsync(e.xp_bar, 0, sizeof(unsigned int) * (size_t)(c.num_inference_steps + 1) * e.xp_bar_words(), st));
     e.launches += 5;
     VL_TRY(vit());
     if (e.stop_after == 1) return 0;
@@ -1102,11 +1112,12 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_timing" || k == "expert_flags") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_timing" || k == "expert_flags") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
     else if (k == "expert_mega") h->e.mega = (int)value;
+    else if (k == "expert_streams") h->e.xp_streams = (int)value;
     else if (k == "expert_timing") h->e.xp_time = (int)value;
     else if (k == "expert_flags") h->e.xp_flags = (int)value;
     else if (k == "pair_gemm") h->e.pair_gemm = (int)value;

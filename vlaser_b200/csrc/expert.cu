@@ -14,6 +14,13 @@
 // o/down projections meet in L2 (red.global.add.f32 into the fp32 residual stream), the following norm phase reads
 // them back with ld.cg.
 // A-operand rows beyond M come from zero-initialised padding of the activation buffers (never written).
+//
+// Sub-grids: every phase of a pass at M <= 512 is latency-bound (ring round trips, epilogue, barrier), not throughput-
+// bound, and samples are independent. With p.n_streams = S > 1 the grid is cut into S independent sub-grids of
+// gridDim.x / S CTAs; sub-grid s owns samples [s * batch/S, ...) = rows [s * M/S, ...) (a multiple of 32 rows, so no
+// 32-row reduce-add box straddles two owners), has its own barrier counters and runs the whole pass on its rows.
+// The sub-grids drift freely against each other, so one sub-grid's GEMM phase fills the SMs and the L2->SM fabric
+// while another sits in a barrier or an epilogue. Each streams the weights itself; the second reader hits L2.
 #include "expert.cuh"
 
 #include "attention_device.cuh"
@@ -34,6 +41,7 @@ constexpr uint32_t XP_OUT_BYTES = XP_WORKER_WARPS * 4096;  // one 32-row x 128-b
 constexpr uint32_t XP_SMEM = XP_RING_BYTES + XP_OUT_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr uint32_t XP_ACC_COLS = 256;                // TMEM columns per accumulator stage (two 128-column sub-tiles)
 constexpr int XP_PHASES = 7;
+constexpr int XP_MAX_STREAMS = EXPERT_MAX_STREAMS;
 enum : int { PH_NORM1 = 0, PH_QKV = 1, PH_ATTN = 2, PH_O = 3, PH_NORM2 = 4, PH_GU = 5, PH_DOWN = 6 };
 
 static_assert(2 * attention_tile_smem<128>() <= (int)XP_RING_BYTES, "attention staging must fit in the idle ring");
@@ -48,11 +56,11 @@ struct GemmPhase {
   int ahead;       // W blocks may be issued before the grid barrier (the ring is not aliased by the previous phase)
 };
 
-__device__ __forceinline__ GemmPhase gemm_phase(const ExpertPass& p, const CUtensorMap* tmXn, const CUtensorMap* tmAo,
-                                                const CUtensorMap* tmAct, int layer, int j) {
+__device__ __forceinline__ GemmPhase gemm_phase(const ExpertPass& p, int rows, const CUtensorMap* tmXn,
+                                                const CUtensorMap* tmAo, const CUtensorMap* tmAct, int layer, int j) {
   const ExpertLayerDev* L = p.layers + layer;
   const int qdim = p.n_q_heads * 128;
-  const int mt = p.M > BLOCK_M ? 2 : 1;
+  const int mt = rows > BLOCK_M ? 2 : 1;
   GemmPhase g;
   if (j == PH_QKV) g = GemmPhase{tmXn, &L->tm_qkv, qdim + 2 * p.n_kv_heads * 128, p.he, 1, EPI_QKV_ROPE, 1, 1};
   else if (j == PH_O) g = GemmPhase{tmAo, &L->tm_o, p.he, qdim, mt, EPI_RESID_F32, 32, 0};  // ring aliased by attention
@@ -64,14 +72,14 @@ __device__ __forceinline__ GemmPhase gemm_phase(const ExpertPass& p, const CUten
 struct Sched {
   int m_groups, base, kb_per_split, k_blocks, total;
 };
-__device__ __forceinline__ Sched make_sched(const GemmPhase& g, int M, int flags = 0) {
+__device__ __forceinline__ Sched make_sched(const GemmPhase& g, int M, int ctas, int flags) {
   Sched s;
   s.m_groups = (M + g.MT * BLOCK_M - 1) / (g.MT * BLOCK_M);
   s.k_blocks = g.K / BLOCK_K;
   s.base = s.m_groups * (g.N / 128);
   int splits = 1;
   if (g.max_splits > 1) {
-    splits = min(min((int)gridDim.x / s.base, g.max_splits), s.k_blocks / 2);  // >= two k-blocks per split
+    splits = min(min(ctas / s.base, g.max_splits), s.k_blocks / 2);  // >= two k-blocks per split
     if (splits < 1) splits = 1;
   }
   s.kb_per_split = (s.k_blocks + splits - 1) / splits;
@@ -96,22 +104,22 @@ __device__ __forceinline__ Tile tile_of(const Sched& s, int t) {
 // ---- grid barrier: one arrival counter per phase (a CTA without work in a GEMM phase arrives at once and may run
 // several phases ahead of a busy one, so a single running sum over phases would not prove that EVERY CTA is done);
 // phase ph may consume other CTAs' output once counter[ph - 1] == gridDim.x
-// Arrival (one thread per CTA, after a CTA barrier over the workers): a single gpu-scope fence is cumulative over the
-// writes of every thread that synchronised with this one. Waiting polls with relaxed loads (an acquire load would
-// invalidate L1 on every iteration) and fences once after the counter is full.
+// Arrival (one thread per CTA, after a CTA barrier over the workers): a gpu-scope release is cumulative over the
+// writes of every thread that synchronised with this one. red.release + ld.acquire polling measured 1.16 us per
+// barrier on 148 CTAs against 1.43 us for fence + relaxed red / relaxed poll + fence and 3.4 us for per-CTA flag
+// words polled by a warp (tools/probes/barrier_probe.cu, profiles/r01_barrier_probe.txt).
 __device__ __forceinline__ void grid_arrive(unsigned int* ctr) {
-  asm volatile("fence.acq_rel.gpu;\n\tred.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
 }
 __device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int target) {
   unsigned int v;
   long long t0 = 0;
   while (true) {
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
     if (v >= target) break;
     if (t0 == 0) t0 = clock64();
     else if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a CTA of the grid is missing; fail loudly, do not hang
   }
-  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 // mbarrier wait that traps instead of hanging the GPU if a pipeline partner never arrives (bring-up insurance: a
 // persistent kernel with a grid barrier must never spin forever)
@@ -151,7 +159,16 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const unsigned int G = gridDim.x;
+  // sub-grid of this CTA: G CTAs, index cta, rows [row_base, row_base + Mg), samples [b_base, b_base + Bg)
+  const int S = p.n_streams > 1 ? p.n_streams : 1;
+  const unsigned int G = gridDim.x / S;
+  const int sg = (int)(blockIdx.x / G);
+  const int cta = (int)(blockIdx.x - sg * G);
+  const bool idle = sg >= S;  // gridDim.x % S left-over CTAs
+  const int rows_sg = p.M / S, batch_sg = p.batch / S;
+  const int row_base = sg * rows_sg, b_base = sg * batch_sg;
+  const int Mg = rows_sg, Bg = batch_sg;
+  unsigned int* const bar = p.barrier + (size_t)sg * XP_PHASES * p.n_layers;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmXn);
@@ -178,7 +195,9 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
 
-  if (warp == 0) {
+  if (idle) {
+    // nothing to do (keeps the TMEM allocation symmetric; falls through to the common exit)
+  } else if (warp == 0) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
       int stage = 0;
@@ -189,8 +208,8 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
           const int j = jj == 0 ? PH_QKV : jj == 1 ? PH_O : jj == 2 ? PH_GU : PH_DOWN;
           if (kv_only && j != PH_QKV) break;
           const unsigned int ph = (unsigned int)(layer * XP_PHASES + j);
-          const GemmPhase g = gemm_phase(p, &tmXn, &tmAo, &tmAct, layer, j);
-          const Sched sc = make_sched(g, p.M, p.flags);
+          const GemmPhase g = gemm_phase(p, Mg, &tmXn, &tmAo, &tmAct, layer, j);
+          const Sched sc = make_sched(g, Mg, (int)G, p.flags);
           const uint32_t tx = (uint32_t)(g.MT + 1) * XP_SUB;
           bool open = false;
           int npend = 0;
@@ -203,7 +222,7 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
           auto open_gate = [&]() {
             // every CTA has published all of its work of the earlier phases (and the previous grid is complete:
             // the workers arrive only after their own griddepcontrol.wait)
-            grid_wait(p.barrier + (ph - 1), G);
+            grid_wait(bar + (ph - 1), G);
             fence_proxy_async_all();  // generic-proxy writes of other SMs -> this thread's async-proxy (TMA) reads
             for (int i = 0; i < npend; ++i) load_a(pend_stage[i], pend_kb[i], pend_row[i]);
             npend = 0;
@@ -212,9 +231,9 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
           // the attention phase stages K/V in the ring: nothing may be loaded (not even by a CTA without o-proj
           // tiles, which would otherwise run ahead into the gate/up weights) before every attention tile is done
           if (j == PH_O) open_gate();
-          for (int t = blockIdx.x; t < sc.total; t += (int)G) {
+          for (int t = cta; t < sc.total; t += (int)G) {
             const Tile tc = tile_of(sc, t);
-            const int row0 = tc.m_grp * g.MT * BLOCK_M;
+            const int row0 = row_base + tc.m_grp * g.MT * BLOCK_M;
             for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
               if (!open && (!g.ahead || npend == XP_STAGES)) open_gate();
               mbar_wait_guard(&empty_bar[stage], phase ^ 1);
@@ -251,9 +270,9 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
         for (int jj = 0; jj < 4; ++jj) {
           const int j = jj == 0 ? PH_QKV : jj == 1 ? PH_O : jj == 2 ? PH_GU : PH_DOWN;
           if (kv_only && j != PH_QKV) break;
-          const GemmPhase g = gemm_phase(p, &tmXn, &tmAo, &tmAct, layer, j);
-          const Sched sc = make_sched(g, p.M, p.flags);
-          for (int t = blockIdx.x; t < sc.total; t += (int)G) {
+          const GemmPhase g = gemm_phase(p, Mg, &tmXn, &tmAo, &tmAct, layer, j);
+          const Sched sc = make_sched(g, Mg, (int)G, p.flags);
+          for (int t = cta; t < sc.total; t += (int)G) {
             const Tile tc = tile_of(sc, t);
             mbar_wait_guard(&tempty_bar[as], aphase ^ 1);
             tc_fence_after();
@@ -308,16 +327,16 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
           // the per-sample segment table is constant: pull this group's first entry into L1 ahead of the barrier
           const int grp0 = wtid >> 7;
           const int qblocks0 = ((p.n_q_heads / p.n_kv_heads) * p.max_q_len + ATT_BM - 1) / ATT_BM;
-          const int it0 = (int)blockIdx.x + (int)G * grp0;
-          if (it0 < p.batch * p.n_kv_heads * qblocks0) {
-            const int b0 = it0 / qblocks0 / p.n_kv_heads;
+          const int it0 = cta + (int)G * grp0;
+          if (it0 < Bg * p.n_kv_heads * qblocks0) {
+            const int b0 = b_base + it0 / qblocks0 / p.n_kv_heads;
             const int pre = p.q_len[b0] + p.q_start[b0] + p.kv_len[b0] + p.kv_start[b0];
             asm volatile("" ::"r"(pre));
           }
         }
         if (j == PH_NORM1 || j == PH_NORM2 || j == PH_ATTN) {
           if (ph > 0) {
-            if (wtid == 0) grid_wait(p.barrier + (ph - 1), G);
+            if (wtid == 0) grid_wait(bar + (ph - 1), G);
             worker_bar();
           }
         }
@@ -326,7 +345,7 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
           const float* gamma = j == PH_NORM1 ? L->ln_in : L->ln_post;
           const int nch = p.he >> 7;  // float4 chunks per lane
           const float inv_w = 1.0f / (float)p.he;
-          for (int r = (int)blockIdx.x + (int)G * wwarp; r < ((p.flags & 8) ? 0 : p.M); r += (int)G * XP_WORKER_WARPS) {
+          for (int r = row_base + cta + (int)G * wwarp; r < ((p.flags & 8) ? 0 : row_base + Mg); r += (int)G * XP_WORKER_WARPS) {
             const float4* src = reinterpret_cast<const float4*>(p.x + (size_t)r * p.he);
             float4 v[8];
             float qs = 0.f;
@@ -373,20 +392,20 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
           const int grp = wtid >> 7, gtid = wtid & 127;
           uint8_t* asmem = smem + grp * attention_tile_smem<128>();
           const int qblocks = (ap.group * p.max_q_len + ATT_BM - 1) / ATT_BM;
-          const int items = p.batch * p.n_kv_heads * qblocks;
-          for (int it = (int)blockIdx.x + (int)G * grp; it < ((p.flags & 2) ? 0 : items); it += 2 * (int)G) {
+          const int items = Bg * p.n_kv_heads * qblocks;
+          for (int it = cta + (int)G * grp; it < ((p.flags & 2) ? 0 : items); it += 2 * (int)G) {
             const int qb = it % qblocks;
             const int rest = it / qblocks;
             const int kvh = rest % p.n_kv_heads;
-            const int b = rest / p.n_kv_heads;
+            const int b = b_base + rest / p.n_kv_heads;
             attention_tile<128>(ap, b, kvh, qb, asmem, gtid,
                                 [grp] { asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory"); });
           }
           fence_proxy_async();  // this thread's generic-proxy smem accesses precede the TMA writes that reuse the ring
         } else {
           // ---- GEMM epilogue
-          const GemmPhase g = gemm_phase(p, &tmXn, &tmAo, &tmAct, layer, j);
-          const Sched sc = make_sched(g, p.M, p.flags);
+          const GemmPhase g = gemm_phase(p, Mg, &tmXn, &tmAo, &tmAct, layer, j);
+          const Sched sc = make_sched(g, Mg, (int)G, p.flags);
           EpiParams ep;
           if (j == PH_QKV) {
             ep.out = p.q;
@@ -408,14 +427,14 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
             ep.out = p.x;
             ep.ldo = p.he;
           }
-          for (int t = blockIdx.x; t < sc.total; t += (int)G) {
+          for (int t = cta; t < sc.total; t += (int)G) {
             const Tile tc = tile_of(sc, t);
             mbar_wait_guard(&tfull_bar[as], aphase);
             tc_fence_after();
             const int n0 = tc.n_idx * 128;
             for (int sub = 0; sub < g.MT; ++sub) {
-              const int row = (tc.m_grp * g.MT + sub) * BLOCK_M + quarter * 32 + lane;
-              const bool row_ok = row < p.M;
+              const int row = row_base + (tc.m_grp * g.MT + sub) * BLOCK_M + quarter * 32 + lane;
+              const bool row_ok = row < row_base + Mg;
               const uint32_t taddr =
                   tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * XP_ACC_COLS + sub * 128;
               float ss = 0.f;
@@ -423,7 +442,7 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
               // and plain loads of x could hit a stale L1 line of an earlier layer
               if (j == PH_QKV) epilogue_tile<128, EPI_QKV_ROPE>(ep, g.N, taddr, half, row, row_ok, n0, true, false, 1.f, ss);
               else if (j == PH_GU) epilogue_tile<128, EPI_SWIGLU_BF16>(ep, g.N, taddr, half, row, row_ok, n0, true, false, 1.f, ss);
-              else if (!(p.flags & 1)) {
+              else if (!(p.flags & 1) && row - lane < row_base + Mg) {  // (a box past the sub-grid's rows: not ours)
                 // split-K partial sums meet in L2: the 32 x 32 fp32 chunk of this warp leaves as one bulk tensor
                 // reduce-add (full 128-byte lines; per-lane red.v4 costs 32 L2 transactions per instruction)
 #pragma unroll 1
@@ -453,9 +472,9 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
           if ((j == PH_O || j == PH_DOWN) && lane == 0) bulk_wait<0>();  // this warp's reduce-adds have been performed
           fence_proxy_async_all();  // this thread's global writes are ordered before async-proxy (TMA) reads of them
           worker_bar();             // every worker's writes happen-before the CTA's single (fenced) arrival
-          if (wtid == 0) grid_arrive(p.barrier + ph);
+          if (wtid == 0) grid_arrive(bar + ph);
           if (p.timing && blockIdx.x == 0 && wtid == 0) {  // profiling aid: when did the whole grid finish this phase
-            grid_wait(p.barrier + ph, G);
+            grid_wait(bar + ph, G);
             long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             p.timing[ph] = now;
@@ -480,6 +499,9 @@ int expert_pass_launch(const ExpertPass& p, const CUtensorMap& tmXn, const CUten
   VL_CHECK(p.mlp % 64 == 0, "expert pass: MLP width must be a multiple of 64");
   VL_CHECK(p.n_kv_heads > 0 && p.n_q_heads % p.n_kv_heads == 0, "expert pass: bad head counts");
   VL_CHECK(p.barrier != nullptr, "expert pass: null barrier counter");
+  const int S = p.n_streams > 1 ? p.n_streams : 1;
+  VL_CHECK(S == 1 || (p.batch % S == 0 && p.M % p.batch == 0 && (p.M / S) % 32 == 0 && S <= XP_MAX_STREAMS),
+           "expert pass: sub-grids need whole samples and a multiple of 32 rows each");
   static int max_ctas = -1;
   if (max_ctas < 0) {
     VL_CUDA_CHECK(cudaFuncSetAttribute(expert_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XP_SMEM));

@@ -16,6 +16,8 @@
 
 namespace vlaser {
 
+constexpr int EXPERT_MAX_STREAMS = 4;
+
 // Per-layer operands, resident in device memory (array of `layers` entries, 64-byte aligned for the tensor maps).
 struct alignas(64) ExpertLayerDev {
   CUtensorMap tm_qkv, tm_o, tm_gu, tm_down;  // W operands, [N, K] bf16, box 128 rows x 64
@@ -58,7 +60,8 @@ struct ExpertPass {
   int flags = 0;                      // profiling aids (wrong results!): 1 = drop the residual red.adds, 2 = skip attention,
                                       // 4 = no GEMM tiles, 8 = no norm rows (2|4|8 = the bare grid-barrier skeleton)
   long long* timing = nullptr;        // optional [7 * n_layers]: globaltimer (ns) at which CTA 0 saw each phase complete
-  unsigned int* barrier = nullptr;    // grid-barrier arrival counters of this pass, [7 * n_layers], zero on entry
+  unsigned int* barrier = nullptr;    // grid-barrier arrival counters of this pass, [n_streams][7 * n_layers], zero on entry
+  int n_streams = 1;                  // independent sub-grids (see expert.cu); needs batch % S == 0, (M / S) % 32 == 0
 };
 
 // tmXn / tmAo / tmAct: A-operand maps (box 128 rows x 64) of p.xn / p.ao / p.act; tmX: output map of the fp32 residual

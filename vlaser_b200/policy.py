@@ -112,7 +112,8 @@ class PiZeroInference:
         self._loaded = set()
         self.dtype = torch.bfloat16
         for env, opt in (("VLASER_PDL", "pdl"), ("VLASER_EXP_STAGES", "exp_stages"), ("VLASER_FUSE_NORM", "fuse_norm"),
-                         ("VLASER_PAIR_GEMM", "pair_gemm"), ("VLASER_EXPERT_MEGA", "expert_mega")):  # measurement switches
+                         ("VLASER_PAIR_GEMM", "pair_gemm"), ("VLASER_EXPERT_MEGA", "expert_mega"),
+                         ("VLASER_EXPERT_STREAMS", "expert_streams")):  # measurement switches
             if env in os.environ:
                 self.set_option(opt, int(os.environ[env]))
 
