@@ -43,6 +43,19 @@ def _peaks():
     return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "which": "fallback (B200_PROFILING.md)"}
 
 
+def _ncu_traffic(kernel: str):
+    """DRAM bytes (read + write) per launch of a kernel family from the committed ncu pass over one policy call
+    (tools/summarize_traffic.py -> profiles/r01_traffic.json); None when that capture does not exist. ncu cannot run
+    inside the timed bench, so this is the same workload measured once under the profiler."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(p) as f:
+            k = json.load(f)["kernels"][kernel]
+        return k["traffic_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons while the timed region runs (NVML)."""
 
@@ -192,6 +205,24 @@ def run_ours(args):
             return gather_actions(out.to(dev), global_B).cpu()
         return out
 
+    # widened boundary: u8 camera frames cross PCIe, resize + normalisation run on the device
+    from vlaser_b200.adapter import FrameStager
+    stager = FrameStager(cfg.image_size)
+    gf = torch.Generator().manual_seed(100 + rank)
+    frames_h = torch.randint(0, 256, (Bg * cfg.num_images, 480, 640, 3), generator=gf, dtype=torch.uint8).pin_memory()
+    frames_d = torch.empty_like(frames_h, device=dev)
+    ids_s, prop_s, noise_s = torch.empty_like(ids_d), torch.empty_like(prop_d), torch.empty_like(noise_d)
+    ids_hp = ids_h.pin_memory()
+
+    def step_staged():
+        frames_d.copy_(frames_h, non_blocking=True)
+        ids_s.copy_(ids_hp, non_blocking=True)
+        prop_s.copy_(prop_h, non_blocking=True)
+        noise_s.copy_(noise_h, non_blocking=True)
+        out = pol.infer_action(ids_s, stager(frames_d), proprios=prop_s, noise=noise_s)
+        out = gather_actions(out, global_B)
+        return out.cpu()
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -222,12 +253,20 @@ def run_ours(args):
         step_host()
     barrier()
     e2e_s = time.perf_counter() - t0
+    for _ in range(2):
+        step_staged()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_staged()
+    barrier()
+    staged_s = time.perf_counter() - t0
     sampler.stop_flag = True
     sampler.join()
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s * 1e3, staged_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+    ms, e2e_ms, staged_ms = float(t[0]), float(t[1]), float(t[2])
 
     # ---- in-situ kernel timing for the roofline figures (rank 0; direct launches, CUDA events on the launch stream
     # around every GEMM launch). Dominant kernel = the CTA-pair tcgen05 GEMM (all large-M projections of ViT + prefill).
@@ -251,7 +290,8 @@ def run_ours(args):
             ach = pr["flops"] / (pr["ms"] * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "gemm_tcgen05_pair_kernel (cta_group::2 256x256 tiles: ViT + LLM-prefill projections)",
                     "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
-                    "traffic": None, "peak_source": peaks["which"],
+                    "traffic": _ncu_traffic("gemm_tcgen05_pair_kernel"), "traffic_unit": "bytes per launch (ncu dram read+write)",
+                    "algorithmic_mbytes_per_launch": pr["bytes"] / pr["launches"] / 1e6, "peak_source": peaks["which"],
                     "launches_per_call": int(pr["launches"] / reps), "avg_launch_us": 1e3 * pr["ms"] / pr["launches"],
                     "algorithmic_gflop_per_launch": pr["flops"] / pr["launches"] / 1e9,
                     "ms_per_call": pr["ms"] / reps, "share_of_step": (pr["ms"] / reps) / step_ms}
@@ -259,7 +299,8 @@ def run_ours(args):
             ach = sg["bytes"] / (sg["ms"] * 1e-3) / 1e9
             roof_small = {"bound": "hbm", "kernel": "gemm_tcgen05_kernel (M<=256 expert / action-head GEMMs, weight streaming)",
                           "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                          "traffic": None, "launches_per_call": int(sg["launches"] / reps),
+                          "traffic": _ncu_traffic("gemm_tcgen05_kernel"), "launches_per_call": int(sg["launches"] / reps),
+                          "algorithmic_mbytes_per_launch": sg["bytes"] / sg["launches"] / 1e6,
                           "avg_launch_us": 1e3 * sg["ms"] / sg["launches"], "ms_per_call": sg["ms"] / reps,
                           "share_of_step": (sg["ms"] / reps) / step_ms,
                           "achieved_tflops": sg["flops"] / (sg["ms"] * 1e-3) / 1e12}
@@ -269,7 +310,7 @@ def run_ours(args):
             roof_expert = {"bound": "hbm", "kernel": "expert_pass_kernel (persistent: 28 expert layers of one proprio / "
                            "denoise pass per launch, weights streamed once per pass)",
                            "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                           "traffic": None, "launches_per_call": int(xp["launches"] / reps),
+                           "traffic": _ncu_traffic("expert_pass_kernel"), "launches_per_call": int(xp["launches"] / reps),
                            "avg_launch_us": 1e3 * xp["ms"] / xp["launches"], "ms_per_call": xp["ms"] / reps,
                            "algorithmic_mbytes_per_launch": xp["bytes"] / xp["launches"] / 1e6,
                            "share_of_step": (xp["ms"] / reps) / step_ms,
@@ -319,6 +360,11 @@ def run_ours(args):
         "clocks": sampler.result(),
         "e2e": {"value": e2e_value, "unit": "actions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps},
+        "e2e_staged": {"value": global_B * args.steps / (staged_ms * 1e-3) * cfg.horizon_steps, "unit": "actions/s",
+                       "what": "u8 640x480 camera frames from pinned host memory -> device Lanczos4 resize + normalise "
+                               "(vlaser_op_stage_frames) -> infer_action -> actions to host",
+                       "h2d_bytes_per_step": frames_h.numel() + ids_h.numel() * 8 + (prop_h.numel() + noise_h.numel()) * 2,
+                       "d2h_bytes_per_step": d2h, "ms_per_step": staged_ms / args.steps},
         "gpu_launches": launches,
     }
     if roof is not None:

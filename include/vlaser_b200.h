@@ -92,7 +92,7 @@ void vlaser_destroy(vlaser_t* h);
 /* Options: "pdl" (process-wide; 0 off, 1 (default) programmatic dependent launch inside the denoise steps, 2 everywhere),
  * "pair_gemm" (default 1: large-M GEMMs on the cta_group::2 kernel), "fuse_norm" (default 0; 1 fuses the expert streams' RMSNorm across the GEMM chain), "exp_stages" (smem ring depth
  * of the expert GEMMs, 0 = default),
- * "expert_mega" (default 1: each proprio / denoise pass of the action expert is ONE persistent kernel, csrc/expert.cu),
+ * "expert_mega" (default 0; 1 runs each proprio / denoise pass of the action expert as ONE persistent kernel, csrc/expert.cu),
  * "expert_streams" (default 2: independent sub-grids of that kernel, each owning a slice of the batch),
  * "use_graph" (default 1: replay the whole call as one CUDA graph per batch size),
  * "stop_after" (debug: 0 all, 1 ViT, 2 prefix embedding, 3 prefill, 4 first denoise step),

@@ -208,6 +208,7 @@ def test_full_size_2b_bench_batch_expert_stream():
     B = 64
     inp = make_inputs(cfg, B, 5)
     pol = _policy(cfg, sd, B)
+    pol.set_option("expert_mega", 1)
     a1 = _run(pol, inp, dtype=torch.bfloat16)
     pol.set_option("expert_mega", 0)
     a0 = _run(pol, inp, dtype=torch.bfloat16)

@@ -149,8 +149,10 @@ struct Engine {
                                // (measured: the M<=256 expert GEMMs are latency-bound and do not gain from pairs)
   int tma_epi = 1;             // 1: pair-kernel epilogues leave through TMA stores / reduce-adds
   int pair_gemm = 1;           // 1: large-M GEMMs run on the CTA-pair (cta_group::2) kernel
-  int mega = 1;                // 1: the expert streams (proprio pass of the prefill, every denoise step) run as ONE
-                               // persistent kernel per pass (expert.cu) instead of 7 kernels per layer
+  int mega = 0;                // 1: the expert streams (proprio pass of the prefill, every denoise step) run as ONE
+                               // persistent kernel per pass (expert.cu) instead of 7 kernels per layer. Measured on
+                               // B200 at B=64 (profiles/r01e_schedule_ab.txt): 43.2 ms per call against 40.3 ms for the
+                               // per-kernel schedule with PDL, so the per-kernel schedule is the default
   int fuse_norm = 0;           // 1: RMSNorm of the expert streams fused across the GEMM chain (see exp_pre/exp_post)
   int profile_gemm = 0;        // bracket every GEMM launch with CUDA events (non-graph runs only)
   long long profile_mtot = 0;  // live packed-row count used for the FLOP accounting of var-len GEMMs
