@@ -288,7 +288,7 @@ def run_ours(args):
         pr, sg = cls["pair"], cls["single"]
         if pr["launches"]:
             ach = pr["flops"] / (pr["ms"] * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "gemm_tcgen05_pair_kernel (cta_group::2 256x256 tiles: ViT + LLM-prefill projections)",
+            roof = {"bound": "tensor", "kernel": "gemm_tcgen05_pair_kernel at M > 512 (cta_group::2 256x256 tiles: ViT + LLM-prefill projections)",
                     "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
                     "traffic": _ncu_traffic("gemm_tcgen05_pair_kernel"), "traffic_unit": "bytes per launch (ncu dram read+write)",
                     "algorithmic_mbytes_per_launch": pr["bytes"] / pr["launches"] / 1e6, "peak_source": peaks["which"],
@@ -297,7 +297,7 @@ def run_ours(args):
                     "ms_per_call": pr["ms"] / reps, "share_of_step": (pr["ms"] / reps) / step_ms}
         if sg["launches"]:
             ach = sg["bytes"] / (sg["ms"] * 1e-3) / 1e9
-            roof_small = {"bound": "hbm", "kernel": "gemm_tcgen05_kernel (M<=256 expert / action-head GEMMs, weight streaming)",
+            roof_small = {"bound": "hbm", "kernel": "tcgen05 GEMMs at M <= 512 (single-CTA kernel + CTA-pair kernel on gate/up: action-expert / action-head projections, weight streaming)",
                           "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                           "traffic": _ncu_traffic("gemm_tcgen05_kernel"), "launches_per_call": int(sg["launches"] / reps),
                           "algorithmic_mbytes_per_launch": sg["bytes"] / sg["launches"] / 1e6,

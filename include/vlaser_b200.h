@@ -109,8 +109,8 @@ int64_t vlaser_last_launch_count(vlaser_t* h);
  * CUDA events on its launch stream; this returns (and resets) the summed device time, the summed
  * algorithmic FLOPs (2*M*N*K with the live M) and the number of GEMM launches. */
 int32_t vlaser_profile_read(vlaser_t* h, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
-/* Same counters split by kernel: out12 = {ms, flops, bytes, launches} of the single-CTA kernel (small-M / split-K GEMMs,
- * weight-streaming bound), then of the CTA-pair kernel (large-M GEMMs, tensor bound), then of the persistent
+/* Same counters split by regime: out12 = {ms, flops, bytes, launches} of the GEMMs at M <= 512 (action-expert / action-
+ * head projections, weight-streaming bound), then of the CTA-pair kernel at M > 512 (ViT + prefill, tensor bound), then of the persistent
  * expert-stream kernel (one launch per pass; flops = its projections, bytes = the expert weights streamed once).
  * bytes of the GEMM classes = both operands once + the output once (fp32 residual epilogues: read + write). */
 int32_t vlaser_profile_read_classes(vlaser_t* h, double* out12);

@@ -225,3 +225,51 @@ def test_full_size_2b_bench_batch_expert_stream():
     for b in (7, 40, 63):   # one sample of each sub-grid (and the last row of the batch) run alone
         one = {k: v[b:b + 1] for k, v in inp.items() if k in ("input_ids", "pixel_values", "proprios", "noise")}
         assert max_err(_run(pol, one, dtype=torch.bfloat16), a1[b:b + 1]) <= ACTION_TOL
+
+
+@pytest.mark.skipif(os.environ.get("VLASER_SKIP_FULL", "0") == "1", reason="full-size parity skipped by env")
+@pytest.mark.parametrize("preset,B", [("vlaser_2b_fractal", 2), ("vlaser_2b_robotwin", 1)])
+def test_full_size_other_configs_parity(preset, B):
+    """BASELINE configs 3 and 4 at full model size: Google Robot / fractal (proprio_dim 8, time_max_period 100) and the
+    RoboTwin shapes (3 cameras, 14-DoF chunk, S=896, H=6 action tokens) against the fp32 oracle, pre-clamp."""
+    from vlaser_b200.config import PRESETS
+    cfg = PRESETS[preset]().with_(final_action_clip_value=None)
+    sd = random_state_dict(cfg, 0)
+    inp = make_inputs(cfg, B, 3)
+    pol = _policy(cfg, sd, B)
+    got = _run(pol, inp)
+    ref = O.infer_action(cfg, sd, inp["input_ids"], inp["pixel_values"], inp["proprios"], inp["noise"])
+    assert got.shape == (B, cfg.horizon_steps, cfg.action_dim)
+    assert max_err(got.clamp(-1, 1), ref.clamp(-1, 1)) <= ACTION_TOL
+    pol.set_option("expert_mega", 1)
+    assert max_err(_run(pol, inp).clamp(-1, 1), ref.clamp(-1, 1)) <= ACTION_TOL
+
+
+def test_checkpoint_key_aliases_load():
+    """eval.py:196-212: the released checkpoints carry `_orig_mod.` prefixes (torch.compile), the expert weights under
+    `mixtures.proprio.*` as well as `mixtures.action.*` (shared modules), duplicates under `internvl_model.*` and
+    tensors the path never reads (lm_head); `load_state_dict(strict=False)` must take all of that and give the same
+    actions as the canonical state dict."""
+    cfg, sd, inp, gold = load_case("tiny_bridge")
+    B = inp["input_ids"].shape[0]
+    ck = {}
+    for k, v in sd.items():
+        ck["_orig_mod." + k] = v
+        if k.startswith("joint_model.mixtures.action."):
+            ck["_orig_mod." + k.replace("mixtures.action.", "mixtures.proprio.")] = v
+        if k.startswith("vision_tower.vision_model."):
+            ck["_orig_mod." + k.replace("vision_tower.vision_model.", "internvl_model.vision_model.")] = v
+        if k.startswith("multi_modal_projector."):
+            ck["_orig_mod." + k.replace("multi_modal_projector.", "internvl_model.mlp1.")] = v
+    ck["_orig_mod.internvl_model.language_model.lm_head.weight"] = torch.zeros(8, 8)
+    ck["step"] = 123  # non-tensor entries are skipped
+    pol = PiZeroInference(cfg, max_batch=B)
+    res = pol.load_state_dict(ck, strict=False)
+    assert any("lm_head" in k for k in getattr(res, "unexpected_keys", ["lm_head"]))
+    assert max_err(_run(pol, inp), gold["actions"]) <= ACTION_TOL
+    # a missing tensor must fail loudly at finalize, not produce numbers
+    short = dict(list(sd.items())[:-3])
+    pol2 = PiZeroInference(cfg, max_batch=B)
+    pol2.load_state_dict(short, strict=False)
+    with pytest.raises(RuntimeError):
+        _run(pol2, inp)

@@ -158,7 +158,8 @@ struct Engine {
   long long profile_mtot = 0;  // live packed-row count used for the FLOP accounting of var-len GEMMs
   std::vector<cudaEvent_t> prof_events;
   std::vector<double> prof_flops, prof_bytes;
-  std::vector<int> prof_class;  // 0 = single-CTA kernel (small-M / split-K), 1 = CTA-pair kernel (large-M)
+  std::vector<int> prof_class;  // 0 = small-M GEMMs (M <= 512: expert / action-head projections, weight streaming),
+                                // 1 = CTA-pair kernel at large M (ViT + prefill, tensor bound), 2 = expert-stream kernel
   size_t prof_used = 0;
   long long launches = 0, last_launches = 0;
   cudaStream_t own_stream = nullptr;
@@ -633,7 +634,7 @@ struct Run {
       const double out_elems = rows * (double)(epi == EPI_SWIGLU_BF16 ? w.N / 2 : w.N);
       const double out_bytes = (epi == EPI_RESID_F32) ? 8.0 * out_elems : ((epi == EPI_STORE_F32 || epi == EPI_PATCH_EMBED) ? 4.0 : 2.0) * out_elems;
       e.prof_bytes.push_back(2.0 * (rows * (double)w.K + (double)w.N * (double)w.K) + out_bytes);
-      e.prof_class.push_back(d.pair);
+      e.prof_class.push_back((d.pair && rows > 512.0) ? 1 : 0);  // M <= 512: weight-streaming regime whatever the kernel
       VL_CUDA_CHECK(cudaEventRecord(e.prof_events[e.prof_used], st));
     }
     const int rc = gemm_launch(a.tm, bn == 256 ? w.tm256 : w.tm128, d, ep, bn, epi, st, e.tma_epi ? out_tm : nullptr);
