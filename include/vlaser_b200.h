@@ -89,7 +89,7 @@ int32_t vlaser_infer_action_host(vlaser_t* h, const int64_t* input_ids, const vo
                                  int32_t B, int32_t io_dtype);
 void vlaser_destroy(vlaser_t* h);
 
-/* Options: "pdl" (process-wide; 0 off, 1 (default) programmatic dependent launch inside the denoise steps, 2 everywhere),
+/* Options: "pdl" (process-wide; 0 off, 1 programmatic dependent launch inside the denoise steps only, 2 (default) on every launch),
  * "pair_gemm" (default 1: large-M GEMMs on the cta_group::2 kernel), "fuse_norm" (default 0; 1 fuses the expert streams' RMSNorm across the GEMM chain), "exp_stages" (smem ring depth
  * of the expert GEMMs, 0 = default),
  * "expert_mega" (default 0; 1 runs each proprio / denoise pass of the action expert as ONE persistent kernel, csrc/expert.cu),

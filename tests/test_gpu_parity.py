@@ -273,3 +273,30 @@ def test_checkpoint_key_aliases_load():
     pol2.load_state_dict(short, strict=False)
     with pytest.raises(RuntimeError):
         _run(pol2, inp)
+
+
+@pytest.mark.skipif(os.environ.get("VLASER_SKIP_FULL", "0") == "1", reason="full-size parity skipped by env")
+def test_8b_widths_448px_reduced_depth_parity(capsys):
+    """BASELINE config 5 shapes: the Vlaser-8B widths (LLM 3584 / 28:4 heads / MLP 18944, expert MLP 5600 which is
+    padded to 5632 inside the library), a 448 px tile (1025 ViT tokens -> 256 image tokens, generic var-len ViT
+    attention path), at reduced depth (2 LLM / expert layers, 2 ViT layers, 1024-row embedding) so that the fp32
+    oracle runs in seconds. Prefix encode + prefill are checked stage by stage, then the whole call."""
+    from vlaser_b200.config import vlaser_8b_vla
+    cfg = vlaser_8b_vla().with_(layers=2, vit_layers=2, embed_rows=1024, image_token_index=1000, pad_token_id=999,
+                                final_action_clip_value=None)
+    sd = random_state_dict(cfg, 4)
+    B = 2
+    inp = make_inputs(cfg, B, 9)
+    pol = _policy(cfg, sd, B)
+    got = _run(pol, inp)
+    with capsys.disabled():
+        print("\n[vlaser_8b_vla widths, 448 px, 2 layers, B=2] per-stage relative errors vs fp32 oracle:")
+        errs, tr = _stage_report(cfg, sd, inp, pol, B, print)
+    ref = tr["actions_preclamp"][:, -cfg.horizon_steps:]
+    assert errs["vit_out"] < 2e-2 and errs["prefix_embeds"] < 2e-2
+    for k, v in errs.items():
+        if k.startswith(("k_", "v_")):
+            assert v < 3e-2, (k, v)
+    assert max_err(got, ref) <= ACTION_TOL
+    pol.set_option("expert_mega", 1)
+    assert max_err(_run(pol, inp), ref) <= ACTION_TOL

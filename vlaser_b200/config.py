@@ -105,6 +105,13 @@ def vlaser_2b_robotwin() -> VlaserConfig:
     return VlaserConfig(cond_steps=3, action_dim=14, proprio_dim=14, max_image_text_tokens=896)
 
 
+def vlaser_8b_vla() -> VlaserConfig:
+    """BASELINE config 5 dims: Vlaser-8B (InternViT-300M + Qwen2.5-7B: hidden 3584, 28/4 heads, MLP 18944) as the 8B VLA
+    (`model_size="8B"`, pizero_internvl.py:128-131: expert MLP 5600), one 448 px tile per observation (256 image
+    tokens). The prefix encode + bidirectional block prefill of config 5 is this preset with `stop_after=3`."""
+    return VlaserConfig(image_size=448, hidden=3584, n_heads=28, n_kv_heads=4, mlp=18944, mlp_e=5600, embed_rows=151674)
+
+
 def tiny() -> VlaserConfig:
     """Small config with the same structure (GQA 6:1, head_dim 128, ViT head 64, 16x16 patch grid
     -- the reference hard-codes the grid, pizero_internvl.py:739-743) for golden fixtures and fast
@@ -122,5 +129,6 @@ PRESETS = {
     "vlaser_2b_bridge": vlaser_2b_bridge,
     "vlaser_2b_fractal": vlaser_2b_fractal,
     "vlaser_2b_robotwin": vlaser_2b_robotwin,
+    "vlaser_8b_vla": vlaser_8b_vla,
     "tiny": tiny,
 }

@@ -15,9 +15,9 @@ namespace {
 template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(AttnParams p) {
   pdl_launch_dependents();
-  pdl_wait();
   extern __shared__ __align__(128) uint8_t smem[];
-  attention_tile<HD>(p, blockIdx.z, blockIdx.y, blockIdx.x, smem, threadIdx.x, [] { __syncthreads(); });
+  attention_tile<HD>(p, blockIdx.z, blockIdx.y, blockIdx.x, smem, threadIdx.x, [] { __syncthreads(); },
+                     [] { pdl_wait(); });
 }
 
 // ------------------------------------------------------------------------------------------

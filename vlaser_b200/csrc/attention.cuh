@@ -36,6 +36,10 @@ struct AttnParams {
   int n_kv_heads = 1;
   int batch = 0;
   float scale = 1.f;
+  // 1: the K/V rows [0, kv_len - q_len) of every sample (cached prefix + proprio row of a denoise step) were written
+  // by kernels that completed long before the previous launch, so the first K/V block may be fetched BEFORE the
+  // programmatic-dependent-launch wait and overlaps the tail of the q|k|v projection that produces the new rows
+  int stable_prefix = 0;
 };
 
 int attention_launch(const AttnParams& p, int head_dim, cudaStream_t stream);

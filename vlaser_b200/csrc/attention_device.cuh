@@ -20,9 +20,11 @@ __device__ __forceinline__ uint32_t swz(int row, int chunk) {
 template <int HD>
 constexpr int attention_tile_smem() { return (ATT_BM + 4 * ATT_BN) * HD * 2; }
 
-template <int HD, typename Sync>
+// `dep_wait` is called exactly once by every thread that does not return early: after it the outputs of the
+// previous grid (Q and the new K/V rows) may be read.
+template <int HD, typename Sync, typename DepWait>
 __device__ __forceinline__ void attention_tile(const AttnParams& p, int b, int kvh, int qb, uint8_t* smem, int tid,
-                                               Sync sync) {
+                                               Sync sync, DepWait dep_wait) {
   constexpr int CH = HD / 8;  // 16-byte chunks per row
   uint8_t* Qs = smem;                                  // [64][HD]
   uint8_t* Ks = Qs + ATT_BM * HD * 2;                  // [2][64][HD]
@@ -37,7 +39,7 @@ __device__ __forceinline__ void attention_tile(const AttnParams& p, int b, int k
   const int group = p.group;
   const int rows_total = group * (q_len + (has_extra ? 1 : 0));
   const int r0 = qb * ATT_BM;
-  if (r0 >= rows_total) return;
+  if (r0 >= rows_total) return;  // (exits without dep_wait: nothing was read)
   const bool cta_has_extra = has_extra && (r0 + ATT_BM > group * q_len);
   const int kv_hi = kv_len + (cta_has_extra ? 1 : 0);
   const int n_blocks = (kv_hi + ATT_BN - 1) / ATT_BN;
@@ -45,6 +47,25 @@ __device__ __forceinline__ void attention_tile(const AttnParams& p, int b, int k
   const __nv_bfloat16* kbase = p.k + (size_t)kvh * p.kv_head_stride + (size_t)kv_start * p.kv_row_stride;
   const __nv_bfloat16* vbase = p.v + (size_t)kvh * p.kv_head_stride + (size_t)kv_start * p.kv_row_stride;
 
+  auto load_kv = [&](int blk, int buf) {
+    uint8_t* kd = Ks + buf * ATT_BN * HD * 2;
+    uint8_t* vd = Vs + buf * ATT_BN * HD * 2;
+    for (int i = tid; i < ATT_BN * CH; i += ATT_THREADS) {
+      const int row = i / CH, c = i - row * CH;
+      const int kr = blk * ATT_BN + row;
+      const bool ok = kr < kv_hi;
+      const size_t off = (size_t)(ok ? kr : 0) * p.kv_row_stride + c * 8;
+      cp_async_16(kd + swz<HD>(row, c), kbase + off, ok);
+      cp_async_16(vd + swz<HD>(row, c), vbase + off, ok);
+    }
+  };
+  // block 0 lies entirely in the stable prefix: fetch it before waiting on the previous grid
+  const bool pre = p.stable_prefix && !has_extra && (kv_len - q_len >= ATT_BN);
+  if (pre) {
+    load_kv(0, 0);
+    cp_async_commit();
+  }
+  dep_wait();
   // ---- Q tile -> smem (zero-fill rows past rows_total)
   for (int i = tid; i < ATT_BM * CH; i += ATT_THREADS) {
     const int row = i / CH, c = i - row * CH;
@@ -58,19 +79,7 @@ __device__ __forceinline__ void attention_tile(const AttnParams& p, int b, int k
       src = p.q + (size_t)(q_start + t) * p.q_row_stride + (size_t)(kvh * group + hh) * HD + c * 8;
     cp_async_16(Qs + swz<HD>(row, c), src, ok);
   }
-  auto load_kv = [&](int blk, int buf) {
-    uint8_t* kd = Ks + buf * ATT_BN * HD * 2;
-    uint8_t* vd = Vs + buf * ATT_BN * HD * 2;
-    for (int i = tid; i < ATT_BN * CH; i += ATT_THREADS) {
-      const int row = i / CH, c = i - row * CH;
-      const int kr = blk * ATT_BN + row;
-      const bool ok = kr < kv_hi;
-      const size_t off = (size_t)(ok ? kr : 0) * p.kv_row_stride + c * 8;
-      cp_async_16(kd + swz<HD>(row, c), kbase + off, ok);
-      cp_async_16(vd + swz<HD>(row, c), vbase + off, ok);
-    }
-  };
-  load_kv(0, 0);
+  if (!pre) load_kv(0, 0);
   cp_async_commit();
 
   // ---- per-thread row bookkeeping: rows rlo = warp*16 + lane/4 and rlo + 8

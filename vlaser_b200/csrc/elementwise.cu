@@ -309,16 +309,30 @@ __global__ void __launch_bounds__(128) euler_step_kernel(const float* __restrict
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + warp;
   if (r >= rows) return;
+  // the row stays in registers (width <= 1024: up to 32 values per lane), pre-scaled by rstd * gamma once
   const float* xr = x + (size_t)r * width;
+  float xv[32];
   float q = 0.f;
-  for (int c = lane; c < width; c += 32) {
-    const float v = xr[c];
-    q += v * v;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + 32 * i;
+    xv[i] = c < width ? xr[c] : 0.f;
+    q += xv[i] * xv[i];
   }
   const float rstd = rsqrtf(warp_sum(q) / width + eps);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + 32 * i;
+    if (c < width) xv[i] *= rstd * gamma[c];
+  }
   for (int a = 0; a < A; ++a) {
     float acc = 0.f;
-    for (int c = lane; c < width; c += 32) acc += xr[c] * rstd * gamma[c] * Wdec[(size_t)a * width + c];
+    const float* wr = Wdec + (size_t)a * width;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int c = lane + 32 * i;
+      if (c < width) acc += xv[i] * wr[c];
+    }
     acc = warp_sum(acc);
     if (lane == 0) {
       float val = action[(size_t)r * A + a] + dt * (acc + bdec[a]);
@@ -446,6 +460,7 @@ int euler_step_launch(const float* x, const float* gamma, const float* Wdec, con
                       void* out, int out_dtype, int rows, int width, int A, int H, int horizon, float dt, float eps,
                       int last_step, int do_clip, float clip, cudaStream_t stream) {
   if (rows <= 0) return 0;
+  VL_CHECK(width <= 1024, "euler_step: width must be <= 1024");
   const int grid = (rows + 3) / 4;
   if (out_dtype == DT_F32)
     VL_CUDA_CHECK(launch_kernel(euler_step_kernel<float>, dim3(grid), dim3(128), 0, stream, x, gamma, Wdec, bdec, action, (float*)out, rows, width, A, H,

@@ -32,7 +32,7 @@ namespace vlaser {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 // PDL policy: 0 = off, 1 = only inside the latency-bound expert chain of the denoise steps, 2 = every kernel.
-static int g_pdl_mode = 1;
+static int g_pdl_mode = 2;  // 0 off, 1 inside the denoise steps only, 2 (default) every launch: 39.8 vs 40.6 ms per call at B=64 (profiles/r01e_schedule_ab.txt)
 static bool g_pdl_scope = false;  // set by the schedule while it enqueues a latency-bound section
 bool pdl_enabled() { return g_pdl_mode == 2 || (g_pdl_mode == 1 && g_pdl_scope); }
 void set_pdl_enabled(bool on) { g_pdl_scope = on; }
@@ -95,6 +95,7 @@ struct Engine {
   vlaser_cfg c{};
   int device = 0;
   int P = 0, T = 0, G = 0, H = 0, S = 0, Bc = 0, kpad = 0, n_img = 0;
+  int mlp_p = 0, mlp_e_p = 0;  // MLP widths padded to a multiple of 128 (8B expert: 5600 -> 5632); pad rows / columns are zero
   int qdim = 0, kvdim = 0, qkvN = 0;
   long long kv_rows = 0;
   bool finalized = false;
@@ -267,6 +268,8 @@ int engine_build(Engine& e) {
   e.S = c.max_image_text_tokens;
   e.Bc = c.max_batch;
   e.kpad = (3 * c.patch_size * c.patch_size + 63) / 64 * 64;
+  e.mlp_p = (c.mlp + 127) / 128 * 128;
+  e.mlp_e_p = (c.mlp_e + 127) / 128 * 128;
   e.qdim = c.n_heads * 128;
   e.kvdim = c.n_kv_heads * 128;
   e.qkvN = e.qdim + 2 * e.kvdim;
@@ -312,7 +315,9 @@ int engine_build(Engine& e) {
   VL_TRY(e.alloc(&e.embed, (size_t)c.embed_rows * h));
   e.add_slot("embed_tokens.weight", e.embed, DT_BF16, c.embed_rows, h);
   // --- LLM + expert
-  auto add_llm = [&](std::vector<LlmLayer>& Ls, const std::string& prefix, int hid, int mlp) -> int {
+  // gate/up rows and down columns past `mlp` (up to the padded width mp) stay zero: silu(0) * 0 = 0 feeds zero
+  // columns into a zero-weighted slice of the down projection
+  auto add_llm = [&](std::vector<LlmLayer>& Ls, const std::string& prefix, int hid, int mlp, int mp) -> int {
     Ls.resize(c.layers);
     for (int i = 0; i < c.layers; ++i) {
       LlmLayer& L = Ls[i];
@@ -328,15 +333,16 @@ int engine_build(Engine& e) {
       e.add_slot(p + "self_attn.k_proj.bias", L.bqkv + e.qdim, DT_F32, 1, e.kvdim);
       e.add_slot(p + "self_attn.v_proj.bias", L.bqkv + e.qdim + e.kvdim, DT_F32, 1, e.kvdim);
       VL_TRY(e.add_lin(p + "self_attn.o_proj.weight", &L.o, hid, e.qdim));
-      VL_TRY(e.add_lin("", &L.gu, 2 * mlp, hid));
+      VL_TRY(e.add_lin("", &L.gu, 2 * mp, hid));
       e.add_slot(p + "mlp.gate_proj.weight", L.gu.w, DT_BF16, mlp, hid, hid, 0, PK_GATE);
       e.add_slot(p + "mlp.up_proj.weight", L.gu.w, DT_BF16, mlp, hid, hid, 0, PK_UP);
-      VL_TRY(e.add_lin(p + "mlp.down_proj.weight", &L.down, hid, mlp));
+      VL_TRY(e.add_lin("", &L.down, hid, mp));
+      e.add_slot(p + "mlp.down_proj.weight", L.down.w, DT_BF16, hid, mlp, mp);
     }
     return 0;
   };
-  VL_TRY(add_llm(e.llm, "joint_model.mixtures.vlm.", h, c.mlp));
-  VL_TRY(add_llm(e.exp, "joint_model.mixtures.action.", he, c.mlp_e));
+  VL_TRY(add_llm(e.llm, "joint_model.mixtures.vlm.", h, c.mlp, e.mlp_p));
+  VL_TRY(add_llm(e.exp, "joint_model.mixtures.action.", he, c.mlp_e, e.mlp_e_p));
   VL_TRY(e.add_vec("joint_model.mixtures.action.norm.weight", &e.final_norm, he));
   // --- heads
   VL_TRY(e.add_vec("action_encoder.linear_1.weight", &e.ae_w1, (long long)he * c.action_dim));
@@ -373,19 +379,19 @@ int engine_build(Engine& e) {
   VL_TRY(e.add_act(&e.xn, prow, h));
   VL_TRY(e.alloc(&e.q, (size_t)prow * e.qdim));
   VL_TRY(e.add_act(&e.ao, prow, e.qdim));
-  VL_TRY(e.add_act(&e.act, prow, c.mlp));
+  VL_TRY(e.add_act(&e.act, prow, e.mlp_p));
   VL_TRY(e.alloc(&e.xp, (size_t)e.Bc * he));
   VL_TRY(make_tmap_out(&e.xp_otm, e.xp, e.Bc, he, 4));
   VL_TRY(e.add_act(&e.xpn, e.Bc, he));
   VL_TRY(e.alloc(&e.qp, (size_t)e.Bc * e.qdim));
   VL_TRY(e.add_act(&e.aop, e.Bc, e.qdim));
-  VL_TRY(e.add_act(&e.actp, e.Bc, c.mlp_e));
+  VL_TRY(e.add_act(&e.actp, e.Bc, e.mlp_e_p));
   VL_TRY(e.alloc(&e.xa, (size_t)arow * he));
   VL_TRY(make_tmap_out(&e.xa_otm, e.xa, arow, he, 4));
   VL_TRY(e.add_act(&e.xan, arow, he));
   VL_TRY(e.alloc(&e.qa, (size_t)arow * e.qdim));
   VL_TRY(e.add_act(&e.aoa, arow, e.qdim));
-  VL_TRY(e.add_act(&e.acta, arow, c.mlp_e));
+  VL_TRY(e.add_act(&e.acta, arow, e.mlp_e_p));
   VL_TRY(e.add_act(&e.e1, arow, he));
   VL_TRY(e.add_act(&e.h2, arow, he));
   VL_TRY(e.alloc(&e.action, (size_t)arow * c.action_dim));
@@ -804,7 +810,7 @@ struct Run {
     VL_TRY(gemm(ao, L.o, M, nullptr, EPI_RESID_F32, eo, 32, e.exp_stages));
     EpiParams eg;
     eg.out = act.p;
-    eg.ldo = c.mlp_e;
+    eg.ldo = e.mlp_e_p;
     norm_consumer(eg, pass, 2 * li + 1);
     VL_TRY(gemm(xn, L.gu, M, nullptr, EPI_SWIGLU_BF16, eg, 1, e.exp_stages));
     EpiParams ed;
@@ -835,7 +841,7 @@ struct Run {
     p.last_kv_only = last_kv_only ? 1 : 0;
     p.M = M;
     p.he = c.hidden_e;
-    p.mlp = c.mlp_e;
+    p.mlp = e.mlp_e_p;
     p.n_q_heads = c.n_heads;
     p.n_kv_heads = c.n_kv_heads;
     p.eps = c.rms_eps;
@@ -925,10 +931,10 @@ struct Run {
       ap.scale = 0.08838834764831845f;  // 128^-0.5
       VL_TRY(attention_launch(ap, 128, st));
       e.launches++;
-      VL_TRY(block_post(e.llm[li], e.xv, e.xn, e.ao, e.act, cap, e.pb.m_tot, c.hidden, c.mlp, 1, &e.xv_otm));
+      VL_TRY(block_post(e.llm[li], e.xv, e.xn, e.ao, e.act, cap, e.pb.m_tot, c.hidden, e.mlp_p, 1, &e.xv_otm));
       if (mega()) continue;
       if (e.fuse_norm) VL_TRY(exp_post(li, e.xp, e.xpn, e.aop, e.actp, B, 0, false));
-      else VL_TRY(block_post(e.exp[li], e.xp, e.xpn, e.aop, e.actp, B, nullptr, c.hidden_e, c.mlp_e, 32, &e.xp_otm));
+      else VL_TRY(block_post(e.exp[li], e.xp, e.xpn, e.aop, e.actp, B, nullptr, c.hidden_e, e.mlp_e_p, 32, &e.xp_otm));
     }
     if (mega())
       VL_TRY(expert_pass(0, B, e.xp, e.xp_otm, e.xpn, e.qp, e.aop, e.actp, e.pb.prop_pos, e.pb.prop_kvrow, e.pb.prop_q_start,
@@ -973,6 +979,7 @@ struct Run {
       ap.q_len = e.pb.den_q_len;
       ap.kv_start = e.pb.kvoff;
       ap.kv_len = e.pb.den_kv_len;
+      ap.stable_prefix = 1;  // prefix + proprio K/V of this layer date from the prefill
       ap.max_q_len = e.H;
       ap.group = c.n_heads / c.n_kv_heads;
       ap.n_kv_heads = c.n_kv_heads;
@@ -981,7 +988,7 @@ struct Run {
       VL_TRY(attention_launch(ap, 128, st));
       e.launches++;
       if (e.fuse_norm) VL_TRY(exp_post(li, e.xa, e.xan, e.aoa, e.acta, M, step + 1, false));
-      else VL_TRY(block_post(e.exp[li], e.xa, e.xan, e.aoa, e.acta, M, nullptr, he, c.mlp_e, 32, &e.xa_otm));
+      else VL_TRY(block_post(e.exp[li], e.xa, e.xan, e.aoa, e.acta, M, nullptr, he, e.mlp_e_p, 32, &e.xa_otm));
     }
     const int last = step == c.num_inference_steps - 1;
     VL_TRY(euler_step_launch(e.xa, e.final_norm, e.dec_w, e.dec_b, e.action, e.out_act, io, M, he, c.action_dim, e.H,

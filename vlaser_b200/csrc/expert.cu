@@ -399,7 +399,7 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
             const int kvh = rest % p.n_kv_heads;
             const int b = b_base + rest / p.n_kv_heads;
             attention_tile<128>(ap, b, kvh, qb, asmem, gtid,
-                                [grp] { asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory"); });
+                                [grp] { asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory"); }, [] {});
           }
           fence_proxy_async();  // this thread's generic-proxy smem accesses precede the TMA writes that reuse the ring
         } else {
