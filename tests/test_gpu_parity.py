@@ -300,3 +300,41 @@ def test_8b_widths_448px_reduced_depth_parity(capsys):
     assert max_err(got, ref) <= ACTION_TOL
     pol.set_option("expert_mega", 1)
     assert max_err(_run(pol, inp), ref) <= ACTION_TOL
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_single_observation_gemv_kernel(name):
+    """B = 1 routes the expert passes through the weight-streaming kernel (expert_gemv.cu; R = 1 proprio row, R = 4 or 8
+    action rows): same actions as the per-kernel tensor-core schedule and as the reference, K/V rows of the proprio
+    pass and of the last denoise step included."""
+    cfg, sd, inp, gold = load_case(name)
+    one = {k: v[:1] for k, v in inp.items() if k in ("input_ids", "proprios", "noise")}
+    one["pixel_values"] = inp["pixel_values"][: cfg.num_images]
+    pol1 = _policy(cfg, sd, 1, expert_gemv=1)
+    pol0 = _policy(cfg, sd, 1, expert_gemv=0)
+    a1, a0 = _run(pol1, one), _run(pol0, one)
+    assert pol1.last_launch_count() < pol0.last_launch_count()
+    assert max_err(a1, a0) < 2e-3
+    assert max_err(a1, gold["actions"][:1]) <= ACTION_TOL
+    for nm in ("k_cache", "v_cache"):
+        c1, c0 = pol1.debug_buffer(nm, torch.bfloat16).float(), pol0.debug_buffer(nm, torch.bfloat16).float()
+        assert rel_err(c1, c0) < 1e-2
+
+
+@pytest.mark.skipif(os.environ.get("VLASER_SKIP_FULL", "0") == "1", reason="full-size parity skipped by env")
+def test_full_size_2b_single_observation():
+    """BASELINE configs[0] shape on the GPU: Vlaser-2B-VLA, one 224 px observation, 10 flow steps (the p50 B=1 latency
+    path) against the fp32 oracle, with the graph replay equal to the direct launch."""
+    cfg = vlaser_2b_bridge().with_(final_action_clip_value=None)
+    sd = random_state_dict(cfg, 0)
+    inp = make_inputs(cfg, 1, 17)
+    pol = _policy(cfg, sd, 1)
+    got = _run(pol, inp)
+    ref = O.infer_action(cfg, sd, inp["input_ids"], inp["pixel_values"], inp["proprios"], inp["noise"])
+    assert max_err(got.clamp(-1, 1), ref.clamp(-1, 1)) <= ACTION_TOL
+    # graph replay == direct launch up to the order of the split-K red.adds into the fp32 residual stream
+    pol.set_option("use_graph", 0)
+    assert max_err(_run(pol, inp), got) < 4e-3
+    pol.set_option("use_graph", 1)
+    pol.set_option("expert_gemv", 0)
+    assert max_err(_run(pol, inp), got) < 5e-3

@@ -325,17 +325,31 @@ __global__ void __launch_bounds__(128) euler_step_kernel(const float* __restrict
     const int c = lane + 32 * i;
     if (c < width) xv[i] *= rstd * gamma[c];
   }
-  for (int a = 0; a < A; ++a) {
-    float acc = 0.f;
-    const float* wr = Wdec + (size_t)a * width;
+  // eight decoder outputs at a time: all dot products first (independent loads in flight), then lane j finishes
+  // output a0 + j (bias, Euler update, clamp / slice on the last step)
+  for (int a0 = 0; a0 < A; a0 += 8) {
+    float acc[8];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int c = lane + 32 * i;
-      if (c < width) acc += xv[i] * wr[c];
+    for (int j = 0; j < 8; ++j) {
+      acc[j] = 0.f;
+      if (a0 + j < A) {
+        const float* wr = Wdec + (size_t)(a0 + j) * width;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = lane + 32 * i;
+          if (c < width) acc[j] += xv[i] * wr[c];
+        }
+      }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      float val = action[(size_t)r * A + a] + dt * (acc + bdec[a]);
+    float mine = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t = warp_sum(acc[j]);
+      if (lane == j) mine = t;
+    }
+    const int a = a0 + lane;
+    if (lane < 8 && a < A) {
+      float val = action[(size_t)r * A + a] + dt * (mine + bdec[a]);
       action[(size_t)r * A + a] = val;
       if (last_step) {
         const int b = r / H, i = r - b * H;

@@ -154,6 +154,7 @@ struct Engine {
                                // persistent kernel per pass (expert.cu) instead of 7 kernels per layer. Measured on
                                // B200 at B=64 (profiles/r01e_schedule_ab.txt): 43.2 ms per call against 40.3 ms for the
                                // per-kernel schedule with PDL, so the per-kernel schedule is the default
+  int gemv = 1;                // 1: at B = 1 the expert passes run on the weight-streaming kernel (expert_gemv.cu)
   int fuse_norm = 0;           // 1: RMSNorm of the expert streams fused across the GEMM chain (see exp_pre/exp_post)
   int profile_gemm = 0;        // bracket every GEMM launch with CUDA events (non-graph runs only)
   long long profile_mtot = 0;  // live packed-row count used for the FLOP accounting of var-len GEMMs
@@ -545,6 +546,10 @@ int engine_finalize(Engine& e) {
       tab[i].ln_in = L.ln_in;
       tab[i].ln_post = L.ln_post;
       tab[i].bqkv = L.bqkv;
+      tab[i].w_qkv = L.qkv.w;
+      tab[i].w_o = L.o.w;
+      tab[i].w_gu = L.gu.w;
+      tab[i].w_down = L.down.w;
     }
     VL_CUDA_CHECK(cudaMemcpy(e.xp_layers, tab.data(), tab.size() * sizeof(ExpertLayerDev), cudaMemcpyHostToDevice));
   }
@@ -821,7 +826,9 @@ struct Run {
     return gemm(act, L.down, M, nullptr, EPI_RESID_F32, ed, 32, e.exp_stages);
   }
 
-  bool mega() const { return e.mega && !e.simt; }
+  // B = 1 (the latency case): the expert passes run on the weight-streaming single-observation kernel
+  bool gemv() const { return e.gemv && B == 1 && e.H <= 8 && !e.simt; }
+  bool mega() const { return (e.mega || gemv()) && !e.simt; }
   // largest power-of-two sub-grid count <= the option that keeps whole samples, a multiple of 32 rows and at least 64
   // rows per sub-grid
   int expert_streams(int M, int B) const {
@@ -863,6 +870,7 @@ struct Run {
     p.kv_start = e.pb.kvoff;
     p.kv_len = kv_len;
     p.max_q_len = max_q_len;
+    p.max_kv_len = e.S + 1 + e.H;
     p.batch = B;
     p.scale = 0.08838834764831845f;  // 128^-0.5
     p.barrier = e.xp_bar + (size_t)pass * e.xp_bar_words();
@@ -886,7 +894,7 @@ struct Run {
       e.prof_class.push_back(2);
       VL_CUDA_CHECK(cudaEventRecord(e.prof_events[e.prof_used], st));
     }
-    const int rc = expert_pass_launch(p, xn.tm, ao.tm, act.tm, x_otm, st);
+    const int rc = gemv() ? expert_gemv_pass_launch(p, st) : expert_pass_launch(p, xn.tm, ao.tm, act.tm, x_otm, st);
     if (prof) {
       VL_CUDA_CHECK(cudaEventRecord(e.prof_events[e.prof_used + 1], st));
       e.prof_used += 2;
@@ -1122,12 +1130,13 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_timing" || k == "expert_flags") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "expert_timing" || k == "expert_flags") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
     else if (k == "expert_mega") h->e.mega = (int)value;
     else if (k == "expert_streams") h->e.xp_streams = (int)value;
+    else if (k == "expert_gemv") h->e.gemv = (int)value;
     else if (k == "expert_timing") h->e.xp_time = (int)value;
     else if (k == "expert_flags") h->e.xp_flags = (int)value;
     else if (k == "pair_gemm") h->e.pair_gemm = (int)value;

@@ -24,8 +24,13 @@ struct alignas(64) ExpertLayerDev {
   const float* ln_in;
   const float* ln_post;
   const float* bqkv;
-  const void* pad_[5];
+  const void* w_qkv;   // the same four matrices as plain pointers (row-major [N, K] bf16) for the weight-streaming
+  const void* w_o;     // single-observation kernel (expert_gemv.cu)
+  const void* w_gu;
+  const void* w_down;
+  const void* pad_[1];
 };
+static_assert(sizeof(ExpertLayerDev) % 64 == 0, "tensor maps of the next table entry must stay 64-byte aligned");
 
 struct ExpertPass {
   const ExpertLayerDev* layers = nullptr;
@@ -55,10 +60,12 @@ struct ExpertPass {
   const int* kv_start = nullptr;
   const int* kv_len = nullptr;
   int max_q_len = 0;
+  int max_kv_len = 0;                 // upper bound of kv_len[] (sizes the score rows of expert_gemv.cu)
   int batch = 0;
   float scale = 1.f;
   int flags = 0;                      // profiling aids (wrong results!): 1 = drop the residual red.adds, 2 = skip attention,
-                                      // 4 = no GEMM tiles, 8 = no norm rows (2|4|8 = the bare grid-barrier skeleton)
+                                      // 4 = no GEMM tiles, 8 = no norm rows (2|4|8 = the bare grid-barrier skeleton);
+                                      // expert_gemv.cu: 2, 4 as above, 16 = no L2 prefetch of the coming phases' weights
   long long* timing = nullptr;        // optional [7 * n_layers]: globaltimer (ns) at which CTA 0 saw each phase complete
   unsigned int* barrier = nullptr;    // grid-barrier arrival counters of this pass, [n_streams][7 * n_layers], zero on entry
   int n_streams = 1;                  // independent sub-grids (see expert.cu); needs batch % S == 0, (M / S) % 32 == 0
@@ -68,5 +75,10 @@ struct ExpertPass {
 // stream p.x (make_tmap_out, box 32 rows x 32 columns) through which the split-K partial sums are reduce-added.
 int expert_pass_launch(const ExpertPass& p, const CUtensorMap& tmXn, const CUtensorMap& tmAo, const CUtensorMap& tmAct,
                        const CUtensorMap& tmX, cudaStream_t stream);
+
+// Same pass for ONE observation with at most 8 rows (B = 1: the proprio row, the H action rows): no tensor cores, the
+// expert weights are streamed once with coalesced 16-byte loads, 5 phases per layer (expert_gemv.cu). Uses p.x, p.q,
+// p.ao, p.act, the RoPE / KV-cache fields, the per-sample segments of sample 0 and p.barrier ([5 * n_layers] words).
+int expert_gemv_pass_launch(const ExpertPass& p, cudaStream_t stream);
 
 }  // namespace vlaser
