@@ -13,8 +13,20 @@ template <int VPL, bool RMS, bool GATHER>
 __global__ void __launch_bounds__(128) norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                    const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                                    int rows, const int* __restrict__ rows_dev, float eps, int g,
-                                                   int C) {
+                                                   int C, const L2Prefetch pf) {
   pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (pf.bytes[i] == 0) continue;
+      const unsigned long long slice = ((pf.bytes[i] + gridDim.x - 1) / gridDim.x + 127ull) & ~127ull;
+      const unsigned long long lo = blockIdx.x * slice, hi = min(pf.bytes[i], lo + slice);
+      for (unsigned long long off = lo; off < hi; off += 32768ull) {
+        const unsigned int sz = (unsigned int)min(32768ull, hi - off);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(pf.ptr[i]) + off), "r"(sz) : "memory");
+      }
+    }
+  }
   pdl_wait();
   constexpr int W = VPL * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -79,13 +91,14 @@ __global__ void __launch_bounds__(128) norm_kernel(const float* __restrict__ x, 
 
 template <bool RMS, bool GATHER>
 int norm_dispatch(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows,
-                  const int* rows_dev, int width, float eps, int g, int C, cudaStream_t stream) {
+                  const int* rows_dev, int width, float eps, int g, int C, cudaStream_t stream,
+                  const L2Prefetch& pf = L2Prefetch()) {
   VL_CHECK(width % 128 == 0 && width >= 128 && width <= 4096, "norm: width must be a multiple of 128, <= 4096");
   if (rows <= 0) return 0;
   const int grid = (rows + 3) / 4;
 #define VL_NORM_CASE(V)                                                                                          \
   case V:                                                                                                        \
-    VL_CUDA_CHECK(launch_kernel(norm_kernel<V, RMS, GATHER>, dim3(grid), dim3(128), 0, stream, x, gamma, beta, out, rows, rows_dev, eps, g, C));       \
+    VL_CUDA_CHECK(launch_kernel(norm_kernel<V, RMS, GATHER>, dim3(grid), dim3(128), 0, stream, x, gamma, beta, out, rows, rows_dev, eps, g, C, pf));       \
     break;
   switch (width / 128) {
     VL_NORM_CASE(1) VL_NORM_CASE(2) VL_NORM_CASE(3) VL_NORM_CASE(4) VL_NORM_CASE(6) VL_NORM_CASE(8)
@@ -375,8 +388,9 @@ int layernorm_launch(const float* x, const float* gamma, const float* beta, __nv
 }
 
 int rmsnorm_launch(const float* x, const float* gamma, __nv_bfloat16* out, int rows, const int* rows_dev, int width,
-                   float eps, cudaStream_t stream) {
-  return norm_dispatch<true, false>(x, gamma, nullptr, out, rows, rows_dev, width, eps, 0, 0, stream);
+                   float eps, cudaStream_t stream, const L2Prefetch* pf) {
+  return norm_dispatch<true, false>(x, gamma, nullptr, out, rows, rows_dev, width, eps, 0, 0, stream,
+                                    pf ? *pf : L2Prefetch());
 }
 
 int pixel_shuffle_launch(const void* in, void* out, int n, int grid, int channels, int elem_bytes,

@@ -16,8 +16,16 @@ struct ShuffleGather {   // pixel_shuffle(0.5) gather fused into the projector's
 };
 int layernorm_launch(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows, int width,
                      float eps, ShuffleGather sg, cudaStream_t stream);
+// Optional HBM -> L2 prefetch riding on a norm launch: before its dependent-launch wait, thread 0 of every CTA issues
+// bulk L2 prefetches (cp.async.bulk.prefetch.L2, <= 32 KB each) for its slice of up to three constant byte ranges —
+// the weights of the GEMMs a few launches further down the chain, which would otherwise start on cold HBM lines
+// (the 1.3 GB of expert weights streamed per pass flush the 126 MB L2 between passes).
+struct L2Prefetch {
+  const void* ptr[3] = {nullptr, nullptr, nullptr};
+  unsigned long long bytes[3] = {0, 0, 0};  // multiples of 16
+};
 int rmsnorm_launch(const float* x, const float* gamma, __nv_bfloat16* out, int rows, const int* rows_dev, int width,
-                   float eps, cudaStream_t stream);
+                   float eps, cudaStream_t stream, const L2Prefetch* pf = nullptr);
 
 // ---- pixel_shuffle (pizero_internvl.py:706-716), pure re-index, bit exact. elem_bytes in {2,4}.
 int pixel_shuffle_launch(const void* in, void* out, int n, int grid, int channels, int elem_bytes, cudaStream_t stream);

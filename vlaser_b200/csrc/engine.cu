@@ -154,6 +154,8 @@ struct Engine {
                                // persistent kernel per pass (expert.cu) instead of 7 kernels per layer. Measured on
                                // B200 at B=64 (profiles/r01e_schedule_ab.txt): 43.2 ms per call against 40.3 ms for the
                                // per-kernel schedule with PDL, so the per-kernel schedule is the default
+  int l2pf = 0;                // 1: the norm launches of a denoise step prefetch the coming expert weights into L2. Measured at
+                               // B=64 (gpurun r01l, two runs each): 39.8 / 40.7 ms with, 39.5 / 39.8 ms without -> off
   int gemv = 1;                // 1: at B = 1 the expert passes run on the weight-streaming kernel (expert_gemv.cu)
   int fuse_norm = 0;           // 1: RMSNorm of the expert streams fused across the GEMM chain (see exp_pre/exp_post)
   int profile_gemm = 0;        // bracket every GEMM launch with CUDA events (non-graph runs only)
@@ -764,18 +766,18 @@ struct Run {
 
   // one transformer block of a stream (residual x fp32, expert or LLM weights)
   int block_pre(LlmLayer& L, float* x, Act& xn, bf16* qout, int M, const int* M_dev, int hid, const int* pos,
-                const int* kvrow, int layer) {
-    VL_TRY(rmsnorm_launch(x, L.ln_in, xn.p, M, M_dev, hid, e.c.rms_eps, st));
+                const int* kvrow, int layer, const L2Prefetch* pf = nullptr) {
+    VL_TRY(rmsnorm_launch(x, L.ln_in, xn.p, M, M_dev, hid, e.c.rms_eps, st, pf));
     e.launches++;
     return gemm(xn, L.qkv, M, M_dev, EPI_QKV_ROPE, rope_ep(qout, L.bqkv, pos, kvrow, layer));
   }
   int block_post(LlmLayer& L, float* x, Act& xn, Act& ao, Act& act, int M, const int* M_dev, int hid, int mlp,
-                 int splits, const CUtensorMap* x_otm = nullptr) {
+                 int splits, const CUtensorMap* x_otm = nullptr, const L2Prefetch* pf = nullptr) {
     EpiParams eo;
     eo.out = x;
     eo.ldo = hid;
     VL_TRY(gemm(ao, L.o, M, M_dev, EPI_RESID_F32, eo, splits, 0, x_otm));
-    VL_TRY(rmsnorm_launch(x, L.ln_post, xn.p, M, M_dev, hid, e.c.rms_eps, st));
+    VL_TRY(rmsnorm_launch(x, L.ln_post, xn.p, M, M_dev, hid, e.c.rms_eps, st, pf));
     e.launches++;
     EpiParams eg;
     eg.out = act.p;
@@ -971,8 +973,16 @@ struct Run {
       VL_TRY(expert_pass(step + 1, M, e.xa, e.xa_otm, e.xan, e.qa, e.aoa, e.acta, e.pb.act_pos, e.pb.act_kvrow, e.pb.den_q_start,
                          e.pb.den_q_len, e.pb.den_kv_len, e.H, false));
     for (int li = 0; li < (mega() ? 0 : c.layers); ++li) {
+      // HBM -> L2 ahead of the chain (option "l2_prefetch"): the ln_in norm pulls this layer's o and gate/up matrices,
+      // the ln_post norm its down matrix and the next layer's q|k|v
+      auto wbytes = [](const Lin& w) { return (unsigned long long)w.N * w.K * sizeof(bf16); };
+      L2Prefetch pf_in, pf_post;
+      pf_in.ptr[0] = e.exp[li].o.w, pf_in.bytes[0] = wbytes(e.exp[li].o);
+      pf_in.ptr[1] = e.exp[li].gu.w, pf_in.bytes[1] = wbytes(e.exp[li].gu);
+      pf_post.ptr[0] = e.exp[li].down.w, pf_post.bytes[0] = wbytes(e.exp[li].down);
+      if (li + 1 < c.layers) pf_post.ptr[1] = e.exp[li + 1].qkv.w, pf_post.bytes[1] = wbytes(e.exp[li + 1].qkv);
       if (e.fuse_norm) VL_TRY(exp_pre(li, e.xan, e.qa, M, e.pb.act_pos, e.pb.act_kvrow, step + 1));
-      else VL_TRY(block_pre(e.exp[li], e.xa, e.xan, e.qa, M, nullptr, he, e.pb.act_pos, e.pb.act_kvrow, li));
+      else VL_TRY(block_pre(e.exp[li], e.xa, e.xan, e.qa, M, nullptr, he, e.pb.act_pos, e.pb.act_kvrow, li, e.l2pf ? &pf_in : nullptr));
       AttnParams ap;
       const size_t off = (size_t)li * c.n_kv_heads * e.kv_rows * 128;
       ap.q = e.qa;
@@ -996,7 +1006,7 @@ struct Run {
       VL_TRY(attention_launch(ap, 128, st));
       e.launches++;
       if (e.fuse_norm) VL_TRY(exp_post(li, e.xa, e.xan, e.aoa, e.acta, M, step + 1, false));
-      else VL_TRY(block_post(e.exp[li], e.xa, e.xan, e.aoa, e.acta, M, nullptr, he, e.mlp_e_p, 32, &e.xa_otm));
+      else VL_TRY(block_post(e.exp[li], e.xa, e.xan, e.aoa, e.acta, M, nullptr, he, e.mlp_e_p, 32, &e.xa_otm, e.l2pf ? &pf_post : nullptr));
     }
     const int last = step == c.num_inference_steps - 1;
     VL_TRY(euler_step_launch(e.xa, e.final_norm, e.dec_w, e.dec_b, e.action, e.out_act, io, M, he, c.action_dim, e.H,
@@ -1130,13 +1140,14 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "expert_timing" || k == "expert_flags") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "expert_timing" || k == "expert_flags") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
     else if (k == "expert_mega") h->e.mega = (int)value;
     else if (k == "expert_streams") h->e.xp_streams = (int)value;
     else if (k == "expert_gemv") h->e.gemv = (int)value;
+    else if (k == "l2_prefetch") h->e.l2pf = (int)value;
     else if (k == "expert_timing") h->e.xp_time = (int)value;
     else if (k == "expert_flags") h->e.xp_flags = (int)value;
     else if (k == "pair_gemm") h->e.pair_gemm = (int)value;

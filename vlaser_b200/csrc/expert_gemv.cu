@@ -161,30 +161,41 @@ __device__ __forceinline__ void reduce_to_lane(float (&acc)[GV_NR][R], int lane,
 }
 
 // RMSNorm of the M live rows of x into shared memory as bf16 (HF Qwen2RMSNorm: fp32 statistics; the normalised row is
-// the bf16 GEMM operand of the per-kernel schedule as well). Warp r owns row r.
+// the bf16 GEMM operand of the per-kernel schedule as well). All 16 warps: warp w owns part w / R of the columns of row
+// w % R, x is read ONCE (registers), the partial sums of squares meet in shared memory. he <= 512 * (16 / R).
 template <int R>
 __device__ __forceinline__ void norm_rows_to_smem(const float* __restrict__ x, const float* __restrict__ gamma, int M,
-                                                  int he, float eps, __nv_bfloat16* a_s, int warp, int lane) {
-  for (int r = warp; r < R; r += GV_WARPS) {
-    __nv_bfloat16* dst = a_s + (size_t)r * he;
-    if (r < M) {
-      float q = 0.f;
-      for (int c = lane * 4; c < he; c += 128) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(x + (size_t)r * he + c));
-        q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-      }
-      const float rstd = rsqrtf(warp_sum(q) / (float)he + eps);
-      for (int c = lane * 4; c < he; c += 128) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(x + (size_t)r * he + c));  // L1/L2 hit
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-        uint2 o;
-        o.x = pack_bf16(v.x * rstd * g.x, v.y * rstd * g.y);
-        o.y = pack_bf16(v.z * rstd * g.z, v.w * rstd * g.w);
-        *reinterpret_cast<uint2*>(dst + c) = o;
-      }
-    } else {
-      for (int c = lane * 4; c < he; c += 128) *reinterpret_cast<uint2*>(dst + c) = make_uint2(0u, 0u);
+                                                  int he, float eps, __nv_bfloat16* a_s, float* part_ss, int warp, int lane) {
+  constexpr int PARTS = GV_WARPS / R;
+  constexpr int NI = R;  // float2 slots per lane: he / PARTS / 64 <= R for he <= 1024
+  const int r = warp % R, part = warp / R, plen = he / PARTS;
+  const float* xr = x + (size_t)r * he + part * plen;
+  const float* gr = gamma + part * plen;
+  float2 xv[NI], gv[NI];
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int c = lane * 2 + 64 * i;
+    xv[i] = make_float2(0.f, 0.f), gv[i] = xv[i];
+    if (c < plen && r < M) {
+      xv[i] = __ldcg(reinterpret_cast<const float2*>(xr + c));
+      gv[i] = __ldg(reinterpret_cast<const float2*>(gr + c));
     }
+  }
+#pragma unroll
+  for (int i = 0; i < NI; ++i) q += xv[i].x * xv[i].x + xv[i].y * xv[i].y;
+  q = warp_sum(q);
+  if (lane == 0) part_ss[warp] = q;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int pp = 0; pp < PARTS; ++pp) tot += part_ss[pp * R + r];
+  const float rstd = rsqrtf(tot / (float)he + eps);
+  __nv_bfloat16* dst = a_s + (size_t)r * he + part * plen;
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int c = lane * 2 + 64 * i;
+    if (c < plen) *reinterpret_cast<uint32_t*>(dst + c) = pack_bf16(xv[i].x * rstd * gv[i].x, xv[i].y * rstd * gv[i].y);
   }
 }
 
@@ -298,24 +309,60 @@ __device__ __forceinline__ void attention_head(const ExpertPass& p, const Seg& s
     if (tid + x * GV_THREADS < R * 128) qs[tid + x * GV_THREADS] = qv[x];
   __syncthreads();
   gv_stamp(st, 5);
-  // scores: 8 lanes per kv row (16 head dims each), 64 rows per sweep
+  // scores: 8 lanes per kv row (16 head dims each), 64 rows per sweep; sc is laid out [kv row][R]
   {
     const int l8 = tid & 7, jrow = tid >> 3;
     const float sl2 = p.scale * 1.4426950408889634f;
-    for (int it = 0; it * (GV_THREADS / 8) < kv_len; ++it) {
+    {
+      // the two register-resident sweeps share every q fragment read from shared memory
+      float k0[16], k1[16];
+      {
+        float t[8];
+        unpack8(wr[0][0], t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) k0[e] = t[e];
+        unpack8(wr[0][1], t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) k0[8 + e] = t[e];
+        unpack8(wr[1][0], t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) k1[e] = t[e];
+        unpack8(wr[1][1], t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) k1[8 + e] = t[e];
+      }
+      const int j0 = jrow, j1 = jrow + GV_THREADS / 8;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 qv = *reinterpret_cast<const float4*>(qs + r * 128 + l8 * 4 + 32 * c);
+          a0 += k0[4 * c] * qv.x + k0[4 * c + 1] * qv.y + k0[4 * c + 2] * qv.z + k0[4 * c + 3] * qv.w;
+          a1 += k1[4 * c] * qv.x + k1[4 * c + 1] * qv.y + k1[4 * c + 2] * qv.z + k1[4 * c + 3] * qv.w;
+        }
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 4);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 4);
+        if (l8 == 0 && j0 < kv_len) sc[(size_t)j0 * R + r] = a0 * sl2;
+        if (l8 == 0 && j1 < kv_len) sc[(size_t)j1 * R + r] = a1 * sl2;
+      }
+    }
+    for (int it = GV_KIT; it * (GV_THREADS / 8) < kv_len; ++it) {  // kv rows beyond the register-resident 128
       const int j = jrow + (GV_THREADS / 8) * it;
       const bool valid = j < kv_len;
       uint4 u0 = make_uint4(0u, 0u, 0u, 0u), u1 = u0;
-      if (it == 0) u0 = wr[0][0], u1 = wr[0][1];
-      else if (it == 1) u0 = wr[1][0], u1 = wr[1][1];
-      else if (valid) load_k_row(K, j, l8, u0, u1);
+      if (valid) load_k_row(K, j, l8, u0, u1);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         float a = score_part(u0, u1, qs + r * 128 + l8 * 4);
         a += __shfl_xor_sync(0xffffffffu, a, 1);
         a += __shfl_xor_sync(0xffffffffu, a, 2);
         a += __shfl_xor_sync(0xffffffffu, a, 4);
-        if (valid && l8 == 0) sc[(size_t)r * kvpad + j] = a * sl2;
+        if (valid && l8 == 0) sc[(size_t)j * R + r] = a * sl2;
       }
     }
   }
@@ -324,15 +371,15 @@ __device__ __forceinline__ void attention_head(const ExpertPass& p, const Seg& s
   // softmax (exp2 domain), warp r owns row r; the probabilities are rounded to bf16 as the PV operand of the
   // tensor-core path is, the row sum stays fp32
   for (int r = warp; r < R; r += GV_WARPS) {
-    float* row = sc + (size_t)r * kvpad;
+    float* row = sc + r;
     float mx = -INFINITY;
-    for (int j = lane; j < kv_len; j += 32) mx = fmaxf(mx, row[j]);
+    for (int j = lane; j < kv_len; j += 32) mx = fmaxf(mx, row[(size_t)j * R]);
     mx = warp_max(mx);
     float sum = 0.f;
     for (int j = lane; j < kv_len; j += 32) {
-      const float pv = exp2f(row[j] - mx);
+      const float pv = exp2f(row[(size_t)j * R] - mx);
       sum += pv;
-      row[j] = round_bf16(pv);
+      row[(size_t)j * R] = round_bf16(pv);
     }
     sum = warp_sum(sum);
     if (lane == 0) lsum[r] = sum;
@@ -345,32 +392,33 @@ __device__ __forceinline__ void attention_head(const ExpertPass& p, const Seg& s
     float o[R][2];
 #pragma unroll
     for (int r = 0; r < R; ++r) o[r][0] = o[r][1] = 0.f;
+    auto pv_step = [&](int j, uint32_t vw) {
+      const float v0 = bf16_lo(vw), v1 = bf16_hi(vw);
+      float pj[R];
+      if constexpr (R % 4 == 0) {
+#pragma unroll
+        for (int r4 = 0; r4 < R / 4; ++r4) {
+          const float4 t = *reinterpret_cast<const float4*>(sc + (size_t)j * R + 4 * r4);
+          pj[4 * r4] = t.x, pj[4 * r4 + 1] = t.y, pj[4 * r4 + 2] = t.z, pj[4 * r4 + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) pj[r] = sc[(size_t)j * R + r];
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        o[r][0] = fmaf(pj[r], v0, o[r][0]);
+        o[r][1] = fmaf(pj[r], v1, o[r][1]);
+      }
+    };
 #pragma unroll
     for (int t = 0; t < GV_VT; ++t) {
       const int j = js + GV_JS * t;
-      if (j < kv_len) {
-        const uint32_t vw = v_slot(wr, t);
-        const float v0 = bf16_lo(vw), v1 = bf16_hi(vw);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float pj = sc[(size_t)r * kvpad + j];
-          o[r][0] = fmaf(pj, v0, o[r][0]);
-          o[r][1] = fmaf(pj, v1, o[r][1]);
-        }
-      }
+      if (j < kv_len) pv_step(j, v_slot(wr, t));
     }
     const uint32_t* Vw = reinterpret_cast<const uint32_t*>(V) + d2;
 #pragma unroll 4
-    for (int j = GV_KV_REG + js; j < kv_len; j += GV_JS) {
-      const uint32_t u = __ldcg(Vw + (size_t)j * 64);
-      const float v0 = bf16_lo(u), v1 = bf16_hi(u);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float pj = sc[(size_t)r * kvpad + j];
-        o[r][0] = fmaf(pj, v0, o[r][0]);
-        o[r][1] = fmaf(pj, v1, o[r][1]);
-      }
-    }
+    for (int j = GV_KV_REG + js; j < kv_len; j += GV_JS) pv_step(j, __ldcg(Vw + (size_t)j * 64));
 #pragma unroll
     for (int r = 0; r < R; ++r) *reinterpret_cast<float2*>(red + ((size_t)js * R + r) * 128 + 2 * d2) = make_float2(o[r][0], o[r][1]);
   }
@@ -433,6 +481,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) expert_gemv_pass_kernel(const E
   // everything up to the dependent-launch wait touches constants only: the layer table, the first unit's weight
   // loads and the L2 prefetch of layer 0's small matrices and parameters
   __shared__ LayerPtrs lt[GV_MAX_LAYERS];
+  __shared__ float part_ss[GV_WARPS];
   if (tid < p.n_layers) {
     const ExpertLayerDev* e = p.layers + tid;
     LayerPtrs t;
@@ -462,6 +511,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) expert_gemv_pass_kernel(const E
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
     p.timing[7 * p.n_layers - 1] = now;
   }
+  const int my_pos = lane < M ? p.row_pos[lane] : 0, my_kvrow = lane < M ? p.row_kvrow[lane] : 0;
   Seg sg;
   sg.q_len = p.q_len[0], sg.kv_len = p.kv_len[0], sg.kv0 = p.kv_start[0], sg.qs0 = p.q_start[0];
   const int kvh = attn_cta ? d.b / (p.n_q_heads / p.n_kv_heads) : 0;
@@ -499,7 +549,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) expert_gemv_pass_kernel(const E
         const int total = unit_count(d, j);
         int pitch = d.he, abase = 0;
         if (j == 0 || j == 3) {
-          norm_rows_to_smem<R>(p.x, j == 0 ? L->ln_in : L->ln_post, M, d.he, p.eps, a_s, warp, lane);
+          norm_rows_to_smem<R>(p.x, j == 0 ? L->ln_in : L->ln_post, M, d.he, p.eps, a_s, part_ss, warp, lane);
         } else if (j == 2) {
           pitch = d.qdim;
           bf16_rows_to_smem<R>(p.ao, M, d.qdim, 0, d.qdim, pitch, a_s, tid);
@@ -524,6 +574,15 @@ __global__ void __launch_bounds__(GV_THREADS, 1) expert_gemv_pass_kernel(const E
           const int u = base + first_unit(d, j);
           const bool ok = base == 0 ? have : (!skip_units && make_unit(d, L, j, u, U));
           if (ok) {
+            // q|k|v epilogue operands (bias, RoPE factors of this lane's row) fetched ahead of the dot products
+            float eb[4] = {0.f, 0.f, 0.f, 0.f}, ecs[2] = {1.f, 1.f}, esn[2] = {0.f, 0.f};
+            if (j == 0 && lane < M) {
+              const float* bq = L->bqkv + (u >> 5) * 128 + (u & 31);
+              eb[0] = __ldg(bq), eb[1] = __ldg(bq + 64), eb[2] = __ldg(bq + 32), eb[3] = __ldg(bq + 96);
+              const size_t ci = (size_t)my_pos * 64 + (u & 31);
+              ecs[0] = __ldg(p.cos_tab + ci), esn[0] = __ldg(p.sin_tab + ci);
+              ecs[1] = __ldg(p.cos_tab + ci + 32), esn[1] = __ldg(p.sin_tab + ci + 32);
+            }
             float acc[GV_NR][R];
 #pragma unroll
             for (int i = 0; i < GV_NR; ++i)
@@ -544,16 +603,15 @@ __global__ void __launch_bounds__(GV_THREADS, 1) expert_gemv_pass_kernel(const E
                 if (is_q) dst = p.q + (size_t)r * d.qdim + head * 128;
                 else {
                   const int kh = is_k ? head - p.n_q_heads : head - p.n_q_heads - p.n_kv_heads;
-                  dst = (is_k ? kc : vc) + (size_t)kh * p.kv_head_stride + (size_t)p.row_kvrow[r] * 128;
+                  dst = (is_k ? kc : vc) + (size_t)kh * p.kv_head_stride + (size_t)my_kvrow * 128;
                 }
-                const int pos = p.row_pos[r];
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                   const int i = i0 + 32 * hf;
-                  float v0 = mine[2 * hf] + L->bqkv[head * 128 + i];
-                  float v1 = mine[2 * hf + 1] + L->bqkv[head * 128 + i + 64];
+                  float v0 = mine[2 * hf] + eb[2 * hf];
+                  float v1 = mine[2 * hf + 1] + eb[2 * hf + 1];
                   if (is_q || is_k) {
-                    const float cs = p.cos_tab[(size_t)pos * 64 + i], sn = p.sin_tab[(size_t)pos * 64 + i];
+                    const float cs = ecs[hf], sn = esn[hf];
                     const float x0 = v0, x1 = v1;
                     v0 = x0 * cs - x1 * sn;  // x*cos + rotate_half(x)*sin
                     v1 = x1 * cs + x0 * sn;
@@ -634,7 +692,7 @@ int launch_r(const ExpertPass& p, int grid, size_t smem, cudaStream_t stream) {
 int expert_gemv_pass_launch(const ExpertPass& p, cudaStream_t stream) {
   VL_CHECK(p.layers && p.n_layers > 0 && p.M > 0, "expert gemv pass: empty problem");
   VL_CHECK(p.batch == 1 && p.M <= 8, "expert gemv pass: one observation, at most 8 rows");
-  VL_CHECK(p.he % 128 == 0 && p.he >= 64 && p.mlp % 64 == 0, "expert gemv pass: bad widths");
+  VL_CHECK(p.he % 128 == 0 && p.he <= 1024 && p.mlp % 64 == 0, "expert gemv pass: bad widths");
   VL_CHECK(p.barrier != nullptr && p.max_kv_len > 0, "expert gemv pass: null barrier counter / no kv bound");
   VL_CHECK(p.n_layers <= GV_MAX_LAYERS, "expert gemv pass: more layers than the shared-memory layer table holds");
   const int R = p.M <= 1 ? 1 : p.M <= 4 ? 4 : 8;
