@@ -14,6 +14,7 @@ from vlaser_b200.weights import random_state_dict
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["tiny_bridge", "tiny_fractal", "tiny_robotwin"]
+DYNAMIC_TILE_CASES = ["tiny_dynamic_tiles"]  # samples own different numbers of image tiles
 
 
 def load_case(name: str):

@@ -16,7 +16,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import vlaser_oracle as O  # noqa: E402  (checker only)
-from tests.golden_util import CASES, load_case  # noqa: E402
+from tests.golden_util import CASES, DYNAMIC_TILE_CASES, load_case  # noqa: E402
 from tests.ops import max_err, rel_err  # noqa: E402
 from vlaser_b200.config import tiny, vlaser_2b_bridge  # noqa: E402
 from vlaser_b200.policy import PiZeroInference  # noqa: E402
@@ -338,3 +338,24 @@ def test_full_size_2b_single_observation():
     pol.set_option("use_graph", 1)
     pol.set_option("expert_gemv", 0)
     assert max_err(_run(pol, inp), got) < 5e-3
+
+
+def test_dynamic_tiles_parity():
+    """Dynamic tiles: the samples of one batch hold 1 / 3 / 2 / 2 image tiles; projector
+    rows are handed out in batch order as the reference's masked scatter does (oracle pinned to the live reference for
+    this layout in tests/test_oracle.py). Whole call against the fp32 oracle; the token merge is bit-exact."""
+    cfg, sd, inp, gold = load_case(DYNAMIC_TILE_CASES[0])
+    counts = (inp["input_ids"] == cfg.image_token_index).sum(1) // cfg.image_tokens
+    assert counts.tolist() == [1, 3, 2, 2]
+    pol = _policy(cfg, sd, 4)
+    got = _run(pol, inp)
+    assert max_err(got, gold["actions"]) <= ACTION_TOL            # the reference's own output
+    ref = O.infer_action(cfg, sd, inp["input_ids"], inp["pixel_values"], inp["proprios"], inp["noise"])
+    assert max_err(got, ref) <= ACTION_TOL
+    # token merge: image rows of the packed prefix land where the reference's masked scatter puts them
+    # (bit-exact index check: projector row k -> packed prefix row of the k-th image token in batch order)
+    ids = inp["input_ids"]
+    valid = (ids != cfg.pad_token_id).sum(1)
+    cu = torch.cumsum(valid, 0) - valid
+    expected = [int(cu[b]) + j for b in range(ids.shape[0]) for j in range(ids.shape[1]) if int(ids[b, j]) == cfg.image_token_index]
+    assert pol.debug_buffer("img_row_map", torch.int32)[: len(expected)].tolist() == expected

@@ -8,13 +8,13 @@ import torch
 
 from oracle import ref_harness
 from oracle import vlaser_oracle as O
-from tests.golden_util import CASES, load_case
+from tests.golden_util import CASES, DYNAMIC_TILE_CASES, load_case
 from vlaser_b200.config import tiny
 from vlaser_b200.synth import make_inputs
 from vlaser_b200.weights import random_state_dict
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + DYNAMIC_TILE_CASES)
 def test_oracle_matches_golden(name):
     cfg, sd, inp, gold = load_case(name)
     tr = {}
@@ -98,3 +98,19 @@ def test_oracle_matches_live_reference():
     assert (act - ref_act).abs().max() < 2e-5
     assert (tr["vit_out"] - ref_tr["vit_out"]).abs().max() < 2e-5
     assert (tr["expert_out_step0"] - ref_tr["expert_out_step0"]).abs().max() < 2e-5
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="/root/reference not present (GPU box)")
+def test_oracle_matches_live_reference_dynamic_tiles():
+    """Dynamic tiles: samples hold 1 / 3 / 2 / 2 image tiles (8 = B * num_images in total); the
+    reference's masked scatter hands the projector rows out in batch order, and so does the oracle."""
+    from vlaser_b200.config import tiny
+    from vlaser_b200.synth import make_inputs
+    from vlaser_b200.weights import random_state_dict
+    from oracle import vlaser_oracle as O
+    cfg = tiny().with_(cond_steps=2, max_image_text_tokens=224)
+    sd = random_state_dict(cfg, 3)
+    inp = make_inputs(cfg, 4, 11, tiles_per_sample=[1, 3, 2, 2])
+    ref_act, _ = ref_harness.run_reference(cfg, sd, inp["input_ids"], inp["pixel_values"], inp["proprios"], inp["noise"])
+    got = O.infer_action(cfg, sd, inp["input_ids"], inp["pixel_values"], inp["proprios"], inp["noise"])
+    assert float((got - ref_act).abs().max()) <= 1e-5

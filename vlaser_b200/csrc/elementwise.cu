@@ -179,7 +179,7 @@ __global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__
 // planning
 // ------------------------------------------------------------------------------------------
 __global__ void plan_lengths_kernel(const long long* __restrict__ ids, const int* __restrict__ valid_in, PlanBuffers pb,
-                                    int B, int S, int H, int pad_token) {
+                                    int B, int S, int H, int pad_token, int image_token) {
   pdl_launch_dependents();
   pdl_wait();
   // one warp per sample counts non-pad ids
@@ -192,18 +192,27 @@ __global__ void plan_lengths_kernel(const long long* __restrict__ ids, const int
     for (int j = lane; j < S; j += 32) cnt += ids[(size_t)warp * S + j] != pad_token;
     cnt = (int)warp_sum((float)cnt);
   }
-  if (lane == 0) pb.valid_len[warp] = min(max(cnt, 0), S);
+  cnt = min(max(cnt, 0), S);
+  int imgs = 0;
+  for (int j = lane; j < cnt; j += 32) imgs += ids[(size_t)warp * S + j] == image_token;
+  imgs = (int)warp_sum((float)imgs);
+  if (lane == 0) {
+    pb.valid_len[warp] = cnt;
+    pb.img_cnt[warp] = imgs;
+  }
 }
 
 __global__ void plan_scan_kernel(PlanBuffers pb, int B, int H) {
   pdl_launch_dependents();
   pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    int acc = 0;
+    int acc = 0, img = 0;
     for (int b = 0; b < B; ++b) {
       pb.cu[b] = acc;
       pb.kvoff[b] = acc + b * (1 + H);
+      pb.img_off[b] = img;
       acc += pb.valid_len[b];
+      img += pb.img_cnt[b];
     }
     pb.cu[B] = acc;
     *pb.m_tot = acc;
@@ -217,7 +226,7 @@ __global__ void plan_rows_kernel(const long long* __restrict__ ids, PlanBuffers 
   // one warp per sample
   const int b = blockIdx.x, lane = threadIdx.x;
   const int vl = pb.valid_len[b], base = pb.cu[b], kvo = pb.kvoff[b];
-  int seen = 0;
+  int seen = pb.img_off[b];  // image rows are numbered across the batch in row-major order
   for (int j0 = 0; j0 < S; j0 += 32) {
     const int j = j0 + lane;
     const bool valid = j < vl;
@@ -231,8 +240,8 @@ __global__ void plan_rows_kernel(const long long* __restrict__ ids, PlanBuffers 
       int src;
       if (is_img) {
         const int k = seen + __popc(mask & ((1u << lane) - 1u));
-        if (k < img_tokens) {
-          pb.img_row_map[b * img_tokens + k] = m;
+        if (k < B * img_tokens) {
+          pb.img_row_map[k] = m;
           src = -2;
         } else {
           src = -1;
@@ -436,7 +445,7 @@ int plan_launch(const long long* input_ids, const int* valid_len_in, PlanBuffers
                 int img_tokens_per_sample, int image_token, int pad_token, cudaStream_t stream) {
   VL_CHECK(B > 0, "plan: empty batch");
   VL_CUDA_CHECK(cudaMemsetAsync(pb.img_row_map, 0xFF, sizeof(int) * (size_t)B * img_tokens_per_sample, stream));
-  VL_CUDA_CHECK(launch_kernel(plan_lengths_kernel, dim3((B * 32 + 127) / 128), dim3(128), 0, stream, input_ids, valid_len_in, pb, B, S, H, pad_token));
+  VL_CUDA_CHECK(launch_kernel(plan_lengths_kernel, dim3((B * 32 + 127) / 128), dim3(128), 0, stream, input_ids, valid_len_in, pb, B, S, H, pad_token, image_token));
   VL_CUDA_CHECK(launch_kernel(plan_scan_kernel, dim3(1), dim3(32), 0, stream, pb, B, H));
   VL_CUDA_CHECK(launch_kernel(plan_rows_kernel, dim3(B), dim3(32), 0, stream, input_ids, pb, B, S, H, img_tokens_per_sample, image_token, pad_token));
   VL_CUDA_CHECK(cudaGetLastError());

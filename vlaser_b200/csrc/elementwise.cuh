@@ -47,7 +47,11 @@ struct PlanBuffers {
   int* row_pos;       // [B*S] RoPE position per packed row (j+1)
   int* row_kvrow;     // [B*S]
   int* row_src;       // [B*S] >=0 embed row, -1 zeros, -2 image row (written by the projector epilogue)
-  int* img_row_map;   // [B*n_img*T] projector output row -> packed row (or -1)
+  int* img_row_map;   // [B*n_img*T] projector output row -> packed row (or -1); rows are numbered in batch order, so a
+                      // sample owns as many image tiles as its ids hold image tokens (dynamic tiles), like the
+                      // reference's masked scatter (pizero_internvl.py:757-791)
+  int* img_cnt;       // [B] image tokens among the valid ids of a sample
+  int* img_off;       // [B] exclusive scan of img_cnt
   int* prop_pos;      // [B] == 1
   int* prop_kvrow;    // [B]
   int* act_pos;       // [B*H] 2..H+1

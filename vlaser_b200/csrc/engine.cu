@@ -418,6 +418,8 @@ int engine_build(Engine& e) {
   VL_TRY(e.alloc(&pb.row_kvrow, prow));
   VL_TRY(e.alloc(&pb.row_src, prow));
   VL_TRY(e.alloc(&pb.img_row_map, e.Bc * e.n_img * e.T));
+  VL_TRY(e.alloc(&pb.img_cnt, e.Bc));
+  VL_TRY(e.alloc(&pb.img_off, e.Bc));
   VL_TRY(e.alloc(&pb.prop_pos, e.Bc));
   VL_TRY(e.alloc(&pb.prop_kvrow, e.Bc));
   VL_TRY(e.alloc(&pb.act_pos, arow));

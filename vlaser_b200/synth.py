@@ -34,9 +34,14 @@ def process_images(images_u8: torch.Tensor) -> torch.Tensor:
 
 
 def make_inputs(cfg: VlaserConfig, batch: int, seed: int = 1,
-                prompt_tokens: Optional[List[int]] = None) -> Dict[str, torch.Tensor]:
+                prompt_tokens: Optional[List[int]] = None,
+                tiles_per_sample: Optional[List[int]] = None) -> Dict[str, torch.Tensor]:
     """Returns images_u8, pixel_values (fp32), input_ids (i64 [B,S]), attention_mask, proprios
-    (fp32 [B,1,Dp]), noise (fp32 [B,H,A]), valid_len (i32 [B])."""
+    (fp32 [B,1,Dp]), noise (fp32 [B,H,A]), valid_len (i32 [B]).
+
+    `tiles_per_sample` (dynamic tiles): sample b holds tiles_per_sample[b] image tiles (that many
+    times T `<IMG_CONTEXT>` ids); the tiles of the batch are concatenated in order, and their total must be
+    batch * cfg.num_images -- the layout the reference's masked scatter consumes (pizero_internvl.py:757-791)."""
     g = torch.Generator(device="cpu")
     g.manual_seed(seed)
     S, T, n_img = cfg.max_image_text_tokens, cfg.image_tokens, cfg.num_images
@@ -46,15 +51,18 @@ def make_inputs(cfg: VlaserConfig, batch: int, seed: int = 1,
     ids = torch.full((batch, S), cfg.pad_token_id, dtype=torch.int64)
     lo_special = min(cfg.image_token_index, cfg.pad_token_id)
     valid = []
+    if tiles_per_sample is not None:
+        assert len(tiles_per_sample) == batch and sum(tiles_per_sample) == batch * n_img, "tile counts must sum to batch * num_images"
     for b in range(batch):
         n_txt = prompt_tokens[b % len(prompt_tokens)]
         n_pre, n_post = TEMPLATE_PREFIX, TEMPLATE_SUFFIX + n_txt
-        total = n_pre + n_img * T + n_post
+        n_it = (tiles_per_sample[b] if tiles_per_sample is not None else n_img) * T
+        total = n_pre + n_it + n_post
         assert total <= S, f"prefix of {total} tokens does not fit max_image_text_tokens={S}"
         txt = torch.randint(0, lo_special, (n_pre + n_post,), generator=g)
         ids[b, :n_pre] = txt[:n_pre]
-        ids[b, n_pre:n_pre + n_img * T] = cfg.image_token_index
-        ids[b, n_pre + n_img * T:total] = txt[n_pre:]
+        ids[b, n_pre:n_pre + n_it] = cfg.image_token_index
+        ids[b, n_pre + n_it:total] = txt[n_pre:]
         valid.append(total)
     # Values are rounded to the bf16 grid (and kept as fp32): the bf16 device path and the fp32 oracle
     # then see IDENTICAL inputs, so parity measures compute error only (SURVEY.md §7 hard parts).
