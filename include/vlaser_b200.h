@@ -94,6 +94,7 @@ void vlaser_destroy(vlaser_t* h);
  * of the expert GEMMs, 0 = default),
  * "expert_mega" (default 0; 1 runs each proprio / denoise pass of the action expert as ONE persistent kernel, csrc/expert.cu),
  * "expert_streams" (default 2: independent sub-grids of that kernel, each owning a slice of the batch),
+ * "small_m_split" (default 1: split-K over the idle SMs for the ViT / LLM residual projections of small batches),
  * "l2_prefetch" (default 0, measured no gain: the RMSNorm launches of a denoise step issue bulk L2 prefetches of the expert weights the
  * next launches of the chain will read),
  * "expert_gemv" (default 1: at B = 1 the expert passes run on the weight-streaming single-observation kernel, csrc/expert_gemv.cu),

@@ -154,6 +154,7 @@ struct Engine {
                                // persistent kernel per pass (expert.cu) instead of 7 kernels per layer. Measured on
                                // B200 at B=64 (profiles/r01e_schedule_ab.txt): 43.2 ms per call against 40.3 ms for the
                                // per-kernel schedule with PDL, so the per-kernel schedule is the default
+  int small_m_split = 1;       // 1: split-K for the ViT / LLM residual projections when their tiles cover < half of the SMs
   int l2pf = 0;                // 1: the norm launches of a denoise step prefetch the coming expert weights into L2. Measured at
                                // B=64 (gpurun r01l, two runs each): 39.8 / 40.7 ms with, 39.5 / 39.8 ms without -> off
   int gemv = 1;                // 1: at B = 1 the expert passes run on the weight-streaming kernel (expert_gemv.cu)
@@ -622,6 +623,15 @@ struct Run {
     d.stages = stages;
     e.launches++;
     if (e.simt) return gemm_launch_simt(a.p, w.w, d, ep, epi, st);
+    // Few observations (B = 1, 2, ...): a residual projection of the ViT / LLM has a handful of output tiles (down
+    // projection of the LLM at B = 1: 12 tiles for 27.5 MB of weights, 23 us on 12 SMs). Split K over the idle SMs
+    // (fp32 red.adds into the residual stream, single-CTA kernel; the split count follows the live tile count in the
+    // kernel). Large batches are untouched: their tile count already covers the GPU.
+    if (e.small_m_split && epi == EPI_RESID_F32 && max_splits <= 1 && !ep.a_next &&
+        (long long)((M + 127) / 128) * (w.N / 128) * 2 <= gemm_num_sms()) {
+      max_splits = d.max_splits = 32;
+      out_tm = nullptr;
+    }
     int bn = 128;
     // large-M GEMMs: CTA-pair kernel (256x256 tile per pair) when there is at least one tile per pair
     // (with split-K through the TMA reduce-add epilogue the splits multiply the tile count)
@@ -1142,7 +1152,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "expert_timing" || k == "expert_flags") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "expert_timing" || k == "expert_flags") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
@@ -1150,6 +1160,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
     else if (k == "expert_streams") h->e.xp_streams = (int)value;
     else if (k == "expert_gemv") h->e.gemv = (int)value;
     else if (k == "l2_prefetch") h->e.l2pf = (int)value;
+    else if (k == "small_m_split") h->e.small_m_split = (int)value;
     else if (k == "expert_timing") h->e.xp_time = (int)value;
     else if (k == "expert_flags") h->e.xp_flags = (int)value;
     else if (k == "pair_gemm") h->e.pair_gemm = (int)value;
