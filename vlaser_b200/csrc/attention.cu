@@ -7,6 +7,7 @@
 // heavy lifting is in gemm.cu.
 #include "attention.cuh"
 #include "attention_device.cuh"
+#include "gemm.cuh"  // gemm_num_sms()
 
 namespace vlaser {
 
@@ -80,7 +81,9 @@ vit_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
   const int n_kb = (N + 63) >> 6;          // 64-key blocks, the last one possibly ragged
   bool staged_all = false;
 
-  for (int tile = warp; tile < n_tiles || !staged_all; tile += 8) {
+  // few images (B = 1, 2): gridDim.z CTAs share the query tiles of one (image, head), so that a 16-head single image
+  // is not left to 16 SMs with two sweeps each
+  for (int tile = warp + 8 * blockIdx.z; tile < n_tiles || !staged_all; tile += 8 * gridDim.z) {
     const bool active = tile < n_tiles;   // every warp walks the staging barriers of the first sweep
     uint32_t qf[HD / 16][4];
     float o[HD / 8][4];
@@ -212,7 +215,7 @@ vit_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
   }
 
   // ---- left-over query rows (N % 16 of them; the single CLS/patch row at N = 257): CUDA-core pass, all threads
-  for (int r = n_tiles * 16; r < N; ++r) {
+  for (int r = n_tiles * 16; r < N && blockIdx.z == gridDim.z - 1; ++r) {
     __syncthreads();
     // scores: thread t owns keys t, t + 256
     float sc[2] = {-INFINITY, -INFINITY};
@@ -298,7 +301,8 @@ int vit_attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int image
                                        3 * max_nr * 128 + max_nr * 4 + (4 * 64 + 16) * 4));
     attr_set = true;
   }
-  VL_CUDA_CHECK(launch_kernel(vit_attention_kernel, dim3(heads, images), dim3(VA_THREADS), smem, stream, qkv, out, tokens,
+  const int qsplit = (heads * images * 2 <= gemm_num_sms() && tokens > 128) ? 2 : 1;
+  VL_CUDA_CHECK(launch_kernel(vit_attention_kernel, dim3(heads, images, qsplit), dim3(VA_THREADS), smem, stream, qkv, out, tokens,
                               heads, scale));
   return 0;
 }

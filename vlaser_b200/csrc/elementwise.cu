@@ -319,6 +319,9 @@ __global__ void convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, 
 // ------------------------------------------------------------------------------------------
 // final norm + decoder + Euler
 // ------------------------------------------------------------------------------------------
+// One warp per (row, decoder output): every warp normalises its row itself (the row is a few KB in L2) and then has all
+// the loads of ONE decoder-weight row in flight at once -- two dependent load rounds per warp instead of a serial sweep
+// over the A decoder rows, and rows x A warps instead of rows (B = 1: 28 warps instead of 4).
 template <typename TO>
 __global__ void __launch_bounds__(128) euler_step_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                          const float* __restrict__ Wdec,
@@ -327,58 +330,47 @@ __global__ void __launch_bounds__(128) euler_step_kernel(const float* __restrict
                                                          int horizon, float dt, float eps, int last_step, int do_clip,
                                                          float clip) {
   pdl_launch_dependents();
-  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 4 + warp;
-  if (r >= rows) return;
-  // the row stays in registers (width <= 1024: up to 32 values per lane), pre-scaled by rstd * gamma once
-  const float* xr = x + (size_t)r * width;
-  float xv[32];
-  float q = 0.f;
+  const int unit = blockIdx.x * 4 + warp;
+  if (unit >= rows * A) return;
+  const int r = unit / A, a = unit - r * A;
+  // constants first: they do not depend on the previous launch (width <= 1024: up to 8 float4 per lane)
+  const float4* wr = reinterpret_cast<const float4*>(Wdec + (size_t)a * width);
+  const float4* gr = reinterpret_cast<const float4*>(gamma);
+  float4 wv[8], gv[8], xv[8];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int c = lane + 32 * i;
-    xv[i] = c < width ? xr[c] : 0.f;
-    q += xv[i] * xv[i];
+  for (int i = 0; i < 8; ++i) {
+    const int c4 = lane + 32 * i;
+    wv[i] = gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 * 4 < width) wv[i] = __ldg(wr + c4), gv[i] = __ldg(gr + c4);
   }
-  const float rstd = rsqrtf(warp_sum(q) / width + eps);
+  const float bias = __ldg(bdec + a);
+  pdl_wait();
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)r * width);
+  float q = 0.f, dot = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int c = lane + 32 * i;
-    if (c < width) xv[i] *= rstd * gamma[c];
+  for (int i = 0; i < 8; ++i) {
+    const int c4 = lane + 32 * i;
+    xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 * 4 < width) xv[i] = xr[c4];
   }
-  // eight decoder outputs at a time: all dot products first (independent loads in flight), then lane j finishes
-  // output a0 + j (bias, Euler update, clamp / slice on the last step)
-  for (int a0 = 0; a0 < A; a0 += 8) {
-    float acc[8];
+  const float prev = action[(size_t)r * A + a];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[j] = 0.f;
-      if (a0 + j < A) {
-        const float* wr = Wdec + (size_t)(a0 + j) * width;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int c = lane + 32 * i;
-          if (c < width) acc[j] += xv[i] * wr[c];
-        }
-      }
-    }
-    float mine = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float t = warp_sum(acc[j]);
-      if (lane == j) mine = t;
-    }
-    const int a = a0 + lane;
-    if (lane < 8 && a < A) {
-      float val = action[(size_t)r * A + a] + dt * (mine + bdec[a]);
-      action[(size_t)r * A + a] = val;
-      if (last_step) {
-        const int b = r / H, i = r - b * H;
-        if (i >= H - horizon) {
-          if (do_clip) val = fminf(fmaxf(val, -clip), clip);
-          out[((size_t)b * horizon + (i - (H - horizon))) * A + a] = static_cast<TO>(val);
-        }
+  for (int i = 0; i < 8; ++i) {
+    q += (xv[i].x * xv[i].x + xv[i].y * xv[i].y) + (xv[i].z * xv[i].z + xv[i].w * xv[i].w);
+    dot += (xv[i].x * gv[i].x * wv[i].x + xv[i].y * gv[i].y * wv[i].y) + (xv[i].z * gv[i].z * wv[i].z + xv[i].w * gv[i].w * wv[i].w);
+  }
+  q = warp_sum(q);
+  dot = warp_sum(dot);
+  if (lane == 0) {
+    const float rstd = rsqrtf(q / width + eps);
+    float val = prev + dt * (dot * rstd + bias);
+    action[(size_t)r * A + a] = val;
+    if (last_step) {
+      const int b = r / H, i = r - b * H;
+      if (i >= H - horizon) {
+        if (do_clip) val = fminf(fmaxf(val, -clip), clip);
+        out[((size_t)b * horizon + (i - (H - horizon))) * A + a] = static_cast<TO>(val);
       }
     }
   }
@@ -498,7 +490,8 @@ int euler_step_launch(const float* x, const float* gamma, const float* Wdec, con
                       int last_step, int do_clip, float clip, cudaStream_t stream) {
   if (rows <= 0) return 0;
   VL_CHECK(width <= 1024, "euler_step: width must be <= 1024");
-  const int grid = (rows + 3) / 4;
+  VL_CHECK(width % 4 == 0 && width <= 1024, "euler step: width must be a multiple of 4, <= 1024");
+  const int grid = (rows * A + 3) / 4;
   if (out_dtype == DT_F32)
     VL_CUDA_CHECK(launch_kernel(euler_step_kernel<float>, dim3(grid), dim3(128), 0, stream, x, gamma, Wdec, bdec, action, (float*)out, rows, width, A, H,
                                                        horizon, dt, eps, last_step, do_clip, clip));
