@@ -15,6 +15,12 @@
 // the activations of the chunk (bf16, staged once per phase in shared memory) are expanded once per 4 weight rows.
 // The loads of a warp's FIRST unit of the next phase are issued BEFORE the grid barrier (weights do not depend on it),
 // so the barrier and the activation staging hide the HBM latency of the next phase. Weights are read exactly once.
+// One thread per CTA also issues bulk HBM -> L2 prefetches (cp.async.bulk.prefetch.L2, through the TMA unit) of the
+// matrices one to two phases ahead and of the next layer's norm gains / bias / K/V prefix rows, so that HBM keeps
+// streaming while barriers, staging and attention run; the per-layer pointer table lives in shared memory; the
+// attention CTAs hold the K/V rows that date from the prefill in registers across the barrier (attn_load_rows).
+// Measured per-phase times, the ncu capture and the variants that were tried and not kept: DESIGN.md section 4d,
+// profiles/r01k_b1_latency_phases.txt, profiles/r01m_ncu_full_expert_gemv.txt.
 #include "expert.cuh"
 
 namespace vlaser {
