@@ -297,7 +297,7 @@ def run_ours(args):
                     "ms_per_call": pr["ms"] / reps, "share_of_step": (pr["ms"] / reps) / step_ms}
         if sg["launches"]:
             ach = sg["bytes"] / (sg["ms"] * 1e-3) / 1e9
-            roof_small = {"bound": "hbm", "kernel": "tcgen05 GEMMs at M <= 512 (single-CTA kernel + CTA-pair kernel on gate/up: action-expert / action-head projections, weight streaming)",
+            roof_small = {"bound": "hbm", "kernel": "tcgen05 GEMMs at M <= 512 (single-CTA kernel; CTA-pair kernel with TMA reduce-add split-K on the expert down projection: action-expert / action-head projections, weight streaming)",
                           "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                           "traffic": _ncu_traffic("gemm_tcgen05_kernel"), "launches_per_call": int(sg["launches"] / reps),
                           "algorithmic_mbytes_per_launch": sg["bytes"] / sg["launches"] / 1e6,
