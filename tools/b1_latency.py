@@ -63,7 +63,7 @@ for gemv in (1, 0):
 pol.set_option("expert_gemv", 1)
 L, P = cfg.layers, 5
 names = ["norm+qkv", "attention", "o-proj", "norm+gate/up", "down"]
-for fl in (0, 16, 4):
+for fl in (0, 32, 16, 4):
     pol.set_option("expert_timing", 1)
     pol.set_option("expert_flags", fl)
     for _ in range(3):

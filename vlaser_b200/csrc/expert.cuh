@@ -65,7 +65,8 @@ struct ExpertPass {
   float scale = 1.f;
   int flags = 0;                      // profiling aids (wrong results!): 1 = drop the residual red.adds, 2 = skip attention,
                                       // 4 = no GEMM tiles, 8 = no norm rows (2|4|8 = the bare grid-barrier skeleton);
-                                      // expert_gemv.cu: 2, 4 as above, 16 = no L2 prefetch of the coming phases' weights
+                                      // expert_gemv.cu: 2, 4 as above, 16 = no L2 prefetch of the coming phases' weights,
+                                      // 32 = only the even warps load across the grid barrier (correct results; measured slower)
   long long* timing = nullptr;        // optional [7 * n_layers]: globaltimer (ns) at which CTA 0 saw each phase complete
   unsigned int* barrier = nullptr;    // grid-barrier arrival counters of this pass, [n_streams][7 * n_layers], zero on entry
   int n_streams = 1;                  // independent sub-grids (see expert.cu); needs batch % S == 0, (M / S) % 32 == 0

@@ -578,7 +578,8 @@ __global__ void __launch_bounds__(GV_THREADS, 1) expert_gemv_pass_kernel(const E
           if (base == 0 && j == 0) gv_stamp(st, 1);
           if (base == 0 && j == 3) gv_stamp(st, 11);
           const int u = base + first_unit(d, j);
-          const bool ok = base == 0 ? have : (!skip_units && make_unit(d, L, j, u, U));
+          const bool pre = base == 0 && have;  // this unit's loads went out before the grid barrier
+          const bool ok = pre ? true : (!skip_units && make_unit(d, L, j, u, U));
           if (ok) {
             // q|k|v epilogue operands (bias, RoPE factors of this lane's row) fetched ahead of the dot products
             float eb[4] = {0.f, 0.f, 0.f, 0.f}, ecs[2] = {1.f, 1.f}, esn[2] = {0.f, 0.f};
@@ -595,7 +596,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) expert_gemv_pass_kernel(const E
 #pragma unroll
               for (int r = 0; r < R; ++r) acc[i][r] = 0.f;
             for (int k = U.k0; k < U.k1; k += GV_CH) {
-              if (base != 0 || k != U.k0) issue_loads(U, k, lane, wr);
+              if (!pre || k != U.k0) issue_loads(U, k, lane, wr);
               consume<R>(wr, a_s, pitch, abase, k, U.k1, lane, acc);
             }
             float mine[GV_NR];
@@ -650,7 +651,9 @@ __global__ void __launch_bounds__(GV_THREADS, 1) expert_gemv_pass_kernel(const E
         const int nj = j == GV_PHASES - 1 ? 0 : j + 1;
         if (nj != 1) {
           // first unit of the next weight phase into registers
-          have = !skip_units && make_unit(d, j == GV_PHASES - 1 ? L + 1 : L, nj, first_unit(d, nj), U);
+          // (profiling flag 32: only the even warps load across the barrier, so that the warps of a CTA alternate between
+          // loading and computing instead of all doing the same thing at the same time)
+          have = !skip_units && (!(p.flags & 32) || (warp & 1) == 0) && make_unit(d, j == GV_PHASES - 1 ? L + 1 : L, nj, first_unit(d, nj), U);
           if (have) issue_loads(U, U.k0, lane, wr);
         } else if (attn_cta && !skip_attn) {
           attn_load_rows(Kh, Vh, 0, sg.kv_len - M, tid, wr, true);  // K/V rows that date from the prefill
