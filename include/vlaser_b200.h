@@ -94,6 +94,8 @@ void vlaser_destroy(vlaser_t* h);
  * of the expert GEMMs, 0 = default),
  * "expert_mega" (default 0; 1 runs each proprio / denoise pass of the action expert as ONE persistent kernel, csrc/expert.cu),
  * "expert_streams" (default 2: independent sub-grids of that kernel, each owning a slice of the batch),
+ * "prop_stream" (default 1: the proprio expert pass of the prefill is launched on a second stream, forked after the
+ * proprio encoder and joined before the first denoise step; it only reads the prefix K/V of each layer),
  * "small_m_split" (default 1: split-K over the idle SMs for the ViT / LLM residual projections of small batches),
  * "l2_prefetch" (default 0, measured no gain: the RMSNorm launches of a denoise step issue bulk L2 prefetches of the expert weights the
  * next launches of the chain will read),

@@ -154,6 +154,8 @@ struct Engine {
                                // persistent kernel per pass (expert.cu) instead of 7 kernels per layer. Measured on
                                // B200 at B=64 (profiles/r01e_schedule_ab.txt): 43.2 ms per call against 40.3 ms for the
                                // per-kernel schedule with PDL, so the per-kernel schedule is the default
+  int prop_stream = 1;         // 1: the proprio expert pass of the prefill runs on a second stream beside the LLM layers
+                               // (B=64, gpurun r01ab: 38.87 / 38.74 ms with, 39.31 / 39.36 ms without)
   int small_m_split = 1;       // 1: split-K for the ViT / LLM residual projections when their tiles cover < half of the SMs
   int l2pf = 0;                // 1: the norm launches of a denoise step prefetch the coming expert weights into L2. Measured at
                                // B=64 (gpurun r01l, two runs each): 39.8 / 40.7 ms with, 39.5 / 39.8 ms without -> off
@@ -168,6 +170,8 @@ struct Engine {
   size_t prof_used = 0;
   long long launches = 0, last_launches = 0;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t side_stream = nullptr;      // the proprio pass of the prefill when option "prop_stream" is set
+  std::vector<cudaEvent_t> side_events;    // [layers] K/V of LLM layer l written, + fork + join
   struct GraphKey {
     int B, io, stop, simt, has_valid;
     bool operator<(const GraphKey& o) const {
@@ -186,6 +190,8 @@ struct Engine {
     for (void* p : allocs) cudaFree(p);
     if (pinned) cudaFreeHost(pinned);
     if (own_stream) cudaStreamDestroy(own_stream);
+    if (side_stream) cudaStreamDestroy(side_stream);
+    for (cudaEvent_t ev : side_events) cudaEventDestroy(ev);
   }
 
   template <typename Tp>
@@ -281,6 +287,9 @@ int engine_build(Engine& e) {
   VL_CHECK(e.n_img * e.T <= e.S, "image tokens exceed max_image_text_tokens");
   VL_CUDA_CHECK(cudaGetDevice(&e.device));
   VL_CUDA_CHECK(cudaStreamCreateWithFlags(&e.own_stream, cudaStreamNonBlocking));
+  VL_CUDA_CHECK(cudaStreamCreateWithFlags(&e.side_stream, cudaStreamNonBlocking));
+  e.side_events.resize((size_t)c.layers + 1);
+  for (cudaEvent_t& ev : e.side_events) VL_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 
   const int d = c.vit_hidden, f = c.vit_mlp, h = c.hidden, he = c.hidden_e;
   const std::string v = "vision_tower.vision_model.";
@@ -916,12 +925,58 @@ struct Run {
     return rc;
   }
 
+  // proprio expert block of layer li on the current stream `st` (its own attention launch: one query row per sample over
+  // the prefix K/V of the layer and its own K/V row)
+  int proprio_layer(int li) {
+    const vlaser_cfg& c = e.c;
+    VL_TRY(block_pre(e.exp[li], e.xp, e.xpn, e.qp, B, nullptr, c.hidden_e, e.pb.prop_pos, e.pb.prop_kvrow, li));
+    if (li == c.layers - 1) return 0;
+    AttnParams ap;
+    const size_t off = (size_t)li * c.n_kv_heads * e.kv_rows * 128;
+    ap.q = e.qp;
+    ap.q_row_stride = e.qdim;
+    ap.k = e.kc + off;
+    ap.v = e.vc + off;
+    ap.kv_row_stride = 128;
+    ap.kv_head_stride = e.kv_rows * 128;
+    ap.out = e.aop.p;
+    ap.out_row_stride = e.qdim;
+    ap.q_start = e.pb.prop_q_start;
+    ap.q_len = e.pb.prop_q_len;
+    ap.kv_start = e.pb.kvoff;
+    ap.kv_len = e.pb.prop_kv_len;
+    ap.max_q_len = 1;
+    ap.group = c.n_heads / c.n_kv_heads;
+    ap.n_kv_heads = c.n_kv_heads;
+    ap.batch = B;
+    ap.scale = 0.08838834764831845f;
+    VL_TRY(attention_launch(ap, 128, st));
+    e.launches++;
+    return block_post(e.exp[li], e.xp, e.xpn, e.aop, e.actp, B, nullptr, c.hidden_e, e.mlp_e_p, 32, &e.xp_otm);
+  }
+
   int prefill() {
     const vlaser_cfg& c = e.c;
     const int cap = B * e.S;
+    // option "prop_stream": the proprio token never feeds the prefix stream, it only reads the prefix K/V of each layer.
+    // Its 28 x 7 latency-bound launches then run on a second stream (forked here, joined before the first denoise
+    // step) and fill the tails of the LLM launches instead of sitting between them.
+    const bool side = e.prop_stream && !mega() && !e.fuse_norm;
+    cudaStream_t main_st = st;
+    if (side) {
+      VL_CUDA_CHECK(cudaEventRecord(e.side_events[c.layers], main_st));        // fork: xp (proprio encoder) is ready
+      VL_CUDA_CHECK(cudaStreamWaitEvent(e.side_stream, e.side_events[c.layers], 0));
+    }
     for (int li = 0; li < c.layers; ++li) {
       VL_TRY(block_pre(e.llm[li], e.xv, e.xn, e.q, cap, e.pb.m_tot, c.hidden, e.pb.row_pos, e.pb.row_kvrow, li));
-      if (mega()) {
+      if (side) {
+        VL_CUDA_CHECK(cudaEventRecord(e.side_events[li], main_st));            // prefix K/V of layer li written
+        VL_CUDA_CHECK(cudaStreamWaitEvent(e.side_stream, e.side_events[li], 0));
+        st = e.side_stream;
+        const int rc = proprio_layer(li);
+        st = main_st;
+        if (rc) return rc;
+      } else if (mega()) {
         // the proprio token never feeds the prefix stream: its whole expert pass runs after the LLM prefill
       } else if (li == 0 || !e.fuse_norm)  // (fused: the proprio encoder output has no producer epilogue -> plain RMSNorm)
         VL_TRY(block_pre(e.exp[li], e.xp, e.xpn, e.qp, B, nullptr, c.hidden_e, e.pb.prop_pos, e.pb.prop_kvrow, li));
@@ -932,7 +987,7 @@ struct Run {
       const size_t off = (size_t)li * c.n_kv_heads * e.kv_rows * 128;
       ap.q = e.q;
       ap.q_row_stride = e.qdim;
-      ap.q2 = mega() ? nullptr : e.qp;
+      ap.q2 = (mega() || side) ? nullptr : e.qp;
       ap.q2_row_stride = e.qdim;
       ap.k = e.kc + off;
       ap.v = e.vc + off;
@@ -946,7 +1001,7 @@ struct Run {
       ap.q_len = e.pb.valid_len;
       ap.kv_start = e.pb.kvoff;
       ap.kv_len = e.pb.pre_kv_len;
-      ap.max_q_len = e.S + (mega() ? 0 : 1);
+      ap.max_q_len = e.S + ((mega() || side) ? 0 : 1);
       ap.group = c.n_heads / c.n_kv_heads;
       ap.n_kv_heads = c.n_kv_heads;
       ap.batch = B;
@@ -954,9 +1009,13 @@ struct Run {
       VL_TRY(attention_launch(ap, 128, st));
       e.launches++;
       VL_TRY(block_post(e.llm[li], e.xv, e.xn, e.ao, e.act, cap, e.pb.m_tot, c.hidden, e.mlp_p, 1, &e.xv_otm));
-      if (mega()) continue;
+      if (mega() || side) continue;
       if (e.fuse_norm) VL_TRY(exp_post(li, e.xp, e.xpn, e.aop, e.actp, B, 0, false));
       else VL_TRY(block_post(e.exp[li], e.xp, e.xpn, e.aop, e.actp, B, nullptr, c.hidden_e, e.mlp_e_p, 32, &e.xp_otm));
+    }
+    if (side) {
+      VL_CUDA_CHECK(cudaEventRecord(e.side_events[c.layers], e.side_stream));  // join
+      VL_CUDA_CHECK(cudaStreamWaitEvent(main_st, e.side_events[c.layers], 0));
     }
     if (mega())
       VL_TRY(expert_pass(0, B, e.xp, e.xp_otm, e.xpn, e.qp, e.aop, e.actp, e.pb.prop_pos, e.pb.prop_kvrow, e.pb.prop_q_start,
@@ -1152,7 +1211,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "expert_timing" || k == "expert_flags") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
@@ -1161,6 +1220,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
     else if (k == "expert_gemv") h->e.gemv = (int)value;
     else if (k == "l2_prefetch") h->e.l2pf = (int)value;
     else if (k == "small_m_split") h->e.small_m_split = (int)value;
+    else if (k == "prop_stream") h->e.prop_stream = (int)value;
     else if (k == "expert_timing") h->e.xp_time = (int)value;
     else if (k == "expert_flags") h->e.xp_flags = (int)value;
     else if (k == "pair_gemm") h->e.pair_gemm = (int)value;

@@ -114,7 +114,7 @@ class PiZeroInference:
         for env, opt in (("VLASER_PDL", "pdl"), ("VLASER_EXP_STAGES", "exp_stages"), ("VLASER_FUSE_NORM", "fuse_norm"),
                          ("VLASER_PAIR_GEMM", "pair_gemm"), ("VLASER_EXPERT_MEGA", "expert_mega"),
                          ("VLASER_EXPERT_STREAMS", "expert_streams"), ("VLASER_EXPERT_GEMV", "expert_gemv"),
-                         ("VLASER_L2_PREFETCH", "l2_prefetch"), ("VLASER_SMALL_M_SPLIT", "small_m_split"), ("VLASER_PAIR_MIN_TILES", "pair_min_tiles")):  # measurement switches
+                         ("VLASER_L2_PREFETCH", "l2_prefetch"), ("VLASER_SMALL_M_SPLIT", "small_m_split"), ("VLASER_PAIR_MIN_TILES", "pair_min_tiles"), ("VLASER_PROP_STREAM", "prop_stream")):  # measurement switches
             if env in os.environ:
                 self.set_option(opt, int(os.environ[env]))
 
