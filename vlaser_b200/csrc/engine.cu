@@ -961,7 +961,9 @@ struct Run {
     // option "prop_stream": the proprio token never feeds the prefix stream, it only reads the prefix K/V of each layer.
     // Its 28 x 7 latency-bound launches then run on a second stream (forked here, joined before the first denoise
     // step) and fill the tails of the LLM launches instead of sitting between them.
-    const bool side = e.prop_stream && !mega() && !e.fuse_norm;
+    // (B = 1: the denoise passes run on the single-observation kernel, the proprio pass still takes the second stream --
+    // with one observation the LLM launches leave most SMs idle, so its chain hides completely)
+    const bool side = e.prop_stream && !e.mega && !e.fuse_norm;
     cudaStream_t main_st = st;
     if (side) {
       VL_CUDA_CHECK(cudaEventRecord(e.side_events[c.layers], main_st));        // fork: xp (proprio encoder) is ready
@@ -1017,7 +1019,7 @@ struct Run {
       VL_CUDA_CHECK(cudaEventRecord(e.side_events[c.layers], e.side_stream));  // join
       VL_CUDA_CHECK(cudaStreamWaitEvent(main_st, e.side_events[c.layers], 0));
     }
-    if (mega())
+    if (mega() && !side)
       VL_TRY(expert_pass(0, B, e.xp, e.xp_otm, e.xpn, e.qp, e.aop, e.actp, e.pb.prop_pos, e.pb.prop_kvrow, e.pb.prop_q_start,
                          e.pb.prop_q_len, e.pb.prop_kv_len, 1, true));
     return 0;
