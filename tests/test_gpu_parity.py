@@ -365,3 +365,25 @@ def test_dynamic_tiles_parity():
     cu = torch.cumsum(valid, 0) - valid
     expected = [int(cu[b]) + j for b in range(ids.shape[0]) for j in range(ids.shape[1]) if int(ids[b, j]) == cfg.image_token_index]
     assert pol.debug_buffer("img_row_map", torch.int32)[: len(expected)].tolist() == expected
+
+
+def test_prefix_fills_max_tokens_and_batch_bounds():
+    """Edge sizes: a prefix that uses every one of the max_image_text_tokens positions (valid_len == S, no pad) beside a
+    minimal one in the same batch, the full max_batch, and the error behaviour outside it (negative code -> RuntimeError,
+    like the reference's asserts: joint_model.py:427-431)."""
+    cfg = tiny()
+    sd = random_state_dict(cfg, 4)
+    S, T = cfg.max_image_text_tokens, cfg.image_tokens
+    longest = S - (10 + T + 7)                      # prompt tokens that make the prefix exactly S long
+    inp = make_inputs(cfg, 3, 31, [longest, 0, longest])
+    assert inp["valid_len"].tolist() == [S, 10 + T + 7, S]
+    pol = _policy(cfg, sd, 3)
+    got = _run(pol, inp)
+    ref = O.infer_action(cfg, sd, inp["input_ids"], inp["pixel_values"], inp["proprios"], inp["noise"])
+    assert max_err(got, ref) <= ACTION_TOL
+    # more observations than the handle was created for: loud error, no partial result
+    big = make_inputs(cfg, 4, 32)
+    with pytest.raises((RuntimeError, AssertionError)):
+        _run(pol, big)
+    # the handle is still usable afterwards
+    assert max_err(_run(pol, inp), ref) <= ACTION_TOL
