@@ -1,9 +1,9 @@
-"""Spread of the B = 1 full-size parity error over repeated calls (the split-K partial sums land with fp32 atomics, so the
+"""Test infrastructure (run by hand / tools/gpu_r01aa.sh, not collected by pytest). Spread of the B = 1 full-size parity error over repeated calls (the split-K partial sums land with fp32 atomics, so the
 summation order -- not the math -- changes from call to call): max-abs error of the clamped actions vs the fp32 oracle."""
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 import torch
 
 from oracle import vlaser_oracle as O  # checker only
