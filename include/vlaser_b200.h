@@ -97,6 +97,9 @@ void vlaser_destroy(vlaser_t* h);
  * "prop_stream" (default 1: the proprio expert pass of the prefill is launched on a second stream, forked after the
  * proprio encoder and joined before the first denoise step; it only reads the prefix K/V of each layer),
  * "small_m_split" (default 1: split-K over the idle SMs for the ViT / LLM residual projections of small batches),
+ * "det_splitk" (default 1: split-K partial sums go to a workspace and are added to the residual stream in split order by the
+ * next norm launch, so that the same inputs give bit-identical actions; 0 = fp32 atomics / L2 reduce-adds, whose summation
+ * order varies from call to call),
  * "l2_prefetch" (default 0, measured no gain: the RMSNorm launches of a denoise step issue bulk L2 prefetches of the expert weights the
  * next launches of the chain will read),
  * "expert_gemv" (default 1: at B = 1 the expert passes run on the weight-streaming single-observation kernel, csrc/expert_gemv.cu),
@@ -159,6 +162,13 @@ typedef struct vlaser_gemm_args {
   int32_t stages;        /* smem ring depth, 0 = default */
   int32_t pair;          /* 1 = CTA-pair kernel (cta_group::2, 256x256 tile per pair); block_n is ignored */
   int32_t tma_out;       /* pair kernel: epilogue through TMA store / reduce-add (bf16 and residual epilogues) */
+  /* deterministic split-K (residual epilogue, max_splits > 1): split s leaves its partial tile at
+   * partial[s * partial_stride + m * ldo + n] instead of meeting the other splits through fp32 atomics in `out`;
+   * *partial_splits receives the split count used (0 = one split, `out` updated directly). The caller finishes with
+   * vlaser_op_splitk_reduce. partial_stride: a multiple of 256 * ldo covering M rows. */
+  float* partial;
+  int64_t partial_stride;
+  int32_t* partial_splits;
 } vlaser_gemm_args;
 int32_t vlaser_op_gemm(const vlaser_gemm_args* a, void* stream);
 
@@ -182,6 +192,10 @@ int32_t vlaser_op_layernorm(const float* x, const float* gamma, const float* bet
                             int32_t width, float eps, int32_t shuffle_grid, int32_t shuffle_channels, void* stream);
 int32_t vlaser_op_rmsnorm(const float* x, const float* gamma, void* out_bf16, int32_t rows, int32_t width, float eps,
                           void* stream);
+/* x[m, :] += partial[0][m, :] + partial[1][m, :] + ... in split order (one writer per row: bit-identical from call to
+ * call), then, when gamma and out_bf16 are given, out = RMSNorm(x) * gamma as vlaser_op_rmsnorm. */
+int32_t vlaser_op_splitk_reduce(float* x, int32_t rows, int32_t width, const float* part, int64_t part_stride,
+                                const int32_t* splits_dev, const float* gamma, void* out_bf16, float eps, void* stream);
 int32_t vlaser_op_pixel_shuffle(const void* in, void* out, int32_t n, int32_t grid, int32_t channels,
                                 int32_t elem_bytes, void* stream);
 int32_t vlaser_op_im2col(const void* pixel, int32_t pixel_dtype, void* cols_bf16, int32_t n, int32_t px, int32_t ps,

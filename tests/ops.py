@@ -23,7 +23,8 @@ def _stream():
 def gemm(A, W, epi, block_n=128, simt=False, out=None, ldo=None, bias=None, scale=None, M_dev=None, max_splits=1,
          row_map=None, row_pos=None, row_kvrow=None, cos_tab=None, sin_tab=None, k_cache=None, v_cache=None,
          kv_head_stride=0, n_q_heads=0, n_kv_heads=0, pos_emb=None, patches=0, gamma_next=None, a_next=None,
-         ss_next=None, tile_counters=None, row_ss=None, inv_width=0.0, eps=0.0, stages=0, pair=False):
+         ss_next=None, tile_counters=None, row_ss=None, inv_width=0.0, eps=0.0, stages=0, pair=False,
+         partial=None, partial_stride=0, partial_splits=None):
     lib = _lib.load()
     tma_out = False
     if block_n in (512, 513, 515):  # test shorthand for the CTA-pair kernel; 513 = TMA epilogue, 515 = + n-fastest tiles
@@ -44,6 +45,7 @@ def gemm(A, W, epi, block_n=128, simt=False, out=None, ldo=None, bias=None, scal
     a.lda_next = a_next.shape[-1] if a_next is not None else 0
     a.row_ss, a.inv_width, a.eps, a.stages = _p(row_ss), inv_width, eps, stages
     a.pair, a.tma_out = int(pair), int(tma_out)
+    a.partial, a.partial_stride, a.partial_splits = _p(partial), partial_stride, _p(partial_splits)
     _lib.check(lib.vlaser_op_gemm(C.byref(a), _stream()), "op_gemm")
     return out
 
@@ -103,6 +105,15 @@ def rmsnorm(x, gamma, eps):
     lib = _lib.load()
     out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     _lib.check(lib.vlaser_op_rmsnorm(_p(x), _p(gamma), _p(out), x.shape[0], x.shape[1], eps, _stream()), "op_rmsnorm")
+    return out
+
+
+def splitk_reduce(x, partial, partial_stride, partial_splits, gamma=None, eps=0.0):
+    """x += partials in split order; with gamma also returns bf16 RMSNorm(x) * gamma (the fused consumer)."""
+    lib = _lib.load()
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if gamma is not None else None
+    _lib.check(lib.vlaser_op_splitk_reduce(_p(x), x.shape[0], x.shape[1], _p(partial), partial_stride,
+                                           _p(partial_splits), _p(gamma), _p(out), eps, _stream()), "op_splitk_reduce")
     return out
 
 

@@ -115,6 +115,50 @@ def test_gemm_fused_rmsnorm_chain(name, simt, splits, M):
     assert err < 1.5 * BF16_TOL
 
 
+@pytest.mark.parametrize("bn", [128, 513])
+@pytest.mark.parametrize("M,N,K", [(256, 768, 8960), (64, 768, 1536), (257, 1024, 4096), (200, 1536, 1536)])
+def test_gemm_splitk_partials_deterministic(bn, M, N, K):
+    """Deterministic split-K: the splits leave partial tiles in a workspace, the consumer adds them to the residual
+    stream in split order -- alone (splitk_reduce) or fused into the RMSNorm that follows. The result equals the
+    un-split product to fp32 rounding and is bit-identical from call to call (the fp32 atomics it replaces are not)."""
+    A, W = _rand(M, K), _rand(N, K, scale=0.05)
+    bias = torch.randn(N, device=DEV)
+    scale = torch.rand(N, device=DEV) + 0.5
+    gamma = torch.rand(N, device=DEV) + 0.5
+    x0 = torch.randn(M, N, device=DEV)
+    rows_p = (M + 255) // 256 * 256
+    splits = 16
+    part = torch.full((splits, rows_p, N), float("nan"), device=DEV)
+    nsp = torch.full((1,), -1, dtype=torch.int32, device=DEV)
+    ref = x0 + (_ref_mm(A, W) + bias) * scale
+    outs = []
+    for rep in range(3):
+        x = x0.clone()
+        ops.gemm(A, W, EPI_RESID_F32, bn, False, out=x, bias=bias, scale=scale, max_splits=splits, partial=part,
+                 partial_stride=rows_p * N, partial_splits=nsp)
+        used = int(nsp.item())
+        assert 2 <= used <= splits, used
+        assert torch.equal(x, x0), "with partials the residual stream is only touched by the consumer"
+        if rep < 2:
+            ops.splitk_reduce(x, part, rows_p * N, nsp)
+            assert ops.rel_err(x, ref) < 1e-5
+            outs.append(x)
+        else:
+            xn = ops.splitk_reduce(x, part, rows_p * N, nsp, gamma=gamma, eps=1e-6)
+            assert torch.equal(x, outs[0])
+            want = ref * torch.rsqrt((ref * ref).mean(-1, keepdim=True) + 1e-6) * gamma
+            assert ops.rel_err(xn, want) < BF16_TOL
+    assert torch.equal(outs[0], outs[1])
+    # one split: the GEMM updates the stream itself and reports 0 partials
+    x = x0.clone()
+    ops.gemm(A, W, EPI_RESID_F32, bn, False, out=x, bias=bias, scale=scale, max_splits=1, partial=part,
+             partial_stride=rows_p * N, partial_splits=nsp)
+    assert int(nsp.item()) == 0 and ops.rel_err(x, ref) < 1e-5
+    x1 = x.clone()
+    ops.splitk_reduce(x, part, rows_p * N, nsp)
+    assert torch.equal(x, x1)
+
+
 @pytest.mark.parametrize("name,bn,simt", VARIANTS)
 def test_gemm_dynamic_m(name, bn, simt):
     """Live row count from device memory: rows >= M_dev must stay untouched (the TMA epilogue of the pair kernel

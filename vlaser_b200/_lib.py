@@ -44,6 +44,7 @@ class GemmArgs(C.Structure):
         ("gamma_next", C.c_void_p), ("a_next", C.c_void_p), ("lda_next", C.c_int32), ("ss_next", C.c_void_p),
         ("tile_counters", C.c_void_p), ("row_ss", C.c_void_p), ("inv_width", C.c_float), ("eps", C.c_float),
         ("stages", C.c_int32), ("pair", C.c_int32), ("tma_out", C.c_int32),
+        ("partial", C.c_void_p), ("partial_stride", C.c_int64), ("partial_splits", C.c_void_p),
     ]
 
 
@@ -64,6 +65,7 @@ EXPORTS = [
     "vlaser_last_launch_count", "vlaser_flops_per_call", "vlaser_profile_read", "vlaser_op_gemm", "vlaser_op_attention",
     "vlaser_op_layernorm", "vlaser_op_rmsnorm", "vlaser_op_pixel_shuffle", "vlaser_op_im2col", "vlaser_op_euler_step",
     "vlaser_op_vit_attention", "vlaser_profile_read_classes", "vlaser_op_stage_frames", "vlaser_op_postprocess_actions",
+    "vlaser_op_splitk_reduce",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -116,6 +118,8 @@ def load() -> C.CDLL:
     lib.vlaser_op_layernorm.restype = i32
     lib.vlaser_op_rmsnorm.argtypes = [vp, vp, vp, i32, i32, f32, vp]
     lib.vlaser_op_rmsnorm.restype = i32
+    lib.vlaser_op_splitk_reduce.argtypes = [vp, i32, i32, vp, i64, vp, vp, vp, f32, vp]
+    lib.vlaser_op_splitk_reduce.restype = i32
     lib.vlaser_op_pixel_shuffle.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.vlaser_op_pixel_shuffle.restype = i32
     lib.vlaser_op_im2col.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp]

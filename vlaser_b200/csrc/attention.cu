@@ -17,8 +17,11 @@ template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(AttnParams p) {
   pdl_launch_dependents();
   extern __shared__ __align__(128) uint8_t smem[];
+  long long* tr = (blockIdx.x + blockIdx.y + blockIdx.z == 0 && threadIdx.x == 0) ? p.trace : nullptr;
+  trace_stamp(tr, 0);
   attention_tile<HD>(p, blockIdx.z, blockIdx.y, blockIdx.x, smem, threadIdx.x, [] { __syncthreads(); },
-                     [] { pdl_wait(); });
+                     [tr] { pdl_wait(); trace_stamp(tr, 1); });
+  trace_stamp(tr, 6);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -40,6 +40,7 @@ struct AttnParams {
   // by kernels that completed long before the previous launch, so the first K/V block may be fetched BEFORE the
   // programmatic-dependent-launch wait and overlaps the tail of the q|k|v projection that produces the new rows
   int stable_prefix = 0;
+  long long* trace = nullptr;  // optional timeline record of this launch (common.cuh trace_stamp)
 };
 
 int attention_launch(const AttnParams& p, int head_dim, cudaStream_t stream);

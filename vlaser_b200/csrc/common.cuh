@@ -57,6 +57,17 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// ---------------------------------------------------------------- in-situ timeline (option "trace")
+// Block 0 of a launch stamps %globaltimer (ns) into its 8-slot record: 0 entry, 1 after the dependent-launch wait,
+// 2 first operand stage landed, 3 last MMA issued, 4 first accumulator ready, 5 epilogue done, 6 exit.
+__device__ __forceinline__ void trace_stamp(long long* t, int slot) {
+  if (t) {
+    long long now;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+    t[slot] = now;
+  }
+}
+
 // ---------------------------------------------------------------- small device utilities
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -10,11 +10,13 @@ namespace {
 // norms
 // ------------------------------------------------------------------------------------------
 template <int VPL, bool RMS, bool GATHER>
-__global__ void __launch_bounds__(128) norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(128) norm_kernel(float* __restrict__ x, const float* __restrict__ gamma,
                                                    const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                                    int rows, const int* __restrict__ rows_dev, float eps, int g,
-                                                   int C, const L2Prefetch pf) {
+                                                   int C, const L2Prefetch pf, long long* trace) {
   pdl_launch_dependents();
+  long long* tr = (blockIdx.x == 0 && threadIdx.x == 0) ? trace : nullptr;
+  trace_stamp(tr, 0);
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -28,6 +30,7 @@ __global__ void __launch_bounds__(128) norm_kernel(const float* __restrict__ x, 
     }
   }
   pdl_wait();
+  trace_stamp(tr, 1);
   constexpr int W = VPL * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + warp;
@@ -87,18 +90,121 @@ __global__ void __launch_bounds__(128) norm_kernel(const float* __restrict__ x, 
     u.y = pack_bf16(y.z, y.w);
     dst[e4] = u;
   }
+  trace_stamp(tr, 6);
+}
+
+// ---- residual update + norm for a stream with pending split-K partials. One CTA per row; thread (c, g) owns float4
+// column c and the splits g, g + G, g + 2G, ...: all of its loads are in flight at once (one L2 round trip for up to
+// 8 G splits; the warp-per-row kernel above would walk them in dependent batches), the G group sums meet in shared memory
+// and are added in a fixed order, so the result does not depend on scheduling. out == nullptr: residual update only.
+template <bool RMS>
+__global__ void __launch_bounds__(1024) resid_norm_kernel(float* __restrict__ x, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                                                          int rows, const int* __restrict__ rows_dev, int W, float eps,
+                                                          const SplitKPartials sp, long long* trace) {
+  pdl_launch_dependents();
+  extern __shared__ float4 rn_smem[];  // [G - 1][C4] group sums, then 32 floats of reduction scratch
+  long long* tr = (blockIdx.x == 0 && threadIdx.x == 0) ? trace : nullptr;
+  trace_stamp(tr, 0);
+  const int C4 = W >> 2, G = blockDim.x / C4;
+  const int c = threadIdx.x % C4, g = threadIdx.x / C4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* red = reinterpret_cast<float*>(rn_smem + (size_t)(G - 1) * C4);
+  float4 gm = make_float4(0.f, 0.f, 0.f, 0.f), bt = gm;
+  if (g == 0 && out) {  // constants: ahead of the dependent-launch wait
+    gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+    if (!RMS) bt = __ldg(reinterpret_cast<const float4*>(beta) + c);
+  }
+  pdl_wait();
+  trace_stamp(tr, 1);
+  const int row = blockIdx.x;
+  const int nrows = rows_dev ? min(*rows_dev, rows) : rows;
+  if (row >= nrows) return;
+  const int S = sp.splits ? *sp.splits : 0;
+  const size_t off = (size_t)row * W + 4 * c;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (g == 0) v = *reinterpret_cast<const float4*>(x + off);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s0 = g; s0 < S; s0 += 8 * G) {
+    float4 pv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int s = s0 + u * G;
+      pv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (s < S) pv[u] = __ldcg(reinterpret_cast<const float4*>(sp.part + (size_t)s * sp.stride + off));
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      acc.x += pv[u].x;
+      acc.y += pv[u].y;
+      acc.z += pv[u].z;
+      acc.w += pv[u].w;
+    }
+  }
+  if (g > 0) rn_smem[(size_t)(g - 1) * C4 + c] = acc;
+  __syncthreads();
+  if (g == 0) {
+    v.x += acc.x, v.y += acc.y, v.z += acc.z, v.w += acc.w;
+    for (int gg = 1; gg < G; ++gg) {
+      const float4 o = rn_smem[(size_t)(gg - 1) * C4 + c];
+      v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
+    }
+    if (S > 0) *reinterpret_cast<float4*>(x + off) = v;
+  }
+  if (out == nullptr) return;
+  auto block_sum = [&](float val) {
+    val = warp_sum(val);
+    __syncthreads();  // scratch free again
+    if (lane == 0) red[warp] = val;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < nwarps; ++w) t += red[w];
+    return t;
+  };
+  float mean = 0.f;
+  if (!RMS) mean = block_sum(g == 0 ? (v.x + v.y) + (v.z + v.w) : 0.f) / (float)W;
+  const float a = v.x - mean, b = v.y - mean, cc = v.z - mean, dd = v.w - mean;
+  const float q = block_sum(g == 0 ? (a * a + b * b) + (cc * cc + dd * dd) : 0.f);
+  if (g == 0) {
+    const float rstd = rsqrtf(q / (float)W + eps);
+    float4 y = make_float4(a * rstd * gm.x, b * rstd * gm.y, cc * rstd * gm.z, dd * rstd * gm.w);
+    if (!RMS) y.x += bt.x, y.y += bt.y, y.z += bt.z, y.w += bt.w;
+    uint2 u;
+    u.x = pack_bf16(y.x, y.y);
+    u.y = pack_bf16(y.z, y.w);
+    *reinterpret_cast<uint2*>(out + off) = u;
+  }
+  trace_stamp(tr, 6);
+}
+
+template <bool RMS>
+int resid_norm_launch(float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows, const int* rows_dev,
+                      int width, float eps, const SplitKPartials& sp, cudaStream_t stream, long long* trace) {
+  VL_CHECK(width % 128 == 0 && width <= 4096, "resid_norm: width must be a multiple of 128, <= 4096");
+  if (rows <= 0) return 0;
+  const int C4 = width / 4;
+  const int G = std::max(1, std::min(4, 1024 / C4));
+  const size_t smem = (size_t)(G - 1) * C4 * sizeof(float4) + 32 * sizeof(float);
+  VL_CUDA_CHECK(launch_kernel(resid_norm_kernel<RMS>, dim3(rows), dim3(C4 * G), smem, stream, x, gamma, beta, out, rows,
+                              rows_dev, width, eps, sp, trace));
+  return 0;
 }
 
 template <bool RMS, bool GATHER>
-int norm_dispatch(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows,
+int norm_dispatch(float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows,
                   const int* rows_dev, int width, float eps, int g, int C, cudaStream_t stream,
-                  const L2Prefetch& pf = L2Prefetch()) {
+                  const L2Prefetch& pf = L2Prefetch(), long long* trace = nullptr,
+                  const SplitKPartials& sp = SplitKPartials()) {
+  VL_CHECK(!(GATHER && sp.part), "norm: the pixel-shuffle gather variant does not take split-K partials");
+  if constexpr (!GATHER) {
+    if (sp.part) return resid_norm_launch<RMS>(x, gamma, beta, out, rows, rows_dev, width, eps, sp, stream, trace);
+  }
   VL_CHECK(width % 128 == 0 && width >= 128 && width <= 4096, "norm: width must be a multiple of 128, <= 4096");
   if (rows <= 0) return 0;
   const int grid = (rows + 3) / 4;
 #define VL_NORM_CASE(V)                                                                                          \
   case V:                                                                                                        \
-    VL_CUDA_CHECK(launch_kernel(norm_kernel<V, RMS, GATHER>, dim3(grid), dim3(128), 0, stream, x, gamma, beta, out, rows, rows_dev, eps, g, C, pf));       \
+    VL_CUDA_CHECK(launch_kernel(norm_kernel<V, RMS, GATHER>, dim3(grid), dim3(128), 0, stream, x, gamma, beta, out, rows, rows_dev, eps, g, C, pf, trace));       \
     break;
   switch (width / 128) {
     VL_NORM_CASE(1) VL_NORM_CASE(2) VL_NORM_CASE(3) VL_NORM_CASE(4) VL_NORM_CASE(6) VL_NORM_CASE(8)
@@ -328,7 +434,7 @@ __global__ void __launch_bounds__(128) euler_step_kernel(const float* __restrict
                                                          const float* __restrict__ bdec, float* __restrict__ action,
                                                          TO* __restrict__ out, int rows, int width, int A, int H,
                                                          int horizon, float dt, float eps, int last_step, int do_clip,
-                                                         float clip) {
+                                                         float clip, const long long* __restrict__ xfix) {
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x * 4 + warp;
@@ -352,7 +458,17 @@ __global__ void __launch_bounds__(128) euler_step_kernel(const float* __restrict
   for (int i = 0; i < 8; ++i) {
     const int c4 = lane + 32 * i;
     xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c4 * 4 < width) xv[i] = xr[c4];
+    if (c4 * 4 < width) {
+      xv[i] = xr[c4];
+      if (xfix) {
+        const longlong2* f2 = reinterpret_cast<const longlong2*>(xfix + (size_t)r * width) + 2 * c4;
+        const longlong2 f0 = f2[0], f1 = f2[1];
+        xv[i].x += (float)f0.x * (1.f / 1073741824.f);
+        xv[i].y += (float)f0.y * (1.f / 1073741824.f);
+        xv[i].z += (float)f1.x * (1.f / 1073741824.f);
+        xv[i].w += (float)f1.y * (1.f / 1073741824.f);
+      }
+    }
   }
   const float prev = action[(size_t)r * A + a];
 #pragma unroll
@@ -379,19 +495,26 @@ __global__ void __launch_bounds__(128) euler_step_kernel(const float* __restrict
 }  // namespace
 
 // ==========================================================================================
-int layernorm_launch(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows, int width,
-                     float eps, ShuffleGather sg, cudaStream_t stream) {
+int layernorm_launch(float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows, int width,
+                     float eps, ShuffleGather sg, cudaStream_t stream, const SplitKPartials* sp) {
   if (sg.grid > 0) {
     VL_CHECK(width == 4 * sg.channels && sg.channels % 4 == 0 && sg.grid % 2 == 0, "layernorm gather: bad shape");
+    VL_CHECK(!sp || !sp->part, "layernorm gather: reduce the split-K partials first (splitk_reduce_launch)");
     return norm_dispatch<false, true>(x, gamma, beta, out, rows, nullptr, width, eps, sg.grid, sg.channels, stream);
   }
-  return norm_dispatch<false, false>(x, gamma, beta, out, rows, nullptr, width, eps, 0, 0, stream);
+  return norm_dispatch<false, false>(x, gamma, beta, out, rows, nullptr, width, eps, 0, 0, stream, L2Prefetch(), nullptr,
+                                     sp ? *sp : SplitKPartials());
 }
 
-int rmsnorm_launch(const float* x, const float* gamma, __nv_bfloat16* out, int rows, const int* rows_dev, int width,
-                   float eps, cudaStream_t stream, const L2Prefetch* pf) {
+int rmsnorm_launch(float* x, const float* gamma, __nv_bfloat16* out, int rows, const int* rows_dev, int width,
+                   float eps, cudaStream_t stream, const L2Prefetch* pf, long long* trace, const SplitKPartials* sp) {
   return norm_dispatch<true, false>(x, gamma, nullptr, out, rows, rows_dev, width, eps, 0, 0, stream,
-                                    pf ? *pf : L2Prefetch());
+                                    pf ? *pf : L2Prefetch(), trace, sp ? *sp : SplitKPartials());
+}
+
+int splitk_reduce_launch(float* x, int rows, const int* rows_dev, int width, const SplitKPartials& sp, cudaStream_t stream) {
+  VL_CHECK(sp.part && sp.splits, "splitk_reduce: bad arguments");
+  return resid_norm_launch<true>(x, nullptr, nullptr, nullptr, rows, rows_dev, width, 0.f, sp, stream, nullptr);
 }
 
 int pixel_shuffle_launch(const void* in, void* out, int n, int grid, int channels, int elem_bytes,
@@ -487,17 +610,17 @@ int convert_launch(const void* in, int in_dtype, void* out, int out_dtype, long 
 
 int euler_step_launch(const float* x, const float* gamma, const float* Wdec, const float* bdec, float* action,
                       void* out, int out_dtype, int rows, int width, int A, int H, int horizon, float dt, float eps,
-                      int last_step, int do_clip, float clip, cudaStream_t stream) {
+                      int last_step, int do_clip, float clip, cudaStream_t stream, const long long* xfix) {
   if (rows <= 0) return 0;
   VL_CHECK(width <= 1024, "euler_step: width must be <= 1024");
   VL_CHECK(width % 4 == 0 && width <= 1024, "euler step: width must be a multiple of 4, <= 1024");
   const int grid = (rows * A + 3) / 4;
   if (out_dtype == DT_F32)
     VL_CUDA_CHECK(launch_kernel(euler_step_kernel<float>, dim3(grid), dim3(128), 0, stream, x, gamma, Wdec, bdec, action, (float*)out, rows, width, A, H,
-                                                       horizon, dt, eps, last_step, do_clip, clip));
+                                                       horizon, dt, eps, last_step, do_clip, clip, xfix));
   else
     VL_CUDA_CHECK(launch_kernel(euler_step_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, stream, x, gamma, Wdec, bdec, action, (__nv_bfloat16*)out, rows,
-                                                               width, A, H, horizon, dt, eps, last_step, do_clip, clip));
+                                                               width, A, H, horizon, dt, eps, last_step, do_clip, clip, xfix));
   VL_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -14,8 +14,19 @@ struct ShuffleGather {   // pixel_shuffle(0.5) gather fused into the projector's
   int grid = 0;          // g (patch grid side); 0 = no gather
   int channels = 0;      // C (ViT hidden)
 };
-int layernorm_launch(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows, int width,
-                     float eps, ShuffleGather sg, cudaStream_t stream);
+// Deterministic split-K (see EpiParams::part in gemm.cuh): the partial tiles a split-K residual projection left in its
+// workspace. A norm launch that is handed them first finishes the residual update, x[row] += part[0][row] + part[1][row]
+// + ... in split order (one writer per row, so the sum does not depend on scheduling), stores the new x and then
+// normalises it. `splits` is the device word the GEMM wrote (0 = nothing to add).
+struct SplitKPartials {
+  const float* part = nullptr;
+  long long stride = 0;        // floats between consecutive splits
+  const int* splits = nullptr;
+};
+int layernorm_launch(float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows, int width,
+                     float eps, ShuffleGather sg, cudaStream_t stream, const SplitKPartials* sp = nullptr);
+// x[row] += sum of the partials (no norm): for consumers of the residual stream that are not a plain norm launch
+int splitk_reduce_launch(float* x, int rows, const int* rows_dev, int width, const SplitKPartials& sp, cudaStream_t stream);
 // Optional HBM -> L2 prefetch riding on a norm launch: before its dependent-launch wait, thread 0 of every CTA issues
 // bulk L2 prefetches (cp.async.bulk.prefetch.L2, <= 32 KB each) for its slice of up to three constant byte ranges —
 // the weights of the GEMMs a few launches further down the chain, which would otherwise start on cold HBM lines
@@ -24,8 +35,9 @@ struct L2Prefetch {
   const void* ptr[3] = {nullptr, nullptr, nullptr};
   unsigned long long bytes[3] = {0, 0, 0};  // multiples of 16
 };
-int rmsnorm_launch(const float* x, const float* gamma, __nv_bfloat16* out, int rows, const int* rows_dev, int width,
-                   float eps, cudaStream_t stream, const L2Prefetch* pf = nullptr);
+int rmsnorm_launch(float* x, const float* gamma, __nv_bfloat16* out, int rows, const int* rows_dev, int width,
+                   float eps, cudaStream_t stream, const L2Prefetch* pf = nullptr, long long* trace = nullptr,
+                   const SplitKPartials* sp = nullptr);
 
 // ---- pixel_shuffle (pizero_internvl.py:706-716), pure re-index, bit exact. elem_bytes in {2,4}.
 int pixel_shuffle_launch(const void* in, void* out, int n, int grid, int channels, int elem_bytes, cudaStream_t stream);
@@ -82,6 +94,7 @@ int convert_launch(const void* in, int in_dtype, void* out, int out_dtype, long 
 // out[b, i-(H-horizon), :] = clamp(action) for the last `horizon` tokens.
 int euler_step_launch(const float* x, const float* gamma, const float* Wdec, const float* bdec, float* action,
                       void* out, int out_dtype, int rows, int width, int A, int H, int horizon, float dt, float eps,
-                      int last_step, int do_clip, float clip, cudaStream_t stream);
+                      int last_step, int do_clip, float clip, cudaStream_t stream, const long long* xfix = nullptr);
+// (xfix: optional [rows, width] 2^-30 fixed-point increments to add to x, see ExpertPass::xfix)
 
 }  // namespace vlaser

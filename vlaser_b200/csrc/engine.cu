@@ -133,6 +133,8 @@ struct Engine {
   unsigned int* xp_bar = nullptr;
   size_t xp_bar_words() const { return (size_t)EXPERT_MAX_STREAMS * 7 * c.layers; }  // barrier counters of one pass
   int xp_streams = 2;              // sub-grids of the expert-stream kernel (option "expert_streams"), when the rows allow
+  long long* xfix = nullptr;       // [(steps+1)][8][he] fixed-point residual increments of the single-observation kernel
+  size_t xfix_words() const { return (size_t)8 * c.hidden_e; }
   long long* xp_timing = nullptr;  // [(steps+1)][7*layers] phase-completion timestamps, filled when xp_time is set
   int xp_time = 0, xp_flags = 0;
   PlanBuffers pb{};
@@ -160,6 +162,24 @@ struct Engine {
   int l2pf = 0;                // 1: the norm launches of a denoise step prefetch the coming expert weights into L2. Measured at
                                // B=64 (gpurun r01l, two runs each): 39.8 / 40.7 ms with, 39.5 / 39.8 ms without -> off
   int gemv = 1;                // 1: at B = 1 the expert passes run on the weight-streaming kernel (expert_gemv.cu)
+  // deterministic split-K (option "det_splitk", default 1): partial-tile workspaces of the two launch streams, see
+  // EpiParams::part (gemm.cuh) and SplitKPartials (elementwise.cuh)
+  struct SplitWs {
+    float* part = nullptr;
+    size_t floats = 0;
+    int* splits = nullptr;
+    std::map<int, CUtensorMap> maps;  // workspace viewed as [floats / N, N] f32, by N
+  };
+  SplitWs ws_main, ws_side;
+  int det_splitk = 1;
+  // in-situ timeline (option "trace"): one 8-slot %globaltimer record per launch of the call, see common.cuh
+  long long* trace = nullptr;
+  int trace_on = 0;
+  size_t trace_idx = 0;
+  std::string trace_names;
+  static constexpr size_t TRACE_MAX = 8192;
+  int ablate = 0;              // timing aid: bit mask of denoise-step launches to skip (1 norm_in, 2 qkv, 4 attention, 8 o,
+                               // 16 norm_post, 32 gate/up, 64 down); the actions are then garbage
   int fuse_norm = 0;           // 1: RMSNorm of the expert streams fused across the GEMM chain (see exp_pre/exp_post)
   int profile_gemm = 0;        // bracket every GEMM launch with CUDA events (non-graph runs only)
   long long profile_mtot = 0;  // live packed-row count used for the FLOP accounting of var-len GEMMs
@@ -412,9 +432,27 @@ int engine_build(Engine& e) {
   e.ss_floats = (size_t)(c.num_inference_steps + 1) * (2 * c.layers + 1) * e.ss_rows;
   VL_TRY(e.alloc(&e.ss, e.ss_floats));
   VL_TRY(e.alloc(&e.tile_ctr, 4096));
+  VL_TRY(e.alloc(&e.trace, Engine::TRACE_MAX * 8));
+  {
+    // split-K partial workspaces: [splits <= 32][rows padded to 256][width]. The expert streams always split (o / down
+    // projections); the ViT / LLM residual projections only while their tiles cover less than half of the SMs
+    // (option "small_m_split"), i.e. up to rows_trig(N) rows.
+    auto r256 = [](long long r) { return (r + 255) / 256 * 256; };
+    auto rows_trig = [](int N) { return 128LL * std::max(1, 74 / (N / 128)); };
+    size_t need = (size_t)32 * r256(arow) * he;
+    need = std::max<size_t>(need, (size_t)32 * r256(std::min<long long>(vrows, rows_trig(d))) * d);
+    need = std::max<size_t>(need, (size_t)32 * r256(std::min<long long>(prow, rows_trig(h))) * h);
+    e.ws_main.floats = need;
+    VL_TRY(e.alloc(&e.ws_main.part, need));
+    VL_TRY(e.alloc(&e.ws_main.splits, 1));
+    e.ws_side.floats = (size_t)32 * r256(e.Bc) * he;
+    VL_TRY(e.alloc(&e.ws_side.part, e.ws_side.floats));
+    VL_TRY(e.alloc(&e.ws_side.splits, 1));
+  }
   VL_TRY(e.alloc(&e.xp_layers, (size_t)c.layers));
   VL_TRY(e.alloc(&e.xp_bar, (size_t)(c.num_inference_steps + 1) * e.xp_bar_words()));
   VL_TRY(e.alloc(&e.xp_timing, (size_t)(c.num_inference_steps + 1) * 7 * c.layers));
+  VL_TRY(e.alloc(&e.xfix, (size_t)(c.num_inference_steps + 1) * e.xfix_words()));
   const size_t kv_elems = (size_t)c.layers * c.n_kv_heads * e.kv_rows * 128;
   VL_TRY(e.alloc(&e.kc, kv_elems));
   VL_TRY(e.alloc(&e.vc, kv_elems));
@@ -621,9 +659,47 @@ struct Run {
   int io;
   int rc = 0;
 
+  long long* tr(const char* name, int layer = -1) {
+    if (!e.trace_on || e.trace_idx >= Engine::TRACE_MAX) return nullptr;
+    e.trace_names += name;
+    if (layer >= 0) e.trace_names += " L" + std::to_string(layer);
+    e.trace_names += st == e.side_stream ? " [side]\n" : "\n";
+    return e.trace + 8 * e.trace_idx++;
+  }
+  const char* tr_name = "gemm";
+  int tr_layer = -1;
+
+  // ---- deterministic split-K bookkeeping: the partials a split-K residual projection left for the next reader of x
+  struct Pending {
+    float* x = nullptr;
+    SplitKPartials sp;
+    int rows = 0, width = 0;
+    const int* rows_dev = nullptr;
+  };
+  Pending pend[2];  // main stream, side stream
+  int si() const { return st == e.side_stream ? 1 : 0; }
+  // the partials pending on x, for a norm launch that will fold them in (nullptr: none)
+  const SplitKPartials* take(const float* x, SplitKPartials& tmp) {
+    Pending& p = pend[si()];
+    if (p.x == nullptr || p.x != x) return nullptr;
+    tmp = p.sp;
+    p = Pending();
+    return &tmp;
+  }
+  // any other reader of the stream: finish the residual update first
+  int flush() {
+    Pending& p = pend[si()];
+    if (p.x == nullptr) return 0;
+    const Pending q = p;
+    p = Pending();
+    e.launches++;
+    return splitk_reduce_launch(q.x, q.rows, q.rows_dev, q.width, q.sp, st);
+  }
+
   int gemm(const Act& a, const Lin& w, int M, const int* M_dev, int epi, EpiParams ep, int max_splits = 1,
            int stages = 0, const CUtensorMap* out_tm = nullptr) {
     GemmDims d;
+    d.trace = tr(tr_name, tr_layer);
     d.M = M;
     d.N = w.N;
     d.K = w.K;
@@ -640,6 +716,37 @@ struct Run {
         (long long)((M + 127) / 128) * (w.N / 128) * 2 <= gemm_num_sms()) {
       max_splits = d.max_splits = 32;
       out_tm = nullptr;
+    }
+    const CUtensorMap* part_tm = nullptr;
+    if (epi == EPI_RESID_F32 && pend[si()].x == ep.out) VL_TRY(flush());
+    if (e.det_splitk && epi == EPI_RESID_F32 && max_splits > 1 && !ep.a_next) {
+      Engine::SplitWs& ws = si() ? e.ws_side : e.ws_main;
+      const long long stride = (long long)((M + 255) / 256 * 256) * w.N;
+      const int fit = (int)std::min<long long>(max_splits, (long long)(ws.floats / (size_t)stride));
+      if (fit >= 2) {
+        max_splits = d.max_splits = fit;
+        ep.part = ws.part;
+        ep.part_stride = stride;
+        ep.part_splits = ws.splits;
+        auto it = ws.maps.find(w.N);
+        if (it == ws.maps.end()) {
+          CUtensorMap m;
+          VL_TRY(make_tmap_out(&m, ws.part, ws.floats / (size_t)w.N, (uint64_t)w.N, 4));
+          it = ws.maps.emplace(w.N, m).first;
+        }
+        part_tm = &it->second;
+        VL_TRY(flush());
+        Pending& p = pend[si()];
+        p.x = reinterpret_cast<float*>(ep.out);
+        p.sp.part = ws.part;
+        p.sp.stride = stride;
+        p.sp.splits = ws.splits;
+        p.rows = M;
+        p.rows_dev = M_dev;
+        p.width = w.N;
+      } else {
+        max_splits = d.max_splits = 1;  // no room for partials: one split per tile (slower, still deterministic)
+      }
     }
     int bn = 128;
     // large-M GEMMs: CTA-pair kernel (256x256 tile per pair) when there is at least one tile per pair
@@ -671,7 +778,7 @@ struct Run {
       e.prof_class.push_back((d.pair && rows > 512.0) ? 1 : 0);  // M <= 512: weight-streaming regime whatever the kernel
       VL_CUDA_CHECK(cudaEventRecord(e.prof_events[e.prof_used], st));
     }
-    const int rc = gemm_launch(a.tm, bn == 256 ? w.tm256 : w.tm128, d, ep, bn, epi, st, e.tma_epi ? out_tm : nullptr);
+    const int rc = gemm_launch(a.tm, bn == 256 ? w.tm256 : w.tm128, d, ep, bn, epi, st, e.tma_epi ? out_tm : nullptr, part_tm);
     if (prof) {
       VL_CUDA_CHECK(cudaEventRecord(e.prof_events[e.prof_used + 1], st));
       e.prof_used += 2;
@@ -710,14 +817,18 @@ struct Run {
     ep.bias = e.patch_b;
     ep.pos_emb = e.pos;
     ep.patches = e.P;
+    tr_name = "vit_patch";
     VL_TRY(gemm(e.cols, e.patch, Ni * e.P, nullptr, EPI_PATCH_EMBED, ep));
     for (int i = 0; i < c.vit_layers; ++i) {
       VitLayer& L = e.vit[i];
-      VL_TRY(layernorm_launch(e.vx, L.n1w, L.n1b, e.vn.p, rows, d, c.vit_eps, ShuffleGather{}, st));
+      tr_layer = i;
+      SplitKPartials spt;
+      VL_TRY(layernorm_launch(e.vx, L.n1w, L.n1b, e.vn.p, rows, d, c.vit_eps, ShuffleGather{}, st, take(e.vx, spt)));
       EpiParams e1;
       e1.out = e.vqkv;
       e1.ldo = 3 * d;
       e1.bias = L.bqkv;
+      tr_name = "vit_qkv";
       VL_TRY(gemm(e.vn, L.qkv, rows, nullptr, EPI_STORE_BF16, e1, 1, 0, &e.vqkv_otm));
       if (e.P + 1 >= 128 && e.P + 1 <= 320) {
         VL_TRY(vit_attention_launch(e.vqkv, e.vattn.p, Ni, e.P + 1, c.vit_heads, 0.125f, st));
@@ -742,22 +853,25 @@ struct Run {
       e2.ldo = d;
       e2.bias = L.bproj;
       e2.scale = L.ls1;
+      tr_name = "vit_proj";
       VL_TRY(gemm(e.vattn, L.proj, rows, nullptr, EPI_RESID_F32, e2, 1, 0, &e.vx_otm));
-      VL_TRY(layernorm_launch(e.vx, L.n2w, L.n2b, e.vn.p, rows, d, c.vit_eps, ShuffleGather{}, st));
+      VL_TRY(layernorm_launch(e.vx, L.n2w, L.n2b, e.vn.p, rows, d, c.vit_eps, ShuffleGather{}, st, take(e.vx, spt)));
       EpiParams e3;
       e3.out = e.vmlp.p;
       e3.ldo = f;
       e3.bias = L.bfc1;
+      tr_name = "vit_fc1";
       VL_TRY(gemm(e.vn, L.fc1, rows, nullptr, EPI_GELU_BF16, e3, 1, 0, &e.vmlp.otm));
       EpiParams e4;
       e4.out = e.vx;
       e4.ldo = d;
       e4.bias = L.bfc2;
       e4.scale = L.ls2;
+      tr_name = "vit_fc2";
       VL_TRY(gemm(e.vmlp, L.fc2, rows, nullptr, EPI_RESID_F32, e4, 1, 0, &e.vx_otm));
       e.launches += 3;
     }
-    return 0;
+    return flush();  // the last fc2 of a small batch may have left split-K partials
   }
 
   int embed() {
@@ -772,12 +886,15 @@ struct Run {
     e1.out = e.pa.p;
     e1.ldo = h;
     e1.bias = e.pj_b1;
+    tr_name = "proj1";
+    tr_layer = -1;
     VL_TRY(gemm(e.ps, e.pj1, prows, nullptr, EPI_GELU_BF16, e1, 1, 0, &e.pa.otm));
     EpiParams e2;
     e2.out = e.xv;
     e2.ldo = h;
     e2.bias = e.pj_b2;
     e2.row_map = e.pb.img_row_map;
+    tr_name = "proj2";
     VL_TRY(gemm(e.pa, e.pj2, prows, nullptr, EPI_STORE_F32, e2));
     VL_TRY(assemble_text_launch(e.embed, e.pb.row_src, e.pb.m_tot, e.xv, B * e.S, h, st));
     VL_TRY(small_linear_launch(e.in_prop, io, e.pe_w, e.pe_b, e.xp, DT_F32, B, c.proprio_dim, c.hidden_e, st));
@@ -786,10 +903,17 @@ struct Run {
   }
 
   // one transformer block of a stream (residual x fp32, expert or LLM weights)
+  int abl = 0;  // timing aid (option "ablate"): launches of the denoise steps to leave out, results are then garbage
   int block_pre(LlmLayer& L, float* x, Act& xn, bf16* qout, int M, const int* M_dev, int hid, const int* pos,
                 const int* kvrow, int layer, const L2Prefetch* pf = nullptr) {
-    VL_TRY(rmsnorm_launch(x, L.ln_in, xn.p, M, M_dev, hid, e.c.rms_eps, st, pf));
-    e.launches++;
+    tr_layer = layer;
+    if (!(abl & 1)) {
+      SplitKPartials spt;
+      VL_TRY(rmsnorm_launch(x, L.ln_in, xn.p, M, M_dev, hid, e.c.rms_eps, st, pf, tr("norm_in", layer), take(x, spt)));
+      e.launches++;
+    }
+    if (abl & 2) return 0;
+    tr_name = "qkv";
     return gemm(xn, L.qkv, M, M_dev, EPI_QKV_ROPE, rope_ep(qout, L.bqkv, pos, kvrow, layer));
   }
   int block_post(LlmLayer& L, float* x, Act& xn, Act& ao, Act& act, int M, const int* M_dev, int hid, int mlp,
@@ -797,13 +921,20 @@ struct Run {
     EpiParams eo;
     eo.out = x;
     eo.ldo = hid;
-    VL_TRY(gemm(ao, L.o, M, M_dev, EPI_RESID_F32, eo, splits, 0, x_otm));
-    VL_TRY(rmsnorm_launch(x, L.ln_post, xn.p, M, M_dev, hid, e.c.rms_eps, st, pf));
-    e.launches++;
+    tr_name = "o";
+    if (!(abl & 8)) VL_TRY(gemm(ao, L.o, M, M_dev, EPI_RESID_F32, eo, splits, 0, x_otm));
+    if (!(abl & 16)) {
+      SplitKPartials spt;
+      VL_TRY(rmsnorm_launch(x, L.ln_post, xn.p, M, M_dev, hid, e.c.rms_eps, st, pf, tr("norm_post", tr_layer), take(x, spt)));
+      e.launches++;
+    }
     EpiParams eg;
     eg.out = act.p;
     eg.ldo = mlp;
-    VL_TRY(gemm(xn, L.gu, M, M_dev, EPI_SWIGLU_BF16, eg, 1, 0, &act.otm));
+    tr_name = "gate_up";
+    if (!(abl & 32)) VL_TRY(gemm(xn, L.gu, M, M_dev, EPI_SWIGLU_BF16, eg, 1, 0, &act.otm));
+    if (abl & 64) return 0;
+    tr_name = "down";
     return gemm(act, L.down, M, M_dev, EPI_RESID_F32, eo, splits, 0, x_otm);
   }
 
@@ -897,6 +1028,7 @@ struct Run {
     p.batch = B;
     p.scale = 0.08838834764831845f;  // 128^-0.5
     p.barrier = e.xp_bar + (size_t)pass * e.xp_bar_words();
+    p.xfix = (gemv() && e.det_splitk) ? e.xfix + (size_t)pass * e.xfix_words() : nullptr;
     p.n_streams = expert_streams(M, B);
     p.flags = e.xp_flags;
     p.timing = e.xp_time ? e.xp_timing + (size_t)pass * 7 * c.layers : nullptr;
@@ -950,6 +1082,7 @@ struct Run {
     ap.n_kv_heads = c.n_kv_heads;
     ap.batch = B;
     ap.scale = 0.08838834764831845f;
+    ap.trace = tr("attention", li);
     VL_TRY(attention_launch(ap, 128, st));
     e.launches++;
     return block_post(e.exp[li], e.xp, e.xpn, e.aop, e.actp, B, nullptr, c.hidden_e, e.mlp_e_p, 32, &e.xp_otm);
@@ -1008,6 +1141,7 @@ struct Run {
       ap.n_kv_heads = c.n_kv_heads;
       ap.batch = B;
       ap.scale = 0.08838834764831845f;  // 128^-0.5
+      ap.trace = tr("attention", li);
       VL_TRY(attention_launch(ap, 128, st));
       e.launches++;
       VL_TRY(block_post(e.llm[li], e.xv, e.xn, e.ao, e.act, cap, e.pb.m_tot, c.hidden, e.mlp_p, 1, &e.xv_otm));
@@ -1016,9 +1150,14 @@ struct Run {
       else VL_TRY(block_post(e.exp[li], e.xp, e.xpn, e.aop, e.actp, B, nullptr, c.hidden_e, e.mlp_e_p, 32, &e.xp_otm));
     }
     if (side) {
+      st = e.side_stream;
+      const int frc = flush();
+      st = main_st;
+      if (frc) return frc;
       VL_CUDA_CHECK(cudaEventRecord(e.side_events[c.layers], e.side_stream));  // join
       VL_CUDA_CHECK(cudaStreamWaitEvent(main_st, e.side_events[c.layers], 0));
     }
+    VL_TRY(flush());
     if (mega() && !side)
       VL_TRY(expert_pass(0, B, e.xp, e.xp_otm, e.xpn, e.qp, e.aop, e.actp, e.pb.prop_pos, e.pb.prop_kvrow, e.pb.prop_q_start,
                          e.pb.prop_q_len, e.pb.prop_kv_len, 1, true));
@@ -1028,6 +1167,11 @@ struct Run {
   int denoise(int step) {
     const vlaser_cfg& c = e.c;
     const int M = B * e.H, he = c.hidden_e;
+    struct AblScope {
+      int& a;
+      ~AblScope() { a = 0; }
+    } abl_scope{abl};
+    abl = e.ablate;
     // action encoder (modules.py:39-53) with the time term pre-reduced into a per-step bias
     VL_TRY(small_linear_launch(e.action, DT_F32, e.ae_w1, e.ae_b1, e.e1.p, DT_BF16, M, c.action_dim, he, st));
     e.launches++;
@@ -1035,12 +1179,15 @@ struct Run {
     e2.out = e.h2.p;
     e2.ldo = he;
     e2.bias = e.time_bias + (size_t)step * he;
+    tr_name = "act_enc2";
+    tr_layer = -1;
     VL_TRY(gemm(e.e1, e.ae_w2b, M, nullptr, EPI_SILU_BF16, e2));
     EpiParams e3;
     e3.out = e.xa;
     e3.ldo = he;
     e3.bias = e.ae_b3;
     if (e.fuse_norm && !mega()) norm_producer(e3, e.xan, e.exp[0].ln_in, step + 1, 0);
+    tr_name = "act_enc3";
     VL_TRY(gemm(e.h2, e.ae_w3, M, nullptr, EPI_STORE_F32, e3));
     if (mega())
       VL_TRY(expert_pass(step + 1, M, e.xa, e.xa_otm, e.xan, e.qa, e.aoa, e.acta, e.pb.act_pos, e.pb.act_kvrow, e.pb.den_q_start,
@@ -1076,15 +1223,20 @@ struct Run {
       ap.n_kv_heads = c.n_kv_heads;
       ap.batch = B;
       ap.scale = 0.08838834764831845f;
-      VL_TRY(attention_launch(ap, 128, st));
-      e.launches++;
+      if (!(abl & 4)) {
+        ap.trace = tr("attention", li);
+        VL_TRY(attention_launch(ap, 128, st));
+        e.launches++;
+      }
       if (e.fuse_norm) VL_TRY(exp_post(li, e.xa, e.xan, e.aoa, e.acta, M, step + 1, false));
       else VL_TRY(block_post(e.exp[li], e.xa, e.xan, e.aoa, e.acta, M, nullptr, he, e.mlp_e_p, 32, &e.xa_otm, e.l2pf ? &pf_post : nullptr));
     }
     const int last = step == c.num_inference_steps - 1;
+    VL_TRY(flush());  // split-K partials of the last down projection
     VL_TRY(euler_step_launch(e.xa, e.final_norm, e.dec_w, e.dec_b, e.action, e.out_act, io, M, he, c.action_dim, e.H,
                              c.horizon_steps, (float)(1.0 / c.num_inference_steps), c.rms_eps, last, c.clip_enabled,
-                             c.final_action_clip_value, st));
+                             c.final_action_clip_value, st,
+                             (gemv() && e.det_splitk) ? e.xfix + (size_t)(step + 1) * e.xfix_words() : nullptr));
     e.launches++;
     return 0;
   }
@@ -1096,6 +1248,8 @@ struct Run {
     VL_TRY(convert_launch(e.in_noise, io, e.action, DT_F32, (long long)B * e.H * c.action_dim, st));
     if (e.fuse_norm) VL_CUDA_CHECK(cudaMemsetAsync(e.ss, 0, e.ss_floats * sizeof(float), st));
     VL_CUDA_CHECK(cudaMemsetAsync(e.xp_bar, 0, sizeof(unsigned int) * (size_t)(c.num_inference_steps + 1) * e.xp_bar_words(), st));
+    if (gemv() && e.det_splitk)
+      VL_CUDA_CHECK(cudaMemsetAsync(e.xfix, 0, sizeof(long long) * (size_t)(c.num_inference_steps + 1) * e.xfix_words(), st));
     e.launches += 5;
     VL_TRY(vit());
     if (e.stop_after == 1) return 0;
@@ -1119,6 +1273,8 @@ struct Run {
 int engine_execute(Engine& e, int B, int io, bool has_valid, cudaStream_t st) {
   e.launches = 0;
   if (!e.use_graph) {
+    e.trace_idx = 0;
+    e.trace_names.clear();
     Run r{e, st, B, io};
     const int rc = r.all(has_valid);
     e.last_launches = e.launches;
@@ -1131,12 +1287,16 @@ int engine_execute(Engine& e, int B, int io, bool has_valid, cudaStream_t st) {
     // be captured). A warm, non-captured pass first sets the per-kernel attributes outside capture.
     VL_CUDA_CHECK(cudaStreamSynchronize(st));  // staged inputs have landed
     cudaStream_t cs = e.own_stream;
+    e.trace_idx = 0;
+    e.trace_names.clear();
     {
       Run r{e, cs, B, io};
       VL_TRY(r.all(has_valid));
       VL_CUDA_CHECK(cudaStreamSynchronize(cs));
     }
     e.launches = 0;
+    e.trace_idx = 0;
+    e.trace_names.clear();
     cudaGraph_t graph = nullptr;
     VL_CUDA_CHECK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
     Run r{e, cs, B, io};
@@ -1213,7 +1373,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
@@ -1225,6 +1385,9 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
     else if (k == "prop_stream") h->e.prop_stream = (int)value;
     else if (k == "expert_timing") h->e.xp_time = (int)value;
     else if (k == "expert_flags") h->e.xp_flags = (int)value;
+    else if (k == "ablate") h->e.ablate = (int)value;
+    else if (k == "trace") h->e.trace_on = (int)value;
+    else if (k == "det_splitk") h->e.det_splitk = (int)value;
     else if (k == "pair_gemm") h->e.pair_gemm = (int)value;
     else if (k == "tma_epi") h->e.tma_epi = (int)value;
     else if (k == "pair_min_tiles") h->e.pair_min_tiles = (int)value;
@@ -1350,7 +1513,15 @@ int64_t vlaser_debug_copy(vlaser_t* h, const char* name, void* host_dst, int64_t
   else if (n == "img_row_map") src = e.pb.img_row_map, bytes = Ni * e.T * 4;
   else if (n == "row_src") src = e.pb.row_src, bytes = (size_t)e.Bc * e.S * 4;
   else if (n == "expert_timing") src = e.xp_timing, bytes = (size_t)(c.num_inference_steps + 1) * 7 * c.layers * 8;
-  else if (n == "kv_rows") {
+  else if (n == "trace") src = e.trace, bytes = Engine::TRACE_MAX * 8 * 8;
+  else if (n == "trace_names") {
+    // newline-separated launch names in record order (valid after a call that built its graph with option "trace" on)
+    if (host_dst && max_bytes > 0) {
+      const size_t nb = std::min<size_t>(e.trace_names.size(), (size_t)max_bytes);
+      memcpy(host_dst, e.trace_names.data(), nb);
+    }
+    return (int64_t)e.trace_names.size();
+  } else if (n == "kv_rows") {
     const int64_t v = e.kv_rows;
     if (host_dst && max_bytes >= 8) memcpy(host_dst, &v, 8);
     return 8;
@@ -1468,6 +1639,9 @@ int32_t vlaser_op_gemm(const vlaser_gemm_args* a, void* stream) {
   ep.row_ss = a->row_ss;
   ep.inv_width = a->inv_width;
   ep.eps = a->eps;
+  ep.part = a->partial;
+  ep.part_stride = a->partial_stride;
+  ep.part_splits = a->partial_splits;
   d.stages = a->stages;
   d.pair = a->pair & 1;
   d.n_fast = (a->pair >> 1) & 1;
@@ -1481,7 +1655,14 @@ int32_t vlaser_op_gemm(const vlaser_gemm_args* a, void* stream) {
   CUtensorMap tmC;
   const bool tma_out = a->pair && a->tma_out;
   if (tma_out) VL_TRY(make_tmap_out(&tmC, a->out, (uint64_t)a->M, (uint64_t)a->ldo, a->epi == EPI_RESID_F32 ? 4 : 2));
-  return gemm_launch(tmA, tmB, d, ep, a->pair ? 128 : a->block_n, a->epi, st, tma_out ? &tmC : nullptr);
+  CUtensorMap tmP;
+  const bool part_map = a->pair && a->partial != nullptr;
+  if (part_map) {
+    VL_CHECK(a->ldo > 0 && a->partial_stride > 0, "op_gemm: split-K partials need ldo and partial_stride");
+    VL_TRY(make_tmap_out(&tmP, a->partial, (uint64_t)(d.max_splits * (a->partial_stride / a->ldo)), (uint64_t)a->ldo, 4));
+  }
+  return gemm_launch(tmA, tmB, d, ep, a->pair ? 128 : a->block_n, a->epi, st, tma_out ? &tmC : nullptr,
+                     part_map ? &tmP : nullptr);
 }
 
 int32_t vlaser_op_attention(const vlaser_attn_args* a, void* stream) {
@@ -1524,13 +1705,25 @@ int32_t vlaser_op_layernorm(const float* x, const float* gamma, const float* bet
   ShuffleGather sg;
   sg.grid = shuffle_grid;
   sg.channels = shuffle_channels;
-  return layernorm_launch(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, width, eps, sg,
+  return layernorm_launch(const_cast<float*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, width, eps, sg,
                           reinterpret_cast<cudaStream_t>(stream));
 }
 int32_t vlaser_op_rmsnorm(const float* x, const float* gamma, void* out_bf16, int32_t rows, int32_t width, float eps,
                           void* stream) {
-  return rmsnorm_launch(x, gamma, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, nullptr, width, eps,
+  return rmsnorm_launch(const_cast<float*>(x), gamma, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, nullptr, width, eps,
                         reinterpret_cast<cudaStream_t>(stream));
+}
+int32_t vlaser_op_splitk_reduce(float* x, int32_t rows, int32_t width, const float* part, int64_t part_stride,
+                                const int32_t* splits_dev, const float* gamma, void* out_bf16, float eps, void* stream) {
+  VL_CHECK(x && part && splits_dev, "null argument");
+  SplitKPartials sp;
+  sp.part = part;
+  sp.stride = part_stride;
+  sp.splits = splits_dev;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (gamma && out_bf16)
+    return rmsnorm_launch(x, gamma, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, nullptr, width, eps, st, nullptr, nullptr, &sp);
+  return splitk_reduce_launch(x, rows, nullptr, width, sp, st);
 }
 int32_t vlaser_op_pixel_shuffle(const void* in, void* out, int32_t n, int32_t grid, int32_t channels,
                                 int32_t elem_bytes, void* stream) {

@@ -41,6 +41,11 @@ struct ExpertPass {
   int n_q_heads = 0, n_kv_heads = 0;  // head_dim is 128
   float eps = 1e-6f;
   float* x = nullptr;                 // [M, he] fp32 residual stream (in/out)
+  // expert_gemv.cu, deterministic mode: the split-K partial sums of the o / down projections are NOT added to x with
+  // fp32 atomics (their order varies from call to call) but accumulated as 2^-30 fixed point in xfix [M, he] with
+  // 64-bit integer atomics, which commute exactly. x stays what it was on entry for the whole pass; the stream a
+  // reader sees is x + xfix * 2^-30 (one rounding). Zero on entry.
+  long long* xfix = nullptr;
   __nv_bfloat16* xn = nullptr;        // [Mpad, he]   normalised rows (GEMM A operand, tmXn)
   __nv_bfloat16* q = nullptr;         // [M, n_q_heads*128]
   __nv_bfloat16* ao = nullptr;        // [Mpad, n_q_heads*128] attention output (tmAo)

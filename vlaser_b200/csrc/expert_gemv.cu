@@ -169,13 +169,18 @@ __device__ __forceinline__ void reduce_to_lane(float (&acc)[GV_NR][R], int lane,
 // RMSNorm of the M live rows of x into shared memory as bf16 (HF Qwen2RMSNorm: fp32 statistics; the normalised row is
 // the bf16 GEMM operand of the per-kernel schedule as well). All 16 warps: warp w owns part w / R of the columns of row
 // w % R, x is read ONCE (registers), the partial sums of squares meet in shared memory. he <= 512 * (16 / R).
+constexpr float GV_FIX = 1073741824.f;        // 2^30: fixed-point scale of ExpertPass::xfix
+constexpr float GV_FIX_INV = 1.f / 1073741824.f;
+
 template <int R>
-__device__ __forceinline__ void norm_rows_to_smem(const float* __restrict__ x, const float* __restrict__ gamma, int M,
+__device__ __forceinline__ void norm_rows_to_smem(const float* __restrict__ x, const long long* __restrict__ xfix,
+                                                  const float* __restrict__ gamma, int M,
                                                   int he, float eps, __nv_bfloat16* a_s, float* part_ss, int warp, int lane) {
   constexpr int PARTS = GV_WARPS / R;
   constexpr int NI = R;  // float2 slots per lane: he / PARTS / 64 <= R for he <= 1024
   const int r = warp % R, part = warp / R, plen = he / PARTS;
   const float* xr = x + (size_t)r * he + part * plen;
+  const long long* fr = xfix ? xfix + (size_t)r * he + part * plen : nullptr;
   const float* gr = gamma + part * plen;
   float2 xv[NI], gv[NI];
   float q = 0.f;
@@ -185,6 +190,11 @@ __device__ __forceinline__ void norm_rows_to_smem(const float* __restrict__ x, c
     xv[i] = make_float2(0.f, 0.f), gv[i] = xv[i];
     if (c < plen && r < M) {
       xv[i] = __ldcg(reinterpret_cast<const float2*>(xr + c));
+      if (fr) {
+        const longlong2 f = __ldcg(reinterpret_cast<const longlong2*>(fr + c));
+        xv[i].x += (float)f.x * GV_FIX_INV;
+        xv[i].y += (float)f.y * GV_FIX_INV;
+      }
       gv[i] = __ldg(reinterpret_cast<const float2*>(gr + c));
     }
   }
@@ -555,7 +565,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) expert_gemv_pass_kernel(const E
         const int total = unit_count(d, j);
         int pitch = d.he, abase = 0;
         if (j == 0 || j == 3) {
-          norm_rows_to_smem<R>(p.x, j == 0 ? L->ln_in : L->ln_post, M, d.he, p.eps, a_s, part_ss, warp, lane);
+          norm_rows_to_smem<R>(p.x, p.xfix, j == 0 ? L->ln_in : L->ln_post, M, d.he, p.eps, a_s, part_ss, warp, lane);
         } else if (j == 2) {
           pitch = d.qdim;
           bf16_rows_to_smem<R>(p.ao, M, d.qdim, 0, d.qdim, pitch, a_s, tid);
@@ -631,8 +641,16 @@ __global__ void __launch_bounds__(GV_THREADS, 1) expert_gemv_pass_kernel(const E
                     pack_bf16(silu(mine[0]) * mine[2], silu(mine[1]) * mine[3]);
               } else {
                 const int cgs = d.he / GV_NR, cg = u % cgs;
+                if (p.xfix) {
+                  // integer adds commute: the sum does not depend on the order in which the K chunks arrive
 #pragma unroll
-                for (int i = 0; i < GV_NR; ++i) atomicAdd(p.x + (size_t)r * d.he + cg * GV_NR + i, mine[i]);
+                  for (int i = 0; i < GV_NR; ++i)
+                    atomicAdd(reinterpret_cast<unsigned long long*>(p.xfix + (size_t)r * d.he + cg * GV_NR + i),
+                              (unsigned long long)__float2ll_rn(mine[i] * GV_FIX));
+                } else {
+#pragma unroll
+                  for (int i = 0; i < GV_NR; ++i) atomicAdd(p.x + (size_t)r * d.he + cg * GV_NR + i, mine[i]);
+                }
               }
             }
           }

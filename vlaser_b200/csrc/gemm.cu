@@ -94,8 +94,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  long long* tr = (blockIdx.x == 0 && lane == 0) ? d.trace : nullptr;
 
   if (warp == 0 && lane == 0) {
+    trace_stamp(tr, 0);
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
@@ -166,6 +168,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           advance();
         }
         pdl_wait();
+        trace_stamp(tr, 1);
         for (int i = 0; i < npre; ++i)
           tma_load_2d(smem + i * Cfg::STAGE_BYTES, &tmA, &full_bar[i], pre_kb[i] * BLOCK_K, pre_m[i] * BLOCK_M);
         (void)pre_n;
@@ -204,6 +207,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (t == (int)blockIdx.x && kb == tc.kb0) trace_stamp(tr, 2);
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t da = make_umma_desc_sw128(sa);
           const uint64_t db = make_umma_desc_sw128(sa + Cfg::A_BYTES);
@@ -219,6 +223,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         umma_commit(&tfull_bar[as]);  // accumulator ready for the epilogue
+        trace_stamp(tr, 3);
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
@@ -230,21 +235,49 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int half = (warp - 2) >> 2;    // which half of the tile's columns it drains
     int as = 0;
     uint32_t aphase = 0;
+    if (warp != 2) tr = nullptr;
+    if constexpr (EPI == EPI_RESID_F32) {
+      if (ep.part_splits && blockIdx.x == 0 && threadIdx.x == 64) *ep.part_splits = sc.splits > 1 ? sc.splits : 0;
+    }
     for (int t = blockIdx.x; t < sc.total; t += gridDim.x) {
       const TileCoord tc = tile_coord(sc, t);
       const int n_idx = tc.n_idx, m_idx = tc.m_idx;
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
       const int row = m_idx * BLOCK_M + quarter * 32 + lane;
       const bool row_ok = row < M;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
       const int n0 = n_idx * BLOCK_N;
-      const bool first_split = tc.split == 0;
-      const bool atomic = sc.splits > 1;
       float rstd = 1.f;
       if (ep.row_ss && row_ok) rstd = rsqrtf(__ldcg(ep.row_ss + row) * ep.inv_width + ep.eps);
+      // q|k|v projection, 128-column tiles: this warp owns ONE unit of the tile (half-head chunk `half`); its RoPE
+      // factors and KV-cache row are fetched while the mainloop is still running
+      constexpr bool ROPE_PRE = EPI == EPI_QKV_ROPE && BLOCK_N == 128 && EPI_WARPS == 8;
+      RopeOperands ro;
+      if constexpr (ROPE_PRE) rope_prefetch(ep, row, row_ok, n0 + half * 32, ro);
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      if (t == (int)blockIdx.x) trace_stamp(tr, 4);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
+      const bool first_split = tc.split == 0;
+      const bool atomic = sc.splits > 1;
       float ss = 0.f;
-      epilogue_tile<BLOCK_N, EPI>(ep, d.N, taddr, half, row, row_ok, n0, first_split, atomic, rstd, ss);
+      float* part_tile = nullptr;
+      if constexpr (EPI == EPI_RESID_F32) {
+        if (atomic && ep.part && !ep.a_next) part_tile = ep.part + (size_t)tc.split * ep.part_stride;
+      }
+      if constexpr (ROPE_PRE) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(taddr + half * 32, r0);
+        tmem_ld_32x32(taddr + half * 32 + 64, r1);
+        tmem_ld_wait();
+        float v[32], w[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = __uint_as_float(r0[j]) * rstd;
+          w[j] = __uint_as_float(r1[j]) * rstd;
+        }
+        rope_apply(ep, row, row_ok, n0 + half * 32, v, w, ro);
+      } else {
+        epilogue_tile<BLOCK_N, EPI>(ep, d.N, taddr, half, row, row_ok, n0, first_split, atomic, rstd, ss, part_tile);
+      }
       // accumulator drained: hand the TMEM stage back before any slow tail work
       tc_fence_before();
       __syncwarp();
@@ -309,11 +342,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
+    trace_stamp(tr, 5);
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == 2) trace_stamp(tr, 6);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -332,7 +367,8 @@ __device__ __forceinline__ constexpr bool epi_has_tma_out() {
 template <int BN, int EPI, int PARTS, int NBUF>
 __device__ __forceinline__ void epilogue_tile_tma(const EpiParams& ep, const CUtensorMap* tmC, uint8_t* wbuf,
                                                   uint32_t& par, uint32_t taddr, int half, int lane, int row0, int n0,
-                                                  float rstd, bool first_split) {
+                                                  float rstd, bool first_split, const CUtensorMap* tmP = nullptr,
+                                                  int part_row0 = -1) {
   auto acquire = [&]() -> uint8_t* {
     // the staging tile about to be reused (two units ago with NBUF == 2, the previous one otherwise) has been read out
     if (lane == 0) bulk_wait_read<NBUF - 1>();
@@ -372,7 +408,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiParams& ep, const CUt
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        tma_reduce_add_2d(tmC, b, col0, row0);
+        if (part_row0 >= 0) tma_store_2d(tmP, b, col0, part_row0);  // deterministic split-K: partial tile to the workspace
+        else tma_reduce_add_2d(tmC, b, col0, row0);
         bulk_commit();
       }
     }
@@ -466,7 +503,8 @@ constexpr int pair_epi_warps() { return EPI == EPI_GELU_BF16 ? 16 : 8; }  // the
 template <int EPI, int NW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * NW, 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmC, GemmDims d, EpiParams ep) {
+                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, GemmDims d,
+                         EpiParams ep) {
   constexpr int STAGES = pair_stages(NW);
   constexpr int BN = PAIR_BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
@@ -487,11 +525,14 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
   const int n_pairs = gridDim.x >> 1;
+  long long* tr = (blockIdx.x == 0 && lane == 0) ? d.trace : nullptr;
 
   if (warp == 0 && lane == 0) {
+    trace_stamp(tr, 0);
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (d.tma_out) tma_prefetch_desc(&tmC);
+    if (EPI == EPI_RESID_F32 && ep.part) tma_prefetch_desc(&tmP);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -511,14 +552,18 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
-  pdl_wait();
-
-  const int M = d.M_dev ? min(*d.M_dev, d.M) : d.M;
+  // A device-resident row count belongs to this call's plan: it is read after the dependent-launch wait. With a static
+  // M only the threads that touch activations wait (producer: after its weight prefetch; epilogue warps).
+  int M = d.M;
+  if (d.M_dev) {
+    pdl_wait();
+    M = min(*d.M_dev, d.M);
+  }
   const int m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int n_tiles = d.N / BN;
   const int k_blocks = d.K / BLOCK_K;
   const int base = m_tiles * n_tiles;
-  // split-K (residual epilogue through TMA reduce-add only): partial sums meet in L2, no tile counters needed
+  // split-K (residual epilogue through TMA reduce-add / partial stores only): partial sums meet in L2 or in the workspace
   int splits = 1;
   if (EPI == EPI_RESID_F32 && d.max_splits > 1 && d.tma_out && base > 0) {
     splits = min(min(d.max_splits, n_pairs / base), k_blocks / 2);
@@ -527,6 +572,12 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int kb_per_split = (k_blocks + splits - 1) / splits;
   splits = (k_blocks + kb_per_split - 1) / kb_per_split;
   const int total = base * splits;
+  if constexpr (EPI == EPI_RESID_F32) {
+    if (ep.part_splits && blockIdx.x == 0 && threadIdx.x == 64) {
+      pdl_wait();  // the previous reader of the word has finished
+      *ep.part_splits = (splits > 1 && ep.part) ? splits : 0;
+    }
+  }
 
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) ================================
@@ -534,24 +585,62 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const uint32_t full0 = mapa_u32(smem_u32(full_bar), 0);  // the leader's full barriers
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = pair; t < total; t += n_pairs) {
+      // (tile, k-block) cursor of this pair
+      int t = pair, kb = 0, kb1 = 0, row_a = 0, row_b = 0;
+      bool have = t < total;
+      auto open_tile = [&]() {
         int n_idx, m_idx;
         const int split = t / base;
         pair_tile(t - split * base, m_tiles, n_tiles, d.n_fast, m_idx, n_idx);
-        const int row_a = (m_idx * 2 + (int)rank) * BLOCK_M;
-        const int row_b = n_idx * BN + (int)rank * (BN / 2);
-        const int kb0 = split * kb_per_split, kb1 = min(k_blocks, kb0 + kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * PAIR_STAGE_BYTES;
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * PAIR_STAGE_BYTES);
-          tma_load_2d_pair(sa, &tmA, full0 + stage * 8, kb * BLOCK_K, row_a);
-          tma_load_2d_pair(sa + PAIR_A_BYTES, &tmB, full0 + stage * 8, kb * BLOCK_K, row_b);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        row_a = (m_idx * 2 + (int)rank) * BLOCK_M;
+        row_b = n_idx * BN + (int)rank * (BN / 2);
+        kb = split * kb_per_split;
+        kb1 = min(k_blocks, kb + kb_per_split);
+      };
+      auto advance = [&]() {
+        if (++kb >= kb1) {
+          t += n_pairs;
+          have = t < total;
+          if (have) open_tile();
         }
+      };
+      if (have) open_tile();
+      if (!d.M_dev) {
+        // Weights do not depend on the previous kernel: the W halves of the first ring fill go out before the
+        // dependent-launch wait, the A halves (activations written by the previous kernel) after it.
+        int pre_kb[PAIR_MAX_STAGES], pre_row[PAIR_MAX_STAGES];
+        int npre = 0;
+        while (have && npre < STAGES) {
+          pre_kb[npre] = kb;
+          pre_row[npre] = row_a;
+          if (leader) mbar_arrive_expect_tx(&full_bar[npre], 2 * PAIR_STAGE_BYTES);
+          tma_load_2d_pair(smem + npre * PAIR_STAGE_BYTES + PAIR_A_BYTES, &tmB, full0 + npre * 8, kb * BLOCK_K, row_b);
+          ++npre;
+          advance();
+        }
+        pdl_wait();
+        trace_stamp(tr, 1);
+        for (int i = 0; i < npre; ++i)
+          tma_load_2d_pair(smem + i * PAIR_STAGE_BYTES, &tmA, full0 + i * 8, pre_kb[i] * BLOCK_K, pre_row[i]);
+        stage = npre;
+        if (stage == STAGES) {
+          stage = 0;
+          phase = 1;
+        }
+      } else {
+        trace_stamp(tr, 1);
+      }
+      while (have) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * PAIR_STAGE_BYTES;
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * PAIR_STAGE_BYTES);
+        tma_load_2d_pair(sa, &tmA, full0 + stage * 8, kb * BLOCK_K, row_a);
+        tma_load_2d_pair(sa + PAIR_A_BYTES, &tmB, full0 + stage * 8, kb * BLOCK_K, row_b);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+        advance();
       }
     }
   } else if (warp == 1) {
@@ -571,6 +660,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (t == pair && kb == kb0) trace_stamp(tr, 2);
           const uint32_t sa = smem_u32(smem + stage * PAIR_STAGE_BYTES);
           const uint64_t da = make_umma_desc_sw128(sa);
           const uint64_t db = make_umma_desc_sw128(sa + PAIR_A_BYTES);
@@ -584,12 +674,14 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         }
         umma_commit_pair(&tfull_bar[as], 0x3);  // accumulators (both CTAs' TMEM) ready
+        trace_stamp(tr, 3);
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
     }
   } else {
     // ================================ epilogue warps (both CTAs) ================================
+    if (!d.M_dev) pdl_wait();  // residual rows / activations of the previous kernel
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const uint32_t tempty0 = mapa_u32(smem_u32(tempty_bar), 0);
@@ -597,12 +689,14 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint32_t out_par = 0;
     int as = 0;
     uint32_t aphase = 0;
+    if (warp != 2) tr = nullptr;
     for (int t = pair; t < total; t += n_pairs) {
       int n_idx, m_idx;
       const int split = t / base;
       pair_tile(t - split * base, m_tiles, n_tiles, d.n_fast, m_idx, n_idx);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
+      if (t == pair) trace_stamp(tr, 4);
       const int row = (m_idx * 2 + (int)rank) * BLOCK_M + quarter * 32 + lane;
       const bool row_ok = row < M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
@@ -613,8 +707,11 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       bool done = false;
       if constexpr (epi_has_tma_out<EPI>()) {
         if (d.tma_out) {
+          int part_row0 = -1;
+          if (EPI == EPI_RESID_F32 && splits > 1 && ep.part)
+            part_row0 = split * (int)(ep.part_stride / ep.ldo) + (row - lane);
           epilogue_tile_tma<BN, EPI, PARTS, NBUF>(ep, &tmC, wbuf, out_par, taddr, half, lane, row - lane, n0, rstd,
-                                                  split == 0);
+                                                  split == 0, &tmP, part_row0);
           done = true;
         }
       }
@@ -633,11 +730,13 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   }
 
+  if (warp == 2) trace_stamp(tr, 5);
   if (warp >= 2 && lane == 0) bulk_wait<0>();  // this warp's TMA stores have landed
   // neither CTA may exit (or free TMEM) while its peer can still signal its barriers or read its smem
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) tmem_dealloc_pair(tmem_base, 2 * BN);
+  if (warp == 2) trace_stamp(tr, 6);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -730,9 +829,11 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDims d, const
 
 template <int EPI>
 int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, GemmDims d, const EpiParams& ep,
-                cudaStream_t stream) {
+                cudaStream_t stream, const CUtensorMap* tmP) {
   d.tma_out = (tmC != nullptr && epi_has_tma_out<EPI>() && !ep.a_next) ? 1 : 0;
   const CUtensorMap& tc = d.tma_out ? *tmC : tmA;
+  VL_CHECK(!(EPI == EPI_RESID_F32 && ep.part) || tmP != nullptr, "gemm: pair kernel with split-K partials needs the workspace tensor map");
+  const CUtensorMap& tp = tmP ? *tmP : tmA;
   static bool attr_set = false;
   constexpr int NW = pair_epi_warps<EPI>();
   auto kern = gemm_tcgen05_pair_kernel<EPI, NW>;
@@ -747,14 +848,14 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   }
   const int pairs = (int)std::min<long long>(tiles, gemm_num_sms() / 2);
   // __cluster_dims__(2,1,1) is part of the kernel: a plain launch (with the optional PDL attribute) suffices
-  VL_CUDA_CHECK(launch_kernel(kern, dim3(2 * pairs), dim3(64 + 32 * NW), pair_smem_bytes(NW), stream, tmA, tmB, tc, d, ep));
+  VL_CUDA_CHECK(launch_kernel(kern, dim3(2 * pairs), dim3(64 + 32 * NW), pair_smem_bytes(NW), stream, tmA, tmB, tc, tp, d, ep));
   return 0;
 }
 
 template <int EPI>
 int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, const GemmDims& d,
-              const EpiParams& ep, int block_n, int grid, cudaStream_t stream) {
-  if (d.pair) return launch_pair<EPI>(tmA, tmB, tmC, d, ep, stream);
+              const EpiParams& ep, int block_n, int grid, cudaStream_t stream, const CUtensorMap* tmP) {
+  if (d.pair) return launch_pair<EPI>(tmA, tmB, tmC, d, ep, stream, tmP);
   if (block_n == 128) return launch_one<128, EPI>(tmA, tmB, d, ep, grid, stream);
   if constexpr (EPI != EPI_QKV_ROPE) {
     if (block_n == 256) return launch_one<256, EPI>(tmA, tmB, d, ep, grid, stream);
@@ -816,7 +917,10 @@ int make_tmap_out(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t col
 }
 
 int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDims& d, const EpiParams& ep, int block_n,
-                int epi, cudaStream_t stream, const CUtensorMap* tmC) {
+                int epi, cudaStream_t stream, const CUtensorMap* tmC, const CUtensorMap* tmP) {
+  VL_CHECK(!ep.part || (epi == EPI_RESID_F32 && ep.part_stride > 0 && ep.part_stride % ((long long)256 * ep.ldo) == 0 &&
+                        ep.part_stride >= (long long)d.M * ep.ldo && !ep.a_next),
+           "gemm: split-K partials need the residual epilogue and a stride of whole 256-row blocks covering M");
   VL_CHECK(d.K % BLOCK_K == 0 && d.K > 0, "gemm: K must be a positive multiple of 64");
   VL_CHECK(block_n == 128 || block_n == 256, "gemm: block_n must be 128 or 256");
   VL_CHECK(!d.pair || (block_n == 128 && d.N % PAIR_BLOCK_N == 0), "gemm: pair mode needs the 128-row W map, N % 256 == 0");
@@ -831,14 +935,14 @@ int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDims& 
   if (epi == EPI_RESID_F32 && d.max_splits > 1) tiles *= d.max_splits;
   const int grid = (int)std::min<long long>(tiles, gemm_num_sms());
   switch (epi) {
-    case EPI_STORE_BF16: return launch_bn<EPI_STORE_BF16>(tmA, tmB, tmC, d, ep, block_n, grid, stream);
-    case EPI_GELU_BF16: return launch_bn<EPI_GELU_BF16>(tmA, tmB, tmC, d, ep, block_n, grid, stream);
-    case EPI_SILU_BF16: return launch_bn<EPI_SILU_BF16>(tmA, tmB, tmC, d, ep, block_n, grid, stream);
-    case EPI_RESID_F32: return launch_bn<EPI_RESID_F32>(tmA, tmB, tmC, d, ep, block_n, grid, stream);
-    case EPI_SWIGLU_BF16: return launch_bn<EPI_SWIGLU_BF16>(tmA, tmB, tmC, d, ep, block_n, grid, stream);
-    case EPI_QKV_ROPE: return launch_bn<EPI_QKV_ROPE>(tmA, tmB, tmC, d, ep, block_n, grid, stream);
-    case EPI_PATCH_EMBED: return launch_bn<EPI_PATCH_EMBED>(tmA, tmB, tmC, d, ep, block_n, grid, stream);
-    case EPI_STORE_F32: return launch_bn<EPI_STORE_F32>(tmA, tmB, tmC, d, ep, block_n, grid, stream);
+    case EPI_STORE_BF16: return launch_bn<EPI_STORE_BF16>(tmA, tmB, tmC, d, ep, block_n, grid, stream, tmP);
+    case EPI_GELU_BF16: return launch_bn<EPI_GELU_BF16>(tmA, tmB, tmC, d, ep, block_n, grid, stream, tmP);
+    case EPI_SILU_BF16: return launch_bn<EPI_SILU_BF16>(tmA, tmB, tmC, d, ep, block_n, grid, stream, tmP);
+    case EPI_RESID_F32: return launch_bn<EPI_RESID_F32>(tmA, tmB, tmC, d, ep, block_n, grid, stream, tmP);
+    case EPI_SWIGLU_BF16: return launch_bn<EPI_SWIGLU_BF16>(tmA, tmB, tmC, d, ep, block_n, grid, stream, tmP);
+    case EPI_QKV_ROPE: return launch_bn<EPI_QKV_ROPE>(tmA, tmB, tmC, d, ep, block_n, grid, stream, tmP);
+    case EPI_PATCH_EMBED: return launch_bn<EPI_PATCH_EMBED>(tmA, tmB, tmC, d, ep, block_n, grid, stream, tmP);
+    case EPI_STORE_F32: return launch_bn<EPI_STORE_F32>(tmA, tmB, tmC, d, ep, block_n, grid, stream, tmP);
     default: set_last_error("gemm_launch: unknown epilogue"); return -2;
   }
 }

@@ -54,6 +54,14 @@ struct EpiParams {
   const float* row_ss = nullptr;       // [M] sum of squares of the un-normalised row
   float inv_width = 0.f;               // 1 / hidden width of the normalised row
   float eps = 0.f;
+  // ---- deterministic split-K (EPI_RESID_F32). With `part` set the K splits of a tile do not meet through fp32 atomics /
+  // L2 reduce-adds in `out` (whose summation order changes from call to call): split s stores its partial tile -- scaled,
+  // split 0 biased -- to part[s * part_stride + row * ldo + col], and the consumer of the residual stream (the norm
+  // kernels of elementwise.cu, splitk_reduce) adds the partials to `out` in split order. part_splits receives the
+  // split count the launch actually used (0: one split, `out` was updated directly).
+  float* part = nullptr;
+  long long part_stride = 0;           // floats between consecutive splits, a multiple of 256 * ldo covering the rows
+  int* part_splits = nullptr;
 };
 
 struct GemmDims {
@@ -64,6 +72,7 @@ struct GemmDims {
   int pair = 0;                  // 1: CTA-pair kernel (cta_group::2, 256x256 tile per pair; W map with 128-row boxes)
   int n_fast = 0;                // pair kernel tile order: 0 = m fastest, 1 = n fastest
   int tma_out = 0;               // set by the launcher: epilogue leaves through the output tensor map
+  long long* trace = nullptr;    // optional 8-slot timeline record of this launch (common.cuh trace_stamp)
 };
 
 // Host API -------------------------------------------------------------------------------
@@ -75,8 +84,10 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t co
 // 32 rows x 128 bytes, 128B swizzle. For EPI_SWIGLU_BF16 it describes the [M, N/2] result.
 int make_tmap_out(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, int elem_bytes);
 // `tmC` (optional, pair kernel + bf16/residual epilogues only): output tensor map; the epilogue then stores through TMA.
+// `tmP` (pair kernel, split-K with ep.part): make_tmap_out map of the partial workspace viewed as
+// [max_splits * part_stride / ldo, ldo] f32.
 int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDims& d, const EpiParams& ep, int block_n,
-                int epi, cudaStream_t stream, const CUtensorMap* tmC = nullptr);
+                int epi, cudaStream_t stream, const CUtensorMap* tmC = nullptr, const CUtensorMap* tmP = nullptr);
 int gemm_launch_simt(const __nv_bfloat16* A, const __nv_bfloat16* W, const GemmDims& d, const EpiParams& ep, int epi,
                      cudaStream_t stream);
 int gemm_num_sms();

@@ -57,11 +57,69 @@ __device__ __forceinline__ float norm_out_chunk(const EpiParams& ep, int row, in
   return ss;
 }
 
+// ---- EPI_QKV_ROPE: one head = 128 columns; a unit is x[i0..i0+31] (chunk v) and x[i0+64..i0+95] (chunk w) of that
+// head, i0 in {0, 32}. The RoPE factors / KV-cache row of a unit depend on the row only, not on the accumulator:
+// rope_prefetch may run while the mainloop is still in flight (the tcgen05 kernels call it before waiting on the
+// accumulator), rope_apply finishes bias + rotation + the q / KV-cache stores.
+struct RopeOperands {
+  float cs[32], sn[32];
+  int kvrow;
+};
+__device__ __forceinline__ void rope_prefetch(const EpiParams& ep, int row, bool row_ok, int col0, RopeOperands& ro) {
+  const int head = col0 >> 7, i0 = col0 & 127;
+  const bool is_q = head < ep.n_q_heads;
+  const bool is_k = !is_q && head < ep.n_q_heads + ep.n_kv_heads;
+  ro.kvrow = 0;
+  if (!row_ok) return;
+  if (!is_q) ro.kvrow = __ldg(ep.row_kvrow + row);
+  if (is_q || is_k) {
+    const int pos = __ldg(ep.row_pos + row);
+    const float4* c4 = reinterpret_cast<const float4*>(ep.cos_tab + (size_t)pos * 64 + i0);
+    const float4* s4 = reinterpret_cast<const float4*>(ep.sin_tab + (size_t)pos * 64 + i0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 c = __ldg(c4 + i), s = __ldg(s4 + i);
+      ro.cs[4 * i] = c.x, ro.cs[4 * i + 1] = c.y, ro.cs[4 * i + 2] = c.z, ro.cs[4 * i + 3] = c.w;
+      ro.sn[4 * i] = s.x, ro.sn[4 * i + 1] = s.y, ro.sn[4 * i + 2] = s.z, ro.sn[4 * i + 3] = s.w;
+    }
+  }
+}
+__device__ __forceinline__ void rope_apply(const EpiParams& ep, int row, bool row_ok, int col0, float (&v)[32],
+                                           float (&w)[32], const RopeOperands& ro) {
+  const int head = col0 >> 7, i0 = col0 & 127;
+  if (ep.bias) {
+    add_vec32(v, ep.bias + col0);
+    add_vec32(w, ep.bias + col0 + 64);
+  }
+  const bool is_q = head < ep.n_q_heads;
+  const bool is_k = !is_q && head < ep.n_q_heads + ep.n_kv_heads;
+  if (!row_ok) return;
+  if (is_q || is_k) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float a = v[j], b = w[j];
+      v[j] = a * ro.cs[j] - b * ro.sn[j];   // x*cos + rot(x)*sin, rot(x)[i] = -x[i+64]
+      w[j] = b * ro.cs[j] + a * ro.sn[j];   //                     rot(x)[i+64] = x[i]
+    }
+  }
+  __nv_bfloat16* dst;
+  if (is_q) {
+    dst = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + head * 128 + i0;
+  } else {
+    const int kvh = is_k ? head - ep.n_q_heads : head - ep.n_q_heads - ep.n_kv_heads;
+    __nv_bfloat16* base = is_k ? ep.k_cache : ep.v_cache;
+    dst = base + (size_t)kvh * ep.kv_head_stride + (size_t)ro.kvrow * 128 + i0;
+  }
+  store_bf16x32(dst, v);
+  store_bf16x32(dst + 64, w);
+}
+
 // `rstd`: per-row scale of the accumulator (fused RMSNorm consumer side, 1 when unused);
 // `ss`: per-thread running sum of squares of the produced row (producer side).
 template <int EPI>
 __device__ __forceinline__ void epi_chunk(const EpiParams& ep, int N, int row, bool row_ok, int col0, float (&v)[32],
-                                          float (&w)[32], bool first_split, bool atomic, float rstd, float& ss) {
+                                          float (&w)[32], bool first_split, bool atomic, float rstd, float& ss,
+                                          float* part_tile = nullptr) {
   if (ep.row_ss) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= rstd;
@@ -96,7 +154,12 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& ep, int N, int row, b
     }
     if (row_ok) {
       float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0;
-      if (atomic) {
+      if (part_tile) {
+        // deterministic split-K: this split's partial goes to the workspace, the consumer sums in split order
+        float4* p4 = reinterpret_cast<float4*>(part_tile + (size_t)row * ep.ldo + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) __stcg(p4 + i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+      } else if (atomic) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(v[4 * i]),
@@ -126,44 +189,9 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& ep, int N, int row, b
     for (int j = 0; j < 32; ++j) v[j] = silu(v[j]) * w[j];
     if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + (col0 >> 1), v);
   } else if constexpr (EPI == EPI_QKV_ROPE) {
-    // one head = 128 columns; v = x[i0..i0+31], w = x[i0+64..i0+95] of that head, i0 in {0,32}.
-    const int head = col0 >> 7;
-    const int i0 = col0 & 127;
-    if (ep.bias) {
-      add_vec32(v, ep.bias + col0);
-      add_vec32(w, ep.bias + col0 + 64);
-    }
-    const bool is_q = head < ep.n_q_heads;
-    const bool is_k = !is_q && head < ep.n_q_heads + ep.n_kv_heads;
-    if (row_ok) {
-      if (is_q || is_k) {
-        const int pos = ep.row_pos[row];
-        const float4* c4 = reinterpret_cast<const float4*>(ep.cos_tab + (size_t)pos * 64 + i0);
-        const float4* s4 = reinterpret_cast<const float4*>(ep.sin_tab + (size_t)pos * 64 + i0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 c = __ldg(c4 + i), s = __ldg(s4 + i);
-          const float cc[4] = {c.x, c.y, c.z, c.w};
-          const float ss[4] = {s.x, s.y, s.z, s.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float a = v[4 * i + e], b = w[4 * i + e];
-            v[4 * i + e] = a * cc[e] - b * ss[e];   // x*cos + rot(x)*sin, rot(x)[i] = -x[i+64]
-            w[4 * i + e] = b * cc[e] + a * ss[e];   //                     rot(x)[i+64] = x[i]
-          }
-        }
-      }
-      __nv_bfloat16* dst;
-      if (is_q) {
-        dst = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + head * 128 + i0;
-      } else {
-        const int kvh = is_k ? head - ep.n_q_heads : head - ep.n_q_heads - ep.n_kv_heads;
-        __nv_bfloat16* base = is_k ? ep.k_cache : ep.v_cache;
-        dst = base + (size_t)kvh * ep.kv_head_stride + (size_t)ep.row_kvrow[row] * 128 + i0;
-      }
-      store_bf16x32(dst, v);
-      store_bf16x32(dst + 64, w);
-    }
+    RopeOperands ro;
+    rope_prefetch(ep, row, row_ok, col0, ro);
+    rope_apply(ep, row, row_ok, col0, v, w, ro);
   } else if constexpr (EPI == EPI_PATCH_EMBED) {
     if (ep.bias) add_vec32(v, ep.bias + col0);
     const int img = row / ep.patches, p = row - img * ep.patches;
@@ -194,7 +222,8 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& ep, int N, int row, b
 // ------------------------------------------------------------------------------------------
 template <int BN, int EPI, int PARTS = 2>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, int N, uint32_t taddr, int half, int row, bool row_ok,
-                                              int n0, bool first_split, bool atomic, float rstd, float& ss) {
+                                              int n0, bool first_split, bool atomic, float rstd, float& ss,
+                                              float* part_tile = nullptr) {
   if constexpr (EPI == EPI_SWIGLU_BF16) {
     constexpr int U = BN / 64 / PARTS;
 #pragma unroll 1
@@ -238,7 +267,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, int N, uint32
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
-      epi_chunk<EPI>(ep, N, row, row_ok, n0 + c * 32, v, v, first_split, atomic, rstd, ss);
+      epi_chunk<EPI>(ep, N, row, row_ok, n0 + c * 32, v, v, first_split, atomic, rstd, ss, part_tile);
     }
   }
 }
