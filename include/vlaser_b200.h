@@ -188,6 +188,10 @@ int32_t vlaser_op_attention(const vlaser_attn_args* a, void* stream);
 int32_t vlaser_op_vit_attention(const void* qkv, void* out, int32_t images, int32_t tokens, int32_t heads, float scale,
                                 void* stream);
 
+/* The same op on the tcgen05 tensor cores (csrc/attention_tc.cu): tokens == 257 (224 px images). */
+int32_t vlaser_op_vit_attention_tc(const void* qkv, void* out, int32_t images, int32_t tokens, int32_t heads, float scale,
+                                   void* stream);
+
 int32_t vlaser_op_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, int32_t rows,
                             int32_t width, float eps, int32_t shuffle_grid, int32_t shuffle_channels, void* stream);
 int32_t vlaser_op_rmsnorm(const float* x, const float* gamma, void* out_bf16, int32_t rows, int32_t width, float eps,

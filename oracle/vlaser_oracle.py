@@ -34,19 +34,20 @@ import torch.nn.functional as F
 def build_causal_mask_and_position_ids(attention_mask: torch.Tensor, S: int, H: int, dtype=torch.float32):
     """S/vla/pizero_internvl.py:517-587 (non-debug branch). attention_mask: [B,S] 0/1."""
     bsz = attention_mask.size(0)
+    dev = attention_mask.device
     P0, P1 = S, S + 1
     cnts = attention_mask.sum(dim=1)
     L = S + H + 1
-    m = torch.full((bsz, L, L), torch.finfo(dtype).min, dtype=dtype)
+    m = torch.full((bsz, L, L), torch.finfo(dtype).min, dtype=dtype, device=dev)
     for i, c in enumerate(cnts.tolist()):
         m[i, :c, :c] = 0
         m[i, P0:, :c] = 0
     m[:, P0:P1, P0:P1] = 0
     m[:, P1:, P0:] = 0
     m = m.unsqueeze(1)
-    vlm_pos = torch.arange(1, S + 1).repeat(bsz, 1)
-    proprio_pos = torch.arange(1, 2).repeat(bsz, 1)
-    action_pos = torch.arange(2, H + 2).repeat(bsz, 1)
+    vlm_pos = torch.arange(1, S + 1, device=dev).repeat(bsz, 1)
+    proprio_pos = torch.arange(1, 2, device=dev).repeat(bsz, 1)
+    action_pos = torch.arange(2, H + 2, device=dev).repeat(bsz, 1)
     return m, vlm_pos, proprio_pos, action_pos
 
 
@@ -87,7 +88,7 @@ def rms_norm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
 
 def rope_cos_sin(pos: torch.Tensor, head_dim: int, theta: float):
     """HF Qwen2RotaryEmbedding (default rope): inv_freq = theta^(-2i/d); emb = cat(freqs, freqs)."""
-    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64).to(torch.float32) / head_dim))
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64, device=pos.device).to(torch.float32) / head_dim))
     freqs = pos.to(torch.float32)[..., None] * inv  # [B, L, d/2]
     emb = torch.cat((freqs, freqs), dim=-1)
     return emb.cos(), emb.sin()
@@ -101,6 +102,7 @@ def rotate_half(x: torch.Tensor) -> torch.Tensor:
 
 def apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
     """S/vla/joint_model.py:583,597: x [B,heads,L,d], cos/sin [B,L,d] (unsqueeze_dim=1)."""
+    cos, sin = cos.to(x.dtype), sin.to(x.dtype)  # HF casts the fp32 table to the activation dtype
     return x * cos.unsqueeze(1) + rotate_half(x) * sin.unsqueeze(1)
 
 
@@ -181,7 +183,7 @@ def prefix_embedding(cfg, sd, input_ids: torch.Tensor, pixel_values: torch.Tenso
         trace["vit_out"] = vit.clone()
         trace["image_features"] = img.clone()
     bsz, seq = input_ids.shape
-    final = torch.zeros(bsz, seq, emb.shape[-1], dtype=emb.dtype)
+    final = torch.zeros(bsz, seq, emb.shape[-1], dtype=emb.dtype, device=emb.device)
     text_mask = (input_ids != cfg.image_token_index) & (input_ids != cfg.pad_token_id)
     image_mask = input_ids == cfg.image_token_index
     final[text_mask] = emb[text_mask]
@@ -253,7 +255,7 @@ def time_embedding(cfg, t: torch.Tensor) -> torch.Tensor:
     """S/vla/modules.py:9-22 SinusoidalPosEmb(hidden_e, time_max_period)."""
     half = cfg.hidden_e // 2
     e = math.log(cfg.time_max_period) / (half - 1)
-    e = torch.exp(torch.arange(half, dtype=t.dtype) * -e)
+    e = torch.exp(torch.arange(half, dtype=t.dtype, device=t.device) * -e)
     e = t[:, None] * e[None, :]
     return torch.cat((e.sin(), e.cos()), dim=-1)
 
@@ -297,7 +299,8 @@ def infer_action(cfg, sd: Dict[str, torch.Tensor], input_ids: torch.Tensor, pixe
     assert input_ids.shape[1] == S
     if attention_mask is None:
         attention_mask = (input_ids != cfg.pad_token_id).to(torch.int64)
-    mask, vlm_pos, proprio_pos, action_pos = build_causal_mask_and_position_ids(attention_mask, S, H)
+    wdt = sd["proprio_encoder.weight"].dtype  # fp32 on the CPU (parity oracle); bf16 for bench.py's GPU eager baseline leg
+    mask, vlm_pos, proprio_pos, action_pos = build_causal_mask_and_position_ids(attention_mask, S, H, dtype=wdt)
     itp_mask, action_mask = split_full_mask_into_submasks(mask, S, H)
 
     embeds = prefix_embedding(cfg, sd, input_ids, pixel_values, trace)
@@ -313,10 +316,10 @@ def infer_action(cfg, sd: Dict[str, torch.Tensor], input_ids: torch.Tensor, pixe
             trace[f"k_proprio_layer{li}"] = caches["proprio"][li][0].clone()
             trace[f"v_proprio_layer{li}"] = caches["proprio"][li][1].clone()
 
-    action = noise.clone().to(torch.float32)
+    action = noise.clone().to(wdt)
     bsz = action.shape[0]
     dt = 1.0 / cfg.num_inference_steps
-    t = torch.zeros(bsz, dtype=torch.float32)
+    t = torch.zeros(bsz, dtype=wdt, device=action.device)
     for step in range(cfg.num_inference_steps):
         temb = time_embedding(cfg, t)
         x = action_encoder(sd, action, temb)

@@ -83,11 +83,13 @@ def attention(q, k, v, out, head_dim, group, n_kv_heads, batch, scale, q_row_str
     return out
 
 
-def vit_attention(qkv, images, tokens, heads, scale):
-    """qkv bf16 [images*tokens, 3*heads*64] -> out bf16 [images*tokens, heads*64] (InternViT fast path)."""
+def vit_attention(qkv, images, tokens, heads, scale, tc=False):
+    """qkv bf16 [images*tokens, 3*heads*64] -> out bf16 [images*tokens, heads*64] (InternViT fast path; tc: the tcgen05
+    kernel, 257 tokens)."""
     lib = _lib.load()
     out = torch.zeros(images * tokens, heads * 64, dtype=torch.bfloat16, device=qkv.device)
-    _lib.check(lib.vlaser_op_vit_attention(_p(qkv), _p(out), images, tokens, heads, scale, _stream()), "op_vit_attention")
+    fn = lib.vlaser_op_vit_attention_tc if tc else lib.vlaser_op_vit_attention
+    _lib.check(fn(_p(qkv), _p(out), images, tokens, heads, scale, _stream()), "op_vit_attention")
     return out
 
 

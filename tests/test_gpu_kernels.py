@@ -282,6 +282,28 @@ def test_vit_attention_fast_path(N):
     assert err < 1e-2 and float(rows.max()) < 3e-2
 
 
+@pytest.mark.parametrize("B,heads", [(1, 4), (3, 16), (40, 16)])
+def test_vit_attention_tcgen05(B, heads):
+    """tcgen05 kernel (attention_tc.cu), 257 tokens: two 128-row query tiles on the tensor cores with the scores /
+    probabilities / output in TMEM, the left-over key as a rank-1 CUDA-core term, the left-over query row on CUDA cores.
+    B * heads below, at and well above the SM count (one item per CTA, a persistent loop of several items)."""
+    N, hd = 257, 64
+    d = heads * hd
+    qkv = _rand(B * N, 3 * d, seed=B)
+    out = ops.vit_attention(qkv, B, N, heads, hd ** -0.5, tc=True)
+    x = qkv.float().view(B, N, 3, heads, hd).permute(0, 3, 2, 1, 4)          # [B, heads, 3, N, hd]
+    s = torch.einsum("bhqd,bhkd->bhqk", x[:, :, 0], x[:, :, 1]) * hd ** -0.5
+    ref = torch.einsum("bhqk,bhkd->bhqd", torch.softmax(s, dim=-1), x[:, :, 2]).permute(0, 2, 1, 3)  # [B, N, heads, hd]
+    got = out.view(B, N, heads, hd).float()
+    err = ops.rel_err(got, ref)
+    rows = (got - ref).norm(dim=-1) / ref.norm(dim=-1)
+    print(f"vit_attention_tcgen05 B={B} heads={heads} rel={err:.2e} worst row={float(rows.max()):.2e}")
+    assert err < 1e-2 and float(rows.max()) < 3e-2
+    legacy = ops.vit_attention(qkv, B, N, heads, hd ** -0.5).view(B, N, heads, hd).float()
+    assert ops.rel_err(got, legacy) < 1e-2
+    assert torch.equal(out, ops.vit_attention(qkv, B, N, heads, hd ** -0.5, tc=True)), "repeat call differs"
+
+
 def test_attention_prefill_and_denoise():
     """GQA 6:1, ragged lengths, proprio extra row (prefill) then H action queries (denoise)."""
     B, nkv, group, hd, H = 3, 2, 6, 128, 4

@@ -64,3 +64,49 @@ def test_policy_mask_builder_matches_reference_semantics():
     a2, b2 = O.split_full_mask_into_submasks(m2, cfg.max_image_text_tokens, cfg.num_action_tokens)
     assert torch.equal(a, a2) and torch.equal(b, b2)
     assert ((a[:, 0, 0, : cfg.max_image_text_tokens] == 0).sum(-1) == am.sum(-1)).all()
+
+
+def _reference_eval_cfg():
+    """Exactly the keys `PiZero.__init__` is handed by Vlaser_VLA/Simpler/config/eval/bridge_internvl_448.yaml:33-85
+    (after hydra interpolation), as plain nested dicts."""
+    mix = dict(hidden_size=768, intermediate_size=4096, use_final_norm=True, cache=True, use_quantize=False, use_lora=False,
+               adaptive_mode=None, rope_theta=10000.0)
+    return dict(
+        flow_sampling="beta", num_inference_steps=10, final_action_clip_value=1.0, use_torch_compile=True, use_bf16=False,
+        cond_steps=1, horizon_steps=4, act_steps=4, action_dim=7, proprio_dim=7,
+        mixture=dict(vlm=dict(hidden_size=1536, intermediate_size=16384, use_final_norm=False, cache=True, use_quantize=False,
+                              use_lora=False, adaptive_mode=None, rope_theta=10000.0),
+                     proprio=dict(mix), action=dict(mix, cache=False)),
+        action_expert_adaptive_mode=None, time_hidden_size=256, time_max_period=10000.0, action_expert_rope_theta=10000.0,
+        quantize=False, lora=False, lora_r=32, lora_dropout=0.0, max_image_text_tokens=384,
+        image_token_index=151667, vocab_size=151667, pad_token_id=151643,
+    )
+
+
+def test_config_from_reference_eval_yaml_keys():
+    """The drop-in constructor takes the reference's eval cfg as it is: every key that shapes `infer_action` is mapped,
+    and settings the library does not implement raise instead of returning the actions of another model."""
+    import pytest
+    from vlaser_b200.policy import check_supported_cfg, config_from_reference_cfg
+    cfg = _reference_eval_cfg()
+    v = config_from_reference_cfg(cfg)
+    assert (v.max_image_text_tokens, v.cond_steps, v.horizon_steps, v.action_dim, v.proprio_dim) == (384, 1, 4, 7, 7)
+    assert v.num_inference_steps == 10 and v.final_action_clip_value == 1.0 and v.time_max_period == 10000.0
+    assert (v.image_token_index, v.pad_token_id, v.hidden_e) == (151667, 151643, 768)
+    # the yaml's vocab_size (151667) is NOT the embedding row count: the table follows the checkpoint tensor
+    assert v.embed_rows > v.image_token_index
+    # the InternVL path takes the LLM widths from model_size, not from the PaliGemma-era mixture.vlm keys
+    assert (v.hidden, v.mlp) == (1536, 8960)
+    assert config_from_reference_cfg(dict(cfg, model_size="8B")).hidden == 3584
+    # attribute-style cfg objects (omegaconf) work too
+    ns = types.SimpleNamespace(**{k: (types.SimpleNamespace(**{kk: types.SimpleNamespace(**vv) for kk, vv in val.items()})
+                                      if k == "mixture" else val) for k, val in cfg.items()})
+    assert config_from_reference_cfg(ns) == v
+    for bad in (dict(integration_method="rk4"), dict(action_expert_adaptive_mode="adaLN"), dict(lora=True), dict(quantize=True)):
+        with pytest.raises(NotImplementedError):
+            check_supported_cfg(dict(cfg, **bad))
+    broken = _reference_eval_cfg()
+    broken["mixture"]["proprio"]["hidden_size"] = 1024
+    with pytest.raises(ValueError):
+        check_supported_cfg(broken)
+    check_supported_cfg(dict(cfg, integration_method="euler"))

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libvlaser_b200.so")
-SOURCES = ["gemm.cu", "attention.cu", "elementwise.cu", "expert.cu", "expert_gemv.cu", "staging.cu", "engine.cu"]
+SOURCES = ["gemm.cu", "attention.cu", "attention_tc.cu", "elementwise.cu", "expert.cu", "expert_gemv.cu", "staging.cu", "engine.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",

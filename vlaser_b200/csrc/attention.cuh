@@ -50,4 +50,10 @@ int attention_launch(const AttnParams& p, int head_dim, cudaStream_t stream);
 int vit_attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int images, int tokens, int heads, float scale,
                          cudaStream_t stream);
 
+// The same op on the tcgen05 tensor cores for tokens == 257 (224 px): attention_tc.cu. tmQKV: make_tmap_bf16 map of qkv
+// [images*257, 3*heads*64] with 128-row boxes; tmOut: the same kind of map of out [images*257 (or more rows), heads*64].
+int vit_attention_tc_launch(const CUtensorMap& tmQKV, const CUtensorMap& tmOut, const __nv_bfloat16* qkv,
+                            __nv_bfloat16* out, int images, int tokens, int heads, float scale, cudaStream_t stream,
+                            long long* trace = nullptr);
+
 }  // namespace vlaser

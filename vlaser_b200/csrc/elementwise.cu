@@ -326,7 +326,7 @@ __global__ void plan_scan_kernel(PlanBuffers pb, int B, int H) {
 }
 
 __global__ void plan_rows_kernel(const long long* __restrict__ ids, PlanBuffers pb, int B, int S, int H,
-                                 int img_tokens, int image_token, int pad_token) {
+                                 int img_tokens, int image_token, int pad_token, int embed_rows) {
   pdl_launch_dependents();
   pdl_wait();
   // one warp per sample
@@ -354,6 +354,10 @@ __global__ void plan_rows_kernel(const long long* __restrict__ ids, PlanBuffers 
         }
       } else {
         src = (id == pad_token) ? -1 : (int)id;
+        if (id != pad_token && (id < 0 || id >= embed_rows)) {  // out of the embedding table: zeros + error flag
+          src = -1;
+          atomicCAS(pb.bad_id, 0, 1 + (int)min(max(id, (long long)0), (long long)0x7ffffff0));
+        }
       }
       pb.row_src[m] = src;
     }
@@ -557,12 +561,12 @@ int cls_rows_launch(float* x, const float* cls, const float* pos, int n, int tok
 }
 
 int plan_launch(const long long* input_ids, const int* valid_len_in, PlanBuffers pb, int B, int S, int H,
-                int img_tokens_per_sample, int image_token, int pad_token, cudaStream_t stream) {
+                int img_tokens_per_sample, int image_token, int pad_token, int embed_rows, cudaStream_t stream) {
   VL_CHECK(B > 0, "plan: empty batch");
   VL_CUDA_CHECK(cudaMemsetAsync(pb.img_row_map, 0xFF, sizeof(int) * (size_t)B * img_tokens_per_sample, stream));
   VL_CUDA_CHECK(launch_kernel(plan_lengths_kernel, dim3((B * 32 + 127) / 128), dim3(128), 0, stream, input_ids, valid_len_in, pb, B, S, H, pad_token, image_token));
   VL_CUDA_CHECK(launch_kernel(plan_scan_kernel, dim3(1), dim3(32), 0, stream, pb, B, H));
-  VL_CUDA_CHECK(launch_kernel(plan_rows_kernel, dim3(B), dim3(32), 0, stream, input_ids, pb, B, S, H, img_tokens_per_sample, image_token, pad_token));
+  VL_CUDA_CHECK(launch_kernel(plan_rows_kernel, dim3(B), dim3(32), 0, stream, input_ids, pb, B, S, H, img_tokens_per_sample, image_token, pad_token, embed_rows));
   VL_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -75,9 +75,11 @@ struct PlanBuffers {
   int* prop_q_start;  // [B]  == b   (proprio pass of the expert stream: one query row per sample)
   int* prop_q_len;    // [B]  == 1
   int* prop_kv_len;   // [B]  valid_len + 1 (prefix + the proprio token itself)
+  int* bad_id;        // [1]  0, or 1 + the first token id seen outside [0, embed_rows) (nn.Embedding would raise IndexError;
+                      //      here the row embeds as zeros and the call reports the error, engine.cu)
 };
 int plan_launch(const long long* input_ids, const int* valid_len_in, PlanBuffers pb, int B, int S, int H,
-                int img_tokens_per_sample, int image_token, int pad_token, cudaStream_t stream);
+                int img_tokens_per_sample, int image_token, int pad_token, int embed_rows, cudaStream_t stream);
 // text rows of the packed prefix: x[m,:] = embed[row_src[m],:] (bf16 -> fp32) or zeros
 int assemble_text_launch(const __nv_bfloat16* embed, const int* row_src, const int* m_tot, float* x, int rows_cap,
                          int width, cudaStream_t stream);

@@ -119,7 +119,8 @@ struct Engine {
   // activations
   Act cols, vn, vattn, vmlp, ps, pa, xn, ao, act, xpn, aop, actp, xan, aoa, acta, e1, h2;
   float *vx = nullptr, *xv = nullptr, *xp = nullptr, *xa = nullptr, *action = nullptr;
-  CUtensorMap vx_otm, xv_otm, vqkv_otm, xp_otm, xa_otm;  // output maps of the fp32 residual streams / ViT qkv buffer
+  CUtensorMap vx_otm, xv_otm, vqkv_otm, xp_otm, xa_otm;
+  CUtensorMap vqkv_tm;  // load map (128-row boxes) of the ViT q|k|v buffer for the tcgen05 attention kernel  // output maps of the fp32 residual streams / ViT qkv buffer
   bf16 *vqkv = nullptr, *q = nullptr, *qp = nullptr, *qa = nullptr;
   bf16 *kc = nullptr, *vc = nullptr;  // [layers][kv_heads][kv_rows][128]
   // fused RMSNorm chain of the expert streams: per pass (prefill proprio, then each denoise step) one row-sum-of-
@@ -148,8 +149,9 @@ struct Engine {
   // options / state
   int use_graph = 1, stop_after = 0, simt = 0;
   int exp_stages = 0;          // smem ring depth of the expert-stream GEMMs (0 = kernel default)
-  int pair_min_tiles = 74;     // fewest pair tiles (x splits) for which the pair kernel is preferred: one per SM pair
-                               // (measured: the M<=256 expert GEMMs are latency-bound and do not gain from pairs)
+  int pair_min_tiles = 36;     // fewest pair tiles (x splits) for which the pair kernel is preferred. 36 puts the o / gate-up /
+                               // down projections of the action expert (36 / 70 / 72 pair tiles at 256 rows) on it: one
+                               // 256-row tile reads every weight once (gpurun r02e: 42.5 ms per call at 74, 41.9 at 70 / 36)
   int tma_epi = 1;             // 1: pair-kernel epilogues leave through TMA stores / reduce-adds
   int pair_gemm = 1;           // 1: large-M GEMMs run on the CTA-pair (cta_group::2) kernel
   int mega = 0;                // 1: the expert streams (proprio pass of the prefill, every denoise step) run as ONE
@@ -178,6 +180,11 @@ struct Engine {
   size_t trace_idx = 0;
   std::string trace_names;
   static constexpr size_t TRACE_MAX = 8192;
+  int dry_epi = 0;             // 1: one-tile-per-CTA GEMM launches run a dry epilogue pass during the mainloop (gemm.cu). Measured
+                               // SLOWER (gpurun r02f: 42.6 vs 41.6 ms per call): the dry pass competes with the mainloop and the real
+                               // pass is no faster, i.e. the one-shot epilogue is not paced by a cold instruction cache
+  int xs_o = 12, xs_down = 24; // split-K caps of the action expert's o / down projections (options "exp_splits_o/down")
+  int vit_tc = 1;              // 1: InternViT attention of 257-token images on the tcgen05 kernel (attention_tc.cu)
   int ablate = 0;              // timing aid: bit mask of denoise-step launches to skip (1 norm_in, 2 qkv, 4 attention, 8 o,
                                // 16 norm_post, 32 gate/up, 64 down); the actions are then garbage
   int fuse_norm = 0;           // 1: RMSNorm of the expert streams fused across the GEMM chain (see exp_pre/exp_post)
@@ -403,6 +410,7 @@ int engine_build(Engine& e) {
   VL_TRY(e.add_act(&e.vn, vrows, d));
   VL_TRY(e.alloc(&e.vqkv, (size_t)vrows * 3 * d));
   VL_TRY(make_tmap_out(&e.vqkv_otm, e.vqkv, vrows, 3 * d, 2));
+  if (vrows >= 128) VL_TRY(make_tmap_bf16(&e.vqkv_tm, e.vqkv, vrows, 3 * d, 128));
   VL_TRY(e.add_act(&e.vattn, vrows, d));
   VL_TRY(e.add_act(&e.vmlp, vrows, f));
   VL_TRY(e.add_act(&e.ps, Ni * e.T, 4 * d));
@@ -479,6 +487,7 @@ int engine_build(Engine& e) {
   VL_TRY(e.alloc(&pb.prop_q_start, e.Bc));
   VL_TRY(e.alloc(&pb.prop_q_len, e.Bc));
   VL_TRY(e.alloc(&pb.prop_kv_len, e.Bc));
+  VL_TRY(e.alloc(&pb.bad_id, 1));
   // --- I/O staging
   VL_TRY(e.alloc(&e.in_ids, (size_t)e.Bc * e.S));
   VL_TRY(e.alloc(&e.in_valid, e.Bc));
@@ -490,6 +499,7 @@ int engine_build(Engine& e) {
   e.pinned_bytes = (size_t)e.Bc * e.S * 8 + pix_elems * 4 + (size_t)e.Bc * 4 + (size_t)e.Bc * c.proprio_dim * 4 +
                    (size_t)arow * c.action_dim * 4 + (size_t)e.Bc * c.horizon_steps * c.action_dim * 4 + 4096;
   VL_CUDA_CHECK(cudaMallocHost(&e.pinned, e.pinned_bytes));
+  memset(e.pinned, 0, e.pinned_bytes);
   return 0;
 }
 
@@ -700,6 +710,7 @@ struct Run {
            int stages = 0, const CUtensorMap* out_tm = nullptr) {
     GemmDims d;
     d.trace = tr(tr_name, tr_layer);
+    d.no_dry_epilogue = e.dry_epi ? 0 : 1;
     d.M = M;
     d.N = w.N;
     d.K = w.K;
@@ -830,7 +841,10 @@ struct Run {
       e1.bias = L.bqkv;
       tr_name = "vit_qkv";
       VL_TRY(gemm(e.vn, L.qkv, rows, nullptr, EPI_STORE_BF16, e1, 1, 0, &e.vqkv_otm));
-      if (e.P + 1 >= 128 && e.P + 1 <= 320) {
+      if (e.vit_tc && e.P + 1 == 257 && !e.simt) {
+        VL_TRY(vit_attention_tc_launch(e.vqkv_tm, e.vattn.tm, e.vqkv, e.vattn.p, Ni, e.P + 1, c.vit_heads, 0.125f, st,
+                                       tr("vit_attention", i)));
+      } else if (e.P + 1 >= 128 && e.P + 1 <= 320) {
         VL_TRY(vit_attention_launch(e.vqkv, e.vattn.p, Ni, e.P + 1, c.vit_heads, 0.125f, st));
       } else {
       AttnParams ap;
@@ -922,7 +936,7 @@ struct Run {
     eo.out = x;
     eo.ldo = hid;
     tr_name = "o";
-    if (!(abl & 8)) VL_TRY(gemm(ao, L.o, M, M_dev, EPI_RESID_F32, eo, splits, 0, x_otm));
+    if (!(abl & 8)) VL_TRY(gemm(ao, L.o, M, M_dev, EPI_RESID_F32, eo, splits > 1 ? std::min(splits, e.xs_o) : 1, 0, x_otm));
     if (!(abl & 16)) {
       SplitKPartials spt;
       VL_TRY(rmsnorm_launch(x, L.ln_post, xn.p, M, M_dev, hid, e.c.rms_eps, st, pf, tr("norm_post", tr_layer), take(x, spt)));
@@ -935,7 +949,7 @@ struct Run {
     if (!(abl & 32)) VL_TRY(gemm(xn, L.gu, M, M_dev, EPI_SWIGLU_BF16, eg, 1, 0, &act.otm));
     if (abl & 64) return 0;
     tr_name = "down";
-    return gemm(act, L.down, M, M_dev, EPI_RESID_F32, eo, splits, 0, x_otm);
+    return gemm(act, L.down, M, M_dev, EPI_RESID_F32, eo, splits > 1 ? std::min(splits, e.xs_down) : 1, 0, x_otm);
   }
 
   // ---- expert streams (proprio token in the prefill, action tokens in the denoise steps): RMSNorm is fused across
@@ -1244,7 +1258,7 @@ struct Run {
   int all(bool has_valid) {
     const vlaser_cfg& c = e.c;
     VL_TRY(plan_launch(e.in_ids, has_valid ? e.in_valid : nullptr, e.pb, B, e.S, e.H, e.n_img * e.T,
-                       c.image_token_index, c.pad_token_id, st));
+                       c.image_token_index, c.pad_token_id, c.embed_rows, st));
     VL_TRY(convert_launch(e.in_noise, io, e.action, DT_F32, (long long)B * e.H * c.action_dim, st));
     if (e.fuse_norm) VL_CUDA_CHECK(cudaMemsetAsync(e.ss, 0, e.ss_floats * sizeof(float), st));
     VL_CUDA_CHECK(cudaMemsetAsync(e.xp_bar, 0, sizeof(unsigned int) * (size_t)(c.num_inference_steps + 1) * e.xp_bar_words(), st));
@@ -1373,7 +1387,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "dry_epilogue" || k == "exp_splits_o" || k == "exp_splits_down") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
@@ -1388,6 +1402,10 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
     else if (k == "ablate") h->e.ablate = (int)value;
     else if (k == "trace") h->e.trace_on = (int)value;
     else if (k == "det_splitk") h->e.det_splitk = (int)value;
+    else if (k == "vit_tc") h->e.vit_tc = (int)value;
+    else if (k == "dry_epilogue") h->e.dry_epi = (int)value;
+    else if (k == "exp_splits_o") h->e.xs_o = std::max(1, (int)value);
+    else if (k == "exp_splits_down") h->e.xs_down = std::max(1, (int)value);
     else if (k == "pair_gemm") h->e.pair_gemm = (int)value;
     else if (k == "tma_epi") h->e.tma_epi = (int)value;
     else if (k == "pair_min_tiles") h->e.pair_min_tiles = (int)value;
@@ -1428,9 +1446,21 @@ int32_t vlaser_infer_action(vlaser_t* h, const int64_t* input_ids, const void* p
   VL_CUDA_CHECK(cudaMemcpyAsync(e.in_prop, proprios, (size_t)B * c.proprio_dim * es, cudaMemcpyDeviceToDevice, st));
   VL_CUDA_CHECK(cudaMemcpyAsync(e.in_noise, noise, (size_t)B * e.H * c.action_dim * es, cudaMemcpyDeviceToDevice, st));
   if (valid_len) VL_CUDA_CHECK(cudaMemcpyAsync(e.in_valid, valid_len, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  // token ids outside the embedding table: the device call cannot synchronise, so the flag of the PREVIOUS call (copied to
+  // pinned memory behind it) is reported here, at the latest one call late
+  int* host_bad = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(e.pinned) + e.pinned_bytes - 64);
+  if (*host_bad != 0) {
+    const int bad = *host_bad - 1;
+    *host_bad = 0;
+    cudaMemsetAsync(e.pb.bad_id, 0, sizeof(int), st);
+    set_last_error("infer_action: an earlier call passed token id " + std::to_string(bad) + " outside the embedding table of " +
+                   std::to_string(c.embed_rows) + " rows (nn.Embedding would raise IndexError)");
+    return -4;
+  }
   VL_TRY(engine_execute(e, B, io_dtype, valid_len != nullptr, st));
   VL_CUDA_CHECK(cudaMemcpyAsync(actions_out, e.out_act, (size_t)B * c.horizon_steps * c.action_dim * es,
                                 cudaMemcpyDeviceToDevice, st));
+  VL_CUDA_CHECK(cudaMemcpyAsync(host_bad, e.pb.bad_id, sizeof(int), cudaMemcpyDeviceToHost, st));
   return 0;
 }
 
@@ -1460,7 +1490,7 @@ int32_t vlaser_infer_action_host(vlaser_t* h, const int64_t* input_ids, const vo
   uint8_t* p_noise = p_prop + up(n_prop);
   uint8_t* p_valid = p_noise + up(n_noise);
   uint8_t* p_out = p_valid + up((size_t)B * 4);
-  VL_CHECK((size_t)(p_out + n_out - pin) <= e.pinned_bytes, "pinned staging buffer too small");
+  VL_CHECK((size_t)(p_out + up(n_out) + 256 - pin) <= e.pinned_bytes, "pinned staging buffer too small");
   // page-locked caller buffers are copied from directly; pageable ones are staged through the pinned buffer
   auto stage = [&](uint8_t* pin_dst, const void* src, size_t n) -> const void* {
     cudaPointerAttributes attr{};
@@ -1478,8 +1508,17 @@ int32_t vlaser_infer_action_host(vlaser_t* h, const int64_t* input_ids, const vo
                                   cudaMemcpyHostToDevice, st));
   VL_TRY(engine_execute(e, B, io_dtype, valid_len != nullptr, st));
   VL_CUDA_CHECK(cudaMemcpyAsync(p_out, e.out_act, n_out, cudaMemcpyDeviceToHost, st));
+  int* p_bad = reinterpret_cast<int*>(p_out + up(n_out));
+  VL_CUDA_CHECK(cudaMemcpyAsync(p_bad, e.pb.bad_id, sizeof(int), cudaMemcpyDeviceToHost, st));
   VL_CUDA_CHECK(cudaStreamSynchronize(st));
   memcpy(actions_out, p_out, n_out);
+  if (*p_bad != 0) {
+    const int bad = *p_bad - 1;
+    cudaMemsetAsync(e.pb.bad_id, 0, sizeof(int), st);
+    set_last_error("infer_action: input_ids holds token id " + std::to_string(bad) + " outside the embedding table of " +
+                   std::to_string(c.embed_rows) + " rows (nn.Embedding would raise IndexError)");
+    return -4;
+  }
   return 0;
 }
 
@@ -1698,6 +1737,16 @@ int32_t vlaser_op_vit_attention(const void* qkv, void* out, int32_t images, int3
                                 void* stream) {
   return vit_attention_launch(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), images,
                               tokens, heads, scale, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t vlaser_op_vit_attention_tc(const void* qkv, void* out, int32_t images, int32_t tokens, int32_t heads, float scale,
+                                   void* stream) {
+  VL_CHECK(qkv && out, "null argument");
+  CUtensorMap tq, to;
+  VL_TRY(make_tmap_bf16(&tq, qkv, (uint64_t)images * tokens, (uint64_t)3 * heads * 64, 128));
+  VL_TRY(make_tmap_bf16(&to, out, (uint64_t)images * tokens, (uint64_t)heads * 64, 128));
+  return vit_attention_tc_launch(tq, to, reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out),
+                                 images, tokens, heads, scale, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int32_t vlaser_op_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, int32_t rows,

@@ -73,6 +73,7 @@ struct GemmDims {
   int n_fast = 0;                // pair kernel tile order: 0 = m fastest, 1 = n fastest
   int tma_out = 0;               // set by the launcher: epilogue leaves through the output tensor map
   long long* trace = nullptr;    // optional 8-slot timeline record of this launch (common.cuh trace_stamp)
+  int no_dry_epilogue = 0;       // 1: do not warm the instruction cache with a dry epilogue pass (see gemm.cu; A/B switch)
 };
 
 // Host API -------------------------------------------------------------------------------

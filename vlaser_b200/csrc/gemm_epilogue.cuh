@@ -70,7 +70,11 @@ __device__ __forceinline__ void rope_prefetch(const EpiParams& ep, int row, bool
   const bool is_q = head < ep.n_q_heads;
   const bool is_k = !is_q && head < ep.n_q_heads + ep.n_kv_heads;
   ro.kvrow = 0;
-  if (!row_ok) return;
+  if (!row_ok) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) ro.cs[j] = 1.f, ro.sn[j] = 0.f;
+    return;
+  }
   if (!is_q) ro.kvrow = __ldg(ep.row_kvrow + row);
   if (is_q || is_k) {
     const int pos = __ldg(ep.row_pos + row);
@@ -84,17 +88,15 @@ __device__ __forceinline__ void rope_prefetch(const EpiParams& ep, int row, bool
     }
   }
 }
-__device__ __forceinline__ void rope_apply(const EpiParams& ep, int row, bool row_ok, int col0, float (&v)[32],
-                                           float (&w)[32], const RopeOperands& ro) {
-  const int head = col0 >> 7, i0 = col0 & 127;
+// bias + rotation of one unit in registers
+__device__ __forceinline__ void rope_rotate(const EpiParams& ep, int col0, float (&v)[32], float (&w)[32],
+                                            const RopeOperands& ro) {
+  const int head = col0 >> 7;
   if (ep.bias) {
     add_vec32(v, ep.bias + col0);
     add_vec32(w, ep.bias + col0 + 64);
   }
-  const bool is_q = head < ep.n_q_heads;
-  const bool is_k = !is_q && head < ep.n_q_heads + ep.n_kv_heads;
-  if (!row_ok) return;
-  if (is_q || is_k) {
+  if (head < ep.n_q_heads + ep.n_kv_heads) {  // q or k head
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const float a = v[j], b = w[j];
@@ -102,14 +104,20 @@ __device__ __forceinline__ void rope_apply(const EpiParams& ep, int row, bool ro
       w[j] = b * ro.cs[j] + a * ro.sn[j];   //                     rot(x)[i+64] = x[i]
     }
   }
-  __nv_bfloat16* dst;
-  if (is_q) {
-    dst = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + head * 128 + i0;
-  } else {
-    const int kvh = is_k ? head - ep.n_q_heads : head - ep.n_q_heads - ep.n_kv_heads;
-    __nv_bfloat16* base = is_k ? ep.k_cache : ep.v_cache;
-    dst = base + (size_t)kvh * ep.kv_head_stride + (size_t)ro.kvrow * 128 + i0;
-  }
+}
+// where x[i0] of this row's unit goes: the q buffer, or the row's slot in the K / V cache
+__device__ __forceinline__ __nv_bfloat16* rope_dst(const EpiParams& ep, int row, int col0, const RopeOperands& ro) {
+  const int head = col0 >> 7, i0 = col0 & 127;
+  if (head < ep.n_q_heads) return reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + head * 128 + i0;
+  const bool is_k = head < ep.n_q_heads + ep.n_kv_heads;
+  const int kvh = is_k ? head - ep.n_q_heads : head - ep.n_q_heads - ep.n_kv_heads;
+  return (is_k ? ep.k_cache : ep.v_cache) + (size_t)kvh * ep.kv_head_stride + (size_t)ro.kvrow * 128 + i0;
+}
+__device__ __forceinline__ void rope_apply(const EpiParams& ep, int row, bool row_ok, int col0, float (&v)[32],
+                                           float (&w)[32], const RopeOperands& ro) {
+  rope_rotate(ep, col0, v, w, ro);
+  if (!row_ok) return;
+  __nv_bfloat16* dst = rope_dst(ep, row, col0, ro);
   store_bf16x32(dst, v);
   store_bf16x32(dst + 64, w);
 }

@@ -39,15 +39,60 @@ def _cfg_get(cfg, name, default=None):
     return getattr(cfg, name, default)
 
 
+def _nested_get(cfg, path, default=None):
+    cur = cfg
+    for name in path:
+        if cur is None:
+            return default
+        cur = _cfg_get(cur, name, None)
+    return default if cur is None else cur
+
+
+def check_supported_cfg(cfg) -> None:
+    """Raises for cfg settings that change the numbers of `infer_action` and that this library does not implement,
+    instead of silently returning actions of a different model:
+      * `integration_method` other than "euler" (pizero_internvl.py:164, 910-922, 1309-1334)
+      * a non-empty `action_expert_adaptive_mode` (adaLN / adaLN-Zero time conditioning, :292-305, 890-905)
+      * LoRA / quantised mixtures (:`lora`, `quantize`)
+      * `mixture.{proprio,action}.hidden_size` that disagree with each other (the two mixtures share one expert)"""
+    if isinstance(cfg, VlaserConfig):
+        return
+    meth = str(_cfg_get(cfg, "integration_method", "euler"))
+    if meth != "euler":
+        raise NotImplementedError(f"integration_method={meth!r}: vlaser_b200 implements the Euler flow integration only "
+                                  "(pizero_internvl.py:910-912)")
+    mode = _cfg_get(cfg, "action_expert_adaptive_mode", None)
+    if mode:
+        raise NotImplementedError(f"action_expert_adaptive_mode={mode!r}: adaLN time conditioning is not implemented "
+                                  "(released Vlaser-VLA checkpoints use None, config/eval/*internvl*.yaml)")
+    for key in ("lora", "quantize"):
+        if _cfg_get(cfg, key, False):
+            raise NotImplementedError(f"{key}=True: LoRA / quantised mixtures are outside the inference hot path of vlaser_b200")
+    hp = _nested_get(cfg, ("mixture", "proprio", "hidden_size"))
+    ha = _nested_get(cfg, ("mixture", "action", "hidden_size"))
+    if hp is not None and ha is not None and int(hp) != int(ha):
+        raise ValueError(f"mixture.proprio.hidden_size={hp} != mixture.action.hidden_size={ha}: the proprio and action "
+                         "mixtures share one expert (pizero_internvl.py:1213-1232)")
+
+
 def config_from_reference_cfg(cfg) -> VlaserConfig:
     """Maps the hydra cfg keys `PiZero.__init__` reads (pizero_internvl.py:156-337) plus the
-    `IMAGE_448` env switch (:180-183) and `model_size` (:116-135) onto a VlaserConfig."""
+    `IMAGE_448` env switch (:180-183) and `model_size` (:116-135) onto a VlaserConfig. The LLM / expert widths of
+    the InternVL path come from `model_size` (the `mixture.*.hidden_size` / `intermediate_size` keys of the yaml are
+    the PaliGemma leftovers the reference overrides at :116-135); the expert hidden width is taken from
+    `mixture.action.hidden_size` when present. `vocab_size` of the yaml (151667) is not the embedding row count --
+    the reference resizes the table to len(tokenizer) (:88-89, 335) -- so embed_rows follows the checkpoint tensor
+    (`PiZeroInference.load_state_dict`)."""
     if isinstance(cfg, VlaserConfig):
         return cfg
+    check_supported_cfg(cfg)
     model_size = str(_cfg_get(cfg, "model_size", "2B"))
     kw = {}
     if model_size == "8B":  # InternVL3-8B: Qwen2.5-7B LLM, expert MLP 5600 (pizero_internvl.py:128-131)
         kw.update(hidden=3584, n_heads=28, n_kv_heads=4, mlp=18944, mlp_e=5600)
+    he = _nested_get(cfg, ("mixture", "action", "hidden_size"))
+    if he is not None:
+        kw["hidden_e"] = int(he)
     clip = _cfg_get(cfg, "final_action_clip_value", None)
     return VlaserConfig(
         image_size=448 if "IMAGE_448" in os.environ else 224,
@@ -105,24 +150,49 @@ class PiZeroInference:
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.max_batch = int(max_batch if max_batch is not None else _cfg_get(cfg, "max_batch", 64))
         self._handle = C.c_void_p()
-        with torch.cuda.device(self.device):
-            ccfg = _to_c_cfg(v, self.max_batch)
-            _lib.check(self._lib.vlaser_create(C.byref(ccfg), C.byref(self._handle)), "vlaser_create")
+        self._options: Dict[str, int] = {}
         self._finalized = False
         self._loaded = set()
+        # The library computes in bf16 with fp32 accumulation / residual streams whatever dtype is asked for (see `to`)
         self.dtype = torch.bfloat16
         for env, opt in (("VLASER_PDL", "pdl"), ("VLASER_EXP_STAGES", "exp_stages"), ("VLASER_FUSE_NORM", "fuse_norm"),
                          ("VLASER_PAIR_GEMM", "pair_gemm"), ("VLASER_EXPERT_MEGA", "expert_mega"),
                          ("VLASER_EXPERT_STREAMS", "expert_streams"), ("VLASER_EXPERT_GEMV", "expert_gemv"),
-                         ("VLASER_L2_PREFETCH", "l2_prefetch"), ("VLASER_SMALL_M_SPLIT", "small_m_split"), ("VLASER_PAIR_MIN_TILES", "pair_min_tiles"), ("VLASER_PROP_STREAM", "prop_stream")):  # measurement switches
+                         ("VLASER_L2_PREFETCH", "l2_prefetch"), ("VLASER_SMALL_M_SPLIT", "small_m_split"),
+                         ("VLASER_PAIR_MIN_TILES", "pair_min_tiles"), ("VLASER_PROP_STREAM", "prop_stream"),
+                         ("VLASER_DET_SPLITK", "det_splitk")):  # measurement switches
             if env in os.environ:
-                self.set_option(opt, int(os.environ[env]))
+                self._options[opt] = int(os.environ[env])
+        self._create_handle()
+
+    def _create_handle(self):
+        """(Re)creates the library handle for self.vcfg and replays the options set so far."""
+        if self._handle.value:
+            self._lib.vlaser_destroy(self._handle)
+            self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            ccfg = _to_c_cfg(self.vcfg, self.max_batch)
+            _lib.check(self._lib.vlaser_create(C.byref(ccfg), C.byref(self._handle)), "vlaser_create")
+        for k, val in self._options.items():
+            _lib.check(self._lib.vlaser_set_option(self._handle, k.encode(), int(val)), f"set_option({k})")
 
     # ---- nn.Module-like surface used by EvalAgent ------------------------------------------------
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
         """eval.py:196-212 — feeds every tensor of the path to the library by its state-dict key."""
         if self._finalized:
             raise RuntimeError("weights are frozen after the first forward")
+        # the embedding table has as many rows as the checkpoint's tokenizer had tokens (the reference resizes it to
+        # len(tokenizer), pizero_internvl.py:88-89, 335): follow the tensor, not a constant
+        for key, t in state_dict.items():
+            if torch.is_tensor(t) and canonical_key(key) == "embed_tokens.weight" and t.dim() == 2 \
+                    and int(t.shape[0]) != self.vcfg.embed_rows:
+                if self._loaded:
+                    raise RuntimeError(f"embed_tokens.weight has {t.shape[0]} rows but the handle was built for "
+                                       f"{self.vcfg.embed_rows}: load the embedding table first")
+                if int(t.shape[0]) <= max(self.vcfg.image_token_index, self.vcfg.pad_token_id):
+                    raise ValueError(f"embed_tokens.weight has {t.shape[0]} rows: fewer than the image / pad token ids")
+                self.vcfg = self.vcfg.with_(embed_rows=int(t.shape[0]))
+                self._create_handle()
         unexpected = []
         with torch.cuda.device(self.device):
             for key, t in state_dict.items():
@@ -160,9 +230,27 @@ class PiZeroInference:
         return self
 
     def to(self, *args, **kwargs):
+        """`.to(dtype)` / `.to(device)` of the reference (eval.py:43-45). The compute path is fixed: bf16 tensor-core
+        GEMMs with fp32 accumulation, fp32 residual streams and norms, weights rounded to bf16 at load. Asking for
+        float32 (the shipped evaluator configs set `use_bf16: False`) therefore does NOT give the reference's fp32
+        arithmetic: it is accepted -- the I/O tensors may be float32 -- and a warning says so once. Actions stay within
+        the 1e-2 bound of the fp32 reference (tests/test_gpu_parity.py, incl. un-rounded fp32 weights)."""
+        import warnings
         for a in list(args) + list(kwargs.values()):
             if isinstance(a, torch.dtype):
+                if a == torch.float32 and not getattr(self, "_warned_fp32", False):
+                    warnings.warn("vlaser_b200 computes in bf16 (fp32 accumulation / residuals) even when float32 is "
+                                  "requested; weights are rounded to bf16 at load", RuntimeWarning, stacklevel=2)
+                    self._warned_fp32 = True
+                elif a not in (torch.float32, torch.bfloat16):
+                    raise TypeError(f"vlaser_b200: unsupported dtype {a} (float32 or bfloat16)")
                 self.dtype = a
+            elif isinstance(a, (torch.device, str, int)) and not isinstance(a, bool):
+                dev = torch.device(a) if not isinstance(a, int) else torch.device("cuda", a)
+                if dev.type != "cuda":
+                    raise RuntimeError("vlaser_b200 has no CPU path")
+                if dev.index is not None and dev.index != self.device.index:
+                    raise RuntimeError(f"the handle lives on {self.device}; construct PiZeroInference(device={dev.index}) instead")
         return self
 
     def eval(self):
@@ -173,6 +261,8 @@ class PiZeroInference:
 
     def set_option(self, key: str, value: int):
         _lib.check(self._lib.vlaser_set_option(self._handle, key.encode(), int(value)), f"set_option({key})")
+        if key not in ("stop_after", "profile_gemm", "profile_mtot"):
+            self._options[key] = int(value)
         return self
 
     def __del__(self):
@@ -236,6 +326,16 @@ class PiZeroInference:
         pixel_values = pixel_values.to(dev).contiguous()
         proprios = proprios.to(dev, dtype).contiguous()
         assert input_ids.shape == (B, S), f"input_ids must be [B,{S}]"
+        # The reference uses whatever position ids it is handed (pizero_internvl.py:854-855, 895); the kernels bake in
+        # the ids build_causal_mask_and_position_ids produces. Anything else would silently change the RoPE phases.
+        for name, ids_t, first, n in (("vlm_position_ids", vlm_position_ids, 1, S), ("proprio_position_ids", proprio_position_ids, 1, 1),
+                                      ("action_position_ids", action_position_ids, 2, H)):
+            if ids_t is None:
+                continue
+            want = torch.arange(first, first + n, device=ids_t.device, dtype=ids_t.dtype)
+            if tuple(ids_t.shape[-1:]) != (n,) or not bool((ids_t.reshape(-1, n) == want).all()):
+                raise NotImplementedError(f"{name} differs from the ids of build_causal_mask_and_position_ids "
+                                          f"({first}..{first + n - 1}): custom position ids are not supported")
         valid_len = None
         if image_text_proprio_mask is not None:
             # number of keys the first prefix row may attend to == valid prefix length
