@@ -115,7 +115,7 @@ def test_gemm_fused_rmsnorm_chain(name, simt, splits, M):
     assert err < 1.5 * BF16_TOL
 
 
-@pytest.mark.parametrize("bn", [128, 513])
+@pytest.mark.parametrize("bn", [128, 513, 517])
 @pytest.mark.parametrize("M,N,K", [(256, 768, 8960), (64, 768, 1536), (257, 1024, 4096), (200, 1536, 1536)])
 def test_gemm_splitk_partials_deterministic(bn, M, N, K):
     """Deterministic split-K: the splits leave partial tiles in a workspace, the consumer adds them to the residual

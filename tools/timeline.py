@@ -39,7 +39,7 @@ for _ in range(4):
     pol.infer_action(ids, pix, proprios=prop, noise=noise)
 torch.cuda.synchronize()
 names = bytes(pol.debug_buffer("trace_names", torch.uint8).tolist()).decode().strip().split("\n")
-tr = pol.debug_buffer("trace", torch.int64).view(-1, 8)[: len(names)].double()
+tr = pol.debug_buffer("trace", torch.int64).view(-1, 16)[: len(names)].double()
 print(f"config {a.config} B={a.batch} opts [{a.opts}]: {len(names)} traced launches")
 
 # split the records of the main stream into stages: everything after the first "act_enc2" is a denoise step
@@ -64,7 +64,8 @@ def show(sel, title):
     print(f"{'launch':22s} " + " ".join(f"{s:>10s}" for s in SLOTS))
     for r in sel:
         vals = " ".join(f"{(float(v) - t0) / 1e3:10.2f}" if v > 0 else f"{'-':>10s}" for v in r["t"][:7])
-        print(f"{(r['kind'] + ' L' + str(r['layer'])):22s} {vals}")
+        fine = " ".join(f"{(float(v) - t0) / 1e3:.2f}" for v in r["t"][8:16] if v > 0)
+        print(f"{(r['kind'] + ' L' + str(r['layer'])):22s} {vals}" + (f"   fine: {fine}" if fine else ""))
 
 
 stage, sstep, slayer = a.show.split(":")

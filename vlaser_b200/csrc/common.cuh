@@ -58,8 +58,9 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
 }
 
 // ---------------------------------------------------------------- in-situ timeline (option "trace")
-// Block 0 of a launch stamps %globaltimer (ns) into its 8-slot record: 0 entry, 1 after the dependent-launch wait,
-// 2 first operand stage landed, 3 last MMA issued, 4 first accumulator ready, 5 epilogue done, 6 exit.
+// Block 0 of a launch stamps %globaltimer (ns) into its 16-slot record: 0 entry, 1 after the dependent-launch wait,
+// 2 first operand stage landed, 3 last MMA issued, 4 first accumulator ready, 5 epilogue done, 6 exit; 8.. finer stamps
+// inside the epilogue of the first epilogue warp (kernel specific).
 __device__ __forceinline__ void trace_stamp(long long* t, int slot) {
   if (t) {
     long long now;

@@ -73,7 +73,7 @@ __global__ void pack_kernel(const TS* __restrict__ src, TD* __restrict__ dst, lo
 struct Lin {            // one packed projection weight
   bf16* w = nullptr;
   int N = 0, K = 0;
-  CUtensorMap tm128, tm256;
+  CUtensorMap tm128, tm256, tm64;
   bool has256 = false;
 };
 struct Act {            // one bf16 activation buffer usable as GEMM A operand (tm) and as TMA-epilogue output (otm)
@@ -180,9 +180,8 @@ struct Engine {
   size_t trace_idx = 0;
   std::string trace_names;
   static constexpr size_t TRACE_MAX = 8192;
-  int dry_epi = 0;             // 1: one-tile-per-CTA GEMM launches run a dry epilogue pass during the mainloop (gemm.cu). Measured
-                               // SLOWER (gpurun r02f: 42.6 vs 41.6 ms per call): the dry pass competes with the mainloop and the real
-                               // pass is no faster, i.e. the one-shot epilogue is not paced by a cold instruction cache
+  int pair_bn128 = 1;          // 1: 256 x 128 pair tiles for the one-row-tile split-K projections (see Run::gemm)
+  int den_chains = 1;          // sub-batch chains of the denoise steps (1 | 2), see Run::denoise_all
   int xs_o = 12, xs_down = 24; // split-K caps of the action expert's o / down projections (options "exp_splits_o/down")
   int vit_tc = 1;              // 1: InternViT attention of 257-token images on the tcgen05 kernel (attention_tc.cu)
   int ablate = 0;              // timing aid: bit mask of denoise-step launches to skip (1 norm_in, 2 qkv, 4 attention, 8 o,
@@ -261,6 +260,7 @@ struct Engine {
   }
   int make_lin_maps(Lin* l) {
     if (make_tmap_bf16(&l->tm128, l->w, l->N, l->K, 128)) return -1;
+    if (make_tmap_bf16(&l->tm64, l->w, l->N, l->K, 64)) return -1;
     l->has256 = (l->N % 256 == 0);
     if (l->has256 && make_tmap_bf16(&l->tm256, l->w, l->N, l->K, 256)) return -1;
     return 0;
@@ -313,8 +313,13 @@ int engine_build(Engine& e) {
   e.kv_rows = (long long)e.Bc * (e.S + 1 + e.H);
   VL_CHECK(e.n_img * e.T <= e.S, "image tokens exceed max_image_text_tokens");
   VL_CUDA_CHECK(cudaGetDevice(&e.device));
-  VL_CUDA_CHECK(cudaStreamCreateWithFlags(&e.own_stream, cudaStreamNonBlocking));
-  VL_CUDA_CHECK(cudaStreamCreateWithFlags(&e.side_stream, cudaStreamNonBlocking));
+  // The side stream carries latency-bound launches (proprio pass of the prefill) next to the large GEMMs of the main
+  // stream: lowest priority, so that the block scheduler hands free SMs to the main stream's CTAs first (its launches
+  // otherwise queue behind side-stream CTAs that hold an SM each while they wait on a dependent load).
+  int prio_lo = 0, prio_hi = 0;
+  VL_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  VL_CUDA_CHECK(cudaStreamCreateWithPriority(&e.own_stream, cudaStreamNonBlocking, prio_hi));
+  VL_CUDA_CHECK(cudaStreamCreateWithPriority(&e.side_stream, cudaStreamNonBlocking, prio_lo));
   e.side_events.resize((size_t)c.layers + 1);
   for (cudaEvent_t& ev : e.side_events) VL_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 
@@ -440,7 +445,7 @@ int engine_build(Engine& e) {
   e.ss_floats = (size_t)(c.num_inference_steps + 1) * (2 * c.layers + 1) * e.ss_rows;
   VL_TRY(e.alloc(&e.ss, e.ss_floats));
   VL_TRY(e.alloc(&e.tile_ctr, 4096));
-  VL_TRY(e.alloc(&e.trace, Engine::TRACE_MAX * 8));
+  VL_TRY(e.alloc(&e.trace, Engine::TRACE_MAX * 16));
   {
     // split-K partial workspaces: [splits <= 32][rows padded to 256][width]. The expert streams always split (o / down
     // projections); the ViT / LLM residual projections only while their tiles cover less than half of the SMs
@@ -674,7 +679,7 @@ struct Run {
     e.trace_names += name;
     if (layer >= 0) e.trace_names += " L" + std::to_string(layer);
     e.trace_names += st == e.side_stream ? " [side]\n" : "\n";
-    return e.trace + 8 * e.trace_idx++;
+    return e.trace + 16 * e.trace_idx++;
   }
   const char* tr_name = "gemm";
   int tr_layer = -1;
@@ -710,7 +715,6 @@ struct Run {
            int stages = 0, const CUtensorMap* out_tm = nullptr) {
     GemmDims d;
     d.trace = tr(tr_name, tr_layer);
-    d.no_dry_epilogue = e.dry_epi ? 0 : 1;
     d.M = M;
     d.N = w.N;
     d.K = w.K;
@@ -765,13 +769,29 @@ struct Run {
     long long pair_tiles = (long long)((M + 255) / 256) * (w.N / 256);
     const bool pair_split = max_splits > 1 && epi == EPI_RESID_F32 && out_tm != nullptr && e.tma_epi && !ep.a_next;
     if (pair_split) pair_tiles *= std::min(max_splits, std::max(1, w.K / 128));
-    if (e.pair_gemm && w.N % 256 == 0 && (max_splits <= 1 || pair_split) && pair_tiles >= e.pair_min_tiles) d.pair = 1;
+    // (a static M of at most one 128-row tile -- the proprio pass, a sub-batch chain of the denoise steps -- would leave
+    // the second CTA of every pair multiplying zero rows: single-CTA kernel)
+    const bool half_tile = M_dev == nullptr && M <= 128;
+    if (e.pair_gemm && w.N % 256 == 0 && (max_splits <= 1 || pair_split) && pair_tiles >= e.pair_min_tiles && !half_tile) d.pair = 1;
+    // one 256-row tile of rows, split-K partials (the o / down projections of the action expert): 256 x 128 tiles -- every
+    // CTA then stores 64 KB of partials instead of 128 KB (the epilogue of these launches is bound by the ~55 GB/s an SM
+    // stores through TMA, in-situ timeline r02j) and N / 128 x splits pairs cover the GPU with half as many splits
+    if (d.pair && pair_split && ep.part && e.pair_bn128 && M_dev == nullptr && M <= 256 && w.N % 128 == 0) {
+      const int tiles128 = w.N / 128;
+      const int fit = std::max(1, (gemm_num_sms() / 2) / tiles128);
+      if (fit >= 2) {
+        d.pair_bn = 128;
+        max_splits = d.max_splits = std::min(max_splits, fit);
+      }
+    }
     // tile order: with many more rows than weight rows a wave of pairs should share A tiles (n fastest); measured on
     // B200: ViT GEMMs and the LLM o/down projections gain, the wide-N LLM qkv/gate-up GEMMs prefer m fastest
     d.n_fast = (M_dev == nullptr) ? (M > w.N) : (w.N <= 1536);
     if (!d.pair && epi != EPI_QKV_ROPE && w.has256) {
       const long long tiles256 = (long long)((M + 127) / 128) * (w.N / 256);
-      if (tiles256 >= gemm_num_sms()) bn = 256;
+      // wide projections of a half tile (gate/up: N = 17920): 128 x 256 tiles read each weight once per CTA column and keep
+      // the launch at N / 256 CTAs, so that two sub-batch chains fit on the GPU side by side
+      if (tiles256 >= gemm_num_sms() || (half_tile && w.N >= 8192)) bn = 256;
     }
     const bool prof = e.profile_gemm && !e.use_graph;
     if (prof) {
@@ -789,7 +809,8 @@ struct Run {
       e.prof_class.push_back((d.pair && rows > 512.0) ? 1 : 0);  // M <= 512: weight-streaming regime whatever the kernel
       VL_CUDA_CHECK(cudaEventRecord(e.prof_events[e.prof_used], st));
     }
-    const int rc = gemm_launch(a.tm, bn == 256 ? w.tm256 : w.tm128, d, ep, bn, epi, st, e.tma_epi ? out_tm : nullptr, part_tm);
+    const CUtensorMap& wtm = (d.pair && d.pair_bn == 128) ? w.tm64 : (bn == 256 ? w.tm256 : w.tm128);
+    const int rc = gemm_launch(a.tm, wtm, d, ep, bn, epi, st, e.tma_epi ? out_tm : nullptr, part_tm);
     if (prof) {
       VL_CUDA_CHECK(cudaEventRecord(e.prof_events[e.prof_used + 1], st));
       e.prof_used += 2;
@@ -949,7 +970,9 @@ struct Run {
     if (!(abl & 32)) VL_TRY(gemm(xn, L.gu, M, M_dev, EPI_SWIGLU_BF16, eg, 1, 0, &act.otm));
     if (abl & 64) return 0;
     tr_name = "down";
-    return gemm(act, L.down, M, M_dev, EPI_RESID_F32, eo, splits > 1 ? std::min(splits, e.xs_down) : 1, 0, x_otm);
+    // (half tile: 6 output tiles x 12 splits = 72 CTAs, again half of the GPU)
+    const int xs_down = (M_dev == nullptr && M <= 128) ? std::min(e.xs_down, 12) : e.xs_down;
+    return gemm(act, L.down, M, M_dev, EPI_RESID_F32, eo, splits > 1 ? std::min(splits, xs_down) : 1, 0, x_otm);
   }
 
   // ---- expert streams (proprio token in the prefill, action tokens in the denoise steps): RMSNorm is fused across
@@ -1178,31 +1201,75 @@ struct Run {
     return 0;
   }
 
-  int denoise(int step) {
+  // ---- denoise steps. The flow integration of one observation never reads another one's state, so the batch may be cut
+  // into `den_chains` sub-batches whose 10-step chains run side by side on their own streams inside the captured graph
+  // (option "den_chains"): every launch of a chain is a few microseconds of dependent latency on a fraction of the SMs,
+  // and a second chain fills the SMs and the bubbles the first one leaves. A chain owns a row slice of the action-stream
+  // buffers (tensor-map views), its own split-K workspace and its own stream; nothing is shared but the weights.
+  struct Chain {
+    int id = 0;               // 0: main stream, 1: side stream
+    int b0 = 0, nb = 0;       // samples [b0, b0 + nb)
+    int r0 = 0, M = 0;        // action rows [r0, r0 + M)
+    Act xan, aoa, acta, e1, h2;
+    CUtensorMap xa_otm;
+  };
+  int make_chain(Chain& ch, int id, int b0, int nb) {
+    ch.id = id;
+    ch.b0 = b0;
+    ch.nb = nb;
+    ch.r0 = b0 * e.H;
+    ch.M = nb * e.H;
+    if (b0 == 0 && nb == B) {  // the whole batch: the handle's own maps
+      ch.xan = e.xan, ch.aoa = e.aoa, ch.acta = e.acta, ch.e1 = e.e1, ch.h2 = e.h2;
+      ch.xa_otm = e.xa_otm;
+      return 0;
+    }
+    auto view = [&](const Act& a, Act& v) -> int {
+      v.rows = ch.M;
+      v.K = a.K;
+      v.p = a.p + (size_t)ch.r0 * a.K;
+      // the slice ends where the next chain's rows begin: the maps clip there (loads zero-fill, stores are dropped)
+      if (make_tmap_out(&v.otm, v.p, ch.M, a.K, 2)) return -1;
+      return make_tmap_bf16(&v.tm, v.p, ch.M, a.K, 128);
+    };
+    VL_TRY(view(e.xan, ch.xan));
+    VL_TRY(view(e.aoa, ch.aoa));
+    VL_TRY(view(e.acta, ch.acta));
+    VL_TRY(view(e.e1, ch.e1));
+    VL_TRY(view(e.h2, ch.h2));
+    return make_tmap_out(&ch.xa_otm, e.xa + (size_t)ch.r0 * e.c.hidden_e, ch.M, e.c.hidden_e, 4);
+  }
+
+  int denoise(int step, Chain& ch) {
     const vlaser_cfg& c = e.c;
-    const int M = B * e.H, he = c.hidden_e;
+    const int M = ch.M, he = c.hidden_e;
+    float* xa = e.xa + (size_t)ch.r0 * he;
+    bf16* qa = e.qa + (size_t)ch.r0 * e.qdim;
+    float* action = e.action + (size_t)ch.r0 * c.action_dim;
+    const int* act_pos = e.pb.act_pos + ch.r0;
+    const int* act_kvrow = e.pb.act_kvrow + ch.r0;
     struct AblScope {
       int& a;
       ~AblScope() { a = 0; }
     } abl_scope{abl};
     abl = e.ablate;
     // action encoder (modules.py:39-53) with the time term pre-reduced into a per-step bias
-    VL_TRY(small_linear_launch(e.action, DT_F32, e.ae_w1, e.ae_b1, e.e1.p, DT_BF16, M, c.action_dim, he, st));
+    VL_TRY(small_linear_launch(action, DT_F32, e.ae_w1, e.ae_b1, ch.e1.p, DT_BF16, M, c.action_dim, he, st));
     e.launches++;
     EpiParams e2;
-    e2.out = e.h2.p;
+    e2.out = ch.h2.p;
     e2.ldo = he;
     e2.bias = e.time_bias + (size_t)step * he;
     tr_name = "act_enc2";
     tr_layer = -1;
-    VL_TRY(gemm(e.e1, e.ae_w2b, M, nullptr, EPI_SILU_BF16, e2));
+    VL_TRY(gemm(ch.e1, e.ae_w2b, M, nullptr, EPI_SILU_BF16, e2));
     EpiParams e3;
-    e3.out = e.xa;
+    e3.out = xa;
     e3.ldo = he;
     e3.bias = e.ae_b3;
-    if (e.fuse_norm && !mega()) norm_producer(e3, e.xan, e.exp[0].ln_in, step + 1, 0);
+    if (e.fuse_norm && !mega()) norm_producer(e3, ch.xan, e.exp[0].ln_in, step + 1, 0);
     tr_name = "act_enc3";
-    VL_TRY(gemm(e.h2, e.ae_w3, M, nullptr, EPI_STORE_F32, e3));
+    VL_TRY(gemm(ch.h2, e.ae_w3, M, nullptr, EPI_STORE_F32, e3));
     if (mega())
       VL_TRY(expert_pass(step + 1, M, e.xa, e.xa_otm, e.xan, e.qa, e.aoa, e.acta, e.pb.act_pos, e.pb.act_kvrow, e.pb.den_q_start,
                          e.pb.den_q_len, e.pb.den_kv_len, e.H, false));
@@ -1215,11 +1282,11 @@ struct Run {
       pf_in.ptr[1] = e.exp[li].gu.w, pf_in.bytes[1] = wbytes(e.exp[li].gu);
       pf_post.ptr[0] = e.exp[li].down.w, pf_post.bytes[0] = wbytes(e.exp[li].down);
       if (li + 1 < c.layers) pf_post.ptr[1] = e.exp[li + 1].qkv.w, pf_post.bytes[1] = wbytes(e.exp[li + 1].qkv);
-      if (e.fuse_norm) VL_TRY(exp_pre(li, e.xan, e.qa, M, e.pb.act_pos, e.pb.act_kvrow, step + 1));
-      else VL_TRY(block_pre(e.exp[li], e.xa, e.xan, e.qa, M, nullptr, he, e.pb.act_pos, e.pb.act_kvrow, li, e.l2pf ? &pf_in : nullptr));
+      if (e.fuse_norm) VL_TRY(exp_pre(li, ch.xan, qa, M, act_pos, act_kvrow, step + 1));
+      else VL_TRY(block_pre(e.exp[li], xa, ch.xan, qa, M, nullptr, he, act_pos, act_kvrow, li, e.l2pf ? &pf_in : nullptr));
       AttnParams ap;
       const size_t off = (size_t)li * c.n_kv_heads * e.kv_rows * 128;
-      ap.q = e.qa;
+      ap.q = e.qa;  // q / out rows are addressed through the absolute per-sample starts below
       ap.q_row_stride = e.qdim;
       ap.k = e.kc + off;
       ap.v = e.vc + off;
@@ -1227,31 +1294,61 @@ struct Run {
       ap.kv_head_stride = e.kv_rows * 128;
       ap.out = e.aoa.p;
       ap.out_row_stride = e.qdim;
-      ap.q_start = e.pb.den_q_start;
-      ap.q_len = e.pb.den_q_len;
-      ap.kv_start = e.pb.kvoff;
-      ap.kv_len = e.pb.den_kv_len;
+      ap.q_start = e.pb.den_q_start + ch.b0;
+      ap.q_len = e.pb.den_q_len + ch.b0;
+      ap.kv_start = e.pb.kvoff + ch.b0;
+      ap.kv_len = e.pb.den_kv_len + ch.b0;
       ap.stable_prefix = 1;  // prefix + proprio K/V of this layer date from the prefill
       ap.max_q_len = e.H;
       ap.group = c.n_heads / c.n_kv_heads;
       ap.n_kv_heads = c.n_kv_heads;
-      ap.batch = B;
+      ap.batch = ch.nb;
       ap.scale = 0.08838834764831845f;
       if (!(abl & 4)) {
         ap.trace = tr("attention", li);
         VL_TRY(attention_launch(ap, 128, st));
         e.launches++;
       }
-      if (e.fuse_norm) VL_TRY(exp_post(li, e.xa, e.xan, e.aoa, e.acta, M, step + 1, false));
-      else VL_TRY(block_post(e.exp[li], e.xa, e.xan, e.aoa, e.acta, M, nullptr, he, e.mlp_e_p, 32, &e.xa_otm, e.l2pf ? &pf_post : nullptr));
+      if (e.fuse_norm) VL_TRY(exp_post(li, xa, ch.xan, ch.aoa, ch.acta, M, step + 1, false));
+      else VL_TRY(block_post(e.exp[li], xa, ch.xan, ch.aoa, ch.acta, M, nullptr, he, e.mlp_e_p, 32, &ch.xa_otm, e.l2pf ? &pf_post : nullptr));
     }
     const int last = step == c.num_inference_steps - 1;
     VL_TRY(flush());  // split-K partials of the last down projection
-    VL_TRY(euler_step_launch(e.xa, e.final_norm, e.dec_w, e.dec_b, e.action, e.out_act, io, M, he, c.action_dim, e.H,
-                             c.horizon_steps, (float)(1.0 / c.num_inference_steps), c.rms_eps, last, c.clip_enabled,
-                             c.final_action_clip_value, st,
+    const size_t out_off = (size_t)ch.b0 * c.horizon_steps * c.action_dim * (io == DT_F32 ? 4 : 2);
+    VL_TRY(euler_step_launch(xa, e.final_norm, e.dec_w, e.dec_b, action, reinterpret_cast<uint8_t*>(e.out_act) + out_off, io, M, he,
+                             c.action_dim, e.H, c.horizon_steps, (float)(1.0 / c.num_inference_steps), c.rms_eps, last,
+                             c.clip_enabled, c.final_action_clip_value, st,
                              (gemv() && e.det_splitk) ? e.xfix + (size_t)(step + 1) * e.xfix_words() : nullptr));
     e.launches++;
+    return 0;
+  }
+
+  // all denoise steps: one chain, or `den_chains` sub-batch chains forked from / joined into the main stream
+  int denoise_all() {
+    const vlaser_cfg& c = e.c;
+    const int steps = e.stop_after == 4 ? 1 : c.num_inference_steps;
+    int nch = 1;
+    // two chains when asked for and the halves are whole 128-row tiles of whole samples (tensor-map views, one M tile
+    // each); the expert-stream / single-observation / fused-norm schedules keep one chain
+    if (e.den_chains >= 2 && !mega() && !e.fuse_norm && !e.simt && B % 2 == 0 && ((B / 2) * e.H) % 128 == 0) nch = 2;
+    cudaStream_t main_st = st;
+    std::vector<Chain> chains(nch);
+    for (int i = 0; i < nch; ++i) VL_TRY(make_chain(chains[i], i, i * (B / nch), B / nch));
+    if (nch > 1) {
+      VL_CUDA_CHECK(cudaEventRecord(e.side_events[0], main_st));  // fork: prefill complete, noise converted
+      VL_CUDA_CHECK(cudaStreamWaitEvent(e.side_stream, e.side_events[0], 0));
+    }
+    int rc = 0;
+    for (int i = 0; i < nch && rc == 0; ++i) {
+      st = i == 0 ? main_st : e.side_stream;
+      for (int k = 0; k < steps && rc == 0; ++k) rc = denoise(k, chains[i]);
+    }
+    st = main_st;
+    if (rc) return rc;
+    if (nch > 1) {
+      VL_CUDA_CHECK(cudaEventRecord(e.side_events[1], e.side_stream));  // join
+      VL_CUDA_CHECK(cudaStreamWaitEvent(main_st, e.side_events[1], 0));
+    }
     return 0;
   }
 
@@ -1272,15 +1369,9 @@ struct Run {
     VL_TRY(prefill());
     if (e.stop_after == 3) return 0;
     set_pdl_enabled(true);
-    for (int k = 0; k < c.num_inference_steps; ++k) {
-      const int rc = denoise(k);
-      if (rc != 0 || e.stop_after == 4) {
-        set_pdl_enabled(false);
-        return rc;
-      }
-    }
+    const int rc = denoise_all();
     set_pdl_enabled(false);
-    return 0;
+    return rc;
   }
 };
 
@@ -1387,7 +1478,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "dry_epilogue" || k == "exp_splits_o" || k == "exp_splits_down") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
@@ -1403,7 +1494,8 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
     else if (k == "trace") h->e.trace_on = (int)value;
     else if (k == "det_splitk") h->e.det_splitk = (int)value;
     else if (k == "vit_tc") h->e.vit_tc = (int)value;
-    else if (k == "dry_epilogue") h->e.dry_epi = (int)value;
+    else if (k == "den_chains") h->e.den_chains = (int)value;
+    else if (k == "pair_bn128") h->e.pair_bn128 = (int)value;
     else if (k == "exp_splits_o") h->e.xs_o = std::max(1, (int)value);
     else if (k == "exp_splits_down") h->e.xs_down = std::max(1, (int)value);
     else if (k == "pair_gemm") h->e.pair_gemm = (int)value;
@@ -1552,7 +1644,7 @@ int64_t vlaser_debug_copy(vlaser_t* h, const char* name, void* host_dst, int64_t
   else if (n == "img_row_map") src = e.pb.img_row_map, bytes = Ni * e.T * 4;
   else if (n == "row_src") src = e.pb.row_src, bytes = (size_t)e.Bc * e.S * 4;
   else if (n == "expert_timing") src = e.xp_timing, bytes = (size_t)(c.num_inference_steps + 1) * 7 * c.layers * 8;
-  else if (n == "trace") src = e.trace, bytes = Engine::TRACE_MAX * 8 * 8;
+  else if (n == "trace") src = e.trace, bytes = Engine::TRACE_MAX * 16 * 8;
   else if (n == "trace_names") {
     // newline-separated launch names in record order (valid after a call that built its graph with option "trace" on)
     if (host_dst && max_bytes > 0) {
@@ -1684,13 +1776,14 @@ int32_t vlaser_op_gemm(const vlaser_gemm_args* a, void* stream) {
   d.stages = a->stages;
   d.pair = a->pair & 1;
   d.n_fast = (a->pair >> 1) & 1;
+  d.pair_bn = (a->pair & 4) ? 128 : 256;
   if (a->simt)
     return gemm_launch_simt(reinterpret_cast<const __nv_bfloat16*>(a->A), reinterpret_cast<const __nv_bfloat16*>(a->W),
                             d, ep, a->epi, st);
   CUtensorMap tmA, tmB;
   // rows of A beyond M are zero-filled by TMA (the map's row extent is the true M)
   VL_TRY(make_tmap_bf16(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, 128));
-  VL_TRY(make_tmap_bf16(&tmB, a->W, (uint64_t)a->N, (uint64_t)a->K, a->pair ? 128u : (uint32_t)a->block_n));
+  VL_TRY(make_tmap_bf16(&tmB, a->W, (uint64_t)a->N, (uint64_t)a->K, a->pair ? (uint32_t)(d.pair_bn / 2) : (uint32_t)a->block_n));
   CUtensorMap tmC;
   const bool tma_out = a->pair && a->tma_out;
   if (tma_out) VL_TRY(make_tmap_out(&tmC, a->out, (uint64_t)a->M, (uint64_t)a->ldo, a->epi == EPI_RESID_F32 ? 4 : 2));

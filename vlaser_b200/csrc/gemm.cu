@@ -241,14 +241,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if constexpr (EPI == EPI_RESID_F32) {
       if (ep.part_splits && blockIdx.x == 0 && threadIdx.x == 64) *ep.part_splits = sc.splits > 1 ? sc.splits : 0;
     }
-    // One tile per CTA (the small-M launches of the action expert, q|k|v / o / gate-up of a few observations): the
-    // epilogue then runs exactly once per CTA, on a cold instruction cache -- tens of KB of unrolled code fetched line
-    // by line from L2 while the whole dependent chain waits (3-5 us per launch in the in-situ timeline, whatever the
-    // epilogue stores). Where the epilogue only OVERWRITES memory this launch owns (bf16 outputs, KV-cache rows, split-K
-    // partial tiles), it is first run once on whatever the accumulator columns hold, WHILE the mainloop is in flight;
-    // the real pass then hits the instruction cache and overwrites the garbage (same thread, same addresses).
-    constexpr bool DRY_EPI = EPI == EPI_STORE_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_SILU_BF16 ||
-                             EPI == EPI_SWIGLU_BF16 || EPI == EPI_QKV_ROPE || EPI == EPI_RESID_F32;
     for (int t = blockIdx.x; t < sc.total; t += gridDim.x) {
       const TileCoord tc = tile_coord(sc, t);
       const int n_idx = tc.n_idx, m_idx = tc.m_idx;
@@ -265,20 +257,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if constexpr (EPI == EPI_RESID_F32) {
         if (atomic && ep.part && !ep.a_next) part_tile = ep.part + (size_t)tc.split * ep.part_stride;
       }
-      bool dry = DRY_EPI && sc.total <= (int)gridDim.x && !ep.a_next && !d.no_dry_epilogue;
-      if (EPI == EPI_RESID_F32 && part_tile == nullptr) dry = false;  // x += acc is not idempotent
       // q|k|v projection, 128-column tiles: this warp owns ONE unit of the tile (half-head chunk `half`); its RoPE
       // factors and KV-cache row are fetched while the mainloop is still running
       constexpr bool ROPE_PRE = EPI == EPI_QKV_ROPE && BLOCK_N == 128 && EPI_WARPS == 8;
       RopeOperands ro;
-      if constexpr (ROPE_PRE) rope_prefetch(ep, row, row_ok, n0 + half * 32, ro);
-#pragma unroll 1
-      for (int pass = dry ? 0 : 1; pass < 2; ++pass) {
-        if (pass == 1) {
-          mbar_wait(&tfull_bar[as], aphase);
-          tc_fence_after();
-          if (t == (int)blockIdx.x) trace_stamp(tr, 4);
+      if constexpr (ROPE_PRE) {
+        rope_prefetch(ep, row, row_ok, n0 + half * 32, ro);
+        if (ep.bias) {  // this unit's 64 bias values into the head of the warp's staging tile (cold in L2: a DRAM round trip)
+          float* bias_s = reinterpret_cast<float*>(epi_stage + (warp - 2) * 4096);
+          bias_s[lane] = __ldg(ep.bias + n0 + half * 32 + lane);
+          bias_s[32 + lane] = __ldg(ep.bias + n0 + half * 32 + 64 + lane);
+          __syncwarp();
         }
+      }
+      {
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        if (t == (int)blockIdx.x) trace_stamp(tr, 4);
         if constexpr (ROPE_PRE) {
           uint32_t r0[32], r1[32];
           tmem_ld_32x32(taddr + half * 32, r0);
@@ -293,8 +288,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int col0 = n0 + half * 32;
           // Transpose the unit through this warp's 4 KB swizzled staging tile so that every store instruction writes
           // whole 64-byte runs (4 rows x 2 runs) instead of 32 scattered 16-byte pieces
-          rope_rotate(ep, col0, v, w, ro);
           uint8_t* buf = epi_stage + (warp - 2) * 4096;
+          rope_rotate(ep, col0, v, w, ro, reinterpret_cast<const float*>(buf));
+          __syncwarp();  // every lane has read the bias before the tile is overwritten
           stage_row_bf16(buf, lane, 0, v);
           stage_row_bf16(buf, lane, 4, w);
           __nv_bfloat16* my_dst = row_ok ? rope_dst(ep, row, col0, ro) : nullptr;
@@ -402,7 +398,7 @@ template <int BN, int EPI, int PARTS, int NBUF>
 __device__ __forceinline__ void epilogue_tile_tma(const EpiParams& ep, const CUtensorMap* tmC, uint8_t* wbuf,
                                                   uint32_t& par, uint32_t taddr, int half, int lane, int row0, int n0,
                                                   float rstd, bool first_split, const CUtensorMap* tmP = nullptr,
-                                                  int part_row0 = -1, uint8_t* ring = nullptr) {
+                                                  int part_row0 = -1, uint8_t* ring = nullptr, long long* tr = nullptr) {
   auto acquire = [&]() -> uint8_t* {
     // the staging tile about to be reused (two units ago with NBUF == 2, the previous one otherwise) has been read out
     if (lane == 0) bulk_wait_read<NBUF - 1>();
@@ -427,6 +423,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiParams& ep, const CUt
       const int col0 = n0 + c * 32;
       float v[32];
       load_acc32(taddr + c * 32, v);
+      if (c == half * U) trace_stamp(tr, 8);
       scale_rows(v);
       if (ep.bias && first_split) add_vec32(v, ep.bias + col0);
       if (ep.scale) {
@@ -442,6 +439,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiParams& ep, const CUt
       }
       if (ring) {
         stage_row_f32(ring + (c - half * U) * 4096, lane, v);
+        trace_stamp(tr, 9);
         continue;
       }
       uint8_t* b = acquire();
@@ -457,6 +455,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiParams& ep, const CUt
     if (ring) {
       fence_proxy_async();
       __syncwarp();
+      trace_stamp(tr, 10);
       if (lane == 0) {
 #pragma unroll 1
         for (int c = half * U; c < (half + 1) * U; ++c) {
@@ -466,6 +465,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiParams& ep, const CUt
         }
         bulk_commit();
       }
+      trace_stamp(tr, 11);
     }
   } else if constexpr (EPI == EPI_SWIGLU_BF16) {
     static_assert(PARTS == 2, "SwiGLU TMA epilogue: 8 epilogue warps");
@@ -554,13 +554,14 @@ __device__ __forceinline__ void pair_tile(int t, int m_tiles, int n_tiles, int n
 template <int EPI>
 constexpr int pair_epi_warps() { return EPI == EPI_GELU_BF16 ? 16 : 8; }  // the exact-GELU epilogue is issue-bound at 8
 
-template <int EPI, int NW>
+template <int EPI, int NW, int BN = PAIR_BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * NW, 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, GemmDims d,
                          EpiParams ep) {
   constexpr int STAGES = pair_stages(NW);
-  constexpr int BN = PAIR_BLOCK_N;
+  // (BN = 128: the ring keeps its 32 KB slots, the W half of a slot is simply half full)
+  constexpr uint32_t STAGE_TX = 2 * (PAIR_A_BYTES + (BN / 2) * BLOCK_K * 2);  // bytes both CTAs land per stage
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* out_stage = smem + STAGES * PAIR_STAGE_BYTES;  // [NW][NBUF][4096], 1024-byte aligned
@@ -667,7 +668,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         while (have && npre < STAGES) {
           pre_kb[npre] = kb;
           pre_row[npre] = row_a;
-          if (leader) mbar_arrive_expect_tx(&full_bar[npre], 2 * PAIR_STAGE_BYTES);
+          if (leader) mbar_arrive_expect_tx(&full_bar[npre], STAGE_TX);
           tma_load_2d_pair(smem + npre * PAIR_STAGE_BYTES + PAIR_A_BYTES, &tmB, full0 + npre * 8, kb * BLOCK_K, row_b);
           ++npre;
           advance();
@@ -687,7 +688,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       while (have) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * PAIR_STAGE_BYTES;
-        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * PAIR_STAGE_BYTES);
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], STAGE_TX);
         tma_load_2d_pair(sa, &tmA, full0 + stage * 8, kb * BLOCK_K, row_a);
         tma_load_2d_pair(sa + PAIR_A_BYTES, &tmB, full0 + stage * 8, kb * BLOCK_K, row_b);
         if (++stage == STAGES) {
@@ -757,39 +758,30 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       float ss = 0.f;
       int part_row0 = -1;
       if (EPI == EPI_RESID_F32 && splits > 1 && ep.part) part_row0 = split * (int)(ep.part_stride / ep.ldo) + (row - lane);
-      // one tile per pair: a dry epilogue pass while the mainloop is in flight warms the instruction cache (see the
-      // single-CTA kernel); only for epilogues that overwrite (TMA stores of bf16 outputs / split-K partial tiles)
-      bool dry = epi_has_tma_out<EPI>() && d.tma_out && total <= n_pairs && !ep.a_next && !d.no_dry_epilogue;
-      if (EPI == EPI_RESID_F32 && part_row0 < 0) dry = false;  // a reduce-add is not idempotent
-#pragma unroll 1
-      for (int pass = dry ? 0 : 1; pass < 2; ++pass) {
-        if (pass == 1) {
-          mbar_wait(&tfull_bar[as], aphase);
-          tc_fence_after();
-          if (t == pair) trace_stamp(tr, 4);
-        }
+      {
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        if (t == pair) trace_stamp(tr, 4);
         bool done = false;
         if constexpr (epi_has_tma_out<EPI>()) {
           if (d.tma_out) {
             // last tile of this pair: the operand ring (STAGES x 32 KB) is idle once the accumulator is complete
             uint8_t* ring = nullptr;
-            if (pass == 1 && EPI == EPI_RESID_F32 && t + n_pairs >= total &&
+            if (EPI == EPI_RESID_F32 && t + n_pairs >= total &&
                 (BN / 32 / PARTS) * 4096 * NW <= STAGES * (int)PAIR_STAGE_BYTES)
               ring = smem + (warp - 2) * ((BN / 32 / PARTS) * 4096);
             epilogue_tile_tma<BN, EPI, PARTS, NBUF>(ep, &tmC, wbuf, out_par, taddr, half, lane, row - lane, n0, rstd,
-                                                    split == 0, &tmP, part_row0, ring);
+                                                    split == 0, &tmP, part_row0, ring, t == pair ? tr : nullptr);
             done = true;
-            if (pass == 0) {
-              if (lane == 0) bulk_wait<0>();  // the dry stores have landed before the real ones are issued
-              __syncwarp();
-            }
           }
         }
         if (!done) epilogue_tile<BN, EPI, PARTS>(ep, d.N, taddr, half, row, row_ok, n0, true, false, rstd, ss);
       }
       tc_fence_before();
       __syncwarp();
+      if (t == pair) trace_stamp(tr, 12);
       if (lane == 0) mbar_arrive_cluster(tempty0 + as * 8);  // the leader's MMA thread owns both accumulators
+      if (t == pair) trace_stamp(tr, 13);
       as ^= 1;
       if (as == 0) aphase ^= 1;
       if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32) {
@@ -898,21 +890,17 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDims d, const
   return 0;
 }
 
-template <int EPI>
-int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, GemmDims d, const EpiParams& ep,
-                cudaStream_t stream, const CUtensorMap* tmP) {
-  d.tma_out = (tmC != nullptr && epi_has_tma_out<EPI>() && !ep.a_next) ? 1 : 0;
-  const CUtensorMap& tc = d.tma_out ? *tmC : tmA;
-  VL_CHECK(!(EPI == EPI_RESID_F32 && ep.part) || tmP != nullptr, "gemm: pair kernel with split-K partials needs the workspace tensor map");
-  const CUtensorMap& tp = tmP ? *tmP : tmA;
+template <int EPI, int BN>
+int launch_pair_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tc, const CUtensorMap& tp, const GemmDims& d,
+                   const EpiParams& ep, cudaStream_t stream) {
   static bool attr_set = false;
   constexpr int NW = pair_epi_warps<EPI>();
-  auto kern = gemm_tcgen05_pair_kernel<EPI, NW>;
+  auto kern = gemm_tcgen05_pair_kernel<EPI, NW, BN>;
   if (!attr_set) {
     VL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes(NW)));
     attr_set = true;
   }
-  long long tiles = (long long)((d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (d.N / PAIR_BLOCK_N);
+  long long tiles = (long long)((d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (d.N / BN);
   if (EPI == EPI_RESID_F32 && d.max_splits > 1) {
     VL_CHECK(d.tma_out, "gemm: split-K on the pair kernel needs the TMA reduce-add epilogue (output tensor map)");
     tiles *= d.max_splits;
@@ -921,6 +909,20 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   // __cluster_dims__(2,1,1) is part of the kernel: a plain launch (with the optional PDL attribute) suffices
   VL_CUDA_CHECK(launch_kernel(kern, dim3(2 * pairs), dim3(64 + 32 * NW), pair_smem_bytes(NW), stream, tmA, tmB, tc, tp, d, ep));
   return 0;
+}
+
+template <int EPI>
+int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, GemmDims d, const EpiParams& ep,
+                cudaStream_t stream, const CUtensorMap* tmP) {
+  d.tma_out = (tmC != nullptr && epi_has_tma_out<EPI>() && !ep.a_next) ? 1 : 0;
+  const CUtensorMap& tc = d.tma_out ? *tmC : tmA;
+  VL_CHECK(!(EPI == EPI_RESID_F32 && ep.part) || tmP != nullptr, "gemm: pair kernel with split-K partials needs the workspace tensor map");
+  const CUtensorMap& tp = tmP ? *tmP : tmA;
+  if constexpr (EPI == EPI_RESID_F32) {
+    if (d.pair_bn == 128) return launch_pair_bn<EPI, 128>(tmA, tmB, tc, tp, d, ep, stream);
+  }
+  VL_CHECK(d.pair_bn == 256, "gemm: 128-column pair tiles exist for the residual epilogue only");
+  return launch_pair_bn<EPI, PAIR_BLOCK_N>(tmA, tmB, tc, tp, d, ep, stream);
 }
 
 template <int EPI>
@@ -994,7 +996,8 @@ int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDims& 
            "gemm: split-K partials need the residual epilogue and a stride of whole 256-row blocks covering M");
   VL_CHECK(d.K % BLOCK_K == 0 && d.K > 0, "gemm: K must be a positive multiple of 64");
   VL_CHECK(block_n == 128 || block_n == 256, "gemm: block_n must be 128 or 256");
-  VL_CHECK(!d.pair || (block_n == 128 && d.N % PAIR_BLOCK_N == 0), "gemm: pair mode needs the 128-row W map, N % 256 == 0");
+  VL_CHECK(!d.pair || (block_n == 128 && (d.pair_bn == 256 || d.pair_bn == 128) && d.N % d.pair_bn == 0),
+           "gemm: pair mode needs the W map with pair_bn / 2 row boxes, N % pair_bn == 0");
   VL_CHECK(d.N % block_n == 0, "gemm: N must be a multiple of block_n");
   VL_CHECK(ep.out != nullptr, "gemm: null output");
   VL_CHECK(!ep.a_next || (ep.gamma_next && ep.ss_next && ep.lda_next > 0), "gemm: incomplete fused-norm outputs");

@@ -70,10 +70,11 @@ struct GemmDims {
   int max_splits = 1;            // split-K cap (EPI_RESID_F32 only)
   int stages = 0;                // smem ring depth; 0 = default for the tile shape
   int pair = 0;                  // 1: CTA-pair kernel (cta_group::2, 256x256 tile per pair; W map with 128-row boxes)
+  int pair_bn = 256;             // pair kernel tile width: 256, or 128 (residual epilogue only; W map with 64-row boxes): half the
+                                 // output bytes per CTA and twice the CTAs for the one-row-tile split-K projections
   int n_fast = 0;                // pair kernel tile order: 0 = m fastest, 1 = n fastest
   int tma_out = 0;               // set by the launcher: epilogue leaves through the output tensor map
   long long* trace = nullptr;    // optional 8-slot timeline record of this launch (common.cuh trace_stamp)
-  int no_dry_epilogue = 0;       // 1: do not warm the instruction cache with a dry epilogue pass (see gemm.cu; A/B switch)
 };
 
 // Host API -------------------------------------------------------------------------------

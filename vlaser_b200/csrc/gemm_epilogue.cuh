@@ -89,12 +89,23 @@ __device__ __forceinline__ void rope_prefetch(const EpiParams& ep, int row, bool
   }
 }
 // bias + rotation of one unit in registers
+// (bias_s: optional shared-memory copy of bias[col0..col0+31] | bias[col0+64..col0+95], fetched ahead of the accumulator)
 __device__ __forceinline__ void rope_rotate(const EpiParams& ep, int col0, float (&v)[32], float (&w)[32],
-                                            const RopeOperands& ro) {
+                                            const RopeOperands& ro, const float* bias_s = nullptr) {
   const int head = col0 >> 7;
   if (ep.bias) {
-    add_vec32(v, ep.bias + col0);
-    add_vec32(w, ep.bias + col0 + 64);
+    if (bias_s) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(bias_s + 4 * i);
+        const float4 b = *reinterpret_cast<const float4*>(bias_s + 32 + 4 * i);
+        v[4 * i] += a.x, v[4 * i + 1] += a.y, v[4 * i + 2] += a.z, v[4 * i + 3] += a.w;
+        w[4 * i] += b.x, w[4 * i + 1] += b.y, w[4 * i + 2] += b.z, w[4 * i + 3] += b.w;
+      }
+    } else {
+      add_vec32(v, ep.bias + col0);
+      add_vec32(w, ep.bias + col0 + 64);
+    }
   }
   if (head < ep.n_q_heads + ep.n_kv_heads) {  // q or k head
 #pragma unroll
