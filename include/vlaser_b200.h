@@ -235,6 +235,14 @@ int32_t vlaser_op_postprocess_actions(const void* actions, int32_t dtype, int32_
                                       const double* stat_a, const double* stat_b, int32_t gripper, int32_t sticky_repeat,
                                       double* sticky_state, double* out, void* stream);
 
+/* Proprio normalisation / joint de-normalisation — `BaseEnvAdapter.{normalize,denormalize}_{bound,gaussian}`
+ * (Vlaser_VLA/Simpler/src/agent/env_adapter/base.py:8-49) as `SimplerAdapter.preprocess` applies them to the proprio vector
+ * (simpler.py:107-121), elementwise over a DEVICE array [rows, dim], float64 arithmetic like numpy. dtype codes: 0 f32,
+ * 1 bf16, 2 f64. norm 0 = "bound" (stat_a = p01, stat_b = p99; the forward direction clips to [-1, 1]), 1 = "gaussian"
+ * (stat_a = mean, stat_b = std); inverse = 1 de-normalises (RoboTwin: the 14 joint targets of an action chunk). */
+int32_t vlaser_op_normalize(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, int64_t rows, int32_t dim,
+                            int32_t norm, int32_t inverse, const double* stat_a, const double* stat_b, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

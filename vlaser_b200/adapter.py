@@ -6,6 +6,11 @@ over environments. Both are thin ctypes bindings of CUDA kernels in csrc/staging
                          (src/model/vla/processing.py:51-63). uint8 camera frames in, `pixel_values` out, so the
                          host->device copy of a step carries u8 frames instead of bf16 tensors and the dense attention
                          mask is never built (valid lengths are derived from `input_ids` on the device).
+  HistoryStacker       — the camera-history branch of `SimplerAdapter.preprocess` (simpler.py:92-104, `num_images > 1`):
+                         every environment's previous frame is kept on the device and stacked in front of the
+                         current one ([n_env, num_images, ...]); the first call after a reset repeats the current frame.
+  Normalizer           — `BaseEnvAdapter.normalize_* / denormalize_*` (base.py:8-49) for a batch on the device: the proprio
+                         vector of `SimplerAdapter.preprocess` (simpler.py:107-121), or any chunk of joint targets.
   ActionPostprocessor  — `SimplerAdapter.postprocess` (simpler.py:136-177) with the Bridge / EDR gripper rules
                          (:217-221, :259-286) for every environment of the batch at once (the reference handles only
                          `actions[0]`, eval.py:139); the sticky-gripper state lives on the device between calls.
@@ -55,6 +60,85 @@ class FrameStager:
                 self._mean, self._std, C.c_void_p(torch.cuda.current_stream().cuda_stream))
         _lib.check(rc, "stage_frames")
         return out
+
+
+class HistoryStacker:
+    """`history_image` of SimplerAdapter (simpler.py:60-104) for n_env environments, on the device. frames: uint8 CUDA
+    tensor [n_env, ...] of the current step (any trailing layout). Returns [n_env, num_images, ...]: the num_images - 1
+    previous frames then the current one; after `reset` the current frame fills the whole window, as the reference does
+    for its two-frame window."""
+
+    def __init__(self, num_images: int):
+        if num_images < 1:
+            raise ValueError("num_images >= 1")
+        self.num_images = int(num_images)
+        self._hist: Optional[torch.Tensor] = None   # [n_env, num_images - 1, ...]
+        self._fresh: Optional[torch.Tensor] = None  # [n_env] bool: no history yet
+
+    def reset(self, env_ids: Optional[Sequence[int]] = None) -> None:
+        if env_ids is None or self._fresh is None:
+            self._hist = self._fresh = None
+        else:
+            self._fresh[torch.as_tensor(list(env_ids), device=self._fresh.device)] = True
+
+    def __call__(self, frames: torch.Tensor) -> torch.Tensor:
+        if not frames.is_cuda or frames.dtype != torch.uint8:
+            raise RuntimeError("HistoryStacker needs a uint8 CUDA tensor (no CPU fallback)")
+        cur = frames.unsqueeze(1)
+        if self.num_images == 1:
+            return cur
+        n = frames.shape[0]
+        if self._hist is None or self._hist.shape[0] != n or self._hist.shape[2:] != frames.shape[1:]:
+            self._hist = cur.expand(n, self.num_images - 1, *frames.shape[1:]).clone()
+            self._fresh = torch.zeros(n, dtype=torch.bool, device=frames.device)
+        elif bool(self._fresh.any()):
+            idx = self._fresh.nonzero().flatten()
+            self._hist[idx] = cur[idx].expand(-1, self.num_images - 1, *frames.shape[1:])
+            self._fresh.zero_()
+        out = torch.cat([self._hist, cur], dim=1)
+        self._hist = out[:, 1:].clone()
+        return out
+
+
+class Normalizer:
+    """stats: one entry of the reference's dataset statistics json ("proprio" or "action": keys p01 / p99 / mean / std).
+    `normalize(x)`: [..., dim] CUDA tensor (f32 / bf16 / f64) -> normalised, dtype `out_dtype`; `denormalize` the inverse."""
+
+    _CODES = {torch.float32: 0, torch.bfloat16: 1, torch.float64: 2}
+
+    def __init__(self, stats: Dict[str, Sequence[float]], normalization: str = "bound", device=None):
+        if normalization not in ("bound", "gaussian"):
+            raise ValueError("normalization must be 'bound' or 'gaussian'")
+        if not torch.cuda.is_available():
+            raise RuntimeError("vlaser_b200 needs a CUDA device (no CPU fallback)")
+        self._lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        a, b = ("p01", "p99") if normalization == "bound" else ("mean", "std")
+        self._a = torch.tensor(list(stats[a]), dtype=torch.float64, device=self.device)
+        self._b = torch.tensor(list(stats[b]), dtype=torch.float64, device=self.device)
+        self.dim = int(self._a.numel())
+        self.norm = 0 if normalization == "bound" else 1
+
+    def _run(self, x: torch.Tensor, out_dtype: torch.dtype, inverse: int) -> torch.Tensor:
+        if not x.is_cuda or x.dtype not in self._CODES or out_dtype not in self._CODES:
+            raise RuntimeError("Normalizer needs an f32 / bf16 / f64 CUDA tensor (no CPU fallback)")
+        if x.shape[-1] != self.dim:
+            raise ValueError(f"last dimension must be {self.dim}")
+        x = x.contiguous()
+        out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = self._lib.vlaser_op_normalize(
+                C.c_void_p(x.data_ptr()), self._CODES[x.dtype], C.c_void_p(out.data_ptr()), self._CODES[out_dtype],
+                x.numel() // self.dim, self.dim, self.norm, inverse, C.c_void_p(self._a.data_ptr()),
+                C.c_void_p(self._b.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "normalize")
+        return out
+
+    def normalize(self, x: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        return self._run(x, out_dtype, 0)
+
+    def denormalize(self, x: torch.Tensor, out_dtype: torch.dtype = torch.float64) -> torch.Tensor:
+        return self._run(x, out_dtype, 1)
 
 
 class ActionPostprocessor:

@@ -125,10 +125,16 @@ def tiny() -> VlaserConfig:
     )
 
 
+def tiny_robotwin() -> VlaserConfig:
+    """`tiny` with the RoboTwin shapes (3 cameras, 14-DoF chunks) for plugin tests."""
+    return tiny().with_(cond_steps=3, action_dim=14, proprio_dim=14, max_image_text_tokens=224)
+
+
 PRESETS = {
     "vlaser_2b_bridge": vlaser_2b_bridge,
     "vlaser_2b_fractal": vlaser_2b_fractal,
     "vlaser_2b_robotwin": vlaser_2b_robotwin,
     "vlaser_8b_vla": vlaser_8b_vla,
     "tiny": tiny,
+    "tiny_robotwin": tiny_robotwin,
 }

@@ -90,26 +90,22 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-// Exact-erf GELU with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32-exact for a bf16 result):
-// erf(z) = 1 - (a1 t + .. + a5 t^5) exp(-z^2), t = 1/(1 + p z), z >= 0. 2 MUFU + ~12 FMA-class instructions, branch-free;
-// used in the GEMM epilogues where libdevice erff (~35 instructions, divergent) paces the tile loop.
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// erf-GELU for the GEMM epilogues: x Phi(x) = x / (1 + 2^(x p(x^2))) with p an even polynomial fitted (minimax over
+// [-8, 8], |x| clamped at 8 inside p) to 0.5 ln((1 - Phi) / Phi) / x scaled by 2 log2(e): max abs error 2.5e-5 against
+// 0.5 x (1 + erf(x / sqrt 2)) over all x, relative accuracy in both tails (nothing is subtracted), i.e. exact for a bf16
+// result. 7 FP32 instructions + 2 MUFU per element, branch-free; the A&S 7.1.26 form it replaces took 15 + 2 and paced the
+// tile loop of the ViT fc1 GEMM (issue-bound epilogue: profiles/r01_ncu_full_pair_vit_fc1.txt), libdevice erff ~35.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float ax = fabsf(x);
-  const float z = ax * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = p * t * ex2_approx(-0.72134752044448170368f * (x * x));  // erfc(z) = 1 - erf(z); exp(-z^2) = 2^(-x^2 log2e / 2)
-  // 0.5 x (1 + erf(x/sqrt2)) = 0.5 (x + |x|) - 0.5 |x| erfc(z)   (erf is odd), branch-free
-  const float h = 0.5f * ax;
-  return fmaf(-h, e, fmaf(0.5f, x, h));
+  const float x2 = fminf(x * x, 64.0f);
+  float p = fmaf(0.0010142630897462368f, x2, -0.10677572339773178f);
+  p = fmaf(p, x2, -2.3011212348937988f);
+  const float t = ex2_approx(x * p);           // e^(-2 q(x)); +inf for very negative x -> y = -0
+  return __fdividef(x, 1.0f + t);
 }
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 

@@ -180,6 +180,7 @@ struct Engine {
   size_t trace_idx = 0;
   std::string trace_names;
   static constexpr size_t TRACE_MAX = 8192;
+  int gelu_warps = 16;         // epilogue warps of the pair kernel's exact-GELU variant (16 | 8)
   int pair_bn128 = 1;          // 1: 256 x 128 pair tiles for the one-row-tile split-K projections (see Run::gemm)
   int den_chains = 1;          // sub-batch chains of the denoise steps (1 | 2), see Run::denoise_all
   int xs_o = 12, xs_down = 24; // split-K caps of the action expert's o / down projections (options "exp_splits_o/down")
@@ -715,6 +716,7 @@ struct Run {
            int stages = 0, const CUtensorMap* out_tm = nullptr) {
     GemmDims d;
     d.trace = tr(tr_name, tr_layer);
+    d.gelu_warps = e.gelu_warps;
     d.M = M;
     d.N = w.N;
     d.K = w.K;
@@ -1478,7 +1480,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
@@ -1496,6 +1498,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
     else if (k == "vit_tc") h->e.vit_tc = (int)value;
     else if (k == "den_chains") h->e.den_chains = (int)value;
     else if (k == "pair_bn128") h->e.pair_bn128 = (int)value;
+    else if (k == "gelu_warps") h->e.gelu_warps = (int)value == 8 ? 8 : 16;
     else if (k == "exp_splits_o") h->e.xs_o = std::max(1, (int)value);
     else if (k == "exp_splits_down") h->e.xs_down = std::max(1, (int)value);
     else if (k == "pair_gemm") h->e.pair_gemm = (int)value;

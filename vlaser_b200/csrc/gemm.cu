@@ -890,11 +890,10 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDims d, const
   return 0;
 }
 
-template <int EPI, int BN>
+template <int EPI, int BN, int NW = pair_epi_warps<EPI>()>
 int launch_pair_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tc, const CUtensorMap& tp, const GemmDims& d,
                    const EpiParams& ep, cudaStream_t stream) {
   static bool attr_set = false;
-  constexpr int NW = pair_epi_warps<EPI>();
   auto kern = gemm_tcgen05_pair_kernel<EPI, NW, BN>;
   if (!attr_set) {
     VL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes(NW)));
@@ -922,6 +921,9 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     if (d.pair_bn == 128) return launch_pair_bn<EPI, 128>(tmA, tmB, tc, tp, d, ep, stream);
   }
   VL_CHECK(d.pair_bn == 256, "gemm: 128-column pair tiles exist for the residual epilogue only");
+  if constexpr (EPI == EPI_GELU_BF16) {
+    if (d.gelu_warps == 8) return launch_pair_bn<EPI, PAIR_BLOCK_N, 8>(tmA, tmB, tc, tp, d, ep, stream);
+  }
   return launch_pair_bn<EPI, PAIR_BLOCK_N>(tmA, tmB, tc, tp, d, ep, stream);
 }
 

@@ -324,6 +324,34 @@ __global__ void postprocess_actions_kernel(const PostParams p) {
   }
 }
 
+// BaseEnvAdapter (de)normalisation (Vlaser_VLA/Simpler/src/agent/env_adapter/base.py:8-49), elementwise over [rows, dim] in
+// float64 as numpy computes it: bound (stat_a = p01, stat_b = p99): 2 (x - a) / (b - a + 1e-8) - 1 clipped to [-1, 1], inverse
+// (x + 1) / 2 (b - a) + a; gaussian (stat_a = mean, stat_b = std): (x - a) / (b + 1e-8), inverse x (b + 1e-8) + a.
+// dtype codes: 0 f32, 1 bf16, 2 f64.
+__device__ __forceinline__ double load_any(const void* p, int dtype, long long i) {
+  if (dtype == 2) return reinterpret_cast<const double*>(p)[i];
+  if (dtype == 1) return (double)__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+  return (double)reinterpret_cast<const float*>(p)[i];
+}
+__global__ void normalize_kernel(const void* __restrict__ in, int in_dtype, void* __restrict__ out, int out_dtype, long long n,
+                                 int dim, int norm, int inverse, const double* __restrict__ stat_a,
+                                 const double* __restrict__ stat_b) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int d = (int)(i % dim);
+  const double x = load_any(in, in_dtype, i), a = stat_a[d], b = stat_b[d];
+  double y;
+  if (norm == 0) {
+    if (!inverse) y = fmin(fmax(2.0 * (x - a) / (b - a + 1e-8) - 1.0, -1.0), 1.0);
+    else y = (x + 1.0) / 2.0 * (b - a) + a;
+  } else {
+    y = inverse ? x * (b + 1e-8) + a : (x - a) / (b + 1e-8);
+  }
+  if (out_dtype == 2) reinterpret_cast<double*>(out)[i] = y;
+  else if (out_dtype == 1) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16((float)y);
+  else reinterpret_cast<float*>(out)[i] = (float)y;
+}
+
 }  // namespace
 }  // namespace vlaser
 
@@ -374,6 +402,18 @@ int32_t vlaser_op_stage_frames(const uint8_t* frames, int32_t n, int32_t src_h, 
       VL_CUDA_CHECK(cudaFuncSetAttribute(stage_frames_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     stage_frames_kernel<float><<<grid, ST_THREADS, smem, st>>>(p);
   }
+  VL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int32_t vlaser_op_normalize(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, int64_t rows, int32_t dim,
+                            int32_t norm, int32_t inverse, const double* stat_a, const double* stat_b, void* stream) {
+  VL_CHECK(in && out && stat_a && stat_b && rows > 0 && dim > 0, "normalize: bad argument");
+  VL_CHECK(in_dtype >= 0 && in_dtype <= 2 && out_dtype >= 0 && out_dtype <= 2, "normalize: dtype must be f32 (0), bf16 (1) or f64 (2)");
+  VL_CHECK(norm == 0 || norm == 1, "normalize: norm must be 0 (bound) or 1 (gaussian)");
+  const long long n = (long long)rows * dim;
+  normalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      in, in_dtype, out, out_dtype, n, dim, norm, inverse, stat_a, stat_b);
   VL_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
