@@ -13,8 +13,14 @@
  * vlaser_last_error()); one handle per GPU (the current CUDA device at vlaser_create); calls on one
  * handle are serialised by the caller; device entry points are asynchronous w.r.t. the host
  * (stream-ordered on `stream`, a cudaStream_t passed as void*), borrow their pointers for the call
- * only, and never synchronise. There is no CPU fallback: without a CUDA device every compute entry
- * point fails with an error.
+ * only, and do not synchronise -- with one exception: the FIRST vlaser_infer_action call for a new
+ * (batch size, io dtype, valid_len present) combination waits for the staged inputs, runs one
+ * un-captured pass and captures the CUDA graph that later calls replay (csrc/engine.cu,
+ * engine_execute), so it blocks the host for about one call; changing a schedule option drops the
+ * captured graphs. Results are bit-identical from call to call for the same inputs (split-K partial
+ * sums are combined in a fixed order, option "det_splitk"). All GEMMs run in bf16 with fp32
+ * accumulation whatever dtype the I/O tensors have. There is no CPU fallback: without a CUDA device
+ * every compute entry point fails with an error.
  */
 #ifndef VLASER_B200_H
 #define VLASER_B200_H
@@ -191,6 +197,14 @@ int32_t vlaser_op_vit_attention(const void* qkv, void* out, int32_t images, int3
 /* The same op on the tcgen05 tensor cores (csrc/attention_tc.cu): tokens == 257 (224 px images). */
 int32_t vlaser_op_vit_attention_tc(const void* qkv, void* out, int32_t images, int32_t tokens, int32_t heads, float scale,
                                    void* stream);
+
+/* Prefix-prefill attention on the tcgen05 tensor cores (csrc/attention_tc.cu; joint_model.py:631-656 restricted to the valid
+ * prefix): q bf16 [q_rows, n_heads*128] (packed rows, sample b at q_start[b] .. + q_len[b]), k / v cache bf16
+ * [n_kv_heads, kv_rows, 128] (sample b at kv_start[b]), out like q. Bidirectional over the q_len[b] <= 256 tokens of a
+ * sample; longer samples are left untouched (the generic kernel takes them). */
+int32_t vlaser_op_prefill_attention_tc(const void* q, const void* k_cache, const void* v_cache, void* out, const int32_t* q_start,
+                                       const int32_t* q_len, const int32_t* kv_start, int32_t q_rows, int32_t n_heads,
+                                       int32_t n_kv_heads, int64_t kv_rows, int32_t batch, float scale, void* stream);
 
 int32_t vlaser_op_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, int32_t rows,
                             int32_t width, float eps, int32_t shuffle_grid, int32_t shuffle_channels, void* stream);

@@ -94,6 +94,16 @@ def vit_attention(qkv, images, tokens, heads, scale, tc=False):
     return out
 
 
+def prefill_attention_tc(q, k_cache, v_cache, q_start, q_len, kv_start, n_heads, n_kv_heads, scale):
+    """q bf16 [rows, n_heads*128], caches bf16 [n_kv_heads, kv_rows, 128] -> out like q (tcgen05 prefill kernel)."""
+    lib = _lib.load()
+    out = torch.zeros_like(q)
+    _lib.check(lib.vlaser_op_prefill_attention_tc(_p(q), _p(k_cache), _p(v_cache), _p(out), _p(q_start), _p(q_len), _p(kv_start),
+                                                  q.shape[0], n_heads, n_kv_heads, k_cache.shape[1], q_len.numel(), scale,
+                                                  _stream()), "op_prefill_attention_tc")
+    return out
+
+
 def layernorm(x, gamma, beta, eps, shuffle_grid=0, shuffle_channels=0, rows=None, width=None):
     lib = _lib.load()
     rows = x.shape[0] if rows is None else rows

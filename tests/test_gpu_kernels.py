@@ -304,6 +304,40 @@ def test_vit_attention_tcgen05(B, heads):
     assert torch.equal(out, ops.vit_attention(qkv, B, N, heads, hd ** -0.5, tc=True)), "repeat call differs"
 
 
+@pytest.mark.parametrize("nkv,group,lens", [(2, 6, [85, 1, 130, 256, 87, 21, 22, 300]), (4, 7, [60, 200]), (1, 1, [256, 33]),
+                                            (2, 6, [87, 64, 100, 41] * 20)])
+def test_prefill_attention_tcgen05(nkv, group, lens):
+    """tcgen05 prefill kernel: GQA-packed query tiles, ragged valid lengths from device memory (1 .. 256 tokens; the
+    300-token sample is left untouched for the generic kernel), several items per CTA when there are more than SMs."""
+    hd, nq = 128, nkv * group
+    g = torch.Generator().manual_seed(len(lens))
+    B = len(lens)
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    kvoff = [cu[b] + 5 * b for b in range(B)]          # KV rows of a sample: its tokens + room for others (as the engine)
+    rows, kv_rows = cu[-1], cu[-1] + 5 * B + 8
+    q = (torch.randn(rows, nq * hd, generator=g) * 1.5).bfloat16().to(DEV)
+    kc = torch.randn(nkv, kv_rows, hd, generator=g).bfloat16().to(DEV)
+    vc = torch.randn(nkv, kv_rows, hd, generator=g).bfloat16().to(DEV)
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=DEV)
+    out = ops.prefill_attention_tc(q, kc, vc, i32(cu[:-1]), i32(lens), i32(kvoff), nq, nkv, hd ** -0.5)
+    worst = 0.0
+    for b, n in enumerate(lens):
+        got = out[cu[b]: cu[b] + n].float().view(n, nq, hd)
+        if n > 256:
+            assert torch.all(got == 0), "samples beyond 256 tokens belong to the generic kernel"
+            continue
+        qq = q[cu[b]: cu[b] + n].float().view(n, nq, hd)
+        for h in range(nq):
+            kv = h // group
+            ref = _attn_ref(qq[:, h], kc[kv, kvoff[b]: kvoff[b] + n].float(), vc[kv, kvoff[b]: kvoff[b] + n].float(), hd ** -0.5, n)
+            worst = max(worst, ops.rel_err(got[:, h], ref))
+    print(f"prefill_attention_tcgen05 nkv={nkv} group={group}: worst head rel={worst:.2e}")
+    assert worst < 1e-2
+    assert torch.equal(out, ops.prefill_attention_tc(q, kc, vc, i32(cu[:-1]), i32(lens), i32(kvoff), nq, nkv, hd ** -0.5))
+
+
 def test_attention_prefill_and_denoise():
     """GQA 6:1, ragged lengths, proprio extra row (prefill) then H action queries (denoise)."""
     B, nkv, group, hd, H = 3, 2, 6, 128, 4

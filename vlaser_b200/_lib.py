@@ -65,7 +65,7 @@ EXPORTS = [
     "vlaser_last_launch_count", "vlaser_flops_per_call", "vlaser_profile_read", "vlaser_op_gemm", "vlaser_op_attention",
     "vlaser_op_layernorm", "vlaser_op_rmsnorm", "vlaser_op_pixel_shuffle", "vlaser_op_im2col", "vlaser_op_euler_step",
     "vlaser_op_vit_attention", "vlaser_profile_read_classes", "vlaser_op_stage_frames", "vlaser_op_postprocess_actions",
-    "vlaser_op_splitk_reduce", "vlaser_op_vit_attention_tc", "vlaser_op_normalize",
+    "vlaser_op_splitk_reduce", "vlaser_op_vit_attention_tc", "vlaser_op_normalize", "vlaser_op_prefill_attention_tc",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -132,6 +132,8 @@ def load() -> C.CDLL:
     lib.vlaser_op_stage_frames.restype = i32
     lib.vlaser_op_postprocess_actions.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp]
     lib.vlaser_op_postprocess_actions.restype = i32
+    lib.vlaser_op_prefill_attention_tc.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, f32, vp]
+    lib.vlaser_op_prefill_attention_tc.restype = i32
     lib.vlaser_op_normalize.argtypes = [vp, i32, vp, i32, i64, i32, i32, i32, vp, vp, vp]
     lib.vlaser_op_normalize.restype = i32
     _lib = lib

@@ -277,10 +277,9 @@ vit_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 template <int HD>
 int launch_hd(const AttnParams& p, cudaStream_t stream) {
   constexpr int SMEM = (ATT_BM + 4 * ATT_BN) * HD * 2;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;  // devices this kernel's attributes were set on
+  if (vl_first_on_device(attr_devs)) {
     VL_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
   }
   const int rows_max = p.group * p.max_q_len;
   dim3 grid((rows_max + ATT_BM - 1) / ATT_BM, p.n_kv_heads, p.batch);
@@ -297,12 +296,11 @@ int vit_attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int image
   VL_CHECK(images > 0 && images <= 65535 && heads > 0, "vit_attention: bad grid");
   const int NR = (tokens + 15) & ~15;
   const int smem = 3 * NR * 128 + NR * 4 + (4 * 64 + 16) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;  // devices this kernel's attributes were set on
+  if (vl_first_on_device(attr_devs)) {
     const int max_nr = (VA_MAX_N + 15) & ~15;
     VL_CUDA_CHECK(cudaFuncSetAttribute(vit_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        3 * max_nr * 128 + max_nr * 4 + (4 * 64 + 16) * 4));
-    attr_set = true;
   }
   const int qsplit = (heads * images * 2 <= gemm_num_sms() && tokens > 128) ? 2 : 1;
   VL_CUDA_CHECK(launch_kernel(vit_attention_kernel, dim3(heads, images, qsplit), dim3(VA_THREADS), smem, stream, qkv, out, tokens,

@@ -40,6 +40,7 @@ struct AttnParams {
   // by kernels that completed long before the previous launch, so the first K/V block may be fetched BEFORE the
   // programmatic-dependent-launch wait and overlaps the tail of the q|k|v projection that produces the new rows
   int stable_prefix = 0;
+  int min_kv_len = 0;   // samples with fewer kv rows are skipped (they were handled by the tcgen05 prefill kernel)
   long long* trace = nullptr;  // optional timeline record of this launch (common.cuh trace_stamp)
 };
 
@@ -55,5 +56,15 @@ int vit_attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int image
 int vit_attention_tc_launch(const CUtensorMap& tmQKV, const CUtensorMap& tmOut, const __nv_bfloat16* qkv,
                             __nv_bfloat16* out, int images, int tokens, int heads, float scale, cudaStream_t stream,
                             long long* trace = nullptr);
+
+// Prefix-prefill attention (head_dim 128, GQA-packed query tiles, L <= 256 valid tokens per sample read from device memory)
+// on the tcgen05 tensor cores: attention_tc.cu. tmQ: make_tmap_q3d map of the q buffer; tmK / tmV: make_tmap_bf16 maps of
+// the whole K / V cache viewed as [layers * kv_heads * kv_rows, 128] with 32-row boxes; kv_layer_row0 = layer * kv_heads *
+// kv_rows. Samples with L > 256 are skipped (AttnParams::min_kv_len of the generic kernel takes them).
+int prefill_attention_tc_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const int* q_start,
+                                const int* q_len, const int* kv_start, __nv_bfloat16* out, long long out_row_stride,
+                                long long kv_layer_row0, long long kv_rows, int batch, int n_kv_heads, int group, float scale,
+                                cudaStream_t stream, long long* trace = nullptr);
+int make_tmap_q3d(CUtensorMap* out, const void* ptr, uint64_t rows, int n_heads, int group);
 
 }  // namespace vlaser

@@ -39,7 +39,7 @@ __device__ __forceinline__ void attention_tile(const AttnParams& p, int b, int k
   const int group = p.group;
   const int rows_total = group * (q_len + (has_extra ? 1 : 0));
   const int r0 = qb * ATT_BM;
-  if (r0 >= rows_total) return;  // (exits without dep_wait: nothing was read)
+  if (r0 >= rows_total || kv_len < p.min_kv_len) return;  // (exits without dep_wait: nothing was read)
   const bool cta_has_extra = has_extra && (r0 + ATT_BM > group * q_len);
   const int kv_hi = kv_len + (cta_has_extra ? 1 : 0);
   const int n_blocks = (kv_hi + ATT_BN - 1) / ATT_BN;

@@ -19,8 +19,26 @@
 #include "attention.cuh"
 #include "gemm.cuh"  // gemm_num_sms(), make_tmap_bf16
 
+#include <mutex>
+
 namespace vlaser {
 namespace {
+
+typedef CUresult (*PFN_encodeTiled_tc)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled_tc get_encode_fn_tc() {
+  static PFN_encodeTiled_tc fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled_tc>(q);
+  });
+  return fn;
+}
 
 constexpr int VT_THREADS = 448;
 constexpr int VT_HD = 64;
@@ -221,19 +239,24 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       // ---- pass 2: p = exp2(s * sl2 - moff), row sum, bf16 pack written back over the scores
       float sum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-        uint32_t r0[32];
+      for (int c = 0; c < 8; c += 2) {  // two chunks per TMEM round trip (~0.3 us each)
+        uint32_t r0[32], r1[32];
         tmem_ld_32x32(taddr + c * 32, r0);
+        tmem_ld_32x32(taddr + c * 32 + 32, r1);
         tmem_ld_wait();
-        uint32_t pk[16];
+        uint32_t pk0[16], pk1[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float p0 = ex2_approx(fmaf(__uint_as_float(r0[2 * j]), sl2, -moff));
           const float p1 = ex2_approx(fmaf(__uint_as_float(r0[2 * j + 1]), sl2, -moff));
-          sum += p0 + p1;
-          pk[j] = pack_bf16(p0, p1);
+          const float p2 = ex2_approx(fmaf(__uint_as_float(r1[2 * j]), sl2, -moff));
+          const float p3 = ex2_approx(fmaf(__uint_as_float(r1[2 * j + 1]), sl2, -moff));
+          sum += (p0 + p1) + (p2 + p3);
+          pk0[j] = pack_bf16(p0, p1);
+          pk1[j] = pack_bf16(p2, p3);
         }
-        tmem_st_32x16(taddr + c * 16, pk);
+        tmem_st_32x16(taddr + c * 16, pk0);
+        tmem_st_32x16(taddr + c * 16 + 16, pk1);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -341,6 +364,348 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   if (warp == 2) trace_stamp(tr, 6);
 }
 
+
+// ================================================================================================================
+// Prefix-prefill attention of the LLM mixture on the tensor cores (joint_model.py:631-656 over the valid prefix of every
+// sample; eager_attention_forward + repeat_kv): head_dim 128, GQA (the `group` query heads of a kv head are packed into
+// the query tile: row = (token, head-in-group), so K / V of the kv head are loaded once), bidirectional over the L valid
+// tokens of the sample, L <= 256 on this path (L comes from device memory; longer prefixes are left to the generic
+// kernel, which is launched behind this one and skips the short ones).
+// One CTA walks (sample, kv head) items; an item is ceil(L / TOK) query tiles of TOK = 128 / group tokens (126 rows at
+// group 6) against the same L keys:
+//   warp 0       TMA producer: K and V of the item as 32-row boxes of the KV cache (two 64-dim halves each, 128B swizzle),
+//                then the query tiles through a 3-D box {64 dims, group heads, TOK tokens} of the q buffer, 2-deep ring
+//   warp 1       MMA issuer: S = Q K^T (M 128, N = L rounded to 32, K 128 = 8 k-steps), O = P V (P from TMEM, V as MN-major
+//                operand, two 64-dim halves per k-step)
+//   warps 2..5   softmax / epilogue group of the even tiles, warps 6..9 of the odd tiles: one thread per query row; S, P
+//                (bf16, over S) and O (columns 128..255 of the slot) live in a 256-column TMEM slot per group; O leaves
+//                through a transposition tile in the (dead) Q slot and row-contiguous 256-byte global stores
+// ================================================================================================================
+constexpr int PT_THREADS = 320;
+constexpr int PT_KMAX = 256;                         // keys on this path
+constexpr int PT_HALF_BYTES = PT_KMAX * 128;         // one 64-dim half of K or V: [256 rows][128 B]
+constexpr int PT_Q_BYTES = 2 * VT_TILE_BYTES;        // one query tile: two 64-dim halves of [128 rows][128 B]
+constexpr int PT_SMEM = 4 * PT_HALF_BYTES + 2 * PT_Q_BYTES + 1024 + 256;
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+struct PrefillTcParams {
+  const int* q_start;    // [B] first packed row of the sample
+  const int* q_len;      // [B] valid tokens L
+  const int* kv_start;   // [B] first KV-cache row of the sample
+  __nv_bfloat16* out;    // same addressing as q: row r, head h at out + r * out_row_stride + h * 128
+  long long out_row_stride;
+  long long kv_layer_row0;  // row offset of this layer's kv head 0 in the [layers * kv_heads * kv_rows, 128] cache view
+  long long kv_rows;        // rows per kv head
+  int batch, n_kv_heads, group;
+  int tsplit;            // CTAs that share the query tiles of one (sample, kv head): CTA `sp` takes tiles sp, sp + tsplit, ...
+  float scale;
+  long long* trace;
+};
+
+__global__ void __launch_bounds__(PT_THREADS, 1)
+prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                            const __grid_constant__ CUtensorMap tmV, const PrefillTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Ks = smem;                          // [2 halves][256][128 B]
+  uint8_t* Vs = smem + 2 * PT_HALF_BYTES;      // [2 halves][256][128 B]
+  uint8_t* Qs = smem + 4 * PT_HALF_BYTES;      // [2 slots][2 halves][128][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Qs + 2 * PT_Q_BYTES);
+  uint64_t* kv_full = bars;        // [1]
+  uint64_t* kv_empty = bars + 1;   // [1]
+  uint64_t* q_full = bars + 2;     // [2]
+  uint64_t* q_empty = bars + 4;    // [2]
+  uint64_t* s_full = bars + 6;     // [2]
+  uint64_t* p_full = bars + 8;     // [2]
+  uint64_t* o_full = bars + 10;    // [2]
+  uint64_t* t_empty = bars + 12;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* tr = (blockIdx.x == 0 && lane == 0) ? p.trace : nullptr;
+  if (warp == 0 && lane == 0) {
+    trace_stamp(tr, 0);
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&t_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();  // q and the K / V rows of this layer are complete (and the plan, from which L is read)
+  if (warp == 0) trace_stamp(tr, 1);
+
+  const int group = p.group, TOK = 128 / group, rows_tile = TOK * group;
+  const int tsplit = p.tsplit;
+  const int items = p.batch * p.n_kv_heads * tsplit;
+  const float sl2 = p.scale * 1.4426950408889634f;
+  // item -> (sample b, kv head g, tile phase sp); tiles of the item: sp, sp + tsplit, ... (count below)
+#define PT_ITEM(item)                                                       \
+  const int sp = (item) % tsplit, bg = (item) / tsplit;                     \
+  const int b = bg / p.n_kv_heads, g = bg - b * p.n_kv_heads;               \
+  const int L = p.q_len[b];                                                 \
+  (void)g;                                                                  \
+  const int all_tiles = (L + TOK - 1) / TOK;                                \
+  const int n_tiles = all_tiles > sp ? (all_tiles - sp + tsplit - 1) / tsplit : 0; \
+  if (L <= 0 || L > PT_KMAX || n_tiles == 0) continue; /* empty, or left to the generic kernel */
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int ic = 0, tcn = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        PT_ITEM(item)
+        const int nblk = (L + 31) >> 5;
+        const int krow = (int)(p.kv_layer_row0 + (long long)g * p.kv_rows) + p.kv_start[b];
+        mbar_wait(kv_empty, (ic & 1) ^ 1);
+        mbar_arrive_expect_tx(kv_full, (uint32_t)(4 * nblk * 4096));
+        for (int j = 0; j < nblk; ++j) {
+          tma_load_2d(Ks + j * 4096, &tmK, kv_full, 0, krow + j * 32);
+          tma_load_2d(Ks + PT_HALF_BYTES + j * 4096, &tmK, kv_full, 64, krow + j * 32);
+        }
+        for (int j = 0; j < nblk; ++j) {
+          tma_load_2d(Vs + j * 4096, &tmV, kv_full, 0, krow + j * 32);
+          tma_load_2d(Vs + PT_HALF_BYTES + j * 4096, &tmV, kv_full, 64, krow + j * 32);
+        }
+        ++ic;
+        const int q0 = p.q_start[b];
+        for (int ti = 0; ti < n_tiles; ++ti, ++tcn) {
+          const int t = sp + ti * tsplit;
+          const int slot = tcn & 1;
+          mbar_wait(&q_empty[slot], ((tcn >> 1) & 1) ^ 1);
+          uint8_t* qd = Qs + slot * PT_Q_BYTES;
+          mbar_arrive_expect_tx(&q_full[slot], (uint32_t)(2 * rows_tile * 128));
+          tma_load_3d(qd, &tmQ, &q_full[slot], 0, g * group, q0 + t * TOK);
+          tma_load_3d(qd + VT_TILE_BYTES, &tmQ, &q_full[slot], 64, g * group, q0 + t * TOK);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64) | (1u << 16);  // B (= a 64-dim half of V) is MN-major
+      const uint64_t dk0 = make_umma_desc_sw128(smem_u32(Ks)), dk1 = make_umma_desc_sw128(smem_u32(Ks + PT_HALF_BYTES));
+      const uint64_t dv0 = make_umma_desc_sw128(smem_u32(Vs)), dv1 = make_umma_desc_sw128(smem_u32(Vs + PT_HALF_BYTES));
+      int ic = 0, tcn = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        PT_ITEM(item)
+        const int Lp = (L + 31) & ~31;
+        const uint32_t idesc_s = make_idesc_bf16(128, Lp);
+        mbar_wait(kv_full, ic & 1);
+        tc_fence_after();
+        auto issue_s = [&](int tc_i) {
+          const int slot = tc_i & 1;
+          const uint32_t ph = (tc_i >> 1) & 1;
+          mbar_wait(&q_full[slot], ph);
+          mbar_wait(&t_empty[slot], ph ^ 1);
+          tc_fence_after();
+          const uint32_t qa = smem_u32(Qs + slot * PT_Q_BYTES);
+          const uint64_t dq0 = make_umma_desc_sw128(qa), dq1 = make_umma_desc_sw128(qa + VT_TILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + slot * 256, dq0 + 2 * ks, dk0 + 2 * ks, idesc_s, ks > 0);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + slot * 256, dq1 + 2 * ks, dk1 + 2 * ks, idesc_s, 1u);
+          umma_commit(&s_full[slot]);
+        };
+        issue_s(tcn);
+        for (int t = 0; t < n_tiles; ++t) {
+          const int tc_i = tcn + t, slot = tc_i & 1;
+          if (t + 1 < n_tiles) issue_s(tc_i + 1);  // the other group's scores while this group's softmax runs
+          mbar_wait(&p_full[slot], (tc_i >> 1) & 1);
+          tc_fence_after();
+          const uint32_t tb = tmem_base + slot * 256;
+          for (int ks = 0; ks < Lp / 16; ++ks) {
+            umma_bf16_ts(tb + 128, tb + 8 * ks, dv0 + 128 * ks, idesc_o, ks > 0);
+            umma_bf16_ts(tb + 192, tb + 8 * ks, dv1 + 128 * ks, idesc_o, ks > 0);
+          }
+          umma_commit(&o_full[slot]);
+        }
+        umma_commit(kv_empty);  // every MMA that reads this item's K / V has retired
+        tcn += n_tiles;
+        ++ic;
+      }
+    }
+  } else {
+    // ================================ softmax / epilogue groups ================================
+    const int grp = (warp - 2) >> 2;             // tiles with (tile counter & 1) == grp
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;         // packed query row within the tile: token row / group, head row % group
+    const int gtid = threadIdx.x - (2 + 4 * grp) * 32;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + grp * 256;
+    uint8_t* stage = Qs + grp * PT_Q_BYTES;      // [128 rows][256 B], 16-byte chunks XOR-swizzled with the row
+    int tcn = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      PT_ITEM(item)
+      const int Lp = (L + 31) & ~31;
+      const int q0 = p.q_start[b];
+      for (int ti = 0; ti < n_tiles; ++ti) {
+        const int tc_i = tcn + ti;
+        if ((tc_i & 1) != grp) continue;
+        const int t = sp + ti * tsplit;
+        const uint32_t ph = (tc_i >> 1) & 1;
+        const int tok = t * TOK + row / group, hh = row % group;
+        const bool row_ok = row < rows_tile && tok < L;
+        mbar_wait(&s_full[grp], ph);
+        tc_fence_after();
+        if (tc_i == 0 && warp == 2) trace_stamp(tr, 4);
+        float sum = 0.f;
+        if (Lp <= 96) {
+          // up to 3 chunks: the whole score row in registers with ONE TMEM round trip (a tcgen05.ld -> wait is ~0.3 us;
+          // the prefixes of this path are ~90 tokens)
+          uint32_t sreg[3][32];
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            if (c * 32 < Lp) tmem_ld_32x32(taddr + c * 32, sreg[c]);
+          tmem_ld_wait();
+          float mx = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            if (c * 32 < Lp) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c * 32 + j < L) mx = fmaxf(mx, __uint_as_float(sreg[c][j]));
+            }
+          const float moff = mx * sl2;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            if (c * 32 < Lp) {
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float p0 = ex2_approx(fmaf(__uint_as_float(sreg[c][2 * j]), sl2, -moff));
+                float p1 = ex2_approx(fmaf(__uint_as_float(sreg[c][2 * j + 1]), sl2, -moff));
+                if (c * 32 + 2 * j >= L) p0 = 0.f;
+                if (c * 32 + 2 * j + 1 >= L) p1 = 0.f;
+                sum += p0 + p1;
+                pk[j] = pack_bf16(p0, p1);
+              }
+              tmem_st_32x16(taddr + c * 16, pk);
+            }
+        } else {
+          // ---- pass 1: row max over the live keys (two chunks per round trip)
+          float mx = -INFINITY;
+#pragma unroll 1
+          for (int c = 0; c < Lp; c += 64) {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32(taddr + c, r0);
+            tmem_ld_32x32(taddr + c + 32, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (c + j < L) mx = fmaxf(mx, __uint_as_float(r0[j]));
+              if (c + 32 + j < L) mx = fmaxf(mx, __uint_as_float(r1[j]));
+            }
+          }
+          const float moff = mx * sl2;
+          // ---- pass 2: probabilities (0 beyond the live keys), row sum, bf16 pack over the scores
+#pragma unroll 1
+          for (int c = 0; c < Lp; c += 64) {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32(taddr + c, r0);
+            tmem_ld_32x32(taddr + c + 32, r1);
+            tmem_ld_wait();
+            uint32_t pk0[16], pk1[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float p0 = ex2_approx(fmaf(__uint_as_float(r0[2 * j]), sl2, -moff));
+              float p1 = ex2_approx(fmaf(__uint_as_float(r0[2 * j + 1]), sl2, -moff));
+              float p2 = ex2_approx(fmaf(__uint_as_float(r1[2 * j]), sl2, -moff));
+              float p3 = ex2_approx(fmaf(__uint_as_float(r1[2 * j + 1]), sl2, -moff));
+              if (c + 2 * j >= L) p0 = 0.f;
+              if (c + 2 * j + 1 >= L) p1 = 0.f;
+              if (c + 32 + 2 * j >= L) p2 = 0.f;
+              if (c + 32 + 2 * j + 1 >= L) p3 = 0.f;
+              sum += (p0 + p1) + (p2 + p3);
+              pk0[j] = pack_bf16(p0, p1);
+              pk1[j] = pack_bf16(p2, p3);
+            }
+            tmem_st_32x16(taddr + (c >> 1), pk0);
+            tmem_st_32x16(taddr + (c >> 1) + 16, pk1);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[grp]);
+        const float inv = 1.f / sum;
+        mbar_wait(&o_full[grp], ph);
+        tc_fence_after();
+        // ---- O / sum -> bf16 -> this row of the transposition tile (the query slot is dead: S is complete)
+#pragma unroll 1
+        for (int c0 = 0; c0 < 4; c0 += 2) {
+          uint32_t o[2][32];
+          tmem_ld_32x32(taddr + 128 + c0 * 32, o[0]);
+          tmem_ld_32x32(taddr + 128 + c0 * 32 + 32, o[1]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 u;
+              u.x = pack_bf16(__uint_as_float(o[cc][8 * q]) * inv, __uint_as_float(o[cc][8 * q + 1]) * inv);
+              u.y = pack_bf16(__uint_as_float(o[cc][8 * q + 2]) * inv, __uint_as_float(o[cc][8 * q + 3]) * inv);
+              u.z = pack_bf16(__uint_as_float(o[cc][8 * q + 4]) * inv, __uint_as_float(o[cc][8 * q + 5]) * inv);
+              u.w = pack_bf16(__uint_as_float(o[cc][8 * q + 6]) * inv, __uint_as_float(o[cc][8 * q + 7]) * inv);
+              const int ch = (c0 + cc) * 4 + q;  // 16-byte chunk of the 256-byte row
+              *reinterpret_cast<uint4*>(stage + row * 256 + ((ch ^ (row & 15)) << 4)) = u;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[grp]);  // the slot's TMEM columns may take the group's next scores
+        // ---- row-contiguous stores: 16 lanes x 16 B = one 256-byte row, two rows per instruction
+        const unsigned ok_mask = __ballot_sync(0xffffffffu, row_ok);
+#pragma unroll 1
+        for (int it = 0; it < 16; ++it) {
+          const int rl = it * 2 + (lane >> 4), ch = lane & 15;     // row within this warp's 32 rows
+          const int r = quarter * 32 + rl;
+          if ((ok_mask >> rl) & 1u) {
+            const uint4 u = *reinterpret_cast<const uint4*>(stage + r * 256 + ((ch ^ (r & 15)) << 4));
+            const int tk = t * TOK + r / group, h2 = r % group;
+            *reinterpret_cast<uint4*>(p.out + (size_t)(q0 + tk) * p.out_row_stride + (size_t)(g * group + h2) * 128 + ch * 8) = u;
+          }
+        }
+        (void)tok;
+        (void)hh;
+        named_bar_sync(1 + grp, 128);  // every warp of the group has read its rows out of the slot
+        if (gtid == 0) mbar_arrive(&q_empty[grp]);
+      }
+      tcn += n_tiles;
+    }
+    if (grp == 0 && warp == 2) trace_stamp(tr, 5);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 2) trace_stamp(tr, 6);
+}
+
 }  // namespace
 
 int vit_attention_tc_launch(const CUtensorMap& tmQKV, const CUtensorMap& tmOut, const __nv_bfloat16* qkv,
@@ -348,14 +713,53 @@ int vit_attention_tc_launch(const CUtensorMap& tmQKV, const CUtensorMap& tmOut, 
                             long long* trace) {
   VL_CHECK(tokens == 257, "vit_attention_tc: 257 tokens per image (224 px)");
   VL_CHECK(images > 0 && heads > 0, "vit_attention_tc: empty problem");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;  // devices this kernel's attributes were set on
+  if (vl_first_on_device(attr_devs)) {
     VL_CUDA_CHECK(cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM));
-    attr_set = true;
   }
   const int grid = std::min(images * heads, gemm_num_sms());
   VL_CUDA_CHECK(launch_kernel(vit_attention_tc_kernel, dim3(grid), dim3(VT_THREADS), VT_SMEM, stream, tmQKV, tmOut, qkv, out,
                               images, heads, scale, trace));
+  return 0;
+}
+
+int prefill_attention_tc_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const int* q_start,
+                                const int* q_len, const int* kv_start, __nv_bfloat16* out, long long out_row_stride,
+                                long long kv_layer_row0, long long kv_rows, int batch, int n_kv_heads, int group, float scale,
+                                cudaStream_t stream, long long* trace) {
+  VL_CHECK(batch > 0 && n_kv_heads > 0 && group >= 1 && group <= 8, "prefill_attention_tc: bad shape");
+  static unsigned long long attr_devs = 0;  // devices this kernel's attributes were set on
+  if (vl_first_on_device(attr_devs)) {
+    VL_CUDA_CHECK(cudaFuncSetAttribute(prefill_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
+  }
+  PrefillTcParams p;
+  p.q_start = q_start, p.q_len = q_len, p.kv_start = kv_start;
+  p.out = out, p.out_row_stride = out_row_stride;
+  p.kv_layer_row0 = kv_layer_row0, p.kv_rows = kv_rows;
+  p.batch = batch, p.n_kv_heads = n_kv_heads, p.group = group, p.scale = scale, p.trace = trace;
+  // few (sample, kv head) pairs: their query tiles are shared out between up to 8 CTAs each (K / V are then loaded per CTA)
+  const int pairs = batch * n_kv_heads;
+  p.tsplit = std::max(1, std::min(8, (2 * gemm_num_sms()) / std::max(pairs, 1)));
+  const int grid = std::min(pairs * p.tsplit, gemm_num_sms());
+  VL_CUDA_CHECK(launch_kernel(prefill_attention_tc_kernel, dim3(grid), dim3(PT_THREADS), PT_SMEM, stream, tmQ, tmK, tmV, p));
+  return 0;
+}
+
+// q [rows, n_heads, 128] bf16 as a 3-D map with boxes {64 dims, group heads, 128 / group tokens}, 128B swizzle
+int make_tmap_q3d(CUtensorMap* out, const void* ptr, uint64_t rows, int n_heads, int group) {
+  PFN_encodeTiled_tc fn = get_encode_fn_tc();
+  VL_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {128, (cuuint64_t)n_heads, rows};
+  cuuint64_t strides[2] = {256, (cuuint64_t)n_heads * 256};
+  cuuint32_t box[3] = {64, (cuuint32_t)group, (cuuint32_t)(128 / group)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (3-D q map) failed with CUresult " + std::to_string((int)r));
+    return -1;
+  }
   return 0;
 }
 

@@ -30,6 +30,19 @@ void set_last_error(const std::string& msg);
     }                                                                                         \
   } while (0)
 
+// ---------------------------------------------------------------- per-device one-time setup
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: a flag per kernel AND device, so that a second handle on
+// another GPU of the same process gets its attributes too. `VL_ONCE_PER_DEVICE(flags)` is true the first time it is
+// evaluated on the current device (flags: a static std::atomic<unsigned long long>, one bit per device ordinal < 64).
+inline bool vl_first_on_device(unsigned long long& flags) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (flags & bit) return false;
+  flags |= bit;
+  return true;
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch (PDL)
 // Every kernel of the policy call is launched with programmatic stream serialization: its CTAs may start
 // (barrier init, TMEM alloc, weight prefetch) while the previous kernel drains. `pdl_wait()` blocks until the

@@ -120,6 +120,7 @@ struct Engine {
   Act cols, vn, vattn, vmlp, ps, pa, xn, ao, act, xpn, aop, actp, xan, aoa, acta, e1, h2;
   float *vx = nullptr, *xv = nullptr, *xp = nullptr, *xa = nullptr, *action = nullptr;
   CUtensorMap vx_otm, xv_otm, vqkv_otm, xp_otm, xa_otm;
+  CUtensorMap q3d_tm, kc_tm, vc_tm;  // tcgen05 prefill attention: 3-D map of the LLM q buffer, 32-row maps of the K / V caches
   CUtensorMap vqkv_tm;  // load map (128-row boxes) of the ViT q|k|v buffer for the tcgen05 attention kernel  // output maps of the fp32 residual streams / ViT qkv buffer
   bf16 *vqkv = nullptr, *q = nullptr, *qp = nullptr, *qa = nullptr;
   bf16 *kc = nullptr, *vc = nullptr;  // [layers][kv_heads][kv_rows][128]
@@ -180,6 +181,7 @@ struct Engine {
   size_t trace_idx = 0;
   std::string trace_names;
   static constexpr size_t TRACE_MAX = 8192;
+  int prefill_tc = 1;          // 1: prefix-prefill attention on the tcgen05 kernel (samples of <= 256 valid tokens; attention_tc.cu)
   int gelu_warps = 16;         // epilogue warps of the pair kernel's exact-GELU variant (16 | 8)
   int pair_bn128 = 1;          // 1: 256 x 128 pair tiles for the one-row-tile split-K projections (see Run::gemm)
   int den_chains = 1;          // sub-batch chains of the denoise steps (1 | 2), see Run::denoise_all
@@ -470,6 +472,11 @@ int engine_build(Engine& e) {
   const size_t kv_elems = (size_t)c.layers * c.n_kv_heads * e.kv_rows * 128;
   VL_TRY(e.alloc(&e.kc, kv_elems));
   VL_TRY(e.alloc(&e.vc, kv_elems));
+  if (c.n_heads / c.n_kv_heads <= 8) {
+    VL_TRY(make_tmap_q3d(&e.q3d_tm, e.q, (uint64_t)prow, c.n_heads, c.n_heads / c.n_kv_heads));
+    VL_TRY(make_tmap_bf16(&e.kc_tm, e.kc, (uint64_t)c.layers * c.n_kv_heads * e.kv_rows, 128, 32));
+    VL_TRY(make_tmap_bf16(&e.vc_tm, e.vc, (uint64_t)c.layers * c.n_kv_heads * e.kv_rows, 128, 32));
+  }
   // --- plan buffers
   PlanBuffers& pb = e.pb;
   VL_TRY(e.alloc(&pb.valid_len, e.Bc));
@@ -1180,9 +1187,19 @@ struct Run {
       ap.n_kv_heads = c.n_kv_heads;
       ap.batch = B;
       ap.scale = 0.08838834764831845f;  // 128^-0.5
-      ap.trace = tr("attention", li);
-      VL_TRY(attention_launch(ap, 128, st));
-      e.launches++;
+      const bool tc_ok = e.prefill_tc && ap.q2 == nullptr && !e.simt && ap.group <= 8;
+      if (tc_ok) {
+        VL_TRY(prefill_attention_tc_launch(e.q3d_tm, e.kc_tm, e.vc_tm, e.pb.cu, e.pb.valid_len, e.pb.kvoff, e.ao.p, e.qdim,
+                                           (long long)li * c.n_kv_heads * e.kv_rows, e.kv_rows, B, c.n_kv_heads, ap.group,
+                                           ap.scale, st, tr("attention_tc", li)));
+        e.launches++;
+        ap.min_kv_len = 257;  // longer prefixes: generic kernel (every CTA of a short sample exits at once)
+      }
+      if (!tc_ok || e.S > 256) {
+        ap.trace = tr("attention", li);
+        VL_TRY(attention_launch(ap, 128, st));
+        e.launches++;
+      }
       VL_TRY(block_post(e.llm[li], e.xv, e.xn, e.ao, e.act, cap, e.pb.m_tot, c.hidden, e.mlp_p, 1, &e.xv_otm));
       if (mega() || side) continue;
       if (e.fuse_norm) VL_TRY(exp_post(li, e.xp, e.xpn, e.aop, e.actp, B, 0, false));
@@ -1480,7 +1497,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
@@ -1499,6 +1516,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
     else if (k == "den_chains") h->e.den_chains = (int)value;
     else if (k == "pair_bn128") h->e.pair_bn128 = (int)value;
     else if (k == "gelu_warps") h->e.gelu_warps = (int)value == 8 ? 8 : 16;
+    else if (k == "prefill_tc") h->e.prefill_tc = (int)value;
     else if (k == "exp_splits_o") h->e.xs_o = std::max(1, (int)value);
     else if (k == "exp_splits_down") h->e.xs_down = std::max(1, (int)value);
     else if (k == "pair_gemm") h->e.pair_gemm = (int)value;
@@ -1843,6 +1861,20 @@ int32_t vlaser_op_vit_attention_tc(const void* qkv, void* out, int32_t images, i
   VL_TRY(make_tmap_bf16(&to, out, (uint64_t)images * tokens, (uint64_t)heads * 64, 128));
   return vit_attention_tc_launch(tq, to, reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out),
                                  images, tokens, heads, scale, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t vlaser_op_prefill_attention_tc(const void* q, const void* k_cache, const void* v_cache, void* out, const int32_t* q_start,
+                                       const int32_t* q_len, const int32_t* kv_start, int32_t q_rows, int32_t n_heads,
+                                       int32_t n_kv_heads, int64_t kv_rows, int32_t batch, float scale, void* stream) {
+  VL_CHECK(q && k_cache && v_cache && out && q_start && q_len && kv_start, "null argument");
+  VL_CHECK(n_kv_heads > 0 && n_heads % n_kv_heads == 0, "prefill_attention_tc: bad head counts");
+  CUtensorMap tq, tk, tv;
+  VL_TRY(make_tmap_q3d(&tq, q, (uint64_t)q_rows, n_heads, n_heads / n_kv_heads));
+  VL_TRY(make_tmap_bf16(&tk, k_cache, (uint64_t)n_kv_heads * kv_rows, 128, 32));
+  VL_TRY(make_tmap_bf16(&tv, v_cache, (uint64_t)n_kv_heads * kv_rows, 128, 32));
+  return prefill_attention_tc_launch(tq, tk, tv, q_start, q_len, kv_start, reinterpret_cast<__nv_bfloat16*>(out),
+                                     (long long)n_heads * 128, 0, kv_rows, batch, n_kv_heads, n_heads / n_kv_heads, scale,
+                                     reinterpret_cast<cudaStream_t>(stream));
 }
 
 int32_t vlaser_op_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, int32_t rows,

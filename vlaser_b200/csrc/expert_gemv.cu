@@ -705,11 +705,15 @@ __global__ void __launch_bounds__(GV_THREADS, 1) expert_gemv_pass_kernel(const E
 
 template <int R>
 int launch_r(const ExpertPass& p, int grid, size_t smem, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;  // devices this kernel's attributes were set on
+  if (vl_first_on_device(attr_devs)) {
     VL_CUDA_CHECK(cudaFuncSetAttribute(expert_gemv_pass_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
+  // the kernel synchronises its CTAs through a spin barrier: every CTA of the grid has to be resident at once
+  int per_sm = 0;
+  VL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, expert_gemv_pass_kernel<R>, GV_THREADS, smem));
+  VL_CHECK(per_sm >= 1 && per_sm * gemm_num_sms() >= grid,
+           "expert gemv pass: the persistent grid does not fit on the device (use option expert_gemv = 0)");
   VL_CUDA_CHECK(launch_kernel(expert_gemv_pass_kernel<R>, dim3(grid), dim3(GV_THREADS), smem, stream, p));
   return 0;
 }

@@ -29,10 +29,13 @@ struct GemmCfg {
   static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages
-  static constexpr uint32_t EPI_STAGE_BYTES = EPI_WARPS * 4096;  // one 32-row x 128-byte transposition tile per epilogue warp
-  static constexpr uint32_t smem_bytes(int stages) {
-    return stages * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // the q|k|v epilogue transposes its unit through one 32-row x 128-byte tile per epilogue warp; other epilogues need none
+  static constexpr uint32_t epi_stage_bytes(int epi) { return epi == EPI_QKV_ROPE ? EPI_WARPS * 4096 : 0; }
+  static constexpr uint32_t smem_bytes(int stages, int epi) {
+    return stages * STAGE_BYTES + epi_stage_bytes(epi) + 1024 /*align slack*/ + 256 /*barriers*/;
   }
+  // ring depth: the q|k|v variant gives one stage to the transposition tiles (and leaves L1 some room: 198 KB of shared memory)
+  static constexpr int default_stages(int epi) { return epi == EPI_QKV_ROPE ? DEFAULT_STAGES - 1 : DEFAULT_STAGES; }
 };
 
 struct TileSched {
@@ -86,7 +89,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES;  // [EPI_WARPS][4096]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + Cfg::EPI_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + Cfg::epi_stage_bytes(EPI));
   uint64_t* full_bar = bars;                          // [MAX_STAGES]
   uint64_t* empty_bar = bars + MAX_STAGES;            // [MAX_STAGES]
   uint64_t* tfull_bar = bars + 2 * MAX_STAGES;        // [2]
@@ -261,8 +264,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // factors and KV-cache row are fetched while the mainloop is still running
       constexpr bool ROPE_PRE = EPI == EPI_QKV_ROPE && BLOCK_N == 128 && EPI_WARPS == 8;
       RopeOperands ro;
+      int rope_pos = 0;
       if constexpr (ROPE_PRE) {
-        rope_prefetch(ep, row, row_ok, n0 + half * 32, ro);
+        // the row's position id and KV-cache row are fetched while the mainloop runs; the 64 RoPE factors only once the
+        // accumulator is there, beside the TMEM loads (held across the wait they spill: 64 registers per thread)
+        if (row_ok) {
+          rope_pos = __ldg(ep.row_pos + row);
+          ro.kvrow = __ldg(ep.row_kvrow + row);
+        }
         if (ep.bias) {  // this unit's 64 bias values into the head of the warp's staging tile (cold in L2: a DRAM round trip)
           float* bias_s = reinterpret_cast<float*>(epi_stage + (warp - 2) * 4096);
           bias_s[lane] = __ldg(ep.bias + n0 + half * 32 + lane);
@@ -278,6 +287,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint32_t r0[32], r1[32];
           tmem_ld_32x32(taddr + half * 32, r0);
           tmem_ld_32x32(taddr + half * 32 + 64, r1);
+          const int col0 = n0 + half * 32;
+          rope_factors(ep, rope_pos, row_ok, col0, ro);
           tmem_ld_wait();
           float v[32], w[32];
 #pragma unroll
@@ -285,7 +296,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             v[j] = __uint_as_float(r0[j]) * rstd;
             w[j] = __uint_as_float(r1[j]) * rstd;
           }
-          const int col0 = n0 + half * 32;
           // Transpose the unit through this warp's 4 KB swizzled staging tile so that every store instruction writes
           // whole 64-byte runs (4 rows x 2 runs) instead of 32 scattered 16-byte pieces
           uint8_t* buf = epi_stage + (warp - 2) * 4096;
@@ -418,12 +428,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiParams& ep, const CUt
     // `ring` (last tile of this CTA: the operand ring is idle): every chunk gets its own 4 KB staging tile there, so the
     // U stores of the warp are issued back to back behind ONE proxy fence instead of each waiting for the TMA unit to
     // have drained the single staging tile -- the small-M projections, one tile per CTA, are paced by exactly that
-#pragma unroll 1
-    for (int c = half * U; c < (half + 1) * U; ++c) {
+    auto finish = [&](float (&v)[32], int c) -> bool {  // scale / bias / layer-scale one chunk; true: staged in the ring
       const int col0 = n0 + c * 32;
-      float v[32];
-      load_acc32(taddr + c * 32, v);
-      if (c == half * U) trace_stamp(tr, 8);
       scale_rows(v);
       if (ep.bias && first_split) add_vec32(v, ep.bias + col0);
       if (ep.scale) {
@@ -439,8 +445,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiParams& ep, const CUt
       }
       if (ring) {
         stage_row_f32(ring + (c - half * U) * 4096, lane, v);
-        trace_stamp(tr, 9);
-        continue;
+        return true;
       }
       uint8_t* b = acquire();
       stage_row_f32(b, lane, v);
@@ -451,6 +456,17 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiParams& ep, const CUt
         else tma_reduce_add_2d(tmC, b, col0, row0);
         bulk_commit();
       }
+      return false;
+    };
+    static_assert(U % 2 == 0, "residual TMA epilogue: chunks are drained in pairs");
+#pragma unroll 1
+    for (int c = half * U; c < (half + 1) * U; c += 2) {
+      float v0[32], v1[32];
+      load_acc32x2(taddr + c * 32, taddr + c * 32 + 32, v0, v1);
+      if (c == half * U) trace_stamp(tr, 8);
+      finish(v0, c);
+      finish(v1, c + 1);
+      trace_stamp(tr, 9);
     }
     if (ring) {
       fence_proxy_async();
@@ -476,8 +492,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiParams& ep, const CUt
 #pragma unroll 1
       for (int q = 0; q < 2; ++q) {
         float g[32], up[32];
-        load_acc32(taddr + u * 128 + q * 64, g);
-        load_acc32(taddr + u * 128 + q * 64 + 32, up);
+        load_acc32x2(taddr + u * 128 + q * 64, taddr + u * 128 + q * 64 + 32, g, up);
         scale_rows(g);
         scale_rows(up);
 #pragma unroll
@@ -877,27 +892,25 @@ template <int BLOCK_N, int EPI>
 int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDims d, const EpiParams& ep, int grid,
                cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
-  static bool attr_set = false;
+  static unsigned long long attr_devs = 0;  // devices this kernel's attributes were set on
   auto kern = gemm_tcgen05_kernel<BLOCK_N, EPI>;
-  if (!attr_set) {
+  if (vl_first_on_device(attr_devs)) {
     VL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)Cfg::smem_bytes(Cfg::DEFAULT_STAGES)));
-    attr_set = true;
+                                       (int)Cfg::smem_bytes(Cfg::default_stages(EPI), EPI)));
   }
-  if (d.stages <= 0 || d.stages > Cfg::DEFAULT_STAGES) d.stages = Cfg::DEFAULT_STAGES;
+  if (d.stages <= 0 || d.stages > Cfg::default_stages(EPI)) d.stages = Cfg::default_stages(EPI);
   if (d.stages < 2) d.stages = 2;
-  VL_CUDA_CHECK(launch_kernel(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::smem_bytes(d.stages), stream, tmA, tmB, d, ep));
+  VL_CUDA_CHECK(launch_kernel(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::smem_bytes(d.stages, EPI), stream, tmA, tmB, d, ep));
   return 0;
 }
 
 template <int EPI, int BN, int NW = pair_epi_warps<EPI>()>
 int launch_pair_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tc, const CUtensorMap& tp, const GemmDims& d,
                    const EpiParams& ep, cudaStream_t stream) {
-  static bool attr_set = false;
+  static unsigned long long attr_devs = 0;  // devices this kernel's attributes were set on
   auto kern = gemm_tcgen05_pair_kernel<EPI, NW, BN>;
-  if (!attr_set) {
+  if (vl_first_on_device(attr_devs)) {
     VL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes(NW)));
-    attr_set = true;
   }
   long long tiles = (long long)((d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (d.N / BN);
   if (EPI == EPI_RESID_F32 && d.max_splits > 1) {
@@ -942,14 +955,15 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap*
 }  // namespace
 
 int gemm_num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static int sms[64] = {0};  // per device ordinal
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = sms[dev & 63];
+  if (!n) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
   }
-  return sms;
+  return n;
 }
 
 int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {

@@ -88,6 +88,23 @@ __device__ __forceinline__ void rope_prefetch(const EpiParams& ep, int row, bool
     }
   }
 }
+// the cos / sin factors of a row whose position id is already known (see the tcgen05 kernel: issued beside the TMEM loads)
+__device__ __forceinline__ void rope_factors(const EpiParams& ep, int pos, bool row_ok, int col0, RopeOperands& ro) {
+  const int head = col0 >> 7, i0 = col0 & 127;
+  if (row_ok && head < ep.n_q_heads + ep.n_kv_heads) {
+    const float4* c4 = reinterpret_cast<const float4*>(ep.cos_tab + (size_t)pos * 64 + i0);
+    const float4* s4 = reinterpret_cast<const float4*>(ep.sin_tab + (size_t)pos * 64 + i0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 c = __ldg(c4 + i), s = __ldg(s4 + i);
+      ro.cs[4 * i] = c.x, ro.cs[4 * i + 1] = c.y, ro.cs[4 * i + 2] = c.z, ro.cs[4 * i + 3] = c.w;
+      ro.sn[4 * i] = s.x, ro.sn[4 * i + 1] = s.y, ro.sn[4 * i + 2] = s.z, ro.sn[4 * i + 3] = s.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) ro.cs[j] = 1.f, ro.sn[j] = 0.f;
+  }
+}
 // bias + rotation of one unit in registers
 // (bias_s: optional shared-memory copy of bias[col0..col0+31] | bias[col0+64..col0+95], fetched ahead of the accumulator)
 __device__ __forceinline__ void rope_rotate(const EpiParams& ep, int col0, float (&v)[32], float (&w)[32],
@@ -309,6 +326,19 @@ __device__ __forceinline__ void stage_row_bf16(uint8_t* buf, int lane, int j0, c
     u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
     u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
     *reinterpret_cast<uint4*>(buf + lane * 128 + (((j0 + j) ^ (lane & 7)) << 4)) = u;
+  }
+}
+// two 32-column chunks with ONE wait: a tcgen05.ld round trip is ~0.3 us (in-situ stamps, profiles/r02j), and a one-shot
+// epilogue is a chain of them
+__device__ __forceinline__ void load_acc32x2(uint32_t taddr0, uint32_t taddr1, float (&v0)[32], float (&v1)[32]) {
+  uint32_t r0[32], r1[32];
+  tmem_ld_32x32(taddr0, r0);
+  tmem_ld_32x32(taddr1, r1);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    v0[j] = __uint_as_float(r0[j]);
+    v1[j] = __uint_as_float(r1[j]);
   }
 }
 __device__ __forceinline__ void load_acc32(uint32_t taddr, float (&v)[32]) {
