@@ -205,6 +205,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     cfg = PRESETS[args.config]()
     Bg = args.batch_per_gpu
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit("--global-batch must be a multiple of the GPU count")
+        Bg = args.global_batch // world
     peaks = _peaks()
 
     # ---- weights (random-init, bf16). N=1 rank 0 builds them on the CPU so the cpu_baseline leg can share them.
@@ -416,9 +420,10 @@ def run_ours(args):
     d2h = Bg * cfg.horizon_steps * cfg.action_dim * es
     line = {
         "metric": "policy actions/s", "value": value, "unit": "actions/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.global_batch else "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD if args.config == "vlaser_2b_bridge" else args.config,
+        "config": {"workload": WORKLOAD if (args.config == "vlaser_2b_bridge" and Bg == 64) else f"{args.config}, {Bg} observations per GPU",
                    "batch_per_gpu": Bg, "global_batch": global_B, "parallelism": f"dp{world}",
                    "valid_len": f"{int(valid.min())}-{int(valid.max())} of {cfg.max_image_text_tokens} (var-len packed prefix)",
                    "obs_per_s": obs_per_s, "actions_per_obs": cfg.horizon_steps,
@@ -474,6 +479,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="vlaser_2b_bridge", choices=sorted(PRESETS))
     ap.add_argument("--batch-per-gpu", type=int, default=64)
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong-scaling form of BASELINE configs[2]: the global batch is split evenly over the GPUs "
+                         "(512 -> 256 / 128 / 64 per GPU at N = 2 / 4 / 8); overrides --batch-per-gpu")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--gpu-baseline", default="eager", choices=["none", "eager", "compile"],

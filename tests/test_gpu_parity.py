@@ -206,8 +206,8 @@ def _rows(inp, idx):
 
 
 @pytest.mark.skipif(os.environ.get("VLASER_SKIP_FULL", "0") == "1", reason="full-size parity skipped by env")
-@pytest.mark.parametrize("preset", ["vlaser_2b_bridge", "vlaser_2b_fractal"])
-def test_full_size_b64_default_schedule_vs_oracle(preset, capsys):
+@pytest.mark.parametrize("preset,B", [("vlaser_2b_bridge", 64), ("vlaser_2b_fractal", 64), ("vlaser_2b_bridge", 128)])
+def test_full_size_b64_default_schedule_vs_oracle(preset, B, capsys):
     """The benched configuration itself (BASELINE configs[1] / [2] shapes: full-size 2B, B = 64, every option at its
     default) against the fp32 oracle on rows spread over the batch: first / last row and one row of each 128-row tile
     of the action stream (rows 4b..4b+3). Inputs are rounded to bf16 first, so the fp32-I/O call, the bf16-I/O call
@@ -215,7 +215,7 @@ def test_full_size_b64_default_schedule_vs_oracle(preset, capsys):
     from vlaser_b200.config import PRESETS
     cfg = PRESETS[preset]().with_(final_action_clip_value=None)
     sd = random_state_dict(cfg, 0)
-    B = 64
+    # (B = 128: the per-GPU shard of BASELINE configs[2] at 4 GPUs -- 512 action rows take the multi-tile GEMM paths)
     inp = make_inputs(cfg, B, 5)
     for k in ("pixel_values", "proprios", "noise"):
         inp[k] = inp[k].bfloat16().float()
@@ -224,7 +224,7 @@ def test_full_size_b64_default_schedule_vs_oracle(preset, capsys):
     got16 = _run(pol, inp, dtype=torch.bfloat16)
     assert torch.equal(got16, got.bfloat16().float()), "bf16 I/O must only round the returned actions"
     assert torch.equal(_run(pol, inp), got), "repeated calls must agree bit for bit"
-    rows = [0, 13, 31, 32, 47, 63]
+    rows = [0, 13, 31, 32, 47, 63] if B == 64 else [0, 31, 64, 95, 127]
     ref = O.infer_action(cfg, sd, **{k: v for k, v in _rows(inp, rows).items()})
     worst_pre = worst_post = 0.0
     for i, b in enumerate(rows):
@@ -233,7 +233,7 @@ def test_full_size_b64_default_schedule_vs_oracle(preset, capsys):
         worst_pre, worst_post = max(worst_pre, e_pre), max(worst_post, e_post)
         assert e_pre <= ACTION_TOL and e_post <= ACTION_TOL, (preset, b, e_pre, e_post)
     with capsys.disabled():
-        print(f"\n[{preset} B=64 default schedule] rows {rows}: max-abs vs fp32 oracle pre-clamp {worst_pre:.3e} "
+        print(f"\n[{preset} B={B} default schedule] rows {rows}: max-abs vs fp32 oracle pre-clamp {worst_pre:.3e} "
               f"post-clamp {worst_post:.3e}")
 
 
@@ -282,6 +282,34 @@ def test_full_size_other_configs_parity(preset, B):
     assert max_err(got.clamp(-1, 1), ref.clamp(-1, 1)) <= ACTION_TOL
     pol.set_option("expert_mega", 1)
     assert max_err(_run(pol, inp).clamp(-1, 1), ref.clamp(-1, 1)) <= ACTION_TOL
+
+
+def test_fp32_checkpoint_weight_rounding(capsys):
+    """The shipped evaluator configs run the reference in fp32 (`use_bf16: False`); this library rounds every projection
+    weight to bf16 at load. Deviation on a checkpoint whose weights are NOT bf16-representable (plain fp32 random init):
+    library (fp32 weights in, `.to(torch.float32)` requested -> one RuntimeWarning) vs the fp32 oracle on the un-rounded
+    weights, next to the deviation on bf16-representable weights."""
+    import warnings
+    cfg = tiny().with_(final_action_clip_value=None)
+    inp = make_inputs(cfg, 4, 9, [5, 11, 3, 8])
+    res = {}
+    for rounded in (True, False):
+        sd = random_state_dict(cfg, 6, bf16_round=rounded)
+        pol = PiZeroInference(cfg, max_batch=4)
+        pol.load_state_dict(sd, strict=True)
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            pol.to(torch.float32)
+            pol.to(torch.float32)
+        assert sum(issubclass(x.category, RuntimeWarning) for x in w) == 1, "fp32 request must warn exactly once"
+        got = _run(pol, inp)
+        ref = O.infer_action(cfg, sd, inp["input_ids"], inp["pixel_values"], inp["proprios"], inp["noise"])
+        res[rounded] = max_err(got, ref)
+    with capsys.disabled():
+        print(f"\n[tiny, pre-clamp] max-abs vs fp32 oracle: bf16-representable weights {res[True]:.3e}, "
+              f"plain fp32 weights (rounded to bf16 at load) {res[False]:.3e}")
+    assert res[True] <= ACTION_TOL
+    assert res[False] <= 3 * ACTION_TOL, "weight rounding of an fp32 checkpoint moved the actions by more than 3e-2"
 
 
 def test_checkpoint_key_aliases_load():
