@@ -33,7 +33,8 @@ static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 // PDL policy: 0 = off, 1 = only inside the latency-bound expert chain of the denoise steps, 2 = every kernel.
 static int g_pdl_mode = 2;  // 0 off, 1 inside the denoise steps only, 2 (default) every launch: 39.8 vs 40.6 ms per call at B=64 (profiles/r01e_schedule_ab.txt)
-static bool g_pdl_scope = false;  // set by the schedule while it enqueues a latency-bound section
+static thread_local bool g_pdl_scope = false;  // set by the schedule while it enqueues a latency-bound section (per host
+                                               // thread: handles driven from different threads do not see each other's)
 bool pdl_enabled() { return g_pdl_mode == 2 || (g_pdl_mode == 1 && g_pdl_scope); }
 void set_pdl_enabled(bool on) { g_pdl_scope = on; }
 
