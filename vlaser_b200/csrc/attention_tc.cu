@@ -385,7 +385,8 @@ constexpr int PT_THREADS = 320;
 constexpr int PT_KMAX = 256;                         // keys on this path
 constexpr int PT_HALF_BYTES = PT_KMAX * 128;         // one 64-dim half of K or V: [256 rows][128 B]
 constexpr int PT_Q_BYTES = 2 * VT_TILE_BYTES;        // one query tile: two 64-dim halves of [128 rows][128 B]
-constexpr int PT_SMEM = 4 * PT_HALF_BYTES + 2 * PT_Q_BYTES + 1024 + 256;
+constexpr int PT_QSLOTS = 3;                         // query-tile ring: the producer runs a tile ahead of the two softmax groups
+constexpr int PT_SMEM = 4 * PT_HALF_BYTES + PT_QSLOTS * PT_Q_BYTES + 1024 + 256;
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
@@ -416,17 +417,17 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Ks = smem;                          // [2 halves][256][128 B]
   uint8_t* Vs = smem + 2 * PT_HALF_BYTES;      // [2 halves][256][128 B]
-  uint8_t* Qs = smem + 4 * PT_HALF_BYTES;      // [2 slots][2 halves][128][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Qs + 2 * PT_Q_BYTES);
+  uint8_t* Qs = smem + 4 * PT_HALF_BYTES;      // [3 slots][2 halves][128][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Qs + PT_QSLOTS * PT_Q_BYTES);
   uint64_t* kv_full = bars;        // [1]
   uint64_t* kv_empty = bars + 1;   // [1]
-  uint64_t* q_full = bars + 2;     // [2]
-  uint64_t* q_empty = bars + 4;    // [2]
-  uint64_t* s_full = bars + 6;     // [2]
-  uint64_t* p_full = bars + 8;     // [2]
-  uint64_t* o_full = bars + 10;    // [2]
-  uint64_t* t_empty = bars + 12;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* q_full = bars + 2;     // [3] query slot (tile counter % 3)
+  uint64_t* q_empty = bars + 5;    // [3]
+  uint64_t* s_full = bars + 8;     // [2] TMEM slot / softmax group (tile counter & 1)
+  uint64_t* p_full = bars + 10;    // [2]
+  uint64_t* o_full = bars + 12;    // [2]
+  uint64_t* t_empty = bars + 14;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* tr = (blockIdx.x == 0 && lane == 0) ? p.trace : nullptr;
@@ -437,9 +438,11 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     tma_prefetch_desc(&tmV);
     mbar_init(kv_full, 1);
     mbar_init(kv_empty, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < PT_QSLOTS; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
@@ -495,8 +498,8 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         const int q0 = p.q_start[b];
         for (int ti = 0; ti < n_tiles; ++ti, ++tcn) {
           const int t = sp + ti * tsplit;
-          const int slot = tcn & 1;
-          mbar_wait(&q_empty[slot], ((tcn >> 1) & 1) ^ 1);
+          const int slot = tcn % PT_QSLOTS;
+          mbar_wait(&q_empty[slot], ((tcn / PT_QSLOTS) & 1) ^ 1);
           uint8_t* qd = Qs + slot * PT_Q_BYTES;
           mbar_arrive_expect_tx(&q_full[slot], (uint32_t)(2 * rows_tile * 128));
           tma_load_3d(qd, &tmQ, &q_full[slot], 0, g * group, q0 + t * TOK);
@@ -518,12 +521,12 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         mbar_wait(kv_full, ic & 1);
         tc_fence_after();
         auto issue_s = [&](int tc_i) {
-          const int slot = tc_i & 1;
+          const int slot = tc_i & 1, qs = tc_i % PT_QSLOTS;
           const uint32_t ph = (tc_i >> 1) & 1;
-          mbar_wait(&q_full[slot], ph);
+          mbar_wait(&q_full[qs], (tc_i / PT_QSLOTS) & 1);
           mbar_wait(&t_empty[slot], ph ^ 1);
           tc_fence_after();
-          const uint32_t qa = smem_u32(Qs + slot * PT_Q_BYTES);
+          const uint32_t qa = smem_u32(Qs + qs * PT_Q_BYTES);
           const uint64_t dq0 = make_umma_desc_sw128(qa), dq1 = make_umma_desc_sw128(qa + VT_TILE_BYTES);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + slot * 256, dq0 + 2 * ks, dk0 + 2 * ks, idesc_s, ks > 0);
@@ -556,7 +559,6 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     const int row = quarter * 32 + lane;         // packed query row within the tile: token row / group, head row % group
     const int gtid = threadIdx.x - (2 + 4 * grp) * 32;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + grp * 256;
-    uint8_t* stage = Qs + grp * PT_Q_BYTES;      // [128 rows][256 B], 16-byte chunks XOR-swizzled with the row
     int tcn = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       PT_ITEM(item)
@@ -567,6 +569,7 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         if ((tc_i & 1) != grp) continue;
         const int t = sp + ti * tsplit;
         const uint32_t ph = (tc_i >> 1) & 1;
+        uint8_t* stage = Qs + (tc_i % PT_QSLOTS) * PT_Q_BYTES;  // [128 rows][256 B], 16-byte chunks XOR-swizzled with the row
         const int tok = t * TOK + row / group, hh = row % group;
         const bool row_ok = row < rows_tile && tok < L;
         mbar_wait(&s_full[grp], ph);
@@ -693,7 +696,7 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         (void)tok;
         (void)hh;
         named_bar_sync(1 + grp, 128);  // every warp of the group has read its rows out of the slot
-        if (gtid == 0) mbar_arrive(&q_empty[grp]);
+        if (gtid == 0) mbar_arrive(&q_empty[tc_i % PT_QSLOTS]);
       }
       tcn += n_tiles;
     }
