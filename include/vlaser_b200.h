@@ -93,6 +93,21 @@ int32_t vlaser_infer_action(vlaser_t* h, const int64_t* input_ids, const void* p
 int32_t vlaser_infer_action_host(vlaser_t* h, const int64_t* input_ids, const void* pixel_values,
                                  const int32_t* valid_len, const void* proprios, const void* noise, void* actions_out,
                                  int32_t B, int32_t io_dtype);
+/* Flow-matching loss of the training step, forward only — PiZero.forward (pizero_internvl.py:1064-1197) with
+ * is_vlm=False: psi_t = (1-(1-sig_min)t) x0 + t x1 (:1053-1062), ONE pass of the action expert at the per-sample time
+ * t over the prefix / proprio K/V (no block of the training mask attends to a later block, so this equals the reference's
+ * joint forward without KV cache), v_psi = action_decoder(.), loss = mean((v_psi - (x1 - (1-sig_min) x0))^2).
+ * Device pointers:
+ *   input_ids / pixel_values / valid_len / proprios   as vlaser_infer_action
+ *   actions  io_dtype [B, H, action_dim]  x1, the normalised target chunk
+ *   noise    io_dtype [B, H, action_dim]  x0, the draw of torch.randn_like at :1094, made by the caller
+ *   t        io_dtype [B]                 flow time per sample
+ *   loss_out f32 [1];  velocity_out f32 [B, H, action_dim] or NULL (v_psi, for parity checks)
+ * No gradients: the optimiser step stays with the reference trainer (out of scope). */
+int32_t vlaser_flow_matching_loss(vlaser_t* h, const int64_t* input_ids, const void* pixel_values, const int32_t* valid_len,
+                                  const void* proprios, const void* actions, const void* noise, const void* t,
+                                  float flow_sig_min, float* loss_out, float* velocity_out, int32_t B, int32_t io_dtype,
+                                  void* stream);
 void vlaser_destroy(vlaser_t* h);
 
 /* Options: "pdl" (process-wide; 0 off, 1 programmatic dependent launch inside the denoise steps only, 2 (default) on every launch),

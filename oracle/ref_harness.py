@@ -281,3 +281,23 @@ def run_reference_policy(pol, cfg, input_ids, pixel_values, proprios, noise, cap
                 trace[f"k_{name}_layer{li}"] = k.detach().clone()
                 trace[f"v_{name}_layer{li}"] = v.detach().clone()
     return actions, trace
+
+
+def run_reference_flow_loss(cfg, sd, input_ids, pixel_values, proprios, actions, noise, t, flow_sig_min: float = 0.001):
+    """Runs the reference training `PiZero.forward(..., is_vlm=False)` (pizero_internvl.py:1064-1197, fp32 CPU, no
+    grad) with `noise` injected in place of its `torch.randn_like` draw. Returns (loss, v_psi)."""
+    pol = build_reference_policy(cfg, sd)
+    pol.flow_sig_min = flow_sig_min
+    attention_mask = (input_ids != cfg.pad_token_id).to(torch.int64)
+    mask, vp, pp, ap = pol.build_causal_mask_and_position_ids(attention_mask, torch.float32)
+    seen = {}
+    h = pol.action_decoder.register_forward_hook(lambda mod, args, out: seen.__setitem__("v_psi", out.detach().clone()))
+    real = torch.randn_like
+    try:
+        torch.randn_like = lambda a, **k: noise.clone().to(k.get("dtype", a.dtype))
+        with torch.inference_mode():
+            loss = pol.forward(input_ids, pixel_values, mask, vp, pp, ap, proprios, actions, t)
+    finally:
+        torch.randn_like = real
+        h.remove()
+    return loss.detach().clone(), seen["v_psi"]

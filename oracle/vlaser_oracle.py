@@ -336,3 +336,31 @@ def infer_action(cfg, sd: Dict[str, torch.Tensor], input_ids: torch.Tensor, pixe
     if cfg.final_action_clip_value is not None:
         action = torch.clamp(action, -cfg.final_action_clip_value, cfg.final_action_clip_value)
     return action[:, -cfg.horizon_steps:]
+
+
+def flow_matching_loss(cfg, sd: Dict[str, torch.Tensor], input_ids: torch.Tensor, pixel_values: torch.Tensor,
+                       proprios: torch.Tensor, actions: torch.Tensor, noise: torch.Tensor, t: torch.Tensor,
+                       flow_sig_min: float = 0.001, attention_mask: Optional[torch.Tensor] = None):
+    """S/vla/pizero_internvl.py:1064-1197 (`PiZero.forward`, is_vlm=False, imgfeat off), forward only. `noise` replaces the
+    `torch.randn_like` draw at :1094. The reference runs the three mixtures jointly without KV cache under the block mask
+    of build_causal_mask_and_position_ids; no block attends to a later one, so the prefix / proprio K/V are those of
+    `prefill` and the action block is one `denoise_step` over them (psi_t :1053-1062, loss :1190-1193).
+    Returns (loss, v_psi)."""
+    S = cfg.max_image_text_tokens
+    H = cfg.num_action_tokens
+    if attention_mask is None:
+        attention_mask = (input_ids != cfg.pad_token_id).to(torch.int64)
+    wdt = sd["proprio_encoder.weight"].dtype
+    mask, vlm_pos, proprio_pos, action_pos = build_causal_mask_and_position_ids(attention_mask, S, H, dtype=wdt)
+    itp_mask, action_mask = split_full_mask_into_submasks(mask, S, H)
+    x0, x1 = noise.to(wdt), actions.to(wdt)
+    tt = t.to(wdt)[:, None, None]
+    psi = (1 - (1 - flow_sig_min) * tt) * x0 + tt * x1
+    embeds = prefix_embedding(cfg, sd, input_ids, pixel_values)
+    proprio_embeds = F.linear(proprios, sd["proprio_encoder.weight"], sd["proprio_encoder.bias"])
+    caches = prefill(cfg, sd, embeds, proprio_embeds, itp_mask, vlm_pos, proprio_pos)
+    x = action_encoder(sd, psi, time_embedding(cfg, t.to(wdt)))
+    y = denoise_step(cfg, sd, x, caches, action_mask, action_pos)
+    v_psi = F.linear(y, sd["action_decoder.weight"], sd["action_decoder.bias"])
+    d_psi = x1 - (1 - flow_sig_min) * x0
+    return torch.mean((v_psi - d_psi) ** 2), v_psi

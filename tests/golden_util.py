@@ -15,6 +15,7 @@ from vlaser_b200.weights import random_state_dict
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["tiny_bridge", "tiny_fractal", "tiny_robotwin"]
 DYNAMIC_TILE_CASES = ["tiny_dynamic_tiles"]  # samples own different numbers of image tiles
+FLOW_CASES = ["tiny_flow_bridge", "tiny_flow_robotwin"]  # training forward (make_flow_golden.py): loss, v_psi
 
 
 def load_case(name: str):
@@ -30,5 +31,10 @@ def load_case(name: str):
         "proprios": torch.from_numpy(z["proprios"]),
         "noise": torch.from_numpy(z["noise"]),
     }
+    if "v_psi" in z.files:  # flow-matching training forward: `actions` is an INPUT (the target chunk x1)
+        inp["actions"] = torch.from_numpy(z["actions"])
+        inp["t"] = torch.from_numpy(z["t"])
+        inp["flow_sig_min"] = float(z["flow_sig_min"])
+        return cfg, sd, inp, {"loss": torch.from_numpy(z["loss"]), "v_psi": torch.from_numpy(z["v_psi"])}
     golden = {k: torch.from_numpy(z[k]) for k in z.files if k == "actions" or k.startswith("trace_")}
     return cfg, sd, inp, golden

@@ -16,7 +16,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import vlaser_oracle as O  # noqa: E402  (checker only)
-from tests.golden_util import CASES, DYNAMIC_TILE_CASES, load_case  # noqa: E402
+from tests.golden_util import CASES, DYNAMIC_TILE_CASES, FLOW_CASES, load_case  # noqa: E402
 from tests.ops import max_err, rel_err  # noqa: E402
 from vlaser_b200.config import tiny, vlaser_2b_bridge  # noqa: E402
 from vlaser_b200.policy import PiZeroInference  # noqa: E402
@@ -458,3 +458,59 @@ def test_prefix_fills_max_tokens_and_batch_bounds():
         _run(pol, big)
     # the handle is still usable afterwards
     assert max_err(_run(pol, inp), ref) <= ACTION_TOL
+
+
+# ---- flow-matching training forward (pizero_internvl.py:1064-1197) ------------------------------
+def _flow(pol, inp, dtype=torch.float32, masks=False):
+    ids = inp["input_ids"].cuda()
+    kw = {}
+    if masks:
+        am = (inp["input_ids"] != pol.pad_token_id).to(torch.int64)
+        m, vp, pp, ap = pol.build_causal_mask_and_position_ids(am, dtype)
+        kw = dict(causal_mask=m.cuda(), vlm_position_ids=vp, proprio_position_ids=pp, action_position_ids=ap)
+    loss, v = pol.flow_matching_loss(ids, inp["pixel_values"].to(dtype).cuda(), proprios=inp["proprios"].to(dtype).cuda(),
+                                     actions=inp["actions"].to(dtype).cuda(), t=inp["t"].to(dtype).cuda(),
+                                     noise=inp["noise"].to(dtype).cuda(), return_velocity=True, **kw)
+    return float(loss), v.cpu()
+
+
+@pytest.mark.parametrize("name", FLOW_CASES)
+def test_flow_matching_loss_golden(name, capsys):
+    """Loss and velocity of the training forward vs the UNMODIFIED reference (tests/golden/make_flow_golden.py)."""
+    cfg, sd, inp, gold = load_case(name)
+    B = inp["input_ids"].shape[0]
+    pol = _policy(cfg, sd, B)
+    pol.cfg = {"flow_sig_min": inp["flow_sig_min"]}  # the binding reads flow_sig_min from its cfg, like PiZero.__init__
+    loss, v = _flow(pol, inp)
+    loss2, v2 = _flow(pol, inp, masks=True)  # graph replay, mask API
+    assert loss == loss2 and torch.equal(v, v2), "the training forward must be bit-identical from call to call"
+    e_v = max_err(v, gold["v_psi"])
+    with capsys.disabled():
+        print(f"\n[{name}] flow loss {loss:.6f} vs reference {float(gold['loss']):.6f}; v_psi max-abs {e_v:.3e}")
+    assert e_v <= ACTION_TOL
+    assert abs(loss - float(gold["loss"])) <= 5e-3 * float(gold["loss"])
+    # the inference entry still gives the inference result afterwards (separate graphs per mode)
+    cfg_i, sd_i, inp_i, gold_i = load_case("tiny_bridge" if "bridge" in name else "tiny_robotwin")
+    if cfg_i.to_dict() == cfg.to_dict():
+        assert max_err(_run(pol, inp_i), gold_i["actions"]) <= ACTION_TOL
+
+
+def test_flow_matching_loss_full_size_vs_oracle(capsys):
+    """Full-size 2B widths, B = 2, bf16 I/O, against the fp32 oracle on the same bf16-rounded weights and inputs."""
+    cfg = vlaser_2b_bridge()
+    sd = random_state_dict(cfg, 0)
+    B = 2
+    inp = make_inputs(cfg, B, 21)
+    g = torch.Generator().manual_seed(7)
+    inp["actions"] = (torch.rand((B, cfg.num_action_tokens, cfg.action_dim), generator=g) * 2 - 1).bfloat16().float()
+    inp["t"] = torch.tensor([0.25, 0.8125])
+    pol = _policy(cfg, sd, B)
+    loss, v = _flow(pol, inp, torch.bfloat16)
+    ref_loss, ref_v = O.flow_matching_loss(cfg, sd, inp["input_ids"], inp["pixel_values"].bfloat16().float(),
+                                           inp["proprios"].bfloat16().float(), inp["actions"], inp["noise"].bfloat16().float(),
+                                           inp["t"], 0.001)
+    e_v = max_err(v, ref_v)
+    with capsys.disabled():
+        print(f"\n[2B flow loss] {loss:.5f} vs oracle {float(ref_loss):.5f}; v_psi max-abs {e_v:.3e}")
+    assert e_v <= ACTION_TOL
+    assert abs(loss - float(ref_loss)) <= 1e-2 * float(ref_loss)

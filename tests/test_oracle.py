@@ -8,7 +8,7 @@ import torch
 
 from oracle import ref_harness
 from oracle import vlaser_oracle as O
-from tests.golden_util import CASES, DYNAMIC_TILE_CASES, load_case
+from tests.golden_util import CASES, DYNAMIC_TILE_CASES, FLOW_CASES, load_case
 from vlaser_b200.config import tiny
 from vlaser_b200.synth import make_inputs
 from vlaser_b200.weights import random_state_dict
@@ -26,6 +26,17 @@ def test_oracle_matches_golden(name):
     for k in ("vit_out", "image_features", "expert_out_step0", "k_vlm_layer0", "v_vlm_layer0",
               f"k_vlm_layer{cfg.layers - 1}", f"k_proprio_layer{cfg.layers - 1}", f"v_proprio_layer{cfg.layers - 1}"):
         assert (tr[k] - gold["trace_" + k]).abs().max() < 2e-5, k
+
+
+@pytest.mark.parametrize("name", FLOW_CASES)
+def test_oracle_flow_loss_matches_golden(name):
+    """Training forward (PiZero.forward, pizero_internvl.py:1064-1197): the prefill + one-expert-pass restatement gives the
+    loss and velocity of the reference's joint forward without KV cache."""
+    cfg, sd, inp, gold = load_case(name)
+    loss, v = O.flow_matching_loss(cfg, sd, inp["input_ids"], inp["pixel_values"], inp["proprios"], inp["actions"],
+                                   inp["noise"], inp["t"], inp["flow_sig_min"])
+    assert (v - gold["v_psi"]).abs().max() < 2e-5
+    assert abs(float(loss) - float(gold["loss"])) < 1e-5 * max(1.0, float(gold["loss"]))
 
 
 def _tiny_case(B=2, seed=5, prompt_tokens=(5, 11)):

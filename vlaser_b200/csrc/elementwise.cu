@@ -496,6 +496,74 @@ __global__ void __launch_bounds__(128) euler_step_kernel(const float* __restrict
   }
 }
 
+// ---- flow-matching training forward (see elementwise.cuh)
+__device__ __forceinline__ float io_load(const void* p, int io, long long i) {
+  return io == DT_F32 ? reinterpret_cast<const float*>(p)[i] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+
+__global__ void __launch_bounds__(256) flow_prepare_kernel(const void* __restrict__ x0, const void* __restrict__ x1,
+                                                           const void* __restrict__ tin, int io, float sig_min, float emb,
+                                                           const float* __restrict__ W2a, const float* __restrict__ b2,
+                                                           float* __restrict__ action, float* __restrict__ tbias,
+                                                           float* __restrict__ vel, int HA, int he) {
+  extern __shared__ float tau[];  // [he]
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x, half = he / 2;
+  const float t = io_load(tin, io, b);
+  for (int i = threadIdx.x; i < HA; i += blockDim.x) {
+    const long long k = (long long)b * HA + i;
+    action[k] = (1.f - (1.f - sig_min) * t) * io_load(x0, io, k) + t * io_load(x1, io, k);
+    vel[k] = 0.f;
+  }
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float a = t * expf((float)i * -emb);
+    tau[i] = sinf(a);
+    tau[half + i] = cosf(a);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int n = warp; n < he; n += nw) {
+    const float* w = W2a + (size_t)n * he;
+    float acc = 0.f;
+    for (int j = lane; j < he; j += 32) acc = fmaf(__ldg(w + j), tau[j], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) tbias[(size_t)b * he + n] = acc + __ldg(b2 + n);
+  }
+}
+
+__global__ void __launch_bounds__(256) bias_silu_rows_kernel(const float* __restrict__ z, const float* __restrict__ tbias,
+                                                             __nv_bfloat16* __restrict__ h, int rows, int H, int width) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long n = (long long)rows * width;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / width), c = (int)(i - (long long)r * width);
+    const float v = z[i] + tbias[(size_t)(r / H) * width + c];
+    h[i] = __float2bfloat16(silu(v));
+  }
+}
+
+__global__ void __launch_bounds__(256) flow_loss_kernel(const float* __restrict__ vel, const void* __restrict__ x0,
+                                                        const void* __restrict__ x1, int io, float sig_min, long long n,
+                                                        float* __restrict__ loss) {
+  __shared__ float part[256];
+  pdl_launch_dependents();
+  pdl_wait();
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < n; i += 256) {  // fixed thread -> element map and tree: bit-identical from call to call
+    const float d = vel[i] - (io_load(x1, io, i) - (1.f - sig_min) * io_load(x0, io, i));
+    acc = fmaf(d, d, acc);
+  }
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) part[threadIdx.x] += part[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[0] = part[0] / (float)n;
+}
+
 }  // namespace
 
 // ==========================================================================================
@@ -626,6 +694,30 @@ int euler_step_launch(const float* x, const float* gamma, const float* Wdec, con
     VL_CUDA_CHECK(launch_kernel(euler_step_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, stream, x, gamma, Wdec, bdec, action, (__nv_bfloat16*)out, rows,
                                                                width, A, H, horizon, dt, eps, last_step, do_clip, clip, xfix));
   VL_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int flow_prepare_launch(const void* x0, const void* x1, const void* t, int io, float sig_min, float time_max_period,
+                        const float* W2a, const float* b2, float* action, float* tbias, float* vel, int B, int HA, int he,
+                        cudaStream_t stream) {
+  VL_CHECK(he % 2 == 0 && he <= 8192, "flow_prepare: bad expert width");
+  const float emb = (float)(std::log((double)time_max_period) / (he / 2 - 1));
+  VL_CUDA_CHECK(launch_kernel(flow_prepare_kernel, dim3(B), dim3(256), (size_t)he * sizeof(float), stream, x0, x1, t, io, sig_min,
+                              emb, W2a, b2, action, tbias, vel, HA, he));
+  return 0;
+}
+
+int bias_silu_rows_launch(const float* z, const float* tbias, __nv_bfloat16* h, int rows, int H, int width,
+                          cudaStream_t stream) {
+  const long long n = (long long)rows * width;
+  const int grid = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  VL_CUDA_CHECK(launch_kernel(bias_silu_rows_kernel, dim3(grid), dim3(256), 0, stream, z, tbias, h, rows, H, width));
+  return 0;
+}
+
+int flow_loss_launch(const float* vel, const void* x0, const void* x1, int io, float sig_min, long long n, float* loss,
+                     cudaStream_t stream) {
+  VL_CUDA_CHECK(launch_kernel(flow_loss_kernel, dim3(1), dim3(256), 0, stream, vel, x0, x1, io, sig_min, n, loss));
   return 0;
 }
 

@@ -99,4 +99,18 @@ int euler_step_launch(const float* x, const float* gamma, const float* Wdec, con
                       int last_step, int do_clip, float clip, cudaStream_t stream, const long long* xfix = nullptr);
 // (xfix: optional [rows, width] 2^-30 fixed-point increments to add to x, see ExpertPass::xfix)
 
+// ---- flow-matching training forward (pizero_internvl.py:1064-1197, forward only): the pieces around the one expert pass
+// Per sample b with time t[b] (io dtype): action[b] = psi_t = (1 - (1 - sig_min) t) x0 + t x1 (:1053-1062, fp32),
+// tbias[b, n] = b2[n] + sum_j W2a[n, j] * cat(sin(t w), cos(t w))[j]  -- the time half of ActionEncoder.linear_2
+// (modules.py:9-22, 39-53) for an arbitrary per-sample time --, vel[b] = 0. x0 / x1: io dtype [B, HA].
+int flow_prepare_launch(const void* x0, const void* x1, const void* t, int io, float sig_min, float time_max_period,
+                        const float* W2a, const float* b2, float* action, float* tbias, float* vel, int B, int HA, int he,
+                        cudaStream_t stream);
+// h[r, :] = bf16(silu(z[r, :] + tbias[r / H, :]))  (the rest of linear_2 + swish with a per-sample bias)
+int bias_silu_rows_launch(const float* z, const float* tbias, __nv_bfloat16* h, int rows, int H, int width,
+                          cudaStream_t stream);
+// loss = mean((vel - (x1 - (1 - sig_min) x0))^2) over n elements (:1190-1193), one CTA, fixed summation order
+int flow_loss_launch(const float* vel, const void* x0, const void* x1, int io, float sig_min, long long n, float* loss,
+                     cudaStream_t stream);
+
 }  // namespace vlaser

@@ -145,6 +145,12 @@ struct Engine {
   long long* in_ids = nullptr;
   void *in_pix = nullptr, *in_prop = nullptr, *in_noise = nullptr, *out_act = nullptr;
   int* in_valid = nullptr;
+  // flow-matching training forward (vlaser_flow_matching_loss): target actions x1, per-sample times, per-sample time bias
+  // of the action encoder, fp32 pre-activation of its linear_2, velocity, loss
+  void *in_x1 = nullptr, *in_t = nullptr;
+  float *flow_tbias = nullptr, *flow_z = nullptr, *flow_vel = nullptr, *flow_loss = nullptr;
+  float flow_sig_min = 0.001f, flow_sig_graph = -1.f;
+  int mode = 0;                // what engine_execute enqueues: 0 infer_action, 1 flow-matching loss (forward only)
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
 
@@ -203,9 +209,9 @@ struct Engine {
   cudaStream_t side_stream = nullptr;      // the proprio pass of the prefill when option "prop_stream" is set
   std::vector<cudaEvent_t> side_events;    // [layers] K/V of LLM layer l written, + fork + join
   struct GraphKey {
-    int B, io, stop, simt, has_valid;
+    int B, io, stop, simt, has_valid, mode;
     bool operator<(const GraphKey& o) const {
-      return std::tie(B, io, stop, simt, has_valid) < std::tie(o.B, o.io, o.stop, o.simt, o.has_valid);
+      return std::tie(B, io, stop, simt, has_valid, mode) < std::tie(o.B, o.io, o.stop, o.simt, o.has_valid, o.mode);
     }
   };
   struct GraphVal {
@@ -510,6 +516,12 @@ int engine_build(Engine& e) {
   VL_TRY(e.alloc((float**)&e.in_prop, (size_t)e.Bc * c.proprio_dim));
   VL_TRY(e.alloc((float**)&e.in_noise, (size_t)arow * c.action_dim));
   VL_TRY(e.alloc((float**)&e.out_act, (size_t)e.Bc * c.horizon_steps * c.action_dim));
+  VL_TRY(e.alloc((float**)&e.in_x1, (size_t)arow * c.action_dim));
+  VL_TRY(e.alloc((float**)&e.in_t, e.Bc));
+  VL_TRY(e.alloc(&e.flow_tbias, (size_t)e.Bc * c.hidden_e));
+  VL_TRY(e.alloc(&e.flow_z, (size_t)arow * c.hidden_e));
+  VL_TRY(e.alloc(&e.flow_vel, (size_t)arow * c.action_dim));
+  VL_TRY(e.alloc(&e.flow_loss, 4));
   e.pinned_bytes = (size_t)e.Bc * e.S * 8 + pix_elems * 4 + (size_t)e.Bc * 4 + (size_t)e.Bc * c.proprio_dim * 4 +
                    (size_t)arow * c.action_dim * 4 + (size_t)e.Bc * c.horizon_steps * c.action_dim * 4 + 4096;
   VL_CUDA_CHECK(cudaMallocHost(&e.pinned, e.pinned_bytes));
@@ -1028,8 +1040,10 @@ struct Run {
   }
 
   // B = 1 (the latency case): the expert passes run on the weight-streaming single-observation kernel
-  bool gemv() const { return e.gemv && B == 1 && e.H <= 8 && !e.simt; }
-  bool mega() const { return (e.mega || gemv()) && !e.simt; }
+  // (the flow-matching loss runs its one expert pass on the per-kernel schedule: the persistent kernels index their time
+  // bias by Euler step)
+  bool gemv() const { return e.gemv && B == 1 && e.H <= 8 && !e.simt && e.mode != 1; }
+  bool mega() const { return (e.mega || gemv()) && !e.simt && e.mode != 1; }
   // largest power-of-two sub-grid count <= the option that keeps whole samples, a multiple of 32 rows and at least 64
   // rows per sub-grid
   int expert_streams(int M, int B) const {
@@ -1260,6 +1274,7 @@ struct Run {
     return make_tmap_out(&ch.xa_otm, e.xa + (size_t)ch.r0 * e.c.hidden_e, ch.M, e.c.hidden_e, 4);
   }
 
+  bool flow = false;  // the pass is the flow-matching training forward (per-sample time bias, velocity out)
   int denoise(int step, Chain& ch) {
     const vlaser_cfg& c = e.c;
     const int M = ch.M, he = c.hidden_e;
@@ -1282,6 +1297,14 @@ struct Run {
     e2.bias = e.time_bias + (size_t)step * he;
     tr_name = "act_enc2";
     tr_layer = -1;
+    if (flow) {
+      // per-sample time: linear_2 leaves its fp32 pre-activation, the per-sample time bias and the swish follow
+      e2.out = e.flow_z + (size_t)ch.r0 * he;
+      e2.bias = nullptr;
+      VL_TRY(gemm(ch.e1, e.ae_w2b, M, nullptr, EPI_STORE_F32, e2));
+      VL_TRY(bias_silu_rows_launch(e.flow_z + (size_t)ch.r0 * he, e.flow_tbias + (size_t)ch.b0 * he, ch.h2.p, M, e.H, he, st));
+      e.launches++;
+    } else
     VL_TRY(gemm(ch.e1, e.ae_w2b, M, nullptr, EPI_SILU_BF16, e2));
     EpiParams e3;
     e3.out = xa;
@@ -1335,6 +1358,12 @@ struct Run {
     const int last = step == c.num_inference_steps - 1;
     VL_TRY(flush());  // split-K partials of the last down projection
     const size_t out_off = (size_t)ch.b0 * c.horizon_steps * c.action_dim * (io == DT_F32 ? 4 : 2);
+    if (flow) {  // the velocity itself: vel = 0 + 1 * (decoder(norm(x)))
+      VL_TRY(euler_step_launch(xa, e.final_norm, e.dec_w, e.dec_b, e.flow_vel + (size_t)ch.r0 * c.action_dim, e.out_act, io, M, he,
+                               c.action_dim, e.H, c.horizon_steps, 1.0f, c.rms_eps, 0, 0, 0.f, st, nullptr));
+      e.launches++;
+      return 0;
+    }
     VL_TRY(euler_step_launch(xa, e.final_norm, e.dec_w, e.dec_b, action, reinterpret_cast<uint8_t*>(e.out_act) + out_off, io, M, he,
                              c.action_dim, e.H, c.horizon_steps, (float)(1.0 / c.num_inference_steps), c.rms_eps, last,
                              c.clip_enabled, c.final_action_clip_value, st,
@@ -1372,6 +1401,29 @@ struct Run {
     return 0;
   }
 
+  // Flow-matching loss of the training step, forward only (pizero_internvl.py:1064-1197): the joint forward over
+  // (prefix, proprio, noisy action chunk) under the block mask equals the prefill followed by ONE pass of the action expert
+  // over the cached prefix / proprio K/V -- no block attends to a later one -- at the per-sample time t, then
+  // v_psi = decoder(norm(x)) and mean((v_psi - (x1 - (1 - sig_min) x0))^2).
+  int flow_loss() {
+    const vlaser_cfg& c = e.c;
+    const int HA = e.H * c.action_dim;
+    VL_TRY(flow_prepare_launch(e.in_noise, e.in_x1, e.in_t, io, e.flow_sig_min, c.time_max_period, e.ae_w2a, e.ae_b2, e.action,
+                               e.flow_tbias, e.flow_vel, B, HA, c.hidden_e, st));
+    e.launches++;
+    Chain ch;
+    VL_TRY(make_chain(ch, 0, 0, B));
+    flow = true;
+    set_pdl_enabled(true);
+    const int rc = denoise(0, ch);
+    set_pdl_enabled(false);
+    flow = false;
+    if (rc) return rc;
+    VL_TRY(flow_loss_launch(e.flow_vel, e.in_noise, e.in_x1, io, e.flow_sig_min, (long long)B * HA, e.flow_loss, st));
+    e.launches++;
+    return 0;
+  }
+
   int all(bool has_valid) {
     const vlaser_cfg& c = e.c;
     VL_TRY(plan_launch(e.in_ids, has_valid ? e.in_valid : nullptr, e.pb, B, e.S, e.H, e.n_img * e.T,
@@ -1388,6 +1440,7 @@ struct Run {
     if (e.stop_after == 2) return 0;
     VL_TRY(prefill());
     if (e.stop_after == 3) return 0;
+    if (e.mode == 1) return flow_loss();
     set_pdl_enabled(true);
     const int rc = denoise_all();
     set_pdl_enabled(false);
@@ -1405,7 +1458,7 @@ int engine_execute(Engine& e, int B, int io, bool has_valid, cudaStream_t st) {
     e.last_launches = e.launches;
     return rc;
   }
-  Engine::GraphKey key{B, io, e.stop_after, e.simt, has_valid ? 1 : 0};
+  Engine::GraphKey key{B, io, e.stop_after, e.simt, has_valid ? 1 : 0, e.mode};
   auto it = e.graphs.find(key);
   if (it == e.graphs.end()) {
     // Build on the handle's own stream (the caller's may be the legacy default stream, which cannot
@@ -1575,6 +1628,50 @@ int32_t vlaser_infer_action(vlaser_t* h, const int64_t* input_ids, const void* p
   VL_CUDA_CHECK(cudaMemcpyAsync(actions_out, e.out_act, (size_t)B * c.horizon_steps * c.action_dim * es,
                                 cudaMemcpyDeviceToDevice, st));
   VL_CUDA_CHECK(cudaMemcpyAsync(host_bad, e.pb.bad_id, sizeof(int), cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+int32_t vlaser_flow_matching_loss(vlaser_t* h, const int64_t* input_ids, const void* pixel_values, const int32_t* valid_len,
+                                  const void* proprios, const void* actions, const void* noise, const void* t,
+                                  float flow_sig_min, float* loss_out, float* velocity_out, int32_t B, int32_t io_dtype,
+                                  void* stream) {
+  VL_CHECK(h, "null handle");
+  Engine& e = h->e;
+  VL_CHECK(e.finalized, "flow_matching_loss before finalize");
+  VL_CHECK(B > 0 && B <= e.Bc, "batch exceeds max_batch");
+  VL_CHECK(io_dtype == DT_F32 || io_dtype == DT_BF16, "io_dtype must be f32 or bf16");
+  VL_CHECK(input_ids && pixel_values && proprios && actions && noise && t && loss_out, "null tensor");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const vlaser_cfg& c = e.c;
+  const size_t es = io_size(io_dtype);
+  const size_t pix = (size_t)B * e.n_img * 3 * c.image_size * c.image_size;
+  const size_t na = (size_t)B * e.H * c.action_dim;
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_ids, input_ids, (size_t)B * e.S * 8, cudaMemcpyDeviceToDevice, st));
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_pix, pixel_values, pix * es, cudaMemcpyDeviceToDevice, st));
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_prop, proprios, (size_t)B * c.proprio_dim * es, cudaMemcpyDeviceToDevice, st));
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_noise, noise, na * es, cudaMemcpyDeviceToDevice, st));
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_x1, actions, na * es, cudaMemcpyDeviceToDevice, st));
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_t, t, (size_t)B * es, cudaMemcpyDeviceToDevice, st));
+  if (valid_len) VL_CUDA_CHECK(cudaMemcpyAsync(e.in_valid, valid_len, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  e.flow_sig_min = flow_sig_min;
+  e.mode = 1;
+  // (flow_sig_min is a launch constant of the captured graph: a new value needs a new capture)
+  if (e.flow_sig_graph != flow_sig_min) {
+    for (auto it = e.graphs.begin(); it != e.graphs.end();)
+      if (it->first.mode == 1) {
+        cudaStreamSynchronize(e.own_stream);
+        cudaGraphExecDestroy(it->second.exec);
+        it = e.graphs.erase(it);
+      } else {
+        ++it;
+      }
+    e.flow_sig_graph = flow_sig_min;
+  }
+  const int rc = engine_execute(e, B, io_dtype, valid_len != nullptr, st);
+  e.mode = 0;
+  if (rc) return rc;
+  VL_CUDA_CHECK(cudaMemcpyAsync(loss_out, e.flow_loss, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (velocity_out) VL_CUDA_CHECK(cudaMemcpyAsync(velocity_out, e.flow_vel, na * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 

@@ -355,6 +355,62 @@ class PiZeroInference:
         _lib.check(rc, "vlaser_infer_action")
         return out
 
+    def infer_action_naive(self, input_ids, pixel_values, causal_mask=None, vlm_position_ids=None,
+                           proprio_position_ids=None, action_position_ids=None, proprios=None,
+                           noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """pizero_internvl.py:938-1003: the same flow integration with the whole joint model re-run in every Euler step
+        (cache_mode="no_append"). Under the block mask the prefix and proprio blocks never see the action block, so the
+        result is the one `infer_action` returns; this entry runs the cached schedule. (With the InternVL backbone the
+        reference's own method cannot run -- it does not hand `position_embeddings_all` to the joint model and fails at
+        joint_model.py:549 -- so there is no golden vector for it; it exists here for signature compatibility.)"""
+        itp = None
+        if causal_mask is not None:
+            itp, _ = self.split_full_mask_into_submasks(causal_mask)
+        return self.infer_action(input_ids, pixel_values, itp, None, vlm_position_ids, proprio_position_ids,
+                                 action_position_ids, proprios, noise=noise)
+
+    def flow_matching_loss(self, input_ids, pixel_values, causal_mask=None, vlm_position_ids=None,
+                           proprio_position_ids=None, action_position_ids=None, proprios=None, actions=None, t=None,
+                           noise: Optional[torch.Tensor] = None, return_velocity: bool = False):
+        """`PiZero.forward(..., is_vlm=False)` of the training step, forward only (pizero_internvl.py:1064-1197): the
+        flow-matching loss mean((v_psi - (x1 - (1 - sig_min) x0))^2) for target chunks `actions` [B, H, A] at the
+        per-sample times `t` [B]. `noise` (optional) replaces the `torch.randn_like` draw of :1094. Returns the loss as a
+        0-d float32 tensor on the device (and v_psi [B, H, A] float32 with return_velocity). No gradients are produced."""
+        v = self.vcfg
+        self.finalize()
+        dev = self.device
+        dtype = pixel_values.dtype
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("pixel_values must be float32 or bfloat16")
+        io = _lib.BF16 if dtype == torch.bfloat16 else _lib.F32
+        B = pixel_values.size(0) // v.num_images
+        S, H, A = v.max_image_text_tokens, v.num_action_tokens, v.action_dim
+        input_ids = input_ids.to(dev, torch.int64).contiguous()
+        pixel_values = pixel_values.to(dev).contiguous()
+        proprios = proprios.to(dev, dtype).contiguous()
+        actions = actions.to(dev, dtype).contiguous()
+        t = t.to(dev, dtype).contiguous()
+        assert input_ids.shape == (B, S) and actions.shape == (B, H, A) and t.shape == (B,)
+        valid_len = None
+        if causal_mask is not None:
+            valid_len = (causal_mask[:, 0, 0, :S] == 0).sum(-1).to(dev, torch.int32).contiguous()
+        if noise is None:
+            noise = torch.randn_like(actions)  # :1094
+        noise = noise.to(dev, dtype).contiguous()
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        vel = torch.empty((B, H, A), device=dev, dtype=torch.float32) if return_velocity else None
+        sig = float(_cfg_get(self.cfg, "flow_sig_min", 0.001))
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = self._lib.vlaser_flow_matching_loss(
+                self._handle, C.c_void_p(input_ids.data_ptr()), C.c_void_p(pixel_values.data_ptr()),
+                C.c_void_p(valid_len.data_ptr()) if valid_len is not None else None, C.c_void_p(proprios.data_ptr()),
+                C.c_void_p(actions.data_ptr()), C.c_void_p(noise.data_ptr()), C.c_void_p(t.data_ptr()), sig,
+                C.c_void_p(loss.data_ptr()), C.c_void_p(vel.data_ptr()) if vel is not None else None, B, io,
+                C.c_void_p(stream))
+        _lib.check(rc, "vlaser_flow_matching_loss")
+        return (loss, vel) if return_velocity else loss
+
     def infer_action_host(self, input_ids, pixel_values, proprios, noise, valid_len=None) -> torch.Tensor:
         """Same call on HOST tensors (CPU torch tensors): H2D staging, compute, D2H, synchronise."""
         v = self.vcfg
