@@ -108,6 +108,26 @@ int32_t vlaser_flow_matching_loss(vlaser_t* h, const int64_t* input_ids, const v
                                   const void* proprios, const void* actions, const void* noise, const void* t,
                                   float flow_sig_min, float* loss_out, float* velocity_out, int32_t B, int32_t io_dtype,
                                   void* stream);
+/* Greedy text generation of the chat VLM — InternVLChatModel.generate
+ * (Vlaser_VLM/internvl_chat/internvl/model/internvl_chat/modeling_internvl_chat.py:401-439: extract_feature, image rows
+ * scattered into the token embeddings, then HF `language_model.generate(inputs_embeds, do_sample=False, use_cache=True)`),
+ * which is also the loop of pizero_internvl.py:1412-1447 around PiZero.infer_text (:1005-1046). The LLM mixture alone:
+ * causal attention, RoPE positions 0.. (HF), all layers complete, final RMSNorm, output head, argmax; the prompt K/V stay
+ * in the handle's cache and every decode step (one CUDA graph, replayed) appends one row per sample.
+ *   input_ids      i64 [B, max_image_text_tokens], right padded with pad_token_id; image rows = image_token_index
+ *   pixel_values   io_dtype [B*cond_steps, 3, image_size, image_size] image tiles in batch order (a sample owns as many as
+ *                  its ids hold runs of image tokens), or NULL for a text-only prompt
+ *   valid_len      i32 [B] or NULL (count of non-pad ids)
+ *   max_new_tokens 1 .. max_image_text_tokens + 1 + H: a sample's K/V window holds prompt + generated tokens; a sample
+ *                  that fills it stops like one that emitted eos
+ *   tokens_out     i64 [B, max_new_tokens]; positions after a sample's eos hold fill_token_id
+ *   first_logits_out f32 [B, embed_rows] or NULL: logits of the last prompt position (== infer_text(...)["logits"][:, -1])
+ * Needs the LLM's final norm (`joint_model.mixtures.vlm.norm.weight` / `...language_model.model.norm.weight`) and takes
+ * `lm_head.weight` when the checkpoint has one (else the tied embedding table, Qwen2.5-1.5B). Device pointers;
+ * stream-ordered like vlaser_infer_action (the first call per batch size captures two graphs). */
+int32_t vlaser_generate(vlaser_t* h, const int64_t* input_ids, const void* pixel_values, const int32_t* valid_len,
+                        int32_t max_new_tokens, int64_t eos_token_id, int64_t fill_token_id, int64_t* tokens_out,
+                        float* first_logits_out, int32_t B, int32_t io_dtype, void* stream);
 void vlaser_destroy(vlaser_t* h);
 
 /* Options: "pdl" (process-wide; 0 off, 1 programmatic dependent launch inside the denoise steps only, 2 (default) on every launch),
@@ -202,6 +222,7 @@ typedef struct vlaser_attn_args {
   const int32_t* q_start; const int32_t* q_len; const int32_t* kv_start; const int32_t* kv_len;
   int32_t uni_q_len, uni_kv_len, max_q_len, group, n_kv_heads, batch, head_dim;
   float scale;
+  int32_t causal;  /* 1: query token t of a sample sees keys [0, kv_len - q_len + t] (text prefill of the chat VLM) */
 } vlaser_attn_args;
 int32_t vlaser_op_attention(const vlaser_attn_args* a, void* stream);
 /* InternViT self-attention fast path (_naive_attn, modeling_intern_vit.py:210-227): qkv bf16 [images*tokens, 3*heads*64]

@@ -104,8 +104,9 @@ class _VisionTower(nn.Module):
         return self.vision_model(pixel_values=pixel_values)
 
 
-def build_reference_policy(cfg, sd: Dict[str, torch.Tensor]):
-    """Reference `PiZero` instance (fp32, CPU, eval) holding the weights in `sd`."""
+def build_reference_policy(cfg, sd: Dict[str, torch.Tensor], parts: dict = None):
+    """Reference `PiZero` instance (fp32, CPU, eval) holding the weights in `sd`. `parts` (optional dict) receives the HF
+    `Qwen2ForCausalLM` objects whose decoder layers the joint model holds ("llm", "expert")."""
     from transformers import Qwen2Config, Qwen2ForCausalLM
 
     ref = load_reference()
@@ -201,14 +202,19 @@ def build_reference_policy(cfg, sd: Dict[str, torch.Tensor]):
         raise ValueError("reference supports only 16x16 / 32x32 patch grids; use patched_grid()")
     pol.image_448 = cfg.grid == 32
 
-    missing, unexpected = pol.load_state_dict(sd, strict=False)
+    # (the harness instance carries no `lm_head` module -- pizero_internvl.py:325-334 -- run_reference_generate loads it into
+    # the HF model itself)
+    missing, unexpected = pol.load_state_dict({k: v for k, v in sd.items() if k != "lm_head.weight"}, strict=False)
     assert not unexpected, f"unexpected keys: {unexpected[:5]}"
     allowed_missing = ("joint_model.mixtures.vlm.norm.weight",)
     real_missing = [k for k in missing if not k.endswith(allowed_missing) and "proprio" not in k]
     assert not real_missing, f"missing keys: {real_missing[:8]}"
-    # vlm final norm is never used on this path (skip rule); give it a value anyway
-    with torch.no_grad():
-        llm.model.norm.weight.fill_(1.0)
+    # vlm final norm is never used on the policy path (skip rule); give it a value when the weights have none
+    if "joint_model.mixtures.vlm.norm.weight" not in sd:
+        with torch.no_grad():
+            llm.model.norm.weight.fill_(1.0)
+    if parts is not None:
+        parts.update(llm=llm, expert=expert)
     pol.eval()
     return pol
 
@@ -301,3 +307,32 @@ def run_reference_flow_loss(cfg, sd, input_ids, pixel_values, proprios, actions,
         torch.randn_like = real
         h.remove()
     return loss.detach().clone(), seen["v_psi"]
+
+
+def run_reference_generate(cfg, sd, input_ids, pixel_values, max_new_tokens: int):
+    """Greedy decode of the chat VLM with the reference's modules: the merged prompt embeddings come from the reference's
+    own `PiZero._forward_siglip_and_text_embedding` (pizero_internvl.py:718-796 -- the same extract_feature + masked scatter
+    as `InternVLChatModel.generate`, V/.../modeling_internvl_chat.py:415-428), and the text is produced by the unmodified HF
+    `Qwen2ForCausalLM.generate(inputs_embeds=..., do_sample=False, use_cache=True)` that `generate` calls at :430-437, one
+    sample at a time (no padding). `sd` must hold `joint_model.mixtures.vlm.norm.weight` and optionally `lm_head.weight`
+    (else tied to the embedding table). Returns (tokens [B, max_new_tokens], first_logits [B, vocab])."""
+    parts = {}
+    pol = build_reference_policy(cfg, sd, parts)
+    llm = parts["llm"]
+    with torch.no_grad():
+        llm.model.embed_tokens.weight.copy_(sd["embed_tokens.weight"])
+        llm.lm_head.weight.copy_(sd.get("lm_head.weight", sd["embed_tokens.weight"]))
+    llm.eval()
+    llm.generation_config.pad_token_id = cfg.pad_token_id
+    llm.generation_config.eos_token_id = None
+    valid = (input_ids != cfg.pad_token_id).sum(-1).tolist()
+    toks, first = [], []
+    with torch.inference_mode():
+        emb = pol._forward_siglip_and_text_embedding(input_ids, pixel_values)
+        for b in range(input_ids.shape[0]):
+            e = emb[b:b + 1, : valid[b]]
+            first.append(llm(inputs_embeds=e).logits[0, -1].clone())
+            out = llm.generate(inputs_embeds=e, attention_mask=torch.ones(e.shape[:2], dtype=torch.int64),
+                               max_new_tokens=max_new_tokens, min_new_tokens=max_new_tokens, do_sample=False, use_cache=True)
+            toks.append(out[0, -max_new_tokens:].clone())
+    return torch.stack(toks), torch.stack(first)

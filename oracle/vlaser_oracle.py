@@ -364,3 +364,59 @@ def flow_matching_loss(cfg, sd: Dict[str, torch.Tensor], input_ids: torch.Tensor
     v_psi = F.linear(y, sd["action_decoder.weight"], sd["action_decoder.bias"])
     d_psi = x1 - (1 - flow_sig_min) * x0
     return torch.mean((v_psi - d_psi) ** 2), v_psi
+
+
+# --------------------------------------------------------------------------------------
+# chat VLM: causal LLM over the merged prompt embeddings, greedy decode
+# --------------------------------------------------------------------------------------
+def causal_lm_logits(cfg, sd, embeds: torch.Tensor) -> torch.Tensor:
+    """HF Qwen2ForCausalLM.forward(inputs_embeds=...) restated (transformers Qwen2Model / Qwen2DecoderLayer /
+    eager_attention_forward with the causal mask; call sites: V/internvl/model/internvl_chat/modeling_internvl_chat.py:
+    430-437 `language_model.generate(inputs_embeds=...)`, S/vla/pizero_internvl.py:1027-1040 `infer_text`). embeds
+    [B, L, hidden] without padding; positions 0..L-1. Returns logits [B, L, vocab]. Weights: the `vlm` mixture layers,
+    `joint_model.mixtures.vlm.norm.weight`, and `lm_head.weight` (or the tied `embed_tokens.weight`)."""
+    groups = cfg.n_heads // cfg.n_kv_heads
+    scaling = cfg.head_dim ** -0.5
+    B_, L_, _ = embeds.shape
+    pos = torch.arange(L_, device=embeds.device).unsqueeze(0).expand(B_, -1)
+    cos, sin = rope_cos_sin(pos, cfg.head_dim, cfg.rope_theta)
+    mask = torch.full((L_, L_), torch.finfo(embeds.dtype).min, dtype=embeds.dtype, device=embeds.device).triu(1)[None, None]
+    x = embeds
+    for li in range(cfg.layers):
+        q, k, v = _attn_block(cfg, sd, VLM, li, x)
+        q, k = apply_rope(q, cos, sin), apply_rope(k, cos, sin)
+        o = eager_attention(q, k, v, mask, scaling, groups)
+        x = _post_attn(cfg, sd, VLM, li, x, o.reshape(B_, L_, -1))
+    x = rms_norm(x, sd["joint_model.mixtures.vlm.norm.weight"], cfg.rms_eps)
+    return F.linear(x, sd.get("lm_head.weight", sd["embed_tokens.weight"]))
+
+
+def generate(cfg, sd, input_ids: torch.Tensor, pixel_values: Optional[torch.Tensor], max_new_tokens: int,
+             eos_token_id: int = -1, fill_token_id: int = 0, forced: Optional[torch.Tensor] = None):
+    """Greedy decode of the chat VLM: V/.../modeling_internvl_chat.py:401-439 (image rows scattered into the token
+    embeddings, then HF generate with do_sample=False). No KV cache here: every step re-runs the causal forward over the
+    sample's whole sequence (an oracle; the sizes are tiny). `forced` [B, max_new_tokens] (optional): teacher forcing --
+    the tokens fed back are the given ones, so that the per-step logits can be compared with a run whose argmax went
+    another way on a near tie. Returns (tokens [B, max_new_tokens], step_logits: list over samples of [steps, vocab])."""
+    if pixel_values is not None:
+        embeds = prefix_embedding(cfg, sd, input_ids, pixel_values)
+    else:
+        embeds = F.embedding(input_ids.clamp(max=cfg.embed_rows - 1), sd["embed_tokens.weight"])
+    valid = (input_ids != cfg.pad_token_id).sum(-1).tolist()
+    B_ = input_ids.shape[0]
+    tokens = torch.full((B_, max_new_tokens), fill_token_id, dtype=torch.int64)
+    all_logits = []
+    for b in range(B_):
+        seq = embeds[b:b + 1, : valid[b]]
+        rows = []
+        for k in range(max_new_tokens):
+            logits = causal_lm_logits(cfg, sd, seq)[0, -1]
+            rows.append(logits)
+            tok = int(torch.argmax(logits))
+            tokens[b, k] = tok
+            fed = int(forced[b, k]) if forced is not None else tok
+            if forced is None and tok == eos_token_id:
+                break
+            seq = torch.cat([seq, sd["embed_tokens.weight"][fed].view(1, 1, -1).to(seq.dtype)], dim=1)
+        all_logits.append(torch.stack(rows))
+    return tokens, all_logits

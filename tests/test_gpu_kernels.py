@@ -390,6 +390,53 @@ def test_attention_prefill_and_denoise():
     assert max(errs) < 1e-2
 
 
+def test_attention_causal():
+    """Text prefill of the chat VLM (HF causal mask): GQA 6:1 and 7:1, ragged lengths incl. several query blocks, and the
+    decode shape (one query row over kv_len keys)."""
+    for group, lens in ((6, [85, 1, 130, 300]), (7, [64, 129])):
+        B, nkv, hd = len(lens), 2, 128
+        nq = nkv * group
+        cu = [0]
+        for L in lens:
+            cu.append(cu[-1] + L)
+        window = max(lens) + 8
+        kvoff = [b * window for b in range(B)]
+        q = _rand(cu[-1], nq * hd, seed=11)
+        kc = _rand(nkv, B * window, hd, seed=12)
+        vc = _rand(nkv, B * window, hd, seed=13)
+        i32 = lambda x: torch.tensor(x, dtype=torch.int32, device=DEV)
+        out = torch.zeros_like(q)
+        scale = hd ** -0.5
+        ops.attention(q, kc, vc, out, hd, group, nkv, B, scale, nq * hd, hd, B * window * hd, nq * hd, max_q_len=max(lens),
+                      q_start=i32(cu[:-1]), q_len=i32(lens), kv_start=i32(kvoff), kv_len=i32(lens), causal=1)
+        errs = []
+        for b in range(B):
+            L = lens[b]
+            mask = torch.full((L, L), float("-inf"), device=DEV).triu(1)
+            for h in range(nq):
+                g = h // group
+                K = kc[g, kvoff[b]:kvoff[b] + L].float()
+                V = vc[g, kvoff[b]:kvoff[b] + L].float()
+                Q = q[cu[b]:cu[b] + L, h * hd:(h + 1) * hd].float()
+                r = torch.softmax(Q @ K.T * scale + mask, -1) @ V
+                errs.append(ops.rel_err(out[cu[b]:cu[b] + L, h * hd:(h + 1) * hd], r))
+        print(f"attention_causal group={group} max rel={max(errs):.2e}")
+        assert max(errs) < 1e-2
+        # decode: one new query per sample sees its kv_len keys (no mask needed, causal flag harmless)
+        qd = _rand(B, nq * hd, seed=14)
+        outd = torch.zeros_like(qd)
+        ops.attention(qd, kc, vc, outd, hd, group, nkv, B, scale, nq * hd, hd, B * window * hd, nq * hd, max_q_len=1,
+                      q_start=i32(list(range(B))), q_len=i32([1] * B), kv_start=i32(kvoff), kv_len=i32(lens), causal=1)
+        errs = []
+        for b in range(B):
+            for h in range(nq):
+                g = h // group
+                r = _attn_ref(qd[b:b + 1, h * hd:(h + 1) * hd].float(), kc[g, kvoff[b]:kvoff[b] + lens[b]].float(),
+                              vc[g, kvoff[b]:kvoff[b] + lens[b]].float(), scale, lens[b])
+                errs.append(ops.rel_err(outd[b:b + 1, h * hd:(h + 1) * hd], r))
+        assert max(errs) < 1e-2
+
+
 @pytest.mark.parametrize("width", [128, 768, 1024, 1536, 4096])
 def test_norms(width):
     rows = 515

@@ -16,12 +16,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import vlaser_oracle as O  # noqa: E402  (checker only)
-from tests.golden_util import CASES, DYNAMIC_TILE_CASES, FLOW_CASES, load_case  # noqa: E402
+from tests.golden_util import CASES, DYNAMIC_TILE_CASES, FLOW_CASES, GENERATE_CASES, load_case  # noqa: E402
 from tests.ops import max_err, rel_err  # noqa: E402
 from vlaser_b200.config import tiny, vlaser_2b_bridge  # noqa: E402
 from vlaser_b200.policy import PiZeroInference  # noqa: E402
 from vlaser_b200.synth import make_inputs  # noqa: E402
-from vlaser_b200.weights import random_state_dict  # noqa: E402
+from vlaser_b200.weights import random_state_dict, text_head_state_dict  # noqa: E402
 
 ACTION_TOL = 1e-2
 
@@ -514,3 +514,114 @@ def test_flow_matching_loss_full_size_vs_oracle(capsys):
         print(f"\n[2B flow loss] {loss:.5f} vs oracle {float(ref_loss):.5f}; v_psi max-abs {e_v:.3e}")
     assert e_v <= ACTION_TOL
     assert abs(loss - float(ref_loss)) <= 1e-2 * float(ref_loss)
+
+
+# ---- chat VLM: causal prefill + greedy decode (modeling_internvl_chat.py:401-439) ----------------
+def _real_tokens(cfg, inp, b, n_new):
+    """Tokens sample b can emit: its K/V window of S + 1 + H rows holds the prompt and every token that is fed back; the
+    last emitted token is not fed back."""
+    valid = int((inp["input_ids"][b] != cfg.pad_token_id).sum())
+    return min(n_new, cfg.max_image_text_tokens + 1 + cfg.num_action_tokens - valid + 1)
+
+
+def _check_generation(cfg, sd, inp, toks, first_logits, log, tag):
+    """bf16 tensor-core logits against the fp32 oracle, robust to near ties: the oracle is teacher-forced with the tokens
+    the GPU emitted, and every emitted token must be within `tol` of the oracle's best logit at that step; the logits
+    of the last prompt position are compared directly."""
+    n_new = toks.shape[1]
+    _, ref = O.generate(cfg, sd, inp["input_ids"], inp["pixel_values"], n_new, forced=toks)
+    ref_first = torch.stack([l[0] for l in ref])
+    scale = float(ref_first.std())
+    e_first = max_err(first_logits, ref_first)
+    worst = 0.0
+    for b in range(toks.shape[0]):
+        for k in range(_real_tokens(cfg, inp, b, n_new)):
+            worst = max(worst, float(ref[b][k].max() - ref[b][k][toks[b, k]]))
+        assert bool((toks[b, _real_tokens(cfg, inp, b, n_new):] == cfg.pad_token_id).all()), "fill token behind a full window"
+    e_rms = float((first_logits - ref_first).pow(2).mean().sqrt())
+    log(f"\n[{tag}] first-step logits vs fp32 oracle: max-abs {e_first:.3e} rms {e_rms:.3e} (logit std {scale:.2f}); "
+        f"worst oracle-logit gap of an emitted token {worst:.3e}")
+    # bf16 operands: well under 1 % of the logit spread rms; the maximum over B x vocab logits sits ~5 sigma out
+    assert e_rms <= 1e-2 * scale and e_first <= 5e-2 * scale
+    assert worst <= 2e-2 * scale
+    return ref
+
+
+@pytest.mark.parametrize("name", GENERATE_CASES)
+def test_generate_golden(name, capsys):
+    """Greedy decode through the C ABI vs the HF / reference golden (tiny configs; untied head, and tied head with dynamic
+    tiles 1/3/2/2)."""
+    cfg, sd, inp, gold = load_case(name)
+    B, n_new = gold["tokens"].shape
+    pol = PiZeroInference(cfg, max_batch=B)
+    pol.load_state_dict(sd, strict=False)
+    toks, logits = pol.generate(inp["input_ids"].cuda(), inp["pixel_values"].cuda(), max_new_tokens=n_new, return_first_logits=True)
+    toks2 = pol.generate(inp["input_ids"].cuda(), inp["pixel_values"].cuda(), max_new_tokens=n_new)  # graph replays
+    assert torch.equal(toks, toks2), "generation must be bit-identical from call to call"
+    toks, logits = toks.cpu(), logits.cpu()
+    scale = float(gold["first_logits"].std())
+    assert max_err(logits, gold["first_logits"]) <= 5e-2 * scale
+    with capsys.disabled():
+        ref = _check_generation(cfg, sd, inp, toks, logits, print, name)
+    # where the reference's own margin is clear, the tokens are the reference's
+    for b in range(B):
+        for k in range(_real_tokens(cfg, inp, b, n_new)):
+            top2 = ref[b][k].topk(2).values
+            if not torch.equal(toks[b, : k + 1], gold["tokens"][b, : k + 1]):
+                assert float(top2[0] - top2[1]) <= 4e-2 * scale, f"sample {b} step {k}: token differs at a clear margin"
+                break
+    # eos stops a sample: its first emitted token as eos -> everything after it is the fill token
+    eos = int(toks[0, 0])
+    t3 = pol.generate(inp["input_ids"].cuda(), inp["pixel_values"].cuda(), max_new_tokens=n_new, eos_token_id=eos,
+                      fill_token_id=7).cpu()
+    assert int(t3[0, 0]) == eos and bool((t3[0, 1:] == 7).all())
+    for b in range(1, B):
+        if eos not in toks[b].tolist():
+            n = _real_tokens(cfg, inp, b, n_new)
+            assert torch.equal(t3[b, :n], toks[b, :n]) and bool((t3[b, n:] == 7).all())
+    # the policy call still works on the same handle (its own graphs and K/V layout)
+    pinp = make_inputs(cfg, B, 5)
+    if name == "tiny_generate":
+        a = _run(pol, pinp)
+        ref_a = O.infer_action(cfg, sd, pinp["input_ids"], pinp["pixel_values"], pinp["proprios"], pinp["noise"])
+        assert max_err(a, ref_a) <= ACTION_TOL
+
+
+def test_generate_text_only_and_window():
+    """A text-only prompt (no tile goes through the ViT) and a sample that fills its K/V window."""
+    cfg = tiny()
+    sd = random_state_dict(cfg, 0)
+    sd.update(text_head_state_dict(cfg, 0))
+    B, S = 2, cfg.max_image_text_tokens
+    g = torch.Generator().manual_seed(3)
+    ids = torch.full((B, S), cfg.pad_token_id, dtype=torch.int64)
+    ids[0, :7] = torch.randint(0, 400, (7,), generator=g)
+    ids[1, :S] = torch.randint(0, 400, (S,), generator=g)  # full prompt: window = S + 1 + H leaves 1 + H new tokens
+    pol = PiZeroInference(cfg, max_batch=B)
+    pol.load_state_dict(sd, strict=False)
+    n_new = 2 + cfg.num_action_tokens + 1
+    toks = pol.generate(ids.cuda(), None, max_new_tokens=n_new, fill_token_id=9).cpu()
+    _, logits = O.generate(cfg, sd, ids, None, n_new, forced=toks)
+    scale = float(logits[0][0].std())
+    for k in range(n_new):
+        assert float(logits[0][k].max() - logits[0][k][toks[0, k]]) <= 2e-2 * scale
+    # sample 1: its window (S + 1 + H rows) takes the prompt and 1 + H fed-back tokens, so 2 + H tokens are emitted (the
+    # last one is never fed back); the rest is the fill token
+    for k in range(2 + cfg.num_action_tokens):
+        assert float(logits[1][k].max() - logits[1][k][toks[1, k]]) <= 2e-2 * scale
+    assert bool((toks[1, 2 + cfg.num_action_tokens:] == 9).all())
+
+
+def test_generate_full_width_reduced_depth(capsys):
+    """2B widths (1536 / 12:2 heads / MLP 8960, vocab 151 930) at depth 2, B = 3, bf16 tiles, 12 new tokens."""
+    cfg = vlaser_2b_bridge().with_(layers=2, vit_layers=2)
+    sd = random_state_dict(cfg, 0)
+    sd.update(text_head_state_dict(cfg, 0, tied=True))
+    B = 3
+    inp = make_inputs(cfg, B, 9)
+    pol = PiZeroInference(cfg, max_batch=B)
+    pol.load_state_dict(sd, strict=False)
+    toks, logits = pol.generate(inp["input_ids"].cuda(), inp["pixel_values"].bfloat16().cuda(), max_new_tokens=12,
+                                return_first_logits=True)
+    with capsys.disabled():
+        _check_generation(cfg, sd, inp, toks.cpu(), logits.cpu(), print, "2B widths depth 2")

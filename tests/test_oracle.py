@@ -8,7 +8,7 @@ import torch
 
 from oracle import ref_harness
 from oracle import vlaser_oracle as O
-from tests.golden_util import CASES, DYNAMIC_TILE_CASES, FLOW_CASES, load_case
+from tests.golden_util import CASES, DYNAMIC_TILE_CASES, FLOW_CASES, GENERATE_CASES, load_case
 from vlaser_b200.config import tiny
 from vlaser_b200.synth import make_inputs
 from vlaser_b200.weights import random_state_dict
@@ -37,6 +37,21 @@ def test_oracle_flow_loss_matches_golden(name):
                                    inp["noise"], inp["t"], inp["flow_sig_min"])
     assert (v - gold["v_psi"]).abs().max() < 2e-5
     assert abs(float(loss) - float(gold["loss"])) < 1e-5 * max(1.0, float(gold["loss"]))
+
+
+@pytest.mark.parametrize("name", GENERATE_CASES)
+def test_oracle_generate_matches_golden(name):
+    """Chat-VLM greedy decode: the causal-LM restatement reproduces the tokens and first-step logits of the unmodified HF
+    Qwen2ForCausalLM.generate fed by the reference's own prompt embedding (make_generate_golden.py)."""
+    cfg, sd, inp, gold = load_case(name)
+    n_new = gold["tokens"].shape[1]
+    toks, logits = O.generate(cfg, sd, inp["input_ids"], inp["pixel_values"], n_new)
+    assert torch.equal(toks, gold["tokens"])
+    first = torch.stack([l[0] for l in logits])
+    assert (first - gold["first_logits"]).abs().max() < 1e-4 * max(1.0, float(gold["first_logits"].abs().max()))
+    # teacher forcing with the same tokens reproduces the free-running logits
+    _, forced = O.generate(cfg, sd, inp["input_ids"], inp["pixel_values"], n_new, forced=toks)
+    assert all(torch.equal(a, b) for a, b in zip(logits, forced))
 
 
 def _tiny_case(B=2, seed=5, prompt_tokens=(5, 11)):

@@ -56,6 +56,7 @@ class AttnArgs(C.Structure):
         ("q_start", C.c_void_p), ("q_len", C.c_void_p), ("kv_start", C.c_void_p), ("kv_len", C.c_void_p),
         ("uni_q_len", C.c_int32), ("uni_kv_len", C.c_int32), ("max_q_len", C.c_int32), ("group", C.c_int32),
         ("n_kv_heads", C.c_int32), ("batch", C.c_int32), ("head_dim", C.c_int32), ("scale", C.c_float),
+        ("causal", C.c_int32),
     ]
 
 
@@ -66,7 +67,7 @@ EXPORTS = [
     "vlaser_op_layernorm", "vlaser_op_rmsnorm", "vlaser_op_pixel_shuffle", "vlaser_op_im2col", "vlaser_op_euler_step",
     "vlaser_op_vit_attention", "vlaser_profile_read_classes", "vlaser_op_stage_frames", "vlaser_op_postprocess_actions",
     "vlaser_op_splitk_reduce", "vlaser_op_vit_attention_tc", "vlaser_op_normalize", "vlaser_op_prefill_attention_tc",
-    "vlaser_flow_matching_loss",
+    "vlaser_flow_matching_loss", "vlaser_generate",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -97,6 +98,8 @@ def load() -> C.CDLL:
     lib.vlaser_infer_action_host.restype = i32
     lib.vlaser_flow_matching_loss.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, i32, i32, vp]
     lib.vlaser_flow_matching_loss.restype = i32
+    lib.vlaser_generate.argtypes = [vp, vp, vp, vp, i32, i64, i64, vp, vp, i32, i32, vp]
+    lib.vlaser_generate.restype = i32
     lib.vlaser_destroy.argtypes = [vp]
     lib.vlaser_destroy.restype = None
     lib.vlaser_set_option.argtypes = [vp, C.c_char_p, i64]

@@ -41,6 +41,7 @@ struct AttnParams {
   // programmatic-dependent-launch wait and overlaps the tail of the q|k|v projection that produces the new rows
   int stable_prefix = 0;
   int min_kv_len = 0;   // samples with fewer kv rows are skipped (they were handled by the tcgen05 prefill kernel)
+  int causal = 0;       // 1: query token t of a sample sees keys [0, kv_len - q_len + t] (HF causal mask; no q2 row)
   long long* trace = nullptr;  // optional timeline record of this launch (common.cuh trace_stamp)
 };
 

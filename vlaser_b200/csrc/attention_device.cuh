@@ -41,7 +41,11 @@ __device__ __forceinline__ void attention_tile(const AttnParams& p, int b, int k
   const int r0 = qb * ATT_BM;
   if (r0 >= rows_total || kv_len < p.min_kv_len) return;  // (exits without dep_wait: nothing was read)
   const bool cta_has_extra = has_extra && (r0 + ATT_BM > group * q_len);
-  const int kv_hi = kv_len + (cta_has_extra ? 1 : 0);
+  // causal (text prefill of the chat VLM): query token t sees keys [0, kv_len - q_len + t]; the CTA stops at the last key
+  // its last token sees
+  const int causal_off = kv_len - q_len;
+  const int t_last = min(q_len - 1, (r0 + ATT_BM - 1) / group);
+  const int kv_hi = p.causal ? min(kv_len, causal_off + t_last + 1) : kv_len + (cta_has_extra ? 1 : 0);
   const int n_blocks = (kv_hi + ATT_BN - 1) / ATT_BN;
 
   const __nv_bfloat16* kbase = p.k + (size_t)kvh * p.kv_head_stride + (size_t)kv_start * p.kv_row_stride;
@@ -89,6 +93,7 @@ __device__ __forceinline__ void attention_tile(const AttnParams& p, int b, int k
   for (int h = 0; h < 2; ++h) {
     const int r = r0 + rlo + h * 8;
     if (r >= rows_total) lim[h] = 0;
+    else if (p.causal) lim[h] = min(kv_len, causal_off + r / group + 1);
     else lim[h] = (has_extra && (r / group) == q_len) ? kv_len + 1 : kv_len;
   }
   const bool warp_active = (r0 + warp * 16) < rows_total;

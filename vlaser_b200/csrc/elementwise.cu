@@ -308,14 +308,16 @@ __global__ void plan_lengths_kernel(const long long* __restrict__ ids, const int
   }
 }
 
-__global__ void plan_scan_kernel(PlanBuffers pb, int B, int H) {
+__global__ void plan_scan_kernel(PlanBuffers pb, int B, int H, int kv_stride) {
   pdl_launch_dependents();
   pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     int acc = 0, img = 0;
     for (int b = 0; b < B; ++b) {
       pb.cu[b] = acc;
-      pb.kvoff[b] = acc + b * (1 + H);
+      // policy call: K/V rows packed like the prefix (+ proprio + H action rows per sample); text generation: every sample
+      // owns a fixed window of kv_stride rows that its decode steps fill
+      pb.kvoff[b] = kv_stride > 0 ? b * kv_stride : acc + b * (1 + H);
       pb.img_off[b] = img;
       acc += pb.valid_len[b];
       img += pb.img_cnt[b];
@@ -326,7 +328,7 @@ __global__ void plan_scan_kernel(PlanBuffers pb, int B, int H) {
 }
 
 __global__ void plan_rows_kernel(const long long* __restrict__ ids, PlanBuffers pb, int B, int S, int H,
-                                 int img_tokens, int image_token, int pad_token, int embed_rows) {
+                                 int img_tokens, int image_token, int pad_token, int embed_rows, int pos0) {
   pdl_launch_dependents();
   pdl_wait();
   // one warp per sample
@@ -341,7 +343,7 @@ __global__ void plan_rows_kernel(const long long* __restrict__ ids, PlanBuffers 
     const unsigned mask = __ballot_sync(0xffffffffu, is_img);
     if (valid) {
       const int m = base + j;
-      pb.row_pos[m] = j + 1;
+      pb.row_pos[m] = j + pos0;  // policy call: ids start at 1 (pizero_internvl.py:575-577); chat VLM: at 0 (HF)
       pb.row_kvrow[m] = kvo + j;
       int src;
       if (is_img) {
@@ -564,6 +566,88 @@ __global__ void __launch_bounds__(256) flow_loss_kernel(const float* __restrict_
   if (threadIdx.x == 0) loss[0] = part[0] / (float)n;
 }
 
+// ---- greedy text generation of the chat VLM (see elementwise.cuh)
+__global__ void __launch_bounds__(256) last_rows_kernel(const float* __restrict__ x, const int* __restrict__ cu,
+                                                        const int* __restrict__ valid_len, float* __restrict__ out, int width) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  const int vl = valid_len[b];
+  const float* src = x + (size_t)(cu[b] + max(vl, 1) - 1) * width;
+  for (int c = threadIdx.x * 4; c < width; c += 1024)
+    *reinterpret_cast<float4*>(out + (size_t)b * width + c) =
+        vl > 0 ? *reinterpret_cast<const float4*>(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(1024) argmax_rows_kernel(const float* __restrict__ logits, long long ld, int n,
+                                                           int* __restrict__ next_tok, int* __restrict__ n_gen, int bump) {
+  __shared__ float bv[32];
+  __shared__ int bi[32];
+  pdl_launch_dependents();
+  pdl_wait();
+  const float* row = logits + (size_t)blockIdx.x * ld;
+  float best = -INFINITY;
+  int idx = 0x7fffffff;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {  // strictly greater: the first maximum wins, like torch.argmax
+    const float v = row[i];
+    if (v > best || (v == best && i < idx)) best = v, idx = i;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > best || (ov == best && oi < idx)) best = ov, idx = oi;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) bv[warp] = best, bi[warp] = idx;
+  __syncthreads();
+  if (warp == 0) {
+    best = lane < (int)(blockDim.x >> 5) ? bv[lane] : -INFINITY;
+    idx = lane < (int)(blockDim.x >> 5) ? bi[lane] : 0x7fffffff;
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ov > best || (ov == best && oi < idx)) best = ov, idx = oi;
+    }
+    if (lane == 0) {
+      next_tok[blockIdx.x] = idx == 0x7fffffff ? 0 : idx;
+      if (bump && blockIdx.x == 0) *n_gen += 1;  // (every reader of n_gen in this step ran in an earlier launch)
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) decode_advance_kernel(TextGenBuffers g, const int* __restrict__ valid_len,
+                                                             const int* __restrict__ kvoff,
+                                                             const __nv_bfloat16* __restrict__ embed, float* __restrict__ x,
+                                                             int width, int window, int gen_cap, long long eos, long long fill) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  const int k = *g.n_gen;  // tokens emitted so far
+  const int vl = valid_len[b];
+  const bool done = g.finished[b] != 0;
+  long long tok = done ? fill : (long long)g.next_tok[b];
+  // the emitted token becomes the input of the next step at position vl + k; a full window ends the sample
+  const bool full = vl + k + 1 > window;
+  __syncthreads();  // every thread has read finished[b] before thread 0 updates it
+  if (threadIdx.x == 0) {
+    if (k < gen_cap) g.tokens[(size_t)b * gen_cap + k] = tok;
+    if (!done && (tok == eos || full)) g.finished[b] = 1;
+    const int pos = min(vl + k, window - 1);
+    g.pos[b] = pos;
+    g.kvrow[b] = kvoff[b] + pos;
+    g.kv_len[b] = pos + 1;
+    g.q_start[b] = b;
+    g.q_len[b] = 1;
+  }
+  const __nv_bfloat16* src = embed + (size_t)(done ? 0 : tok) * width;
+  for (int c = threadIdx.x * 8; c < width; c += 2048) {
+    const uint4 u = *reinterpret_cast<const uint4*>(src + c);
+    float* dst = x + (size_t)b * width + c;
+    *reinterpret_cast<float4*>(dst) = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w));
+  }
+}
+
 }  // namespace
 
 // ==========================================================================================
@@ -629,12 +713,14 @@ int cls_rows_launch(float* x, const float* cls, const float* pos, int n, int tok
 }
 
 int plan_launch(const long long* input_ids, const int* valid_len_in, PlanBuffers pb, int B, int S, int H,
-                int img_tokens_per_sample, int image_token, int pad_token, int embed_rows, cudaStream_t stream) {
+                int img_tokens_per_sample, int image_token, int pad_token, int embed_rows, cudaStream_t stream,
+                int text_kv_stride) {
   VL_CHECK(B > 0, "plan: empty batch");
   VL_CUDA_CHECK(cudaMemsetAsync(pb.img_row_map, 0xFF, sizeof(int) * (size_t)B * img_tokens_per_sample, stream));
   VL_CUDA_CHECK(launch_kernel(plan_lengths_kernel, dim3((B * 32 + 127) / 128), dim3(128), 0, stream, input_ids, valid_len_in, pb, B, S, H, pad_token, image_token));
-  VL_CUDA_CHECK(launch_kernel(plan_scan_kernel, dim3(1), dim3(32), 0, stream, pb, B, H));
-  VL_CUDA_CHECK(launch_kernel(plan_rows_kernel, dim3(B), dim3(32), 0, stream, input_ids, pb, B, S, H, img_tokens_per_sample, image_token, pad_token, embed_rows));
+  VL_CUDA_CHECK(launch_kernel(plan_scan_kernel, dim3(1), dim3(32), 0, stream, pb, B, H, text_kv_stride));
+  VL_CUDA_CHECK(launch_kernel(plan_rows_kernel, dim3(B), dim3(32), 0, stream, input_ids, pb, B, S, H, img_tokens_per_sample, image_token, pad_token, embed_rows,
+                              text_kv_stride > 0 ? 0 : 1));
   VL_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -718,6 +804,26 @@ int bias_silu_rows_launch(const float* z, const float* tbias, __nv_bfloat16* h, 
 int flow_loss_launch(const float* vel, const void* x0, const void* x1, int io, float sig_min, long long n, float* loss,
                      cudaStream_t stream) {
   VL_CUDA_CHECK(launch_kernel(flow_loss_kernel, dim3(1), dim3(256), 0, stream, vel, x0, x1, io, sig_min, n, loss));
+  return 0;
+}
+
+int last_rows_launch(const float* x, const int* cu, const int* valid_len, float* out, int B, int width, cudaStream_t stream) {
+  VL_CHECK(width % 4 == 0, "last_rows: width % 4");
+  VL_CUDA_CHECK(launch_kernel(last_rows_kernel, dim3(B), dim3(256), 0, stream, x, cu, valid_len, out, width));
+  return 0;
+}
+
+int argmax_rows_launch(const float* logits, long long ld, int n, int rows, int* next_tok, int* n_gen, int bump,
+                       cudaStream_t stream) {
+  VL_CUDA_CHECK(launch_kernel(argmax_rows_kernel, dim3(rows), dim3(1024), 0, stream, logits, ld, n, next_tok, n_gen, bump));
+  return 0;
+}
+
+int decode_advance_launch(const TextGenBuffers& g, const int* valid_len, const int* kvoff, const __nv_bfloat16* embed, float* x,
+                          int B, int width, int window, int gen_cap, long long eos, long long fill, cudaStream_t stream) {
+  VL_CHECK(width % 8 == 0, "decode_advance: width % 8");
+  VL_CUDA_CHECK(launch_kernel(decode_advance_kernel, dim3(B), dim3(256), 0, stream, g, valid_len, kvoff, embed, x, width, window,
+                              gen_cap, eos, fill));
   return 0;
 }
 

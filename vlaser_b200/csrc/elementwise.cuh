@@ -78,8 +78,11 @@ struct PlanBuffers {
   int* bad_id;        // [1]  0, or 1 + the first token id seen outside [0, embed_rows) (nn.Embedding would raise IndexError;
                       //      here the row embeds as zeros and the call reports the error, engine.cu)
 };
+// text_kv_stride > 0: the chat-VLM layout -- sample b owns K/V rows [b * stride, (b + 1) * stride) and RoPE positions start
+// at 0 (HF Qwen2) instead of 1
 int plan_launch(const long long* input_ids, const int* valid_len_in, PlanBuffers pb, int B, int S, int H,
-                int img_tokens_per_sample, int image_token, int pad_token, int embed_rows, cudaStream_t stream);
+                int img_tokens_per_sample, int image_token, int pad_token, int embed_rows, cudaStream_t stream,
+                int text_kv_stride = 0);
 // text rows of the packed prefix: x[m,:] = embed[row_src[m],:] (bf16 -> fp32) or zeros
 int assemble_text_launch(const __nv_bfloat16* embed, const int* row_src, const int* m_tot, float* x, int rows_cap,
                          int width, cudaStream_t stream);
@@ -112,5 +115,26 @@ int bias_silu_rows_launch(const float* z, const float* tbias, __nv_bfloat16* h, 
 // loss = mean((vel - (x1 - (1 - sig_min) x0))^2) over n elements (:1190-1193), one CTA, fixed summation order
 int flow_loss_launch(const float* vel, const void* x0, const void* x1, int io, float sig_min, long long n, float* loss,
                      cudaStream_t stream);
+
+// ---- greedy text generation of the chat VLM (InternVLChatModel.generate -> HF generate(do_sample=False),
+// Vlaser_VLM/internvl_chat/internvl/model/internvl_chat/modeling_internvl_chat.py:401-439; the loop of
+// pizero_internvl.py:1412-1447 around PiZero.infer_text :1005-1046)
+struct TextGenBuffers {
+  int* next_tok;       // [B] argmax of the latest logits
+  int* n_gen;          // [1] tokens emitted so far
+  int* finished;       // [B] the sample has emitted eos (or filled its window)
+  long long* tokens;   // [B, gen_cap]
+  int *pos, *kvrow, *kv_len, *q_start, *q_len;  // [B] plan of the coming decode step
+};
+// out[b, :] = x[cu[b] + valid_len[b] - 1, :]: the residual row of the last prompt token of every sample
+int last_rows_launch(const float* x, const int* cu, const int* valid_len, float* out, int B, int width, cudaStream_t stream);
+// next_tok[r] = argmax(logits[r, :n]) (first maximum); bump: *n_gen += 1 afterwards
+int argmax_rows_launch(const float* logits, long long ld, int n, int rows, int* next_tok, int* n_gen, int bump,
+                       cudaStream_t stream);
+// Emits token k = *n_gen of every sample (next_tok, or `fill` once the sample is finished; eos / a full window finish it),
+// writes the plan of the decode step that consumes it (position valid_len + k, its K/V row, kv_len) and gathers its
+// embedding row into x[b, :] (fp32).
+int decode_advance_launch(const TextGenBuffers& g, const int* valid_len, const int* kvoff, const __nv_bfloat16* embed, float* x,
+                          int B, int width, int window, int gen_cap, long long eos, long long fill, cudaStream_t stream);
 
 }  // namespace vlaser

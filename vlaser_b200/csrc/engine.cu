@@ -55,6 +55,7 @@ struct Slot {
   long long dst_ld = 0, dst_row_off = 0;
   int mode = PK_PLAIN;
   bool filled = false;
+  bool optional = false;  // finalize does not insist on it (text head of the chat VLM)
 };
 
 template <typename TS, typename TD>
@@ -150,7 +151,21 @@ struct Engine {
   void *in_x1 = nullptr, *in_t = nullptr;
   float *flow_tbias = nullptr, *flow_z = nullptr, *flow_vel = nullptr, *flow_loss = nullptr;
   float flow_sig_min = 0.001f, flow_sig_graph = -1.f;
-  int mode = 0;                // what engine_execute enqueues: 0 infer_action, 1 flow-matching loss (forward only)
+  int mode = 0;                // what engine_execute enqueues: 0 infer_action, 1 flow-matching loss (forward only),
+                               // 2 causal text prefill + first token, 3 one greedy decode step
+  // ---- greedy text generation of the chat VLM (vlaser_generate): final norm of the LLM and its output head (optional
+  // weights; the head falls back to the tied embedding table), the residual rows of the tokens being decoded, logits
+  float* llm_norm = nullptr;
+  bool llm_norm_set = false;
+  Lin lm_head;                 // N = embed_rows padded to 128; the tensor maps clip at embed_rows (zero rows behind)
+  bool lm_head_own = false;
+  float* x_dec = nullptr;      // [Bc padded to 256, hidden] fp32
+  CUtensorMap xdec_otm;
+  float* logits = nullptr;     // [Bc, lm_head.N] fp32
+  TextGenBuffers gen{};
+  int gen_cap = 0;             // = the K/V window of a sample, S + 1 + H
+  long long gen_eos = -1, gen_fill = 0;
+  int text_no_image = 0;       // the prompt of this vlaser_generate call holds no image tile
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
 
@@ -209,9 +224,10 @@ struct Engine {
   cudaStream_t side_stream = nullptr;      // the proprio pass of the prefill when option "prop_stream" is set
   std::vector<cudaEvent_t> side_events;    // [layers] K/V of LLM layer l written, + fork + join
   struct GraphKey {
-    int B, io, stop, simt, has_valid, mode;
+    int B, io, stop, simt, has_valid, mode, no_img;
     bool operator<(const GraphKey& o) const {
-      return std::tie(B, io, stop, simt, has_valid, mode) < std::tie(o.B, o.io, o.stop, o.simt, o.has_valid, o.mode);
+      return std::tie(B, io, stop, simt, has_valid, mode, no_img) <
+             std::tie(o.B, o.io, o.stop, o.simt, o.has_valid, o.mode, o.no_img);
     }
   };
   struct GraphVal {
@@ -397,6 +413,9 @@ int engine_build(Engine& e) {
     return 0;
   };
   VL_TRY(add_llm(e.llm, "joint_model.mixtures.vlm.", h, c.mlp, e.mlp_p));
+  // text head of the chat VLM (optional: the policy call never reads them, pizero_internvl.py:192-193 skip rule)
+  VL_TRY(e.add_vec("joint_model.mixtures.vlm.norm.weight", &e.llm_norm, h));
+  e.slots.find("joint_model.mixtures.vlm.norm.weight")->second.optional = true;
   VL_TRY(add_llm(e.exp, "joint_model.mixtures.action.", he, c.mlp_e, e.mlp_e_p));
   VL_TRY(e.add_vec("joint_model.mixtures.action.norm.weight", &e.final_norm, he));
   // --- heads
@@ -522,6 +541,23 @@ int engine_build(Engine& e) {
   VL_TRY(e.alloc(&e.flow_z, (size_t)arow * c.hidden_e));
   VL_TRY(e.alloc(&e.flow_vel, (size_t)arow * c.action_dim));
   VL_TRY(e.alloc(&e.flow_loss, 4));
+  {
+    const int bpad = (e.Bc + 255) / 256 * 256;
+    e.gen_cap = e.S + 1 + e.H;
+    e.lm_head.N = (c.embed_rows + 127) / 128 * 128;
+    e.lm_head.K = h;
+    VL_TRY(e.alloc(&e.x_dec, (size_t)bpad * h));
+    VL_TRY(make_tmap_out(&e.xdec_otm, e.x_dec, bpad, h, 4));
+    VL_TRY(e.alloc(&e.gen.next_tok, e.Bc));
+    VL_TRY(e.alloc(&e.gen.n_gen, 4));
+    VL_TRY(e.alloc(&e.gen.finished, e.Bc));
+    VL_TRY(e.alloc(&e.gen.tokens, (size_t)e.Bc * e.gen_cap));
+    VL_TRY(e.alloc(&e.gen.pos, e.Bc));
+    VL_TRY(e.alloc(&e.gen.kvrow, e.Bc));
+    VL_TRY(e.alloc(&e.gen.kv_len, e.Bc));
+    VL_TRY(e.alloc(&e.gen.q_start, e.Bc));
+    VL_TRY(e.alloc(&e.gen.q_len, e.Bc));
+  }
   e.pinned_bytes = (size_t)e.Bc * e.S * 8 + pix_elems * 4 + (size_t)e.Bc * 4 + (size_t)e.Bc * c.proprio_dim * 4 +
                    (size_t)arow * c.action_dim * 4 + (size_t)e.Bc * c.horizon_steps * c.action_dim * 4 + 4096;
   VL_CUDA_CHECK(cudaMallocHost(&e.pinned, e.pinned_bytes));
@@ -541,10 +577,19 @@ int engine_set_weight(Engine& e, std::string key, const void* data, const int64_
       {"internvl_model.language_model.model.layers.", "joint_model.mixtures.vlm.layers."},
       {"internvl_model.action_expert.model.layers.", "joint_model.mixtures.action.layers."},
       {"internvl_model.action_expert.model.norm.", "joint_model.mixtures.action.norm."},
+      {"internvl_model.language_model.model.norm.", "joint_model.mixtures.vlm.norm."},
+      {"internvl_model.language_model.lm_head.", "lm_head."},
+      {"language_model.lm_head.", "lm_head."},
   };
   for (auto& a : aliases) {
     const size_t n = strlen(a.first);
     if (key.compare(0, n, a.first) == 0) key = std::string(a.second) + key.substr(n);
+  }
+  if (key == "lm_head.weight" && e.slots.find(key) == e.slots.end()) {
+    // output head of the chat VLM: storage only when a checkpoint brings one (otherwise the tied embedding table)
+    VL_TRY(e.alloc(&e.lm_head.w, (size_t)e.c.embed_rows * e.c.hidden));
+    e.add_slot(key, e.lm_head.w, DT_BF16, e.c.embed_rows, e.c.hidden);
+    e.lm_head_own = true;
   }
   auto range = e.slots.equal_range(key);
   if (range.first == range.second) return 1;  // not a tensor of this path
@@ -597,7 +642,7 @@ int engine_set_weight(Engine& e, std::string key, const void* data, const int64_
 int engine_finalize(Engine& e) {
   const vlaser_cfg& c = e.c;
   for (auto& kv : e.slots) {
-    if (!kv.second.filled) {
+    if (!kv.second.filled && !kv.second.optional) {
       set_last_error("finalize: missing weight " + kv.first);
       return -3;
     }
@@ -623,6 +668,15 @@ int engine_finalize(Engine& e) {
   VL_TRY(e.make_lin_maps(&e.ae_w2b));
   VL_TRY(e.make_lin_maps(&e.ae_w3));
   {
+    // text head: maps over the true row count -- TMA zero-fills the rows of the last 128-row box behind embed_rows
+    if (!e.lm_head_own) e.lm_head.w = e.embed;  // tie_word_embeddings (Qwen2.5-1.5B; pizero_internvl.py:325-334)
+    VL_TRY(make_tmap_bf16(&e.lm_head.tm128, e.lm_head.w, c.embed_rows, c.hidden, 128));
+    VL_TRY(make_tmap_bf16(&e.lm_head.tm64, e.lm_head.w, c.embed_rows, c.hidden, 64));
+    e.lm_head.has256 = false;
+    e.llm_norm_set = e.slots.find("joint_model.mixtures.vlm.norm.weight")->second.filled;
+    VL_TRY(e.alloc(&e.logits, (size_t)e.Bc * e.lm_head.N));
+  }
+  {
     std::vector<ExpertLayerDev> tab(c.layers);
     for (int i = 0; i < c.layers; ++i) {
       const LlmLayer& L = e.exp[i];
@@ -642,7 +696,7 @@ int engine_finalize(Engine& e) {
     VL_CUDA_CHECK(cudaMemcpy(e.xp_layers, tab.data(), tab.size() * sizeof(ExpertLayerDev), cudaMemcpyHostToDevice));
   }
   // RoPE tables (HF Qwen2RotaryEmbedding, default rope): cos/sin(pos * theta^(-2i/128)), i < 64
-  const int max_pos = std::max(e.S, e.H + 1) + 1;
+  const int max_pos = e.S + e.H + 2;  // policy call: ids 1..S, 2..H+1; text generation: 0..S+H (the K/V window)
   std::vector<float> ct((size_t)max_pos * 64), st((size_t)max_pos * 64);
   for (int p = 0; p < max_pos; ++p)
     for (int i = 0; i < 64; ++i) {
@@ -938,6 +992,11 @@ struct Run {
     ShuffleGather sg;
     sg.grid = e.G;
     sg.channels = d;
+    if (e.text_no_image) {  // text-only prompt of the chat VLM: no tile went through the ViT
+      VL_TRY(assemble_text_launch(e.embed, e.pb.row_src, e.pb.m_tot, e.xv, B * e.S, h, st));
+      e.launches++;
+      return 0;
+    }
     VL_TRY(layernorm_launch(e.vx, e.pj_lnw, e.pj_lnb, e.ps.p, prows, 4 * d, c.proj_eps, sg, st));
     EpiParams e1;
     e1.out = e.pa.p;
@@ -954,7 +1013,7 @@ struct Run {
     tr_name = "proj2";
     VL_TRY(gemm(e.pa, e.pj2, prows, nullptr, EPI_STORE_F32, e2));
     VL_TRY(assemble_text_launch(e.embed, e.pb.row_src, e.pb.m_tot, e.xv, B * e.S, h, st));
-    VL_TRY(small_linear_launch(e.in_prop, io, e.pe_w, e.pe_b, e.xp, DT_F32, B, c.proprio_dim, c.hidden_e, st));
+    if (e.mode < 2) VL_TRY(small_linear_launch(e.in_prop, io, e.pe_w, e.pe_b, e.xp, DT_F32, B, c.proprio_dim, c.hidden_e, st));
     e.launches += 3;
     return 0;
   }
@@ -1042,8 +1101,8 @@ struct Run {
   // B = 1 (the latency case): the expert passes run on the weight-streaming single-observation kernel
   // (the flow-matching loss runs its one expert pass on the per-kernel schedule: the persistent kernels index their time
   // bias by Euler step)
-  bool gemv() const { return e.gemv && B == 1 && e.H <= 8 && !e.simt && e.mode != 1; }
-  bool mega() const { return (e.mega || gemv()) && !e.simt && e.mode != 1; }
+  bool gemv() const { return e.gemv && B == 1 && e.H <= 8 && !e.simt && e.mode == 0; }
+  bool mega() const { return (e.mega || gemv()) && !e.simt && e.mode == 0; }
   // largest power-of-two sub-grid count <= the option that keeps whole samples, a multiple of 32 rows and at least 64
   // rows per sub-grid
   int expert_streams(int M, int B) const {
@@ -1424,8 +1483,97 @@ struct Run {
     return 0;
   }
 
+  // ---- greedy text generation of the chat VLM (modeling_internvl_chat.py:401-439 -> HF Qwen2 generate, do_sample=False;
+  // PiZero.infer_text, pizero_internvl.py:1005-1046): the LLM mixture alone, causal, RoPE positions from 0, every layer
+  // complete (no last-layer skip), final RMSNorm, output head, argmax.
+  // final norm of the B residual rows in x_dec -> logits -> next_tok
+  int text_head(int bump) {
+    const vlaser_cfg& c = e.c;
+    SplitKPartials spt;
+    VL_TRY(rmsnorm_launch(e.x_dec, e.llm_norm, e.xn.p, B, nullptr, c.hidden, c.rms_eps, st, nullptr, nullptr, take(e.x_dec, spt)));
+    e.launches++;
+    EpiParams ep;
+    ep.out = e.logits;
+    ep.ldo = e.lm_head.N;
+    tr_name = "lm_head";
+    tr_layer = -1;
+    VL_TRY(gemm(e.xn, e.lm_head, B, nullptr, EPI_STORE_F32, ep));
+    VL_TRY(argmax_rows_launch(e.logits, e.lm_head.N, c.embed_rows, B, e.gen.next_tok, e.gen.n_gen, bump, st));
+    e.launches++;
+    return 0;
+  }
+  AttnParams text_attn(int li) {
+    const vlaser_cfg& c = e.c;
+    AttnParams ap;
+    const size_t off = (size_t)li * c.n_kv_heads * e.kv_rows * 128;
+    ap.q = e.q;
+    ap.q_row_stride = e.qdim;
+    ap.k = e.kc + off;
+    ap.v = e.vc + off;
+    ap.kv_row_stride = 128;
+    ap.kv_head_stride = e.kv_rows * 128;
+    ap.out = e.ao.p;
+    ap.out_row_stride = e.qdim;
+    ap.kv_start = e.pb.kvoff;
+    ap.group = c.n_heads / c.n_kv_heads;
+    ap.n_kv_heads = c.n_kv_heads;
+    ap.batch = B;
+    ap.scale = 0.08838834764831845f;
+    ap.causal = 1;
+    return ap;
+  }
+  int text_prefill() {
+    const vlaser_cfg& c = e.c;
+    const int cap = B * e.S;
+    for (int li = 0; li < c.layers; ++li) {
+      VL_TRY(block_pre(e.llm[li], e.xv, e.xn, e.q, cap, e.pb.m_tot, c.hidden, e.pb.row_pos, e.pb.row_kvrow, li));
+      AttnParams ap = text_attn(li);
+      ap.q_start = e.pb.cu;
+      ap.q_len = e.pb.valid_len;
+      ap.kv_len = e.pb.pre_kv_len;
+      ap.max_q_len = e.S;
+      VL_TRY(attention_launch(ap, 128, st));
+      e.launches++;
+      VL_TRY(block_post(e.llm[li], e.xv, e.xn, e.ao, e.act, cap, e.pb.m_tot, c.hidden, e.mlp_p, 1, &e.xv_otm));
+    }
+    VL_TRY(flush());
+    VL_TRY(last_rows_launch(e.xv, e.pb.cu, e.pb.valid_len, e.x_dec, B, c.hidden, st));
+    e.launches++;
+    return text_head(0);
+  }
+  // one decode step: emit the pending token, run it through the LLM over its K/V window, leave the next argmax
+  int text_decode() {
+    const vlaser_cfg& c = e.c;
+    VL_TRY(decode_advance_launch(e.gen, e.pb.valid_len, e.pb.kvoff, e.embed, e.x_dec, B, c.hidden, e.gen_cap, e.gen_cap,
+                                 e.gen_eos, e.gen_fill, st));
+    e.launches++;
+    for (int li = 0; li < c.layers; ++li) {
+      VL_TRY(block_pre(e.llm[li], e.x_dec, e.xn, e.q, B, nullptr, c.hidden, e.gen.pos, e.gen.kvrow, li));
+      AttnParams ap = text_attn(li);
+      ap.q_start = e.gen.q_start;
+      ap.q_len = e.gen.q_len;
+      ap.kv_len = e.gen.kv_len;
+      ap.max_q_len = 1;
+      VL_TRY(attention_launch(ap, 128, st));
+      e.launches++;
+      VL_TRY(block_post(e.llm[li], e.x_dec, e.xn, e.ao, e.act, B, nullptr, c.hidden, e.mlp_p, 1, &e.xdec_otm));
+    }
+    return text_head(1);
+  }
+
   int all(bool has_valid) {
     const vlaser_cfg& c = e.c;
+    if (e.mode == 3) return text_decode();
+    if (e.mode == 2) {
+      VL_TRY(plan_launch(e.in_ids, has_valid ? e.in_valid : nullptr, e.pb, B, e.S, e.H, e.n_img * e.T, c.image_token_index,
+                         c.pad_token_id, c.embed_rows, st, e.gen_cap));
+      VL_CUDA_CHECK(cudaMemsetAsync(e.gen.n_gen, 0, sizeof(int), st));
+      VL_CUDA_CHECK(cudaMemsetAsync(e.gen.finished, 0, sizeof(int) * (size_t)B, st));
+      e.launches += 5;
+      if (!e.text_no_image) VL_TRY(vit());
+      VL_TRY(embed());
+      return text_prefill();
+    }
     VL_TRY(plan_launch(e.in_ids, has_valid ? e.in_valid : nullptr, e.pb, B, e.S, e.H, e.n_img * e.T,
                        c.image_token_index, c.pad_token_id, c.embed_rows, st));
     VL_TRY(convert_launch(e.in_noise, io, e.action, DT_F32, (long long)B * e.H * c.action_dim, st));
@@ -1458,7 +1606,7 @@ int engine_execute(Engine& e, int B, int io, bool has_valid, cudaStream_t st) {
     e.last_launches = e.launches;
     return rc;
   }
-  Engine::GraphKey key{B, io, e.stop_after, e.simt, has_valid ? 1 : 0, e.mode};
+  Engine::GraphKey key{B, io, e.stop_after, e.simt, has_valid ? 1 : 0, e.mode, e.mode >= 2 ? e.text_no_image : 0};
   auto it = e.graphs.find(key);
   if (it == e.graphs.end()) {
     // Build on the handle's own stream (the caller's may be the legacy default stream, which cannot
@@ -1489,6 +1637,10 @@ int engine_execute(Engine& e, int B, int io, bool has_valid, cudaStream_t st) {
     VL_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
     cudaGraphDestroy(graph);
     it = e.graphs.emplace(key, Engine::GraphVal{exec, e.launches}).first;
+    if (e.mode == 3) {  // a decode step changes state: the un-captured pass above WAS this step
+      e.last_launches = it->second.launches;
+      return 0;
+    }
   }
   VL_CUDA_CHECK(cudaGraphLaunch(it->second.exec, st));
   e.last_launches = it->second.launches;
@@ -1672,6 +1824,58 @@ int32_t vlaser_flow_matching_loss(vlaser_t* h, const int64_t* input_ids, const v
   if (rc) return rc;
   VL_CUDA_CHECK(cudaMemcpyAsync(loss_out, e.flow_loss, sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (velocity_out) VL_CUDA_CHECK(cudaMemcpyAsync(velocity_out, e.flow_vel, na * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int32_t vlaser_generate(vlaser_t* h, const int64_t* input_ids, const void* pixel_values, const int32_t* valid_len,
+                        int32_t max_new_tokens, int64_t eos_token_id, int64_t fill_token_id, int64_t* tokens_out,
+                        float* first_logits_out, int32_t B, int32_t io_dtype, void* stream) {
+  VL_CHECK(h, "null handle");
+  Engine& e = h->e;
+  VL_CHECK(e.finalized, "generate before finalize");
+  VL_CHECK(e.llm_norm_set, "generate: the final norm of the LLM (joint_model.mixtures.vlm.norm.weight / "
+                           "language_model.model.norm.weight) was not loaded");
+  VL_CHECK(B > 0 && B <= e.Bc, "batch exceeds max_batch");
+  VL_CHECK(io_dtype == DT_F32 || io_dtype == DT_BF16, "io_dtype must be f32 or bf16");
+  VL_CHECK(input_ids && tokens_out, "null tensor");
+  VL_CHECK(max_new_tokens >= 1 && max_new_tokens <= e.gen_cap, "max_new_tokens must be in [1, max_image_text_tokens + 1 + H]");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const vlaser_cfg& c = e.c;
+  const size_t es = io_size(io_dtype);
+  VL_CUDA_CHECK(cudaMemcpyAsync(e.in_ids, input_ids, (size_t)B * e.S * 8, cudaMemcpyDeviceToDevice, st));
+  if (pixel_values)
+    VL_CUDA_CHECK(cudaMemcpyAsync(e.in_pix, pixel_values, (size_t)B * e.n_img * 3 * c.image_size * c.image_size * es,
+                                  cudaMemcpyDeviceToDevice, st));
+  if (valid_len) VL_CUDA_CHECK(cudaMemcpyAsync(e.in_valid, valid_len, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  if (e.gen_eos != eos_token_id || e.gen_fill != fill_token_id) {  // launch constants of the captured decode step
+    for (auto it = e.graphs.begin(); it != e.graphs.end();)
+      if (it->first.mode == 3) {
+        cudaStreamSynchronize(e.own_stream);
+        cudaGraphExecDestroy(it->second.exec);
+        it = e.graphs.erase(it);
+      } else {
+        ++it;
+      }
+    e.gen_eos = eos_token_id;
+    e.gen_fill = fill_token_id;
+  }
+  e.text_no_image = pixel_values ? 0 : 1;
+  int rc = 0;
+  e.mode = 2;
+  rc = engine_execute(e, B, io_dtype, valid_len != nullptr, st);
+  if (rc == 0 && first_logits_out)
+    rc = cudaMemcpy2DAsync(first_logits_out, (size_t)c.embed_rows * 4, e.logits, (size_t)e.lm_head.N * 4, (size_t)c.embed_rows * 4, B,
+                           cudaMemcpyDeviceToDevice, st) == cudaSuccess ? 0 : -1;
+  e.mode = 3;
+  for (int k = 0; k + 1 < max_new_tokens && rc == 0; ++k) rc = engine_execute(e, B, io_dtype, valid_len != nullptr, st);
+  e.mode = 0;
+  e.text_no_image = 0;
+  if (rc) return rc;
+  // the last token: emitted, not run through the model
+  VL_TRY(decode_advance_launch(e.gen, e.pb.valid_len, e.pb.kvoff, e.embed, e.x_dec, B, c.hidden, e.gen_cap, e.gen_cap, e.gen_eos,
+                               e.gen_fill, st));
+  VL_CUDA_CHECK(cudaMemcpy2DAsync(tokens_out, (size_t)max_new_tokens * 8, e.gen.tokens, (size_t)e.gen_cap * 8,
+                                  (size_t)max_new_tokens * 8, B, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
@@ -1942,6 +2146,8 @@ int32_t vlaser_op_attention(const vlaser_attn_args* a, void* stream) {
   p.n_kv_heads = a->n_kv_heads;
   p.batch = a->batch;
   p.scale = a->scale;
+  p.causal = a->causal;
+  VL_CHECK(!(p.causal && p.q2), "attention: the causal rule has no extra query row");
   return attention_launch(p, a->head_dim, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -411,6 +411,45 @@ class PiZeroInference:
         _lib.check(rc, "vlaser_flow_matching_loss")
         return (loss, vel) if return_velocity else loss
 
+    def generate(self, input_ids, pixel_values=None, attention_mask=None, max_new_tokens: int = 32,
+                 eos_token_id: Optional[int] = None, fill_token_id: Optional[int] = None, return_first_logits: bool = False):
+        """Greedy text generation of the chat VLM -- `InternVLChatModel.generate(pixel_values, input_ids, attention_mask,
+        do_sample=False)` (Vlaser_VLM/internvl_chat/internvl/model/internvl_chat/modeling_internvl_chat.py:401-439), also
+        the decode loop around `PiZero.infer_text` (pizero_internvl.py:1412-1447). `input_ids` [B, max_image_text_tokens]
+        right padded with pad_token_id, `pixel_values` [tiles, 3, px, px] the image tiles of the batch in order (None: a
+        text-only prompt). Returns tokens [B, max_new_tokens] int64 (fill_token_id after a sample's eos; default: the pad
+        token) and, with return_first_logits, the float32 logits [B, vocab] of the last prompt position."""
+        v = self.vcfg
+        self.finalize()
+        dev = self.device
+        dtype = pixel_values.dtype if pixel_values is not None else torch.bfloat16
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("pixel_values must be float32 or bfloat16")
+        io = _lib.BF16 if dtype == torch.bfloat16 else _lib.F32
+        input_ids = input_ids.to(dev, torch.int64).contiguous()
+        B, S = input_ids.shape
+        assert S == v.max_image_text_tokens, f"input_ids must be [B,{v.max_image_text_tokens}]"
+        if pixel_values is not None:
+            pixel_values = pixel_values.to(dev).contiguous()
+            assert pixel_values.size(0) == B * v.num_images, "one tile per (sample, image slot): B * cond_steps tiles"
+        valid_len = None
+        if attention_mask is not None:
+            valid_len = attention_mask.sum(-1).to(dev, torch.int32).contiguous()
+        eos = -1 if eos_token_id is None else int(eos_token_id)
+        fill = v.pad_token_id if fill_token_id is None else int(fill_token_id)
+        out = torch.empty((B, int(max_new_tokens)), device=dev, dtype=torch.int64)
+        logits = torch.empty((B, v.embed_rows), device=dev, dtype=torch.float32) if return_first_logits else None
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = self._lib.vlaser_generate(
+                self._handle, C.c_void_p(input_ids.data_ptr()),
+                C.c_void_p(pixel_values.data_ptr()) if pixel_values is not None else None,
+                C.c_void_p(valid_len.data_ptr()) if valid_len is not None else None, int(max_new_tokens), eos, fill,
+                C.c_void_p(out.data_ptr()), C.c_void_p(logits.data_ptr()) if logits is not None else None, B, io,
+                C.c_void_p(stream))
+        _lib.check(rc, "vlaser_generate")
+        return (out, logits) if return_first_logits else out
+
     def infer_action_host(self, input_ids, pixel_values, proprios, noise, valid_len=None) -> torch.Tensor:
         """Same call on HOST tensors (CPU torch tensors): H2D staging, compute, D2H, synchronise."""
         v = self.vcfg

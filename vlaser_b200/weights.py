@@ -125,6 +125,21 @@ def random_state_dict(cfg: VlaserConfig, seed: int = 0, bf16_round: bool = True)
     return out
 
 
+def text_head_state_dict(cfg: VlaserConfig, seed: int = 0, tied: bool = False, bf16_round: bool = True) -> Dict[str, torch.Tensor]:
+    """The two tensors the chat-VLM text path reads on top of `random_state_dict` (they are optional for the policy
+    call, which never reaches the LLM's final norm or head: pizero_internvl.py:192-193): the final RMSNorm gain of the
+    `vlm` mixture and, unless `tied` (Qwen2.5-1.5B ties the head to the embedding table), `lm_head.weight`. The head is
+    drawn wide (N(0, 0.5)) so that the greedy argmax of a random-init model has a clear margin."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(1000 + seed)
+    out = {"joint_model.mixtures.vlm.norm.weight": 1.0 + torch.randn((cfg.hidden,), generator=g) * 0.1}
+    if not tied:
+        out["lm_head.weight"] = torch.randn((cfg.embed_rows, cfg.hidden), generator=g) * 0.5
+    if bf16_round:
+        out = {k: v.to(torch.bfloat16).to(torch.float32) for k, v in out.items()}
+    return out
+
+
 _ALIASES = (
     ("_orig_mod.", ""),
     ("joint_model.mixtures.proprio.", "joint_model.mixtures.action."),
@@ -134,6 +149,9 @@ _ALIASES = (
     ("internvl_model.language_model.model.layers.", "joint_model.mixtures.vlm.layers."),
     ("internvl_model.action_expert.model.layers.", "joint_model.mixtures.action.layers."),
     ("internvl_model.action_expert.model.norm.", "joint_model.mixtures.action.norm."),
+    ("internvl_model.language_model.model.norm.", "joint_model.mixtures.vlm.norm."),
+    ("internvl_model.language_model.lm_head.", "lm_head."),
+    ("language_model.lm_head.", "lm_head."),
 )
 
 
