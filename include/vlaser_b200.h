@@ -230,7 +230,8 @@ int32_t vlaser_op_attention(const vlaser_attn_args* a, void* stream);
 int32_t vlaser_op_vit_attention(const void* qkv, void* out, int32_t images, int32_t tokens, int32_t heads, float scale,
                                 void* stream);
 
-/* The same op on the tcgen05 tensor cores (csrc/attention_tc.cu): tokens == 257 (224 px images). */
+/* The same op on the tcgen05 tensor cores (csrc/attention_tc.cu): tokens == 257 (224 px images, single-pass kernel) or
+ * 1 + a multiple of 256 up to 1025 (448 px tiles: exact two-pass softmax, K resident in shared memory). */
 int32_t vlaser_op_vit_attention_tc(const void* qkv, void* out, int32_t images, int32_t tokens, int32_t heads, float scale,
                                    void* stream);
 

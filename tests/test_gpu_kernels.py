@@ -304,6 +304,36 @@ def test_vit_attention_tcgen05(B, heads):
     assert torch.equal(out, ops.vit_attention(qkv, B, N, heads, hd ** -0.5, tc=True)), "repeat call differs"
 
 
+@pytest.mark.parametrize("B,heads,N", [(1, 4, 1025), (3, 16, 1025), (21, 16, 1025), (2, 3, 513)])
+def test_vit_attention_tcgen05_long_rows(B, heads, N):
+    """tcgen05 two-pass kernel (attention_tc.cu), 448 px tiles: 1025 tokens = 8 query tiles of 128 rows against 1024 keys
+    resident in shared memory + the left-over key (rank-1 term) + the left-over query row (CUDA-core kernel). Items below,
+    at and above the SM count (contiguous item ranges: several query pairs of a head per CTA, heads split between CTAs)."""
+    hd = 64
+    d = heads * hd
+    qkv = _rand(B * N, 3 * d, seed=B + N)
+    out = ops.vit_attention(qkv, B, N, heads, hd ** -0.5, tc=True)
+    x = qkv.float().view(B, N, 3, heads, hd).permute(0, 3, 2, 1, 4)          # [B, heads, 3, N, hd]
+    s = torch.einsum("bhqd,bhkd->bhqk", x[:, :, 0], x[:, :, 1]) * hd ** -0.5
+    ref = torch.einsum("bhqk,bhkd->bhqd", torch.softmax(s, dim=-1), x[:, :, 2]).permute(0, 2, 1, 3)  # [B, N, heads, hd]
+    got = out.view(B, N, heads, hd).float()
+    err = ops.rel_err(got, ref)
+    rows = (got - ref).norm(dim=-1) / ref.norm(dim=-1)
+    print(f"vit_attention_tcgen05 N={N} B={B} heads={heads} rel={err:.2e} worst row={float(rows.max()):.2e} "
+          f"last row={float(rows[:, -1].max()):.2e}")
+    assert err < 1e-2 and float(rows.max()) < 3e-2
+    assert torch.equal(out, ops.vit_attention(qkv, B, N, heads, hd ** -0.5, tc=True)), "repeat call differs"
+    # peaked rows (one dominant key per query): the two-pass maximum must be the exact one
+    qkv2 = qkv.clone().view(B, N, 3, heads, hd)
+    qkv2[:, :, 0] *= 6.0
+    qkv2 = qkv2.view(B * N, 3 * d).contiguous()
+    out2 = ops.vit_attention(qkv2, B, N, heads, hd ** -0.5, tc=True).view(B, N, heads, hd).float()
+    x2 = qkv2.float().view(B, N, 3, heads, hd).permute(0, 3, 2, 1, 4)
+    s2 = torch.einsum("bhqd,bhkd->bhqk", x2[:, :, 0], x2[:, :, 1]) * hd ** -0.5
+    ref2 = torch.einsum("bhqk,bhkd->bhqd", torch.softmax(s2, dim=-1), x2[:, :, 2]).permute(0, 2, 1, 3)
+    assert ops.rel_err(out2, ref2) < 1e-2
+
+
 @pytest.mark.parametrize("nkv,group,lens", [(2, 6, [85, 1, 130, 256, 87, 21, 22, 300]), (4, 7, [60, 200]), (1, 1, [256, 33]),
                                             (2, 6, [87, 64, 100, 41] * 20)])
 def test_prefill_attention_tcgen05(nkv, group, lens):

@@ -315,7 +315,7 @@ def test_fp32_checkpoint_weight_rounding(capsys):
 def test_checkpoint_key_aliases_load():
     """eval.py:196-212: the released checkpoints carry `_orig_mod.` prefixes (torch.compile), the expert weights under
     `mixtures.proprio.*` as well as `mixtures.action.*` (shared modules), duplicates under `internvl_model.*` and
-    tensors the path never reads (lm_head); `load_state_dict(strict=False)` must take all of that and give the same
+    tensors the path never reads (the expert's lm_head); `load_state_dict(strict=False)` must take all of that and give the same
     actions as the canonical state dict."""
     cfg, sd, inp, gold = load_case("tiny_bridge")
     B = inp["input_ids"].shape[0]
@@ -328,11 +328,14 @@ def test_checkpoint_key_aliases_load():
             ck["_orig_mod." + k.replace("vision_tower.vision_model.", "internvl_model.vision_model.")] = v
         if k.startswith("multi_modal_projector."):
             ck["_orig_mod." + k.replace("multi_modal_projector.", "internvl_model.mlp1.")] = v
-    ck["_orig_mod.internvl_model.language_model.lm_head.weight"] = torch.zeros(8, 8)
+    # the output head of the LLM is taken (the chat-VLM text path reads it); a tensor no path reads is reported back
+    ck["_orig_mod.internvl_model.language_model.lm_head.weight"] = torch.zeros(cfg.embed_rows, cfg.hidden)
+    ck["_orig_mod.internvl_model.action_expert.lm_head.weight"] = torch.zeros(8, 8)
     ck["step"] = 123  # non-tensor entries are skipped
     pol = PiZeroInference(cfg, max_batch=B)
     res = pol.load_state_dict(ck, strict=False)
-    assert any("lm_head" in k for k in getattr(res, "unexpected_keys", ["lm_head"]))
+    assert any("action_expert.lm_head" in k for k in res.unexpected_keys)
+    assert not any("language_model.lm_head" in k for k in res.unexpected_keys)
     assert max_err(_run(pol, inp), gold["actions"]) <= ACTION_TOL
     # a missing tensor must fail loudly at finalize, not produce numbers
     short = dict(list(sd.items())[:-3])

@@ -17,14 +17,20 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--graph", type=int, default=0)
 ap.add_argument("--config", default="vlaser_2b_bridge")
 ap.add_argument("--stop-after", type=int, default=0)
+ap.add_argument("--px", type=int, default=0, help="image size override (448: the 1025-token ViT rows)")
+ap.add_argument("--opt", action="append", default=[], help="schedule option k=v (repeatable)")
 a = ap.parse_args()
 cfg = PRESETS[a.config]()
+if a.px:
+    cfg = cfg.with_(image_size=a.px)
 dev = torch.device("cuda", 0)
 pol = PiZeroInference(cfg, max_batch=a.batch)
 for k, t in _device_state_dict_stream(cfg, 0, dev):
     pol.load_state_dict({k: t}, strict=False)
 pol.set_option("use_graph", a.graph)
 pol.set_option("stop_after", a.stop_after)
+for kv in a.opt:
+    pol.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 inp = make_inputs(cfg, a.batch, 1)
 ids, pix = inp["input_ids"].to(dev), inp["pixel_values"].to(torch.bfloat16).to(dev)
 prop, noise = inp["proprios"].to(torch.bfloat16).to(dev), inp["noise"].to(torch.bfloat16).to(dev)

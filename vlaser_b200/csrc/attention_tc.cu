@@ -1,5 +1,6 @@
 // InternViT self-attention on the 5th-generation tensor cores (modeling_intern_vit.py:210-227, _naive_attn; no mask):
-// head_dim 64, N = 257 tokens per image (224 px: 256 patches + CLS). See attention.cuh (vit_attention_tc_launch).
+// head_dim 64, N = 257 tokens per image (224 px: 256 patches + CLS). See attention.cuh (vit_attention_tc_launch); the
+// 1025-token rows of 448 px tiles take vit_attention_tc_long_kernel further down.
 //
 // One persistent CTA per SM walks (image, head) items. An item is 2 query tiles of 128 rows + 1 left-over query row
 // against 256 keys + 1 left-over key. Warp-specialised, everything on chip between the q|k|v projection and the output:
@@ -366,6 +367,348 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 
 
 // ================================================================================================================
+// InternViT self-attention of long token rows on the tensor cores: N = 1 + Nk tokens per image with Nk a multiple of 256
+// up to 1024 (448 px tiles: 1024 patches + CLS; modeling_intern_vit.py:210-227, pizero_internvl.py:739-743 image_448).
+// The Nk x Nk block runs here; the left-over token is the last row: as a KEY it is a rank-1 term on CUDA cores (like the
+// 257-token kernel), as a QUERY it is vit_attention_last_row_kernel below.
+// The scores of a query row no longer fit in TMEM, so softmax is exact in TWO passes instead of online: pass A computes
+// S = Q K^T block by block only for the row maximum, pass B recomputes S, turns it into probabilities with the final
+// maximum and accumulates O += P V in TMEM -- no rescaling of O, no correction step; Q K^T is a quarter of the MMA work
+// per pass (head_dim 64) and the kernel is bound by the exponentials (MUFU), not by the tensor core.
+// Work item = (image, head, pair of 128-row query tiles), handed out in contiguous ranges so that consecutive items of a
+// CTA share the head's K, which stays resident in shared memory (128 KB at Nk = 1024); V streams through a 3-slot ring.
+//   warp 0      TMA producer (K once per head, Q pair per item, V blocks of 128 keys)
+//   warp 1      MMA issuer: pass A S_t = Q_t K_j^T with N = 256; pass B per 128 keys S_t (N = 128), then O_t += P_t V_j with P
+//               read from TMEM and V as MN-major operand
+//   warps 2-5 / 6-9  softmax group of query tile 0 / 1: one thread per row
+// TMEM: tile t owns columns [256 t, 256 t + 256): pass A scores in all of them; pass B scores in [0, 128), P (bf16) over
+// them in [0, 64), O in [192, 256).
+// ================================================================================================================
+constexpr int VL_THREADS = 320;
+constexpr int VL_VSLOTS = 3;
+constexpr int VL_MAX_KT = 8;  // resident K tiles of 128 keys
+constexpr int VL_SMEM = (2 + VL_MAX_KT + VL_VSLOTS) * VT_TILE_BYTES + 1024 /*k_x v_x rows*/ + 1024 /*align*/ + 256 /*barriers*/;
+
+__global__ void __launch_bounds__(VL_THREADS, 1)
+vit_attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmOut,
+                             const __nv_bfloat16* __restrict__ qkv, int images, int heads, int N, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = smem;                                   // [2 tiles][128][128 B]
+  uint8_t* Ks = smem + 2 * VT_TILE_BYTES;               // [nk128 tiles][128][128 B]
+  uint8_t* Vs = Ks + VL_MAX_KT * VT_TILE_BYTES;         // [3 slots][128][128 B]
+  uint8_t* xrows = Vs + VL_VSLOTS * VT_TILE_BYTES;      // k_x, v_x (128 B each)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xrows + 1024);
+  uint64_t* q_full = bars;            // [1]
+  uint64_t* q_empty = bars + 1;       // [1] both groups have stored their O tile
+  uint64_t* k_full = bars + 2;        // [1]
+  uint64_t* k_empty = bars + 3;       // [1] MMA commit + both groups
+  uint64_t* v_full = bars + 4;        // [3]
+  uint64_t* v_empty = bars + 7;       // [3]
+  uint64_t* s_full = bars + 10;       // [2]
+  uint64_t* s_free = bars + 12;       // [2] pass-A scores read (4 warps)
+  uint64_t* p_full = bars + 14;       // [2] probabilities written (4 warps)
+  uint64_t* o_full = bars + 16;       // [2]
+  uint64_t* o_free = bars + 18;       // [2] O read out (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Nk = N - 1, nk128 = Nk >> 7, nk256 = Nk >> 8, qpairs = Nk >> 8;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmOut);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 2);
+    mbar_init(k_full, 1);
+    mbar_init(k_empty, 3);
+    for (int i = 0; i < VL_VSLOTS; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_free[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();  // the q|k|v projection is complete
+
+  // contiguous item ranges: items of one (image, head) stay on one CTA where possible
+  const int items = images * heads * qpairs;
+  const int per = (items + gridDim.x - 1) / gridDim.x;
+  const int i0 = min(items, (int)blockIdx.x * per), i1 = min(items, i0 + per);
+  const int ld = 3 * heads * VT_HD;
+  const float sl2 = scale * 1.4426950408889634f;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int prev = -1, vc = 0;
+      for (int item = i0, it = 0; item < i1; ++item, ++it) {
+        const int hd = item / qpairs, qp = item - hd * qpairs;
+        const int img = hd / heads, h = hd - img * heads;
+        const int r0 = img * N;
+        const int cq = h * VT_HD, ck = (heads + h) * VT_HD, cv = (2 * heads + h) * VT_HD;
+        mbar_wait(k_empty, (it & 1) ^ 1);
+        if (hd != prev) {
+          mbar_arrive_expect_tx(k_full, (uint32_t)(nk128 * VT_TILE_BYTES + 256));
+          for (int j = 0; j < nk128; ++j) tma_load_2d(Ks + j * VT_TILE_BYTES, &tmQKV, k_full, ck, r0 + j * 128);
+          const __nv_bfloat16* xrow = qkv + (size_t)(r0 + Nk) * ld;
+          bulk_load_128(xrows, xrow + ck, k_full);
+          bulk_load_128(xrows + 128, xrow + cv, k_full);
+          prev = hd;
+        } else {
+          mbar_arrive(k_full);  // the head's K is still resident
+        }
+        mbar_wait(q_empty, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, 2 * VT_TILE_BYTES);
+        tma_load_2d(Qs, &tmQKV, q_full, cq, r0 + qp * 256);
+        tma_load_2d(Qs + VT_TILE_BYTES, &tmQKV, q_full, cq, r0 + qp * 256 + 128);
+        for (int j = 0; j < nk128; ++j, ++vc) {
+          const int slot = vc % VL_VSLOTS;
+          mbar_wait(&v_empty[slot], ((vc / VL_VSLOTS) & 1) ^ 1);
+          mbar_arrive_expect_tx(&v_full[slot], VT_TILE_BYTES);
+          tma_load_2d(Vs + slot * VT_TILE_BYTES, &tmQKV, &v_full[slot], cv, r0 + j * 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_a = make_idesc_bf16(128, 256);
+      constexpr uint32_t idesc_b = make_idesc_bf16(128, 128);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64) | (1u << 16);  // B (= V) is MN-major
+      const uint32_t qa = smem_u32(Qs), ka = smem_u32(Ks), va = smem_u32(Vs);
+      uint32_t n_sfree[2] = {0, 0}, n_pfull[2] = {0, 0};
+      int vc = 0;
+      for (int item = i0, it = 0; item < i1; ++item, ++it) {
+        mbar_wait(q_full, it & 1);
+        mbar_wait(k_full, it & 1);
+        tc_fence_after();
+        const uint64_t dq[2] = {make_umma_desc_sw128(qa), make_umma_desc_sw128(qa + VT_TILE_BYTES)};
+        // ---- pass A: scores for the row maximum, 256 keys per step
+        for (int j = 0; j < nk256; ++j)
+          for (int t = 0; t < 2; ++t) {
+            if (j == 0) mbar_wait(&o_free[t], (it & 1) ^ 1);
+            else mbar_wait(&s_free[t], n_sfree[t]++ & 1);
+            tc_fence_after();
+            const uint64_t dk = make_umma_desc_sw128(ka + j * 2 * VT_TILE_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < VT_HD / 16; ++ks) umma_bf16(tmem_base + t * 256, dq[t] + 2 * ks, dk + 2 * ks, idesc_a, ks > 0);
+            umma_commit(&s_full[t]);
+          }
+        // ---- pass B: probabilities and O += P V, 128 keys per step
+        auto pv = [&](int jb, int t) {  // O_t += P_t V_jb (P of step jb is in TMEM, V block jb in ring slot vc % 3)
+          const int slot = vc % VL_VSLOTS;
+          mbar_wait(&p_full[t], n_pfull[t]++ & 1);
+          if (t == 0) mbar_wait(&v_full[slot], (vc / VL_VSLOTS) & 1);
+          tc_fence_after();
+          const uint64_t dv = make_umma_desc_sw128(va + slot * VT_TILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_bf16_ts(tmem_base + t * 256 + 192, tmem_base + t * 256 + 8 * ks, dv + 128 * ks, idesc_o, (jb > 0 || ks > 0) ? 1u : 0u);
+          if (t == 1) {
+            umma_commit(&v_empty[slot]);
+            ++vc;
+          }
+        };
+        for (int j = 0; j < nk128; ++j)
+          for (int t = 0; t < 2; ++t) {
+            if (j == 0) {
+              mbar_wait(&s_free[t], n_sfree[t]++ & 1);  // the last pass-A block has been read
+              tc_fence_after();
+            } else {
+              pv(j - 1, t);
+            }
+            const uint64_t dk = make_umma_desc_sw128(ka + j * VT_TILE_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < VT_HD / 16; ++ks) umma_bf16(tmem_base + t * 256, dq[t] + 2 * ks, dk + 2 * ks, idesc_b, ks > 0);
+            umma_commit(&s_full[t]);
+          }
+        for (int t = 0; t < 2; ++t) {
+          pv(nk128 - 1, t);
+          umma_commit(&o_full[t]);
+        }
+        umma_commit(k_empty);  // every MMA that reads this item's Q / K has retired
+      }
+    }
+  } else {
+    // ================================ softmax groups (one per query tile) ================================
+    const int t = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 256;
+    const int gtid = threadIdx.x - (2 + 4 * t) * 32;
+    uint8_t* qt = Qs + t * VT_TILE_BYTES;
+    uint32_t n_sfull = 0;
+    for (int item = i0, it = 0; item < i1; ++item, ++it) {
+      const int hd = item / qpairs, qp = item - hd * qpairs;
+      const int img = hd / heads, h = hd - img * heads;
+      mbar_wait(q_full, it & 1);
+      mbar_wait(k_full, it & 1);
+      float sx = 0.f;  // score of the left-over key
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        sx += dot8(*reinterpret_cast<const uint4*>(qt + sw_off(row, c)), *reinterpret_cast<const uint4*>(xrows + c * 16));
+      // ---- pass A: row maximum
+      float mx = sx;
+      for (int j = 0; j < nk256; ++j) {
+        mbar_wait(&s_full[t], n_sfull++ & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 8; c += 2) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(taddr + c * 32, r0);
+          tmem_ld_32x32(taddr + c * 32 + 32, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[e]), __uint_as_float(r1[e])));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);
+      }
+      const float moff = mx * sl2;
+      // ---- pass B: p = exp2(s * sl2 - moff), row sum, bf16 pack written over the scores
+      float sum = 0.f;
+      for (int j = 0; j < nk128; ++j) {
+        mbar_wait(&s_full[t], n_sfull++ & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 4; c += 2) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(taddr + c * 32, r0);
+          tmem_ld_32x32(taddr + c * 32 + 32, r1);
+          tmem_ld_wait();
+          uint32_t pk0[16], pk1[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(r0[2 * e]), sl2, -moff));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(r0[2 * e + 1]), sl2, -moff));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(r1[2 * e]), sl2, -moff));
+            const float p3 = ex2_approx(fmaf(__uint_as_float(r1[2 * e + 1]), sl2, -moff));
+            sum += (p0 + p1) + (p2 + p3);
+            pk0[e] = pack_bf16(p0, p1);
+            pk1[e] = pack_bf16(p2, p3);
+          }
+          tmem_st_32x16(taddr + c * 16, pk0);
+          tmem_st_32x16(taddr + c * 16 + 16, pk1);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+      const float px = ex2_approx(fmaf(sx, sl2, -moff));
+      sum += px;
+      const float inv = 1.f / sum;
+      uint4 vx[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) vx[c] = *reinterpret_cast<const uint4*>(xrows + 128 + c * 16);
+      mbar_wait(&o_full[t], it & 1);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32(taddr + 192, o0);
+      tmem_ld_32x32(taddr + 224, o1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[t]);
+      // O = (P V + p_x v_x) / sum -> bf16 -> this row of the (dead) Q tile, swizzled as the TMA store expects
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t vw[4] = {vx[c].x, vx[c].y, vx[c].z, vx[c].w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int jj = c * 8 + 2 * e;
+          const float a0 = __uint_as_float(jj < 32 ? o0[jj] : o1[jj - 32]);
+          const float a1 = __uint_as_float(jj < 32 ? o0[jj + 1] : o1[jj - 31]);
+          ow[e] = pack_bf16((a0 + px * bf16_lo(vw[e])) * inv, (a1 + px * bf16_hi(vw[e])) * inv);
+        }
+        *reinterpret_cast<uint4*>(qt + sw_off(row, c)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+      fence_proxy_async();
+      named_bar_sync(1 + t, 128);
+      if (gtid == 0) {
+        tma_store_2d(&tmOut, qt, h * VT_HD, img * N + qp * 256 + t * 128);
+        bulk_commit();
+        bulk_wait_read<0>();  // the tile has been read out of shared memory
+        mbar_arrive(q_empty);
+        mbar_arrive(k_empty);
+      }
+    }
+    if (gtid == 0) bulk_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// The left-over query row (token N - 1) of every (image, head) on CUDA cores: N scores, block softmax, P V. One CTA of 128
+// threads per (image, head); K / V rows are read once from global memory (128 B each, L2 resident after the main kernel).
+__global__ void __launch_bounds__(128) vit_attention_last_row_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                      __nv_bfloat16* __restrict__ out, int heads, int N,
+                                                                      float scale) {
+  extern __shared__ float lr_p[];  // [N] probabilities, then [2][64] partial outputs + [8] reductions
+  float* red = lr_p + ((N + 3) & ~3);
+  pdl_launch_dependents();
+  pdl_wait();
+  const int h = blockIdx.x, img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  const int ld = 3 * heads * VT_HD;
+  const __nv_bfloat16* base = qkv + (size_t)img * N * ld + h * VT_HD;
+  const __nv_bfloat16* kb = base + heads * VT_HD;
+  const __nv_bfloat16* vb = base + 2 * heads * VT_HD;
+  const float sl2 = scale * 1.4426950408889634f;
+  uint4 qx[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) qx[c] = *reinterpret_cast<const uint4*>(base + (size_t)(N - 1) * ld + c * 8);
+  float mx = -INFINITY;
+  for (int j = tid; j < N; j += 128) {
+    float sc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sc += dot8(qx[c], *reinterpret_cast<const uint4*>(kb + (size_t)j * ld + c * 8));
+    lr_p[j] = sc;
+    mx = fmaxf(mx, sc);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[128 + wp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[128], red[129]), fmaxf(red[130], red[131]));
+  const float moff = mx * sl2;
+  float sum = 0.f;
+  for (int j = tid; j < N; j += 128) {
+    const float pj = ex2_approx(fmaf(lr_p[j], sl2, -moff));
+    lr_p[j] = pj;
+    sum += pj;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[132 + wp] = sum;
+  __syncthreads();
+  sum = (red[132] + red[133]) + (red[134] + red[135]);
+  const int d = tid & 63, par = tid >> 6;
+  float acc = 0.f;
+  for (int j = par; j < N; j += 2) acc += lr_p[j] * __bfloat162float(vb[(size_t)j * ld + d]);
+  red[par * 64 + d] = acc;
+  __syncthreads();
+  if (tid < 64) out[((size_t)img * N + N - 1) * (heads * VT_HD) + h * VT_HD + tid] = __float2bfloat16((red[tid] + red[64 + tid]) / sum);
+}
+
+
+// ================================================================================================================
 // Prefix-prefill attention of the LLM mixture on the tensor cores (joint_model.py:631-656 over the valid prefix of every
 // sample; eager_attention_forward + repeat_kv): head_dim 128, GQA (the `group` query heads of a kv head are packed into
 // the query tile: row = (token, head-in-group), so K / V of the kv head are loaded once), bidirectional over the L valid
@@ -714,8 +1057,24 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
 int vit_attention_tc_launch(const CUtensorMap& tmQKV, const CUtensorMap& tmOut, const __nv_bfloat16* qkv,
                             __nv_bfloat16* out, int images, int tokens, int heads, float scale, cudaStream_t stream,
                             long long* trace) {
-  VL_CHECK(tokens == 257, "vit_attention_tc: 257 tokens per image (224 px)");
   VL_CHECK(images > 0 && heads > 0, "vit_attention_tc: empty problem");
+  if (tokens != 257) {
+    // long rows (448 px: 1025 tokens): two-pass kernel for the Nk x Nk block + the left-over query row
+    const int Nk = tokens - 1;
+    VL_CHECK(Nk >= 256 && Nk % 256 == 0 && Nk <= 128 * VL_MAX_KT, "vit_attention_tc: tokens must be 257, or 1 + a multiple of 256 up to 1025");
+    static unsigned long long attr_devs_l = 0;
+    if (vl_first_on_device(attr_devs_l))
+      VL_CUDA_CHECK(cudaFuncSetAttribute(vit_attention_tc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VL_SMEM));
+    const int items = images * heads * (Nk / 256);
+    const int per = (items + gemm_num_sms() - 1) / gemm_num_sms();
+    const int grid = (items + per - 1) / per;
+    VL_CUDA_CHECK(launch_kernel(vit_attention_tc_long_kernel, dim3(grid), dim3(VL_THREADS), VL_SMEM, stream, tmQKV, tmOut, qkv,
+                                images, heads, tokens, scale));
+    const size_t lr_smem = (size_t)(((tokens + 3) & ~3) + 144) * sizeof(float);
+    VL_CUDA_CHECK(launch_kernel(vit_attention_last_row_kernel, dim3(heads, images), dim3(128), lr_smem, stream, qkv, out, heads,
+                                tokens, scale));
+    return 0;
+  }
   static unsigned long long attr_devs = 0;  // devices this kernel's attributes were set on
   if (vl_first_on_device(attr_devs)) {
     VL_CUDA_CHECK(cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM));

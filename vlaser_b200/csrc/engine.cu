@@ -938,7 +938,7 @@ struct Run {
       e1.bias = L.bqkv;
       tr_name = "vit_qkv";
       VL_TRY(gemm(e.vn, L.qkv, rows, nullptr, EPI_STORE_BF16, e1, 1, 0, &e.vqkv_otm));
-      if (e.vit_tc && e.P + 1 == 257 && !e.simt) {
+      if (e.vit_tc && !e.simt && (e.P + 1 == 257 || (e.P % 256 == 0 && e.P <= 1024))) {  // 224 px; 448 px tiles (two-pass kernel)
         VL_TRY(vit_attention_tc_launch(e.vqkv_tm, e.vattn.tm, e.vqkv, e.vattn.p, Ni, e.P + 1, c.vit_heads, 0.125f, st,
                                        tr("vit_attention", i)));
       } else if (e.P + 1 >= 128 && e.P + 1 <= 320) {
