@@ -1148,6 +1148,7 @@ struct Run {
     p.batch = B;
     p.scale = 0.08838834764831845f;  // 128^-0.5
     p.barrier = e.xp_bar + (size_t)pass * e.xp_bar_words();
+    p.err_flag = e.pb.bad_id;  // shares the call's error word (reported by the next call / the host entry)
     p.xfix = (gemv() && e.det_splitk) ? e.xfix + (size_t)pass * e.xfix_words() : nullptr;
     p.n_streams = expert_streams(M, B);
     p.flags = e.xp_flags;
@@ -1772,6 +1773,11 @@ int32_t vlaser_infer_action(vlaser_t* h, const int64_t* input_ids, const void* p
     const int bad = *host_bad - 1;
     *host_bad = 0;
     cudaMemsetAsync(e.pb.bad_id, 0, sizeof(int), st);
+    if (bad + 1 == EXPERT_ERR_BARRIER) {
+      set_last_error("infer_action: a grid barrier of the persistent expert kernel timed out in an earlier call (a CTA of its grid "
+                     "was not resident); the actions of that call are invalid");
+      return -5;
+    }
     set_last_error("infer_action: an earlier call passed token id " + std::to_string(bad) + " outside the embedding table of " +
                    std::to_string(c.embed_rows) + " rows (nn.Embedding would raise IndexError)");
     return -4;
@@ -1930,6 +1936,11 @@ int32_t vlaser_infer_action_host(vlaser_t* h, const int64_t* input_ids, const vo
   if (*p_bad != 0) {
     const int bad = *p_bad - 1;
     cudaMemsetAsync(e.pb.bad_id, 0, sizeof(int), st);
+    if (*p_bad == EXPERT_ERR_BARRIER) {
+      set_last_error("infer_action: a grid barrier of the persistent expert kernel timed out (a CTA of its grid was not resident); "
+                     "the actions are invalid");
+      return -5;
+    }
     set_last_error("infer_action: input_ids holds token id " + std::to_string(bad) + " outside the embedding table of " +
                    std::to_string(c.embed_rows) + " rows (nn.Embedding would raise IndexError)");
     return -4;

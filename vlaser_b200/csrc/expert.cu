@@ -111,14 +111,20 @@ __device__ __forceinline__ Tile tile_of(const Sched& s, int t) {
 __device__ __forceinline__ void grid_arrive(unsigned int* ctr) {
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
 }
-__device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int target) {
+// (~2 s without the other CTAs: one of them is missing -- the launcher checks residency, so this is insurance. No __trap,
+// which would kill the caller's CUDA context: flag the call as failed for the host and run on without waiting.)
+__device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int target, int* err_flag) {
   unsigned int v;
   long long t0 = 0;
   while (true) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
     if (v >= target) break;
+    if (err_flag && *reinterpret_cast<volatile int*>(err_flag) == EXPERT_ERR_BARRIER) break;
     if (t0 == 0) t0 = clock64();
-    else if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a CTA of the grid is missing; fail loudly, do not hang
+    else if (clock64() - t0 > 4000000000LL) {
+      if (err_flag) atomicExch(err_flag, EXPERT_ERR_BARRIER);
+      break;
+    }
   }
 }
 // mbarrier wait that traps instead of hanging the GPU if a pipeline partner never arrives (bring-up insurance: a
@@ -222,7 +228,7 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
           auto open_gate = [&]() {
             // every CTA has published all of its work of the earlier phases (and the previous grid is complete:
             // the workers arrive only after their own griddepcontrol.wait)
-            grid_wait(bar + (ph - 1), G);
+            grid_wait(bar + (ph - 1), G, p.err_flag);
             fence_proxy_async_all();  // generic-proxy writes of other SMs -> this thread's async-proxy (TMA) reads
             for (int i = 0; i < npend; ++i) load_a(pend_stage[i], pend_kb[i], pend_row[i]);
             npend = 0;
@@ -336,7 +342,7 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
         }
         if (j == PH_NORM1 || j == PH_NORM2 || j == PH_ATTN) {
           if (ph > 0) {
-            if (wtid == 0) grid_wait(bar + (ph - 1), G);
+            if (wtid == 0) grid_wait(bar + (ph - 1), G, p.err_flag);
             worker_bar();
           }
         }
@@ -474,7 +480,7 @@ expert_pass_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_consta
           worker_bar();             // every worker's writes happen-before the CTA's single (fenced) arrival
           if (wtid == 0) grid_arrive(bar + ph);
           if (p.timing && blockIdx.x == 0 && wtid == 0) {  // profiling aid: when did the whole grid finish this phase
-            grid_wait(bar + ph, G);
+            grid_wait(bar + ph, G, p.err_flag);
             long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             p.timing[ph] = now;

@@ -32,6 +32,8 @@ struct alignas(64) ExpertLayerDev {
 };
 static_assert(sizeof(ExpertLayerDev) % 64 == 0, "tensor maps of the next table entry must stay 64-byte aligned");
 
+constexpr int EXPERT_ERR_BARRIER = 0x7ffffff1;  // value left in ExpertPass::err_flag by a timed-out grid barrier
+
 struct ExpertPass {
   const ExpertLayerDev* layers = nullptr;
   int n_layers = 0;
@@ -74,6 +76,8 @@ struct ExpertPass {
                                       // 32 = only the even warps load across the grid barrier (correct results; measured slower)
   long long* timing = nullptr;        // optional [7 * n_layers]: globaltimer (ns) at which CTA 0 saw each phase complete
   unsigned int* barrier = nullptr;    // grid-barrier arrival counters of this pass, [n_streams][7 * n_layers], zero on entry
+  int* err_flag = nullptr;            // set to EXPERT_ERR_BARRIER when a grid barrier gives up (~2 s: a CTA of the grid never
+                                      // arrived); the kernel then runs on without waiting and the host reports the call as failed
   int n_streams = 1;                  // independent sub-grids (see expert.cu); needs batch % S == 0, (M / S) % 32 == 0
 };
 

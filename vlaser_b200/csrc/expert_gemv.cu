@@ -37,14 +37,21 @@ constexpr int GV_JS = GV_THREADS / 64;  // kv splits of the PV product
 __device__ __forceinline__ void gv_arrive(unsigned int* ctr) {
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
 }
-__device__ __forceinline__ void gv_wait(const unsigned int* ctr, unsigned int target) {
+// (a CTA of the grid is missing -- the launcher checks that the grid is resident, so this is insurance: give up after
+// ~2 s, flag the call as failed for the host and run on without waiting; no __trap, which would kill the CUDA context of
+// the evaluator that called us)
+__device__ __forceinline__ void gv_wait(const unsigned int* ctr, unsigned int target, int* err_flag) {
   unsigned int v;
   long long t0 = 0;
   while (true) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
     if (v >= target) break;
+    if (err_flag && *reinterpret_cast<volatile int*>(err_flag) == EXPERT_ERR_BARRIER) break;  // another barrier already gave up
     if (t0 == 0) t0 = clock64();
-    else if (clock64() - t0 > 4000000000LL) __trap();  // a CTA of the grid is missing: fail loudly, do not hang
+    else if (clock64() - t0 > 4000000000LL) {
+      if (err_flag) atomicExch(err_flag, EXPERT_ERR_BARRIER);
+      break;
+    }
   }
 }
 // weights: read once, do not pollute L1. volatile: the prefetch before the grid barrier must stay before it
@@ -544,7 +551,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) expert_gemv_pass_kernel(const E
       if (ph >= n_phases) break;
       if (ph > 0) {
         if (tid == 0) {
-          gv_wait(p.barrier + (ph - 1), (unsigned int)d.G);
+          gv_wait(p.barrier + (ph - 1), (unsigned int)d.G, p.err_flag);
           if (p.timing && blockIdx.x == 0) {  // when did the whole grid finish phase ph - 1
             long long now;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
