@@ -144,6 +144,8 @@ void vlaser_destroy(vlaser_t* h);
  * "l2_prefetch" (default 0, measured no gain: the RMSNorm launches of a denoise step issue bulk L2 prefetches of the expert weights the
  * next launches of the chain will read),
  * "expert_gemv" (default 1: at B = 1 the expert passes run on the weight-streaming single-observation kernel, csrc/expert_gemv.cu),
+ * "fuse_tail" (default 0, measured no gain: the o / down projections of the action expert finish the residual update + the
+ * following RMSNorm themselves behind an in-kernel grid barrier instead of leaving them to a norm launch),
  * "use_graph" (default 1: replay the whole call as one CUDA graph per batch size),
  * "stop_after" (debug: 0 all, 1 ViT, 2 prefix embedding, 3 prefill, 4 first denoise step),
  * "simt_gemm" (debug/tests: route GEMMs through the CUDA-core cross-check kernel),

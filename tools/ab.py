@@ -57,4 +57,5 @@ for spec in sys.argv[1:] or ["pdl=1"]:
                 ref = out
             d = float((out - ref).abs().max())
     pol.set_option("stop_after", 0)
-    print(spec, " ".join(f"[stop={s} B64 {a:.3f} ms B1 {b:.3f} ms]" for s, a, b in res), f"maxdiff_vs_first={d:.2e}", flush=True)
+    print(spec, " ".join(f"[stop={s} B64 {a:.3f} ms B1 {b:.3f} ms]" for s, a, b in res), f"maxdiff_vs_first={d:.2e}",
+          f"launches(last call)={pol.last_launch_count()}", flush=True)

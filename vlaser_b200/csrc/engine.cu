@@ -207,6 +207,15 @@ struct Engine {
   int gelu_warps = 16;         // epilogue warps of the pair kernel's exact-GELU variant (16 | 8)
   int pair_bn128 = 1;          // 1: 256 x 128 pair tiles for the one-row-tile split-K projections (see Run::gemm)
   int den_chains = 1;          // sub-batch chains of the denoise steps (1 | 2), see Run::denoise_all
+  int fuse_tail = 0;           // 1: the o / down projections of the action expert at one 256-row tile finish the residual update +
+                               // the following RMSNorm themselves behind an in-kernel grid barrier (EpiParams::tail_ctr): two of
+                               // the seven dependent launches of an expert layer disappear. Bit-identical actions; measured at
+                               // B = 64 (profiles/r02s2k_ab_fuse_tail.txt, three alternations): 39.88 / 39.36 / 39.69 ms with,
+                               // 39.56 / 39.99 / 39.57 ms without -- the in-kernel barrier + the two-rows-per-CTA tail cost what
+                               // the dependent-launch hop + the row-per-CTA norm launch cost. Off.
+  unsigned int* tail_ctrs = nullptr;  // one arrival counter per fused launch of a call, zeroed at the start of the call
+  int tail_used = 0;
+  static constexpr int TAIL_CTRS = 4096;
   int xs_o = 12, xs_down = 24; // split-K caps of the action expert's o / down projections (options "exp_splits_o/down")
   int vit_tc = 1;              // 1: InternViT attention of 257-token images on the tcgen05 kernel (attention_tc.cu)
   int ablate = 0;              // timing aid: bit mask of denoise-step launches to skip (1 norm_in, 2 qkv, 4 attention, 8 o,
@@ -541,6 +550,7 @@ int engine_build(Engine& e) {
   VL_TRY(e.alloc(&e.flow_z, (size_t)arow * c.hidden_e));
   VL_TRY(e.alloc(&e.flow_vel, (size_t)arow * c.action_dim));
   VL_TRY(e.alloc(&e.flow_loss, 4));
+  VL_TRY(e.alloc(&e.tail_ctrs, Engine::TAIL_CTRS));
   {
     const int bpad = (e.Bc + 255) / 256 * 256;
     e.gen_cap = e.S + 1 + e.H;
@@ -786,8 +796,28 @@ struct Run {
     return splitk_reduce_launch(q.x, q.rows, q.rows_dev, q.width, q.sp, st);
   }
 
+  // fused tail (EpiParams::tail_ctr): a caller that will launch RMSNorm(x) * gamma -> out right behind a split-K residual
+  // projection offers it to gemm(); when the launch qualifies (pair kernel, 256 x 128 tiles, deterministic partials) the
+  // projection does that work itself and tail_done tells the caller (and the next block_pre) to skip its norm launch
+  struct Tail {
+    const float* gamma = nullptr;
+    bf16* out = nullptr;
+  } tail_offer;
+  struct {
+    const float* x = nullptr;
+    const float* gamma = nullptr;
+  } tail_done[2];
+  bool take_tail(const float* x, const float* gamma) {
+    auto& t = tail_done[si()];
+    if (t.x == nullptr || t.x != x || t.gamma != gamma) return false;
+    t.x = nullptr;
+    return true;
+  }
+
   int gemm(const Act& a, const Lin& w, int M, const int* M_dev, int epi, EpiParams ep, int max_splits = 1,
            int stages = 0, const CUtensorMap* out_tm = nullptr) {
+    const Tail offer = tail_offer;
+    tail_offer = Tail();
     GemmDims d;
     d.trace = tr(tr_name, tr_layer);
     d.gelu_warps = e.gelu_warps;
@@ -884,6 +914,18 @@ struct Run {
       e.prof_bytes.push_back(2.0 * (rows * (double)w.K + (double)w.N * (double)w.K) + out_bytes);
       e.prof_class.push_back((d.pair && rows > 512.0) ? 1 : 0);  // M <= 512: weight-streaming regime whatever the kernel
       VL_CUDA_CHECK(cudaEventRecord(e.prof_events[e.prof_used], st));
+    }
+    if (e.fuse_tail && offer.gamma && d.pair && d.pair_bn == 128 && ep.part && epi == EPI_RESID_F32 && w.N <= 1024 &&
+        e.tail_used < Engine::TAIL_CTRS) {
+      // all CTAs of the launch resident (one per SM): 2 * min(tiles, SMs / 2) <= SMs
+      ep.tail_ctr = e.tail_ctrs + e.tail_used++;
+      ep.tail_gamma = offer.gamma;
+      ep.tail_out = offer.out;
+      ep.tail_eps = e.c.rms_eps;
+      ep.tail_err = e.pb.bad_id;
+      pend[si()] = Pending();  // the projection itself finishes the residual update
+      tail_done[si()].x = reinterpret_cast<const float*>(ep.out);
+      tail_done[si()].gamma = offer.gamma;
     }
     const CUtensorMap& wtm = (d.pair && d.pair_bn == 128) ? w.tm64 : (bn == 256 ? w.tm256 : w.tm128);
     const int rc = gemm_launch(a.tm, wtm, d, ep, bn, epi, st, e.tma_epi ? out_tm : nullptr, part_tm);
@@ -1023,7 +1065,9 @@ struct Run {
   int block_pre(LlmLayer& L, float* x, Act& xn, bf16* qout, int M, const int* M_dev, int hid, const int* pos,
                 const int* kvrow, int layer, const L2Prefetch* pf = nullptr) {
     tr_layer = layer;
-    if (!(abl & 1)) {
+    if (take_tail(x, L.ln_in)) {
+      // the down projection of the previous layer already left RMSNorm(x) * ln_in in xn
+    } else if (!(abl & 1)) {
       SplitKPartials spt;
       VL_TRY(rmsnorm_launch(x, L.ln_in, xn.p, M, M_dev, hid, e.c.rms_eps, st, pf, tr("norm_in", layer), take(x, spt)));
       e.launches++;
@@ -1033,13 +1077,17 @@ struct Run {
     return gemm(xn, L.qkv, M, M_dev, EPI_QKV_ROPE, rope_ep(qout, L.bqkv, pos, kvrow, layer));
   }
   int block_post(LlmLayer& L, float* x, Act& xn, Act& ao, Act& act, int M, const int* M_dev, int hid, int mlp,
-                 int splits, const CUtensorMap* x_otm = nullptr, const L2Prefetch* pf = nullptr) {
+                 int splits, const CUtensorMap* x_otm = nullptr, const L2Prefetch* pf = nullptr,
+                 const float* next_gamma = nullptr) {
     EpiParams eo;
     eo.out = x;
     eo.ldo = hid;
     tr_name = "o";
+    if (!abl) tail_offer.gamma = L.ln_post, tail_offer.out = xn.p;
     if (!(abl & 8)) VL_TRY(gemm(ao, L.o, M, M_dev, EPI_RESID_F32, eo, splits > 1 ? std::min(splits, e.xs_o) : 1, 0, x_otm));
-    if (!(abl & 16)) {
+    if (take_tail(x, L.ln_post)) {
+      // the o projection already left RMSNorm(x) * ln_post in xn
+    } else if (!(abl & 16)) {
       SplitKPartials spt;
       VL_TRY(rmsnorm_launch(x, L.ln_post, xn.p, M, M_dev, hid, e.c.rms_eps, st, pf, tr("norm_post", tr_layer), take(x, spt)));
       e.launches++;
@@ -1053,6 +1101,7 @@ struct Run {
     tr_name = "down";
     // (half tile: 6 output tiles x 12 splits = 72 CTAs, again half of the GPU)
     const int xs_down = (M_dev == nullptr && M <= 128) ? std::min(e.xs_down, 12) : e.xs_down;
+    if (!abl && next_gamma) tail_offer.gamma = next_gamma, tail_offer.out = xn.p;
     return gemm(act, L.down, M, M_dev, EPI_RESID_F32, eo, splits > 1 ? std::min(splits, xs_down) : 1, 0, x_otm);
   }
 
@@ -1335,6 +1384,7 @@ struct Run {
   }
 
   bool flow = false;  // the pass is the flow-matching training forward (per-sample time bias, velocity out)
+  int nch_active = 1;  // sub-batch chains of the denoise steps running side by side (fused tails need the whole GPU)
   int denoise(int step, Chain& ch) {
     const vlaser_cfg& c = e.c;
     const int M = ch.M, he = c.hidden_e;
@@ -1413,7 +1463,8 @@ struct Run {
         e.launches++;
       }
       if (e.fuse_norm) VL_TRY(exp_post(li, xa, ch.xan, ch.aoa, ch.acta, M, step + 1, false));
-      else VL_TRY(block_post(e.exp[li], xa, ch.xan, ch.aoa, ch.acta, M, nullptr, he, e.mlp_e_p, 32, &ch.xa_otm, e.l2pf ? &pf_post : nullptr));
+      else VL_TRY(block_post(e.exp[li], xa, ch.xan, ch.aoa, ch.acta, M, nullptr, he, e.mlp_e_p, 32, &ch.xa_otm, e.l2pf ? &pf_post : nullptr,
+                             (li + 1 < c.layers && nch_active == 1) ? e.exp[li + 1].ln_in : nullptr));
     }
     const int last = step == c.num_inference_steps - 1;
     VL_TRY(flush());  // split-K partials of the last down projection
@@ -1441,6 +1492,7 @@ struct Run {
     // each); the expert-stream / single-observation / fused-norm schedules keep one chain
     if (e.den_chains >= 2 && !mega() && !e.fuse_norm && !e.simt && B % 2 == 0 && ((B / 2) * e.H) % 128 == 0) nch = 2;
     cudaStream_t main_st = st;
+    nch_active = nch;
     std::vector<Chain> chains(nch);
     for (int i = 0; i < nch; ++i) VL_TRY(make_chain(chains[i], i, i * (B / nch), B / nch));
     if (nch > 1) {
@@ -1564,6 +1616,8 @@ struct Run {
 
   int all(bool has_valid) {
     const vlaser_cfg& c = e.c;
+    VL_CUDA_CHECK(cudaMemsetAsync(e.tail_ctrs, 0, sizeof(unsigned int) * Engine::TAIL_CTRS, st));  // fused-tail barriers
+    e.tail_used = 0;
     if (e.mode == 3) return text_decode();
     if (e.mode == 2) {
       VL_TRY(plan_launch(e.in_ids, has_valid ? e.in_valid : nullptr, e.pb, B, e.S, e.H, e.n_img * e.T, c.image_token_index,
@@ -1580,6 +1634,7 @@ struct Run {
     VL_TRY(convert_launch(e.in_noise, io, e.action, DT_F32, (long long)B * e.H * c.action_dim, st));
     if (e.fuse_norm) VL_CUDA_CHECK(cudaMemsetAsync(e.ss, 0, e.ss_floats * sizeof(float), st));
     VL_CUDA_CHECK(cudaMemsetAsync(e.xp_bar, 0, sizeof(unsigned int) * (size_t)(c.num_inference_steps + 1) * e.xp_bar_words(), st));
+
     if (gemv() && e.det_splitk)
       VL_CUDA_CHECK(cudaMemsetAsync(e.xfix, 0, sizeof(long long) * (size_t)(c.num_inference_steps + 1) * e.xfix_words(), st));
     e.launches += 5;
@@ -1704,7 +1759,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc" || k == "fuse_tail") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
@@ -1724,6 +1779,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
     else if (k == "pair_bn128") h->e.pair_bn128 = (int)value;
     else if (k == "gelu_warps") h->e.gelu_warps = (int)value == 8 ? 8 : 16;
     else if (k == "prefill_tc") h->e.prefill_tc = (int)value;
+    else if (k == "fuse_tail") h->e.fuse_tail = (int)value;
     else if (k == "exp_splits_o") h->e.xs_o = std::max(1, (int)value);
     else if (k == "exp_splits_down") h->e.xs_down = std::max(1, (int)value);
     else if (k == "pair_gemm") h->e.pair_gemm = (int)value;

@@ -566,6 +566,101 @@ __device__ __forceinline__ void pair_tile(int t, int m_tiles, int n_tiles, int n
   }
 }
 
+// Fused tail of a split-K residual projection (see EpiParams::tail_ctr): in-kernel grid barrier, then this CTA's share of
+// the residual update + RMSNorm rows. Called by every thread of every CTA after the CTA-wide (cluster-wide) barrier that
+// follows the completion of its TMA stores. N <= 1024 columns (one float4 per thread of the first N / 4 threads).
+__device__ __forceinline__ void pair_tail_resid_norm(const EpiParams& ep, const GemmDims& d, int M, int S) {
+  __shared__ float tail_red[32];
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ep.tail_ctr) : "memory");
+    unsigned int v;
+    long long t0 = 0;
+    while (true) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ep.tail_ctr) : "memory");
+      if (v >= gridDim.x) break;
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 2000000000LL) {  // a CTA of the launch is not resident: give up, flag the call
+        if (ep.tail_err) atomicExch(ep.tail_err, GEMM_ERR_TAIL_BARRIER);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  const int W = d.N, C4 = W >> 2;
+  const int c = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nw = (C4 + 31) >> 5;  // warps that own columns
+  float* x = reinterpret_cast<float*>(ep.out);
+  float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C4) gm = __ldg(reinterpret_cast<const float4*>(ep.tail_gamma) + c);
+  // two rows per round, all of their loads in flight at once (256 rows over 144 CTAs: one round)
+  for (int row0 = blockIdx.x; row0 < M; row0 += 2 * gridDim.x) {
+    const int rows[2] = {row0, row0 + (int)gridDim.x};
+    float4 v[2];
+    float q[2] = {0.f, 0.f};
+    if (c < C4) {
+      float4 pv[2][12];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const bool ok = rows[r] < M;
+        const size_t off = (size_t)(ok ? rows[r] : row0) * ep.ldo + 4 * c;
+        v[r] = *reinterpret_cast<const float4*>(x + off);
+#pragma unroll
+        for (int u = 0; u < 12; ++u) {
+          pv[r][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (u < S && ok) pv[r][u] = __ldcg(reinterpret_cast<const float4*>(ep.part + (size_t)u * ep.part_stride + off));
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (rows[r] >= M) continue;
+        const size_t off = (size_t)rows[r] * ep.ldo + 4 * c;
+        // four interleaved split groups, each summed in ascending split order from 0 and then added to x in group order:
+        // the association of resid_norm_kernel (G = 4), so the residual stream is bit-identical with the unfused schedule
+        float4 acc[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 12; ++u) {
+          acc[u & 3].x += pv[r][u].x;
+          acc[u & 3].y += pv[r][u].y;
+          acc[u & 3].z += pv[r][u].z;
+          acc[u & 3].w += pv[r][u].w;
+        }
+        for (int s0 = 12; s0 < S; s0 += 4) {  // (more than 12 splits: the rest in dependent batches of one per group)
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (s0 + u < S) {
+              const float4 p = __ldcg(reinterpret_cast<const float4*>(ep.part + (size_t)(s0 + u) * ep.part_stride + off));
+              acc[u].x += p.x, acc[u].y += p.y, acc[u].z += p.z, acc[u].w += p.w;
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) v[r].x += acc[g].x, v[r].y += acc[g].y, v[r].z += acc[g].z, v[r].w += acc[g].w;
+        if (S > 0) *reinterpret_cast<float4*>(x + off) = v[r];
+        q[r] = (v[r].x * v[r].x + v[r].y * v[r].y) + (v[r].z * v[r].z + v[r].w * v[r].w);
+      }
+    }
+    q[0] = warp_sum(q[0]);
+    q[1] = warp_sum(q[1]);
+    __syncthreads();  // scratch free again
+    if (lane == 0 && warp < 16) tail_red[warp] = q[0], tail_red[16 + warp] = q[1];
+    __syncthreads();
+    if (c < C4) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (rows[r] >= M) continue;
+        float tot = 0.f;
+        for (int w = 0; w < nw; ++w) tot += tail_red[16 * r + w];
+        const float rstd = rsqrtf(tot / (float)W + ep.tail_eps);
+        uint2 u;
+        u.x = pack_bf16(v[r].x * rstd * gm.x, v[r].y * rstd * gm.y);
+        u.y = pack_bf16(v[r].z * rstd * gm.z, v[r].w * rstd * gm.w);
+        *reinterpret_cast<uint2*>(ep.tail_out + (size_t)rows[r] * ep.ldo + 4 * c) = u;
+      }
+    }
+  }
+}
+
 template <int EPI>
 constexpr int pair_epi_warps() { return EPI == EPI_GELU_BF16 ? 16 : 8; }  // the exact-GELU epilogue is issue-bound at 8
 
@@ -810,11 +905,17 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   if (warp == 2) trace_stamp(tr, 5);
   if (warp >= 2 && lane == 0) bulk_wait<0>();  // this warp's TMA stores have landed
+  if constexpr (EPI == EPI_RESID_F32 && BN == 128) {
+    if (ep.tail_ctr) fence_proxy_async();  // ... and are ordered before the release below (async proxy -> generic)
+  }
   // neither CTA may exit (or free TMEM) while its peer can still signal its barriers or read its smem
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) tmem_dealloc_pair(tmem_base, 2 * BN);
   if (warp == 2) trace_stamp(tr, 6);
+  if constexpr (EPI == EPI_RESID_F32 && BN == 128) {
+    if (ep.tail_ctr) pair_tail_resid_norm(ep, d, M, (splits > 1 && ep.part) ? splits : 0);
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -62,7 +62,19 @@ struct EpiParams {
   float* part = nullptr;
   long long part_stride = 0;           // floats between consecutive splits, a multiple of 256 * ldo covering the rows
   int* part_splits = nullptr;
+  // ---- fused tail (pair kernel, 256 x 128 tiles, EPI_RESID_F32 with `part`: the o / down projections of the action expert
+  // at one 256-row tile). The launch is one dependent hop of a latency-bound chain and so is the norm launch behind it;
+  // with tail_ctr set every CTA, once its partial tiles have landed, passes an in-kernel grid barrier (all CTAs of the
+  // launch are resident: one per SM, at most gemm_num_sms() of them) and then finishes rows blockIdx.x, + gridDim.x, ...:
+  // out[row] += partials in split order (the same association as resid_norm_kernel), then RMSNorm(out[row]) * tail_gamma
+  // -> tail_out (bf16) -- the work of the norm launch that would follow, without its hop.
+  unsigned int* tail_ctr = nullptr;    // arrival counter of this launch, zero on entry
+  const float* tail_gamma = nullptr;   // [N] gain of the following RMSNorm
+  __nv_bfloat16* tail_out = nullptr;   // [M, ldo]
+  float tail_eps = 0.f;
+  int* tail_err = nullptr;             // receives GEMM_ERR_TAIL_BARRIER if the barrier gives up (~1 s)
 };
+constexpr int GEMM_ERR_TAIL_BARRIER = 0x7ffffff2;
 
 struct GemmDims {
   int M = 0, N = 0, K = 0;       // K % 64 == 0, N % block_n == 0
