@@ -144,6 +144,7 @@ void vlaser_destroy(vlaser_t* h);
  * "l2_prefetch" (default 0, measured no gain: the RMSNorm launches of a denoise step issue bulk L2 prefetches of the expert weights the
  * next launches of the chain will read),
  * "expert_gemv" (default 1: at B = 1 the expert passes run on the weight-streaming single-observation kernel, csrc/expert_gemv.cu),
+ * "decode_chunk" (default 128: keys per CTA of the split-KV decode-step attention of vlaser_generate; 0 = the generic kernel),
  * "fuse_tail" (default 0, measured no gain: the o / down projections of the action expert finish the residual update + the
  * following RMSNorm themselves behind an in-kernel grid barrier instead of leaving them to a norm launch),
  * "use_graph" (default 1: replay the whole call as one CUDA graph per batch size),
@@ -227,6 +228,15 @@ typedef struct vlaser_attn_args {
   int32_t causal;  /* 1: query token t of a sample sees keys [0, kv_len - q_len + t] (text prefill of the chat VLM) */
 } vlaser_attn_args;
 int32_t vlaser_op_attention(const vlaser_attn_args* a, void* stream);
+/* Decode-step attention of the chat VLM (one query row per sample over its K/V window, head_dim 128, GQA; HF Qwen2
+ * eager_attention_forward with q_len = 1): split-KV -- one CTA per (chunk of keys, kv head, sample), then a merge launch.
+ * q / out bf16 [rows, n_heads*128] (sample b at row q_start[b]); caches bf16 [n_kv_heads, kv_rows, 128] (sample b from row
+ * kv_start[b], kv_len[b] keys); chunk 64..256 (multiple of 64); ws_o f32 [batch, n_kv_heads, ceil(max_kv_len/chunk),
+ * group, 128], ws_ml f32 [.., group, 2]. */
+int32_t vlaser_op_decode_attention(const void* q, const void* k_cache, const void* v_cache, void* out, const int32_t* kv_start,
+                                   const int32_t* kv_len, int32_t batch, int32_t n_heads, int32_t n_kv_heads, int64_t kv_rows,
+                                   int32_t max_kv_len, int32_t chunk, float scale, float* ws_o, float* ws_ml, const int32_t* q_start,
+                                   void* stream);
 /* InternViT self-attention fast path (_naive_attn, modeling_intern_vit.py:210-227): qkv bf16 [images*tokens, 3*heads*64]
  * as written by the fused qkv projection, out bf16 [images*tokens, heads*64]; 128 <= tokens <= 320. */
 int32_t vlaser_op_vit_attention(const void* qkv, void* out, int32_t images, int32_t tokens, int32_t heads, float scale,

@@ -85,6 +85,23 @@ def attention(q, k, v, out, head_dim, group, n_kv_heads, batch, scale, q_row_str
     return out
 
 
+def decode_attention(q, k_cache, v_cache, kv_start, kv_len, n_heads, n_kv_heads, scale, chunk=256):
+    """q bf16 [B, n_heads*128] (one query row per sample), caches bf16 [n_kv_heads, kv_rows, 128] -> out like q."""
+    lib = _lib.load()
+    B = q.shape[0]
+    out = torch.zeros_like(q)
+    max_kv = int(kv_len.max())
+    splits = (max_kv + chunk - 1) // chunk
+    group = n_heads // n_kv_heads
+    ws_o = torch.empty(B * n_kv_heads * splits * group * 128, dtype=torch.float32, device=q.device)
+    ws_ml = torch.empty(B * n_kv_heads * splits * group * 2, dtype=torch.float32, device=q.device)
+    q_start = torch.arange(B, dtype=torch.int32, device=q.device)
+    _lib.check(lib.vlaser_op_decode_attention(_p(q), _p(k_cache), _p(v_cache), _p(out), _p(kv_start), _p(kv_len), B, n_heads,
+                                              n_kv_heads, k_cache.shape[1], max_kv, chunk, scale, _p(ws_o), _p(ws_ml), _p(q_start),
+                                              _stream()), "op_decode_attention")
+    return out
+
+
 def vit_attention(qkv, images, tokens, heads, scale, tc=False):
     """qkv bf16 [images*tokens, 3*heads*64] -> out bf16 [images*tokens, heads*64] (InternViT fast path; tc: the tcgen05
     kernel, 257 tokens)."""

@@ -467,6 +467,32 @@ def test_attention_causal():
         assert max(errs) < 1e-2
 
 
+@pytest.mark.parametrize("nkv,group,lens,chunk", [(2, 6, [85, 1, 130, 300, 3353, 64, 257], 256), (4, 7, [3353, 277, 1302, 2000], 256),
+                                                  (1, 1, [100, 63], 64), (2, 8, [129, 128, 1000], 128)])
+def test_decode_attention_split_kv(nkv, group, lens, chunk):
+    """Split-KV decode-step attention: one query row per sample over windows of 1 .. 3353 keys (1 .. 14 chunks), GQA groups
+    1 / 6 / 7 / 8, against the softmax over the whole window; call-to-call bit-identical (fixed merge order)."""
+    hd, nq, B = 128, nkv * group, len(lens)
+    window = max(lens) + 5
+    q = _rand(B, nq * hd, seed=21)
+    kc = _rand(nkv, B * window, hd, seed=22)
+    vc = _rand(nkv, B * window, hd, seed=23)
+    i32 = lambda x: torch.tensor(x, dtype=torch.int32, device=DEV)
+    kvoff = [b * window for b in range(B)]
+    scale = hd ** -0.5
+    out = ops.decode_attention(q, kc, vc, i32(kvoff), i32(lens), nq, nkv, scale, chunk)
+    errs = []
+    for b in range(B):
+        for h in range(nq):
+            g = h // group
+            r = _attn_ref(q[b:b + 1, h * hd:(h + 1) * hd].float(), kc[g, kvoff[b]:kvoff[b] + lens[b]].float(),
+                          vc[g, kvoff[b]:kvoff[b] + lens[b]].float(), scale, lens[b])
+            errs.append(ops.rel_err(out[b:b + 1, h * hd:(h + 1) * hd], r))
+    print(f"decode_attention nkv={nkv} group={group} chunk={chunk} max rel={max(errs):.2e}")
+    assert max(errs) < 1e-2
+    assert torch.equal(out, ops.decode_attention(q, kc, vc, i32(kvoff), i32(lens), nq, nkv, scale, chunk))
+
+
 @pytest.mark.parametrize("width", [128, 768, 1024, 1536, 4096])
 def test_norms(width):
     rows = 515

@@ -550,14 +550,17 @@ def _check_generation(cfg, sd, inp, toks, first_logits, log, tag):
     return ref
 
 
+@pytest.mark.parametrize("decode_chunk", [256, 64, 0])
 @pytest.mark.parametrize("name", GENERATE_CASES)
-def test_generate_golden(name, capsys):
+def test_generate_golden(name, decode_chunk, capsys):
     """Greedy decode through the C ABI vs the HF / reference golden (tiny configs; untied head, and tied head with dynamic
-    tiles 1/3/2/2)."""
+    tiles 1/3/2/2). decode_chunk: the split-KV decode attention with one chunk per window (256), with two or three (64),
+    and the generic attention kernel (0)."""
     cfg, sd, inp, gold = load_case(name)
     B, n_new = gold["tokens"].shape
     pol = PiZeroInference(cfg, max_batch=B)
     pol.load_state_dict(sd, strict=False)
+    pol.set_option("decode_chunk", decode_chunk)
     toks, logits = pol.generate(inp["input_ids"].cuda(), inp["pixel_values"].cuda(), max_new_tokens=n_new, return_first_logits=True)
     toks2 = pol.generate(inp["input_ids"].cuda(), inp["pixel_values"].cuda(), max_new_tokens=n_new)  # graph replays
     assert torch.equal(toks, toks2), "generation must be bit-identical from call to call"

@@ -67,7 +67,7 @@ EXPORTS = [
     "vlaser_op_layernorm", "vlaser_op_rmsnorm", "vlaser_op_pixel_shuffle", "vlaser_op_im2col", "vlaser_op_euler_step",
     "vlaser_op_vit_attention", "vlaser_profile_read_classes", "vlaser_op_stage_frames", "vlaser_op_postprocess_actions",
     "vlaser_op_splitk_reduce", "vlaser_op_vit_attention_tc", "vlaser_op_normalize", "vlaser_op_prefill_attention_tc",
-    "vlaser_flow_matching_loss", "vlaser_generate",
+    "vlaser_flow_matching_loss", "vlaser_generate", "vlaser_op_decode_attention",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -120,6 +120,8 @@ def load() -> C.CDLL:
     lib.vlaser_op_attention.restype = i32
     lib.vlaser_op_vit_attention.argtypes = [vp, vp, i32, i32, i32, f32, vp]
     lib.vlaser_op_vit_attention.restype = i32
+    lib.vlaser_op_decode_attention.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, i32, f32, vp, vp, vp, vp]
+    lib.vlaser_op_decode_attention.restype = i32
     lib.vlaser_op_vit_attention_tc.argtypes = [vp, vp, i32, i32, i32, f32, vp]
     lib.vlaser_op_vit_attention_tc.restype = i32
     lib.vlaser_op_layernorm.argtypes = [vp, vp, vp, vp, i32, i32, f32, i32, i32, vp]

@@ -13,13 +13,13 @@ namespace vlaser {
 
 namespace {
 
-template <int HD>
+template <int HD, bool CAUSAL = false>
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(AttnParams p) {
   pdl_launch_dependents();
   extern __shared__ __align__(128) uint8_t smem[];
   long long* tr = (blockIdx.x + blockIdx.y + blockIdx.z == 0 && threadIdx.x == 0) ? p.trace : nullptr;
   trace_stamp(tr, 0);
-  attention_tile<HD>(p, blockIdx.z, blockIdx.y, blockIdx.x, smem, threadIdx.x, [] { __syncthreads(); },
+  attention_tile<HD, CAUSAL>(p, blockIdx.z, blockIdx.y, blockIdx.x, smem, threadIdx.x, [] { __syncthreads(); },
                      [tr] { pdl_wait(); trace_stamp(tr, 1); });
   trace_stamp(tr, 6);
 }
@@ -274,6 +274,161 @@ vit_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Decode-step attention (see DecodeAttnParams): split-KV, CUDA cores -- a step has `group` query rows per kv head, far
+// too few for an MMA tile, and is bound by streaming the K / V window once.
+// ------------------------------------------------------------------------------------------
+constexpr int DA_THREADS = 128;
+constexpr int DA_MAX_GROUP = 8;
+constexpr int DA_MAX_CHUNK = 256;
+
+__global__ void __launch_bounds__(DA_THREADS) decode_attention_split_kernel(DecodeAttnParams p) {
+  extern __shared__ __align__(128) uint8_t da_smem[];         // K chunk, V chunk: [chunk][256 B], 16-byte chunks XOR-swizzled
+  __shared__ __align__(16) float qs[DA_MAX_GROUP][128];       // queries, scaled into the exp2 domain
+  __shared__ float ps[DA_MAX_GROUP][DA_MAX_CHUNK];            // scores, then probabilities
+  __shared__ float red[DA_MAX_GROUP][4];
+  __shared__ float oacc[DA_MAX_GROUP][128];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int sp = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kv_len = p.kv_len[b];
+  const int k0 = sp * p.chunk;
+  if (k0 >= kv_len) return;
+  const int n = min(p.chunk, kv_len - k0);
+  const int G = p.group;
+  const float sl2 = p.scale * 1.4426950408889634f;
+  uint8_t* Ks = da_smem;
+  uint8_t* Vs = da_smem + (size_t)p.chunk * 256;
+  // ---- the whole K / V chunk in flight at once (a CTA is bound by HBM latency, not by arithmetic)
+  const size_t kvbase = (size_t)kvh * p.kv_head_stride + (size_t)(p.kv_start[b] + k0) * p.kv_row_stride;
+  for (int i = tid; i < n * 16; i += DA_THREADS) {
+    const int row = i >> 4, c = i & 15;
+    cp_async_16(Ks + swz<128>(row, c), p.k + kvbase + (size_t)row * p.kv_row_stride + c * 8, true);
+  }
+  cp_async_commit();
+  for (int i = tid; i < n * 16; i += DA_THREADS) {
+    const int row = i >> 4, c = i & 15;
+    cp_async_16(Vs + swz<128>(row, c), p.v + kvbase + (size_t)row * p.kv_row_stride + c * 8, true);
+  }
+  cp_async_commit();
+  const __nv_bfloat16* qrow = p.q + (size_t)p.q_start[b] * p.q_row_stride + (size_t)kvh * G * 128;
+  for (int i = tid; i < G * 128; i += DA_THREADS) qs[i >> 7][i & 127] = __bfloat162float(qrow[i]) * sl2;
+  cp_async_wait<1>();  // K landed
+  __syncthreads();
+  // ---- scores: one key per thread and round
+  for (int j = tid; j < p.chunk; j += DA_THREADS) {
+    float acc[DA_MAX_GROUP];
+#pragma unroll
+    for (int g = 0; g < DA_MAX_GROUP; ++g) acc[g] = 0.f;
+    if (j < n) {
+#pragma unroll 4
+      for (int c = 0; c < 16; ++c) {
+        const uint4 u = *reinterpret_cast<const uint4*>(Ks + swz<128>(j, c));
+        const float kf[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+        for (int g = 0; g < DA_MAX_GROUP; ++g) {
+          if (g < G) {
+            const float4 q0 = *reinterpret_cast<const float4*>(&qs[g][c * 8]);
+            const float4 q1 = *reinterpret_cast<const float4*>(&qs[g][c * 8 + 4]);
+            acc[g] += (q0.x * kf[0] + q0.y * kf[1]) + (q0.z * kf[2] + q0.w * kf[3]) + (q1.x * kf[4] + q1.y * kf[5]) +
+                      (q1.z * kf[6] + q1.w * kf[7]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < DA_MAX_GROUP; ++g)
+      if (g < G) ps[g][j] = j < n ? acc[g] : -INFINITY;
+  }
+  cp_async_wait<0>();  // V landed
+  __syncthreads();
+  // ---- chunk maximum and probabilities: warp w owns rows w, w + 4
+  for (int g = warp; g < G; g += 4) {
+    float mx = -INFINITY;
+    for (int j = lane; j < p.chunk; j += 32) mx = fmaxf(mx, ps[g][j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < p.chunk; j += 32) {
+      const float pj = exp2f(ps[g][j] - mx);  // -inf -> 0
+      ps[g][j] = pj;
+      sum += pj;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[g][0] = mx, red[g][1] = sum;
+  }
+  __syncthreads();
+  // ---- P V: thread = (two dims, key parity)
+  const int d2 = (tid & 63) * 2, par = tid >> 6;
+  float o[DA_MAX_GROUP][2];
+#pragma unroll
+  for (int g = 0; g < DA_MAX_GROUP; ++g) o[g][0] = o[g][1] = 0.f;
+#pragma unroll 4
+  for (int j = par; j < n; j += 2) {
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(Vs + swz<128>(j, d2 >> 3) + (d2 & 7) * 2);
+    const float v0 = bf16_lo(u), v1 = bf16_hi(u);
+#pragma unroll
+    for (int g = 0; g < DA_MAX_GROUP; ++g)
+      if (g < G) {
+        const float pj = ps[g][j];
+        o[g][0] += pj * v0;
+        o[g][1] += pj * v1;
+      }
+  }
+  if (par == 1) {
+#pragma unroll
+    for (int g = 0; g < DA_MAX_GROUP; ++g)
+      if (g < G) oacc[g][d2] = o[g][0], oacc[g][d2 + 1] = o[g][1];
+  }
+  __syncthreads();
+  const int splits = gridDim.x;
+  const size_t wbase = ((size_t)(b * p.n_kv_heads + kvh) * splits + sp) * G;
+  if (par == 0) {
+#pragma unroll
+    for (int g = 0; g < DA_MAX_GROUP; ++g)
+      if (g < G)
+        *reinterpret_cast<float2*>(p.ws_o + (wbase + g) * 128 + d2) = make_float2(o[g][0] + oacc[g][d2], o[g][1] + oacc[g][d2 + 1]);
+  }
+  if (tid < G) *reinterpret_cast<float2*>(p.ws_ml + (wbase + tid) * 2) = make_float2(red[tid][0], red[tid][1]);
+}
+
+__global__ void __launch_bounds__(128) decode_attention_merge_kernel(DecodeAttnParams p, int splits) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int head = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+  const int kvh = head / p.group, g = head - kvh * p.group;
+  const int ns = (p.kv_len[b] + p.chunk - 1) / p.chunk;
+  const size_t wbase = (size_t)(b * p.n_kv_heads + kvh) * splits;
+  float M = -INFINITY;
+  for (int s = 0; s < ns; ++s) M = fmaxf(M, p.ws_ml[((wbase + s) * p.group + g) * 2]);
+  float L = 0.f, o = 0.f;
+  for (int s = 0; s < ns; ++s) {  // fixed order: bit-identical from call to call
+    const float2 ml = *reinterpret_cast<const float2*>(p.ws_ml + ((wbase + s) * p.group + g) * 2);
+    const float w = exp2f(ml.x - M);
+    L += w * ml.y;
+    o += w * p.ws_o[((wbase + s) * p.group + g) * 128 + d];
+  }
+  p.out[(size_t)p.q_start[b] * p.out_row_stride + (size_t)head * 128 + d] = __float2bfloat16(L > 0.f ? o / L : 0.f);
+}
+
+}  // namespace
+
+int decode_attention_launch(const DecodeAttnParams& p, cudaStream_t stream) {
+  VL_CHECK(p.batch > 0 && p.batch <= 65535 && p.n_kv_heads > 0 && p.group >= 1 && p.group <= DA_MAX_GROUP, "decode attention: bad shape");
+  VL_CHECK(p.chunk >= 64 && p.chunk <= DA_MAX_CHUNK && p.chunk % 64 == 0, "decode attention: chunk must be 64 .. 256, a multiple of 64");
+  VL_CHECK(p.max_kv_len > 0 && p.ws_o && p.ws_ml, "decode attention: no workspace");
+  const int splits = (p.max_kv_len + p.chunk - 1) / p.chunk;
+  static unsigned long long attr_devs = 0;
+  if (vl_first_on_device(attr_devs))
+    VL_CUDA_CHECK(cudaFuncSetAttribute(decode_attention_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_MAX_CHUNK * 512));
+  VL_CUDA_CHECK(launch_kernel(decode_attention_split_kernel, dim3(splits, p.n_kv_heads, p.batch), dim3(DA_THREADS),
+                              (size_t)p.chunk * 512, stream, p));
+  VL_CUDA_CHECK(launch_kernel(decode_attention_merge_kernel, dim3(p.n_kv_heads * p.group, p.batch), dim3(128), 0, stream, p, splits));
+  return 0;
+}
+
+namespace {
+
 template <int HD>
 int launch_hd(const AttnParams& p, cudaStream_t stream) {
   constexpr int SMEM = (ATT_BM + 4 * ATT_BN) * HD * 2;
@@ -283,6 +438,14 @@ int launch_hd(const AttnParams& p, cudaStream_t stream) {
   }
   const int rows_max = p.group * p.max_q_len;
   dim3 grid((rows_max + ATT_BM - 1) / ATT_BM, p.n_kv_heads, p.batch);
+  if (p.causal) {  // text prefill / decode of the chat VLM
+    VL_CHECK(p.q2 == nullptr, "attention: the causal rule has no extra query row");
+    static unsigned long long attr_devs_c = 0;
+    if (vl_first_on_device(attr_devs_c))
+      VL_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    VL_CUDA_CHECK(launch_kernel(attention_kernel<HD, true>, dim3(grid), dim3(ATT_THREADS), SMEM, stream, p));
+    return 0;
+  }
   VL_CUDA_CHECK(launch_kernel(attention_kernel<HD>, dim3(grid), dim3(ATT_THREADS), SMEM, stream, p));
   VL_CUDA_CHECK(cudaGetLastError());
   return 0;

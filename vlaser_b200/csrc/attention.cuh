@@ -47,6 +47,30 @@ struct AttnParams {
 
 int attention_launch(const AttnParams& p, int head_dim, cudaStream_t stream);
 
+// Decode-step attention of the chat VLM (one new query token per sample over its whole K/V window, head_dim 128, GQA):
+// the generic kernel gives such a step batch * n_kv_heads CTAs that each walk the window serially (91 us per layer at 3.3 k
+// keys). Here the window is cut into chunks of `chunk` keys: one CTA per (chunk, kv head, sample) leaves the un-normalised
+// output and the (max, sum) of its chunk in a workspace, a second launch merges the chunks of a row (split-KV softmax).
+struct DecodeAttnParams {
+  const __nv_bfloat16* q = nullptr;   // query row of sample b: q + q_start[b] * q_row_stride, head h at + h * 128
+  long long q_row_stride = 0;
+  const __nv_bfloat16* k = nullptr;   // as AttnParams
+  const __nv_bfloat16* v = nullptr;
+  long long kv_row_stride = 0, kv_head_stride = 0;
+  __nv_bfloat16* out = nullptr;       // addressed like q
+  long long out_row_stride = 0;
+  const int* q_start = nullptr;       // [batch]
+  const int* kv_start = nullptr;      // [batch]
+  const int* kv_len = nullptr;        // [batch]
+  int group = 1, n_kv_heads = 1, batch = 0;
+  int max_kv_len = 0;                 // upper bound of kv_len (grid sizing)
+  int chunk = 256;                    // keys per CTA, a multiple of 64, <= 256
+  float scale = 1.f;
+  float* ws_o = nullptr;              // [batch, n_kv_heads, splits, group, 128] f32, splits = ceil(max_kv_len / chunk)
+  float* ws_ml = nullptr;             // [batch, n_kv_heads, splits, group, 2] f32
+};
+int decode_attention_launch(const DecodeAttnParams& p, cudaStream_t stream);
+
 // InternViT self-attention fast path (head_dim 64, no mask, 128 <= tokens <= 320): qkv [images*tokens, 3*heads*64]
 // packed as the fused qkv projection writes it, out [images*tokens, heads*64]. One CTA per (image, head).
 int vit_attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int images, int tokens, int heads, float scale,

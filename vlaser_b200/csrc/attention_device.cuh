@@ -22,7 +22,8 @@ constexpr int attention_tile_smem() { return (ATT_BM + 4 * ATT_BN) * HD * 2; }
 
 // `dep_wait` is called exactly once by every thread that does not return early: after it the outputs of the
 // previous grid (Q and the new K/V rows) may be read.
-template <int HD, typename Sync, typename DepWait>
+// CAUSAL is a template parameter so that the policy call's instantiation is the code it was before the text path existed.
+template <int HD, bool CAUSAL = false, typename Sync, typename DepWait>
 __device__ __forceinline__ void attention_tile(const AttnParams& p, int b, int kvh, int qb, uint8_t* smem, int tid,
                                                Sync sync, DepWait dep_wait) {
   constexpr int CH = HD / 8;  // 16-byte chunks per row
@@ -44,8 +45,8 @@ __device__ __forceinline__ void attention_tile(const AttnParams& p, int b, int k
   // causal (text prefill of the chat VLM): query token t sees keys [0, kv_len - q_len + t]; the CTA stops at the last key
   // its last token sees
   const int causal_off = kv_len - q_len;
-  const int t_last = min(q_len - 1, (r0 + ATT_BM - 1) / group);
-  const int kv_hi = p.causal ? min(kv_len, causal_off + t_last + 1) : kv_len + (cta_has_extra ? 1 : 0);
+  int kv_hi = kv_len + (cta_has_extra ? 1 : 0);
+  if constexpr (CAUSAL) kv_hi = min(kv_len, causal_off + min(q_len - 1, (r0 + ATT_BM - 1) / group) + 1);
   const int n_blocks = (kv_hi + ATT_BN - 1) / ATT_BN;
 
   const __nv_bfloat16* kbase = p.k + (size_t)kvh * p.kv_head_stride + (size_t)kv_start * p.kv_row_stride;
@@ -93,7 +94,7 @@ __device__ __forceinline__ void attention_tile(const AttnParams& p, int b, int k
   for (int h = 0; h < 2; ++h) {
     const int r = r0 + rlo + h * 8;
     if (r >= rows_total) lim[h] = 0;
-    else if (p.causal) lim[h] = min(kv_len, causal_off + r / group + 1);
+    else if (CAUSAL) lim[h] = min(kv_len, causal_off + r / group + 1);
     else lim[h] = (has_extra && (r / group) == q_len) ? kv_len + 1 : kv_len;
   }
   const bool warp_active = (r0 + warp * 16) < rows_total;

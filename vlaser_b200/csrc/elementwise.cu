@@ -588,7 +588,26 @@ __global__ void __launch_bounds__(1024) argmax_rows_kernel(const float* __restri
   const float* row = logits + (size_t)blockIdx.x * ld;
   float best = -INFINITY;
   int idx = 0x7fffffff;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {  // strictly greater: the first maximum wins, like torch.argmax
+  // ld is a multiple of 128 floats: float4 loads, four in flight per thread; ties keep the lowest index, like torch.argmax
+  const int n4 = n >> 2;
+  const float4* row4 = reinterpret_cast<const float4*>(row);
+  for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * blockDim.x) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      v[u] = i < n4 ? __ldcs(row4 + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = 4 * (i0 + u * (int)blockDim.x);
+      const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (e[k] > best || (e[k] == best && i + k < idx)) best = e[k], idx = i + k;
+    }
+  }
+  for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) {
     const float v = row[i];
     if (v > best || (v == best && i < idx)) best = v, idx = i;
   }

@@ -166,6 +166,8 @@ struct Engine {
   int gen_cap = 0;             // = the K/V window of a sample, S + 1 + H
   long long gen_eos = -1, gen_fill = 0;
   int text_no_image = 0;       // the prompt of this vlaser_generate call holds no image tile
+  float *dec_ws_o = nullptr, *dec_ws_ml = nullptr;  // split-KV workspace of the decode-step attention
+  int dec_chunk = 128;         // keys per CTA of the decode-step attention (option "decode_chunk"; 0: the generic kernel)
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
 
@@ -567,6 +569,9 @@ int engine_build(Engine& e) {
     VL_TRY(e.alloc(&e.gen.kv_len, e.Bc));
     VL_TRY(e.alloc(&e.gen.q_start, e.Bc));
     VL_TRY(e.alloc(&e.gen.q_len, e.Bc));
+    const size_t max_splits = (size_t)(e.gen_cap + 63) / 64;
+    VL_TRY(e.alloc(&e.dec_ws_o, (size_t)e.Bc * c.n_heads * max_splits * 128));
+    VL_TRY(e.alloc(&e.dec_ws_ml, (size_t)e.Bc * c.n_heads * max_splits * 2));
   }
   e.pinned_bytes = (size_t)e.Bc * e.S * 8 + pix_elems * 4 + (size_t)e.Bc * 4 + (size_t)e.Bc * c.proprio_dim * 4 +
                    (size_t)arow * c.action_dim * 4 + (size_t)e.Bc * c.horizon_steps * c.action_dim * 4 + 4096;
@@ -1603,12 +1608,28 @@ struct Run {
     for (int li = 0; li < c.layers; ++li) {
       VL_TRY(block_pre(e.llm[li], e.x_dec, e.xn, e.q, B, nullptr, c.hidden, e.gen.pos, e.gen.kvrow, li));
       AttnParams ap = text_attn(li);
-      ap.q_start = e.gen.q_start;
-      ap.q_len = e.gen.q_len;
-      ap.kv_len = e.gen.kv_len;
-      ap.max_q_len = 1;
-      VL_TRY(attention_launch(ap, 128, st));
-      e.launches++;
+      if (e.dec_chunk > 0 && ap.group <= 8) {
+        // one query row per sample over its whole window: split-KV kernel (the generic one walks the window serially)
+        DecodeAttnParams dp;
+        dp.q = ap.q, dp.q_row_stride = ap.q_row_stride;
+        dp.k = ap.k, dp.v = ap.v, dp.kv_row_stride = ap.kv_row_stride, dp.kv_head_stride = ap.kv_head_stride;
+        dp.out = ap.out, dp.out_row_stride = ap.out_row_stride;
+        dp.q_start = e.gen.q_start, dp.kv_start = e.pb.kvoff, dp.kv_len = e.gen.kv_len;
+        dp.group = ap.group, dp.n_kv_heads = ap.n_kv_heads, dp.batch = B;
+        dp.max_kv_len = e.gen_cap;
+        dp.chunk = e.dec_chunk;
+        dp.scale = ap.scale;
+        dp.ws_o = e.dec_ws_o, dp.ws_ml = e.dec_ws_ml;
+        VL_TRY(decode_attention_launch(dp, st));
+        e.launches += 2;
+      } else {
+        ap.q_start = e.gen.q_start;
+        ap.q_len = e.gen.q_len;
+        ap.kv_len = e.gen.kv_len;
+        ap.max_q_len = 1;
+        VL_TRY(attention_launch(ap, 128, st));
+        e.launches++;
+      }
       VL_TRY(block_post(e.llm[li], e.x_dec, e.xn, e.ao, e.act, B, nullptr, c.hidden, e.mlp_p, 1, &e.xdec_otm));
     }
     return text_head(1);
@@ -1759,7 +1780,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc" || k == "fuse_tail") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc" || k == "fuse_tail" || k == "decode_chunk") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
@@ -1780,6 +1801,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
     else if (k == "gelu_warps") h->e.gelu_warps = (int)value == 8 ? 8 : 16;
     else if (k == "prefill_tc") h->e.prefill_tc = (int)value;
     else if (k == "fuse_tail") h->e.fuse_tail = (int)value;
+    else if (k == "decode_chunk") h->e.dec_chunk = (value <= 0) ? 0 : std::min(256, std::max(64, (int)value / 64 * 64));
     else if (k == "exp_splits_o") h->e.xs_o = std::max(1, (int)value);
     else if (k == "exp_splits_down") h->e.xs_down = std::max(1, (int)value);
     else if (k == "pair_gemm") h->e.pair_gemm = (int)value;
@@ -2216,6 +2238,23 @@ int32_t vlaser_op_attention(const vlaser_attn_args* a, void* stream) {
   p.causal = a->causal;
   VL_CHECK(!(p.causal && p.q2), "attention: the causal rule has no extra query row");
   return attention_launch(p, a->head_dim, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t vlaser_op_decode_attention(const void* q, const void* k_cache, const void* v_cache, void* out, const int32_t* kv_start,
+                                   const int32_t* kv_len, int32_t batch, int32_t n_heads, int32_t n_kv_heads, int64_t kv_rows,
+                                   int32_t max_kv_len, int32_t chunk, float scale, float* ws_o, float* ws_ml, const int32_t* q_start,
+                                   void* stream) {
+  VL_CHECK(q && k_cache && v_cache && out && kv_start && kv_len && ws_o && ws_ml && q_start, "null argument");
+  VL_CHECK(n_kv_heads > 0 && n_heads % n_kv_heads == 0, "decode_attention: bad head counts");
+  DecodeAttnParams p;
+  p.q = reinterpret_cast<const __nv_bfloat16*>(q), p.q_row_stride = (long long)n_heads * 128;
+  p.k = reinterpret_cast<const __nv_bfloat16*>(k_cache), p.v = reinterpret_cast<const __nv_bfloat16*>(v_cache);
+  p.kv_row_stride = 128, p.kv_head_stride = kv_rows * 128;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out), p.out_row_stride = (long long)n_heads * 128;
+  p.q_start = q_start, p.kv_start = kv_start, p.kv_len = kv_len;
+  p.group = n_heads / n_kv_heads, p.n_kv_heads = n_kv_heads, p.batch = batch;
+  p.max_kv_len = max_kv_len, p.chunk = chunk, p.scale = scale, p.ws_o = ws_o, p.ws_ml = ws_ml;
+  return decode_attention_launch(p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int32_t vlaser_op_vit_attention(const void* qkv, void* out, int32_t images, int32_t tokens, int32_t heads, float scale,
