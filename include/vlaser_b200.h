@@ -144,6 +144,8 @@ void vlaser_destroy(vlaser_t* h);
  * "l2_prefetch" (default 0, measured no gain: the RMSNorm launches of a denoise step issue bulk L2 prefetches of the expert weights the
  * next launches of the chain will read),
  * "expert_gemv" (default 1: at B = 1 the expert passes run on the weight-streaming single-observation kernel, csrc/expert_gemv.cu),
+ * "prefill_tc_long" (default 1: prefixes of more than 256 tokens and the causal text prefill on the two-pass tcgen05 attention
+ * kernel instead of the generic mma.sync one),
  * "decode_chunk" (default 128: keys per CTA of the split-KV decode-step attention of vlaser_generate; 0 = the generic kernel),
  * "fuse_tail" (default 0, measured no gain: the o / down projections of the action expert finish the residual update + the
  * following RMSNorm themselves behind an in-kernel grid barrier instead of leaving them to a norm launch),
@@ -254,6 +256,14 @@ int32_t vlaser_op_vit_attention_tc(const void* qkv, void* out, int32_t images, i
 int32_t vlaser_op_prefill_attention_tc(const void* q, const void* k_cache, const void* v_cache, void* out, const int32_t* q_start,
                                        const int32_t* q_len, const int32_t* kv_start, int32_t q_rows, int32_t n_heads,
                                        int32_t n_kv_heads, int64_t kv_rows, int32_t batch, float scale, void* stream);
+
+/* The same attention for samples of min_len <= q_len[b] tokens of any length, bidirectional (causal = 0) or under the HF
+ * causal mask (causal = 1: token t sees keys [0, t]): K / V stream in blocks of 128 keys, exact two-pass softmax, O
+ * accumulated in TMEM (csrc/attention_tc.cu, prefill_attention_tc_long_kernel). max_tokens: upper bound of q_len. */
+int32_t vlaser_op_prefill_attention_tc_long(const void* q, const void* k_cache, const void* v_cache, void* out,
+                                            const int32_t* q_start, const int32_t* q_len, const int32_t* kv_start, int32_t q_rows,
+                                            int32_t n_heads, int32_t n_kv_heads, int64_t kv_rows, int32_t batch, int32_t max_tokens,
+                                            int32_t min_len, int32_t causal, float scale, void* stream);
 
 int32_t vlaser_op_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, int32_t rows,
                             int32_t width, float eps, int32_t shuffle_grid, int32_t shuffle_channels, void* stream);

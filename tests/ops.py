@@ -122,6 +122,17 @@ def prefill_attention_tc(q, k_cache, v_cache, q_start, q_len, kv_start, n_heads,
     return out
 
 
+def prefill_attention_tc_long(q, k_cache, v_cache, q_start, q_len, kv_start, n_heads, n_kv_heads, scale, max_tokens, min_len=1,
+                              causal=0):
+    """Two-pass tcgen05 prefill kernel for samples of any length (bidirectional or causal); out like q, untouched rows 0."""
+    lib = _lib.load()
+    out = torch.zeros_like(q)
+    _lib.check(lib.vlaser_op_prefill_attention_tc_long(_p(q), _p(k_cache), _p(v_cache), _p(out), _p(q_start), _p(q_len), _p(kv_start),
+                                                       q.shape[0], n_heads, n_kv_heads, k_cache.shape[1], q_len.numel(), max_tokens,
+                                                       min_len, causal, scale, _stream()), "op_prefill_attention_tc_long")
+    return out
+
+
 def layernorm(x, gamma, beta, eps, shuffle_grid=0, shuffle_channels=0, rows=None, width=None):
     lib = _lib.load()
     rows = x.shape[0] if rows is None else rows

@@ -368,6 +368,45 @@ def test_prefill_attention_tcgen05(nkv, group, lens):
     assert torch.equal(out, ops.prefill_attention_tc(q, kc, vc, i32(cu[:-1]), i32(lens), i32(kvoff), nq, nkv, hd ** -0.5))
 
 
+@pytest.mark.parametrize("nkv,group,lens,causal,min_len", [
+    (2, 6, [300, 85, 257, 1000, 21, 640], 0, 257), (4, 7, [277, 1302, 2841], 0, 257), (2, 6, [300, 85, 1, 129, 1000], 1, 1),
+    (4, 7, [3353, 277, 18, 19], 1, 1), (1, 1, [256, 513], 1, 1), (2, 8, [400] * 40, 0, 1)])
+def test_prefill_attention_tcgen05_long(nkv, group, lens, causal, min_len):
+    """Two-pass tcgen05 prefill kernel: samples of 1 .. 3353 tokens, bidirectional (samples shorter than min_len are left
+    to the short kernel) and causal, GQA groups 1 / 6 / 7 / 8, odd tile counts, more items than SMs."""
+    hd, nq = 128, nkv * group
+    g = torch.Generator().manual_seed(len(lens) + causal)
+    B = len(lens)
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    kvoff = [cu[b] + 5 * b for b in range(B)]
+    rows, kv_rows = cu[-1], cu[-1] + 5 * B + 8
+    q = (torch.randn(rows, nq * hd, generator=g) * 1.5).bfloat16().to(DEV)
+    kc = torch.randn(nkv, kv_rows, hd, generator=g).bfloat16().to(DEV)
+    vc = torch.randn(nkv, kv_rows, hd, generator=g).bfloat16().to(DEV)
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=DEV)
+    run = lambda: ops.prefill_attention_tc_long(q, kc, vc, i32(cu[:-1]), i32(lens), i32(kvoff), nq, nkv, hd ** -0.5, max(lens),
+                                                min_len, causal)
+    out = run()
+    worst = 0.0
+    for b, n in enumerate(lens):
+        got = out[cu[b]: cu[b] + n].float().view(n, nq, hd)
+        if n < min_len:
+            assert torch.all(got == 0), "samples below min_len belong to the short kernel"
+            continue
+        qq = q[cu[b]: cu[b] + n].float().view(n, nq, hd)
+        mask = torch.full((n, n), float("-inf"), device=DEV).triu(1) if causal else 0.0
+        for h in range(nq):
+            kv = h // group
+            K, V = kc[kv, kvoff[b]: kvoff[b] + n].float(), vc[kv, kvoff[b]: kvoff[b] + n].float()
+            ref = torch.softmax(qq[:, h] @ K.T * hd ** -0.5 + mask, -1) @ V
+            worst = max(worst, ops.rel_err(got[:, h], ref))
+    print(f"prefill_attention_tcgen05_long nkv={nkv} group={group} causal={causal}: worst head rel={worst:.2e}")
+    assert worst < 1e-2
+    assert torch.equal(out, run())
+
+
 def test_attention_prefill_and_denoise():
     """GQA 6:1, ragged lengths, proprio extra row (prefill) then H action queries (denoise)."""
     B, nkv, group, hd, H = 3, 2, 6, 128, 4

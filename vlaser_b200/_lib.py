@@ -68,6 +68,7 @@ EXPORTS = [
     "vlaser_op_vit_attention", "vlaser_profile_read_classes", "vlaser_op_stage_frames", "vlaser_op_postprocess_actions",
     "vlaser_op_splitk_reduce", "vlaser_op_vit_attention_tc", "vlaser_op_normalize", "vlaser_op_prefill_attention_tc",
     "vlaser_flow_matching_loss", "vlaser_generate", "vlaser_op_decode_attention",
+    "vlaser_op_prefill_attention_tc_long",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -142,6 +143,8 @@ def load() -> C.CDLL:
     lib.vlaser_op_postprocess_actions.restype = i32
     lib.vlaser_op_prefill_attention_tc.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, f32, vp]
     lib.vlaser_op_prefill_attention_tc.restype = i32
+    lib.vlaser_op_prefill_attention_tc_long.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, i32, i32, i32, f32, vp]
+    lib.vlaser_op_prefill_attention_tc_long.restype = i32
     lib.vlaser_op_normalize.argtypes = [vp, i32, vp, i32, i64, i32, i32, i32, vp, vp, vp]
     lib.vlaser_op_normalize.restype = i32
     _lib = lib

@@ -90,6 +90,12 @@ int prefill_attention_tc_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, 
                                 const int* q_len, const int* kv_start, __nv_bfloat16* out, long long out_row_stride,
                                 long long kv_layer_row0, long long kv_rows, int batch, int n_kv_heads, int group, float scale,
                                 cudaStream_t stream, long long* trace = nullptr);
+// Long prefixes (samples with min_len <= L tokens; any length) on the tensor cores, bidirectional or causal: K / V stream
+// in blocks of 128 keys, exact two-pass softmax (attention_tc.cu). Same maps as the kernel above.
+int prefill_attention_tc_long_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const int* q_start,
+                                     const int* q_len, const int* kv_start, __nv_bfloat16* out, long long out_row_stride,
+                                     long long kv_layer_row0, long long kv_rows, int batch, int n_kv_heads, int group, int max_tokens,
+                                     int min_len, int causal, float scale, cudaStream_t stream);
 int make_tmap_q3d(CUtensorMap* out, const void* ptr, uint64_t rows, int n_heads, int group);
 
 }  // namespace vlaser

@@ -1052,6 +1052,342 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
   if (warp == 2) trace_stamp(tr, 6);
 }
 
+// ================================================================================================================
+// Long prefixes (more than 256 tokens: 448 px tiles, several cameras, the dynamic tiles of BASELINE config 5, the causal
+// prompt of the chat VLM) on the tensor cores. Same GQA packing and TMEM slots as the kernel above, but the keys of a sample
+// no longer fit in one score tile, so K and V stream through shared memory in blocks of 128 keys and softmax is exact in two
+// passes like vit_attention_tc_long_kernel: pass A computes S = Q K^T block by block for the row maximum only, pass B
+// recomputes S, writes p = exp2(s - max) over it (bf16) and accumulates O += P V in TMEM -- no rescaling of O.
+// `causal`: query token t sees keys [0, t] (HF causal mask of the text prefill); tile pairs stop at the last key their last
+// token sees. Work item = (sample, kv head, pair of query tiles); group t of the CTA owns tile 2 * pair + t.
+// ================================================================================================================
+constexpr int PL_THREADS = 320;
+constexpr int PL_BLK_BYTES = 2 * VT_TILE_BYTES;  // one block of 128 keys: two 64-dim halves of [128 rows][128 B]
+constexpr int PL_SMEM = 2 * PT_Q_BYTES + 4 * PL_BLK_BYTES + 1024 + 256;
+
+struct PrefillLongParams {
+  const int* q_start;
+  const int* q_len;
+  const int* kv_start;
+  __nv_bfloat16* out;
+  long long out_row_stride;
+  long long kv_layer_row0, kv_rows;
+  int batch, n_kv_heads, group;
+  int max_pairs;   // ceil(ceil(max tokens / TOK) / 2)
+  int min_len;     // samples with fewer tokens are left to the short kernel
+  int causal;
+  float scale;
+};
+
+__global__ void __launch_bounds__(PL_THREADS, 1)
+prefill_attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                 const __grid_constant__ CUtensorMap tmV, const PrefillLongParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = smem;                          // [2 tiles][2 halves][128][128 B]
+  uint8_t* Ks = smem + 2 * PT_Q_BYTES;         // [2 slots][2 halves][128][128 B]
+  uint8_t* Vs = Ks + 2 * PL_BLK_BYTES;         // [2 slots][2 halves][128][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + 2 * PL_BLK_BYTES);
+  uint64_t* q_full = bars;         // [1]
+  uint64_t* q_empty = bars + 1;    // [1] both groups are done with their query / staging tile
+  uint64_t* k_full = bars + 2;     // [2]
+  uint64_t* k_empty = bars + 4;    // [2]
+  uint64_t* v_full = bars + 6;     // [2]
+  uint64_t* v_empty = bars + 8;    // [2]
+  uint64_t* s_full = bars + 10;    // [2]
+  uint64_t* s_free = bars + 12;    // [2] pass-A scores read (4 warps)
+  uint64_t* p_full = bars + 14;    // [2] (4 warps)
+  uint64_t* o_full = bars + 16;    // [2]
+  uint64_t* o_free = bars + 18;    // [2] (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 2);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_free[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  const int group = p.group, TOK = 128 / group, rows_tile = TOK * group;
+  const int bgs = p.batch * p.n_kv_heads;
+  const int items = bgs * p.max_pairs;
+  const float sl2 = p.scale * 1.4426950408889634f;
+  // item -> (pair tp, sample b, kv head g), pair-major so that neighbouring CTAs take different samples. nt: tiles of the
+  // pair that exist (1 | 2); nkb: key blocks the pair needs
+#define PL_ITEM(item)                                                                   \
+  const int tp = (item) / bgs, bg = (item) - tp * bgs;                                  \
+  const int b = bg / p.n_kv_heads, g = bg - b * p.n_kv_heads;                           \
+  const int L = p.q_len[b];                                                             \
+  (void)g;                                                                              \
+  const int all_tiles = (L + TOK - 1) / TOK;                                            \
+  if (L < p.min_len || 2 * tp >= all_tiles) continue;                                   \
+  const int nt = min(2, all_tiles - 2 * tp);                                            \
+  const int kmax = p.causal ? min(L, (2 * tp + nt) * TOK) : L;                          \
+  const int nkb = (kmax + 127) >> 7;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int it = 0, kc = 0, vc = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        PL_ITEM(item)
+        const int krow = (int)(p.kv_layer_row0 + (long long)g * p.kv_rows) + p.kv_start[b];
+        const int q0 = p.q_start[b];
+        mbar_wait(q_empty, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, (uint32_t)(nt * 2 * rows_tile * 128));
+        for (int t = 0; t < nt; ++t) {
+          tma_load_3d(Qs + t * PT_Q_BYTES, &tmQ, q_full, 0, g * group, q0 + (2 * tp + t) * TOK);
+          tma_load_3d(Qs + t * PT_Q_BYTES + VT_TILE_BYTES, &tmQ, q_full, 64, g * group, q0 + (2 * tp + t) * TOK);
+        }
+        auto load_blk = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int j) {
+          mbar_arrive_expect_tx(bar, PL_BLK_BYTES);
+          for (int jj = 0; jj < 4; ++jj) {
+            tma_load_2d(dst + jj * 4096, tm, bar, 0, krow + j * 128 + jj * 32);
+            tma_load_2d(dst + VT_TILE_BYTES + jj * 4096, tm, bar, 64, krow + j * 128 + jj * 32);
+          }
+        };
+        for (int j = 0; j < nkb; ++j, ++kc) {  // pass A: keys only
+          mbar_wait(&k_empty[kc & 1], ((kc >> 1) & 1) ^ 1);
+          load_blk(Ks + (kc & 1) * PL_BLK_BYTES, &tmK, &k_full[kc & 1], j);
+        }
+        for (int j = 0; j < nkb; ++j, ++kc, ++vc) {  // pass B: keys and values
+          mbar_wait(&k_empty[kc & 1], ((kc >> 1) & 1) ^ 1);
+          load_blk(Ks + (kc & 1) * PL_BLK_BYTES, &tmK, &k_full[kc & 1], j);
+          mbar_wait(&v_empty[vc & 1], ((vc >> 1) & 1) ^ 1);
+          load_blk(Vs + (vc & 1) * PL_BLK_BYTES, &tmV, &v_full[vc & 1], j);
+        }
+        ++it;
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64) | (1u << 16);  // B (= a 64-dim half of V) is MN-major
+      const uint32_t qa = smem_u32(Qs), ka = smem_u32(Ks), va = smem_u32(Vs);
+      uint32_t n_sfree[2] = {0, 0}, n_pfull[2] = {0, 0}, n_ofree[2] = {0, 0};
+      int it = 0, kc = 0, vc = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        PL_ITEM(item)
+        mbar_wait(q_full, it & 1);
+        tc_fence_after();
+        auto issue_s = [&](int t, int kslot) {
+          const uint64_t dq0 = make_umma_desc_sw128(qa + t * PT_Q_BYTES), dq1 = make_umma_desc_sw128(qa + t * PT_Q_BYTES + VT_TILE_BYTES);
+          const uint64_t dk0 = make_umma_desc_sw128(ka + kslot * PL_BLK_BYTES);
+          const uint64_t dk1 = make_umma_desc_sw128(ka + kslot * PL_BLK_BYTES + VT_TILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + t * 256, dq0 + 2 * ks, dk0 + 2 * ks, idesc_s, ks > 0);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + t * 256, dq1 + 2 * ks, dk1 + 2 * ks, idesc_s, 1u);
+          umma_commit(&s_full[t]);
+        };
+        // ---- pass A
+        for (int j = 0; j < nkb; ++j, ++kc) {
+          mbar_wait(&k_full[kc & 1], (kc >> 1) & 1);
+          tc_fence_after();
+          for (int t = 0; t < nt; ++t) {
+            if (j == 0) mbar_wait(&o_free[t], (n_ofree[t] & 1) ^ 1);  // O of the group's previous tile has been read out
+            else mbar_wait(&s_free[t], n_sfree[t]++ & 1);
+            tc_fence_after();
+            issue_s(t, kc & 1);
+          }
+          umma_commit(&k_empty[kc & 1]);
+        }
+        // ---- pass B
+        auto pv = [&](int jb, int t, bool last_tile) {  // O_t += P_t V_jb; V block jb sits in ring slot vc & 1
+          mbar_wait(&p_full[t], n_pfull[t]++ & 1);
+          if (t == 0) mbar_wait(&v_full[vc & 1], (vc >> 1) & 1);
+          tc_fence_after();
+          const uint32_t tb = tmem_base + t * 256;
+          const uint64_t dv0 = make_umma_desc_sw128(va + (vc & 1) * PL_BLK_BYTES);
+          const uint64_t dv1 = make_umma_desc_sw128(va + (vc & 1) * PL_BLK_BYTES + VT_TILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t acc = (jb > 0 || ks > 0) ? 1u : 0u;
+            umma_bf16_ts(tb + 128, tb + 8 * ks, dv0 + 128 * ks, idesc_o, acc);
+            umma_bf16_ts(tb + 192, tb + 8 * ks, dv1 + 128 * ks, idesc_o, acc);
+          }
+          if (last_tile) {
+            umma_commit(&v_empty[vc & 1]);
+            ++vc;
+          }
+        };
+        for (int j = 0; j < nkb; ++j, ++kc) {
+          mbar_wait(&k_full[kc & 1], (kc >> 1) & 1);
+          tc_fence_after();
+          for (int t = 0; t < nt; ++t) {
+            if (j == 0) {
+              mbar_wait(&s_free[t], n_sfree[t]++ & 1);  // the last pass-A block has been read
+              tc_fence_after();
+            } else {
+              pv(j - 1, t, t == nt - 1);
+            }
+            issue_s(t, kc & 1);
+          }
+          umma_commit(&k_empty[kc & 1]);
+        }
+        for (int t = 0; t < nt; ++t) {
+          pv(nkb - 1, t, t == nt - 1);
+          umma_commit(&o_full[t]);
+          ++n_ofree[t];
+        }
+        ++it;
+      }
+    }
+  } else {
+    // ================================ softmax / epilogue groups ================================
+    const int t = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int gtid = threadIdx.x - (2 + 4 * t) * 32;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 256;
+    uint8_t* stage = Qs + t * PT_Q_BYTES;  // the group's query tile, dead once its last S is complete
+    uint32_t n_sfull = 0, n_ofull = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      PL_ITEM(item)
+      const int q0 = p.q_start[b];
+      if (t >= nt) {  // odd tile count: this group has no tile in the pair
+        mbar_wait(q_full, it & 1);
+        if (gtid == 0) mbar_arrive(q_empty);
+        ++it;
+        continue;
+      }
+      const int tile = 2 * tp + t;
+      const int tok = min(tile * TOK + row / group, L - 1);   // (rows past the sample: any valid token, never stored)
+      const bool row_ok = row < rows_tile && tile * TOK + row / group < L;
+      const int lim = p.causal ? min(L, tok + 1) : L;          // keys [0, lim) are visible
+      // ---- pass A: row maximum over the visible keys
+      float mx = -INFINITY;
+      for (int j = 0; j < nkb; ++j) {
+        mbar_wait(&s_full[t], n_sfull++ & 1);
+        tc_fence_after();
+        const int kb = j * 128;
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 64) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(taddr + c, r0);
+          tmem_ld_32x32(taddr + c + 32, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (kb + c + e < lim) mx = fmaxf(mx, __uint_as_float(r0[e]));
+            if (kb + c + 32 + e < lim) mx = fmaxf(mx, __uint_as_float(r1[e]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);
+      }
+      const float moff = mx * sl2;
+      // ---- pass B: probabilities (0 for hidden keys), row sum, bf16 pack over the scores
+      float sum = 0.f;
+      for (int j = 0; j < nkb; ++j) {
+        mbar_wait(&s_full[t], n_sfull++ & 1);
+        tc_fence_after();
+        const int kb = j * 128;
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 64) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(taddr + c, r0);
+          tmem_ld_32x32(taddr + c + 32, r1);
+          tmem_ld_wait();
+          uint32_t pk0[16], pk1[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(r0[2 * e]), sl2, -moff));
+            float p1 = ex2_approx(fmaf(__uint_as_float(r0[2 * e + 1]), sl2, -moff));
+            float p2 = ex2_approx(fmaf(__uint_as_float(r1[2 * e]), sl2, -moff));
+            float p3 = ex2_approx(fmaf(__uint_as_float(r1[2 * e + 1]), sl2, -moff));
+            if (kb + c + 2 * e >= lim) p0 = 0.f;
+            if (kb + c + 2 * e + 1 >= lim) p1 = 0.f;
+            if (kb + c + 32 + 2 * e >= lim) p2 = 0.f;
+            if (kb + c + 32 + 2 * e + 1 >= lim) p3 = 0.f;
+            sum += (p0 + p1) + (p2 + p3);
+            pk0[e] = pack_bf16(p0, p1);
+            pk1[e] = pack_bf16(p2, p3);
+          }
+          tmem_st_32x16(taddr + (c >> 1), pk0);
+          tmem_st_32x16(taddr + (c >> 1) + 16, pk1);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+      const float inv = 1.f / sum;
+      mbar_wait(&o_full[t], n_ofull++ & 1);
+      tc_fence_after();
+      // ---- O / sum -> bf16 -> this row of the transposition tile
+#pragma unroll 1
+      for (int c0 = 0; c0 < 4; c0 += 2) {
+        uint32_t o[2][32];
+        tmem_ld_32x32(taddr + 128 + c0 * 32, o[0]);
+        tmem_ld_32x32(taddr + 128 + c0 * 32 + 32, o[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(o[cc][8 * q]) * inv, __uint_as_float(o[cc][8 * q + 1]) * inv);
+            u.y = pack_bf16(__uint_as_float(o[cc][8 * q + 2]) * inv, __uint_as_float(o[cc][8 * q + 3]) * inv);
+            u.z = pack_bf16(__uint_as_float(o[cc][8 * q + 4]) * inv, __uint_as_float(o[cc][8 * q + 5]) * inv);
+            u.w = pack_bf16(__uint_as_float(o[cc][8 * q + 6]) * inv, __uint_as_float(o[cc][8 * q + 7]) * inv);
+            const int ch = (c0 + cc) * 4 + q;
+            *reinterpret_cast<uint4*>(stage + row * 256 + ((ch ^ (row & 15)) << 4)) = u;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[t]);
+      const unsigned ok_mask = __ballot_sync(0xffffffffu, row_ok);
+#pragma unroll 1
+      for (int i2 = 0; i2 < 16; ++i2) {
+        const int rl = i2 * 2 + (lane >> 4), ch = lane & 15;
+        const int r = quarter * 32 + rl;
+        if ((ok_mask >> rl) & 1u) {
+          const uint4 u = *reinterpret_cast<const uint4*>(stage + r * 256 + ((ch ^ (r & 15)) << 4));
+          const int tk = tile * TOK + r / group, h2 = r % group;
+          *reinterpret_cast<uint4*>(p.out + (size_t)(q0 + tk) * p.out_row_stride + (size_t)(g * group + h2) * 128 + ch * 8) = u;
+        }
+      }
+      named_bar_sync(1 + t, 128);  // every warp of the group has read its rows out of the tile
+      if (gtid == 0) mbar_arrive(q_empty);
+      ++it;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 
 int vit_attention_tc_launch(const CUtensorMap& tmQKV, const CUtensorMap& tmOut, const __nv_bfloat16* qkv,
@@ -1108,6 +1444,28 @@ int prefill_attention_tc_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, 
 }
 
 // q [rows, n_heads, 128] bf16 as a 3-D map with boxes {64 dims, group heads, 128 / group tokens}, 128B swizzle
+int prefill_attention_tc_long_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const int* q_start,
+                                     const int* q_len, const int* kv_start, __nv_bfloat16* out, long long out_row_stride,
+                                     long long kv_layer_row0, long long kv_rows, int batch, int n_kv_heads, int group, int max_tokens,
+                                     int min_len, int causal, float scale, cudaStream_t stream) {
+  VL_CHECK(batch > 0 && n_kv_heads > 0 && group >= 1 && group <= 8 && max_tokens > 0, "prefill_attention_tc_long: bad shape");
+  static unsigned long long attr_devs = 0;
+  if (vl_first_on_device(attr_devs))
+    VL_CUDA_CHECK(cudaFuncSetAttribute(prefill_attention_tc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM));
+  PrefillLongParams p;
+  p.q_start = q_start, p.q_len = q_len, p.kv_start = kv_start;
+  p.out = out, p.out_row_stride = out_row_stride;
+  p.kv_layer_row0 = kv_layer_row0, p.kv_rows = kv_rows;
+  p.batch = batch, p.n_kv_heads = n_kv_heads, p.group = group;
+  const int TOK = 128 / group;
+  p.max_pairs = ((max_tokens + TOK - 1) / TOK + 1) / 2;
+  p.min_len = min_len, p.causal = causal, p.scale = scale;
+  const long long items = (long long)batch * n_kv_heads * p.max_pairs;
+  const int grid = (int)std::min<long long>(items, gemm_num_sms());
+  VL_CUDA_CHECK(launch_kernel(prefill_attention_tc_long_kernel, dim3(grid), dim3(PL_THREADS), PL_SMEM, stream, tmQ, tmK, tmV, p));
+  return 0;
+}
+
 int make_tmap_q3d(CUtensorMap* out, const void* ptr, uint64_t rows, int n_heads, int group) {
   PFN_encodeTiled_tc fn = get_encode_fn_tc();
   VL_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");

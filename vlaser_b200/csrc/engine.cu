@@ -206,6 +206,7 @@ struct Engine {
   std::string trace_names;
   static constexpr size_t TRACE_MAX = 8192;
   int prefill_tc = 1;          // 1: prefix-prefill attention on the tcgen05 kernel (samples of <= 256 valid tokens; attention_tc.cu)
+  int prefill_tc_long = 1;     // 1: samples of more than 256 tokens (and the causal text prefill) on the two-pass tcgen05 kernel
   int gelu_warps = 16;         // epilogue warps of the pair kernel's exact-GELU variant (16 | 8)
   int pair_bn128 = 1;          // 1: 256 x 128 pair tiles for the one-row-tile split-K projections (see Run::gemm)
   int den_chains = 1;          // sub-batch chains of the denoise steps (1 | 2), see Run::denoise_all
@@ -1323,8 +1324,14 @@ struct Run {
                                            ap.scale, st, tr("attention_tc", li)));
         e.launches++;
         ap.min_kv_len = 257;  // longer prefixes: generic kernel (every CTA of a short sample exits at once)
+        if (e.S > 256 && e.prefill_tc_long) {  // ... or the two-pass tcgen05 kernel
+          VL_TRY(prefill_attention_tc_long_launch(e.q3d_tm, e.kc_tm, e.vc_tm, e.pb.cu, e.pb.valid_len, e.pb.kvoff, e.ao.p, e.qdim,
+                                                  (long long)li * c.n_kv_heads * e.kv_rows, e.kv_rows, B, c.n_kv_heads, ap.group,
+                                                  e.S, 257, 0, ap.scale, st));
+          e.launches++;
+        }
       }
-      if (!tc_ok || e.S > 256) {
+      if (!tc_ok || (e.S > 256 && !e.prefill_tc_long)) {
         ap.trace = tr("attention", li);
         VL_TRY(attention_launch(ap, 128, st));
         e.launches++;
@@ -1586,11 +1593,17 @@ struct Run {
     for (int li = 0; li < c.layers; ++li) {
       VL_TRY(block_pre(e.llm[li], e.xv, e.xn, e.q, cap, e.pb.m_tot, c.hidden, e.pb.row_pos, e.pb.row_kvrow, li));
       AttnParams ap = text_attn(li);
-      ap.q_start = e.pb.cu;
-      ap.q_len = e.pb.valid_len;
-      ap.kv_len = e.pb.pre_kv_len;
-      ap.max_q_len = e.S;
-      VL_TRY(attention_launch(ap, 128, st));
+      if (e.prefill_tc_long && !e.simt && ap.group <= 8) {
+        VL_TRY(prefill_attention_tc_long_launch(e.q3d_tm, e.kc_tm, e.vc_tm, e.pb.cu, e.pb.valid_len, e.pb.kvoff, e.ao.p, e.qdim,
+                                                (long long)li * c.n_kv_heads * e.kv_rows, e.kv_rows, B, c.n_kv_heads, ap.group,
+                                                e.S, 1, 1, ap.scale, st));
+      } else {
+        ap.q_start = e.pb.cu;
+        ap.q_len = e.pb.valid_len;
+        ap.kv_len = e.pb.pre_kv_len;
+        ap.max_q_len = e.S;
+        VL_TRY(attention_launch(ap, 128, st));
+      }
       e.launches++;
       VL_TRY(block_post(e.llm[li], e.xv, e.xn, e.ao, e.act, cap, e.pb.m_tot, c.hidden, e.mlp_p, 1, &e.xv_otm));
     }
@@ -1780,7 +1793,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc" || k == "fuse_tail" || k == "decode_chunk") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc" || k == "fuse_tail" || k == "decode_chunk" || k == "prefill_tc_long") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
@@ -1801,6 +1814,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
     else if (k == "gelu_warps") h->e.gelu_warps = (int)value == 8 ? 8 : 16;
     else if (k == "prefill_tc") h->e.prefill_tc = (int)value;
     else if (k == "fuse_tail") h->e.fuse_tail = (int)value;
+    else if (k == "prefill_tc_long") h->e.prefill_tc_long = (int)value;
     else if (k == "decode_chunk") h->e.dec_chunk = (value <= 0) ? 0 : std::min(256, std::max(64, (int)value / 64 * 64));
     else if (k == "exp_splits_o") h->e.xs_o = std::max(1, (int)value);
     else if (k == "exp_splits_down") h->e.xs_down = std::max(1, (int)value);
@@ -2285,6 +2299,21 @@ int32_t vlaser_op_prefill_attention_tc(const void* q, const void* k_cache, const
   return prefill_attention_tc_launch(tq, tk, tv, q_start, q_len, kv_start, reinterpret_cast<__nv_bfloat16*>(out),
                                      (long long)n_heads * 128, 0, kv_rows, batch, n_kv_heads, n_heads / n_kv_heads, scale,
                                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t vlaser_op_prefill_attention_tc_long(const void* q, const void* k_cache, const void* v_cache, void* out,
+                                            const int32_t* q_start, const int32_t* q_len, const int32_t* kv_start, int32_t q_rows,
+                                            int32_t n_heads, int32_t n_kv_heads, int64_t kv_rows, int32_t batch, int32_t max_tokens,
+                                            int32_t min_len, int32_t causal, float scale, void* stream) {
+  VL_CHECK(q && k_cache && v_cache && out && q_start && q_len && kv_start, "null argument");
+  VL_CHECK(n_kv_heads > 0 && n_heads % n_kv_heads == 0, "prefill_attention_tc_long: bad head counts");
+  CUtensorMap tq, tk, tv;
+  VL_TRY(make_tmap_q3d(&tq, q, (uint64_t)q_rows, n_heads, n_heads / n_kv_heads));
+  VL_TRY(make_tmap_bf16(&tk, k_cache, (uint64_t)n_kv_heads * kv_rows, 128, 32));
+  VL_TRY(make_tmap_bf16(&tv, v_cache, (uint64_t)n_kv_heads * kv_rows, 128, 32));
+  return prefill_attention_tc_long_launch(tq, tk, tv, q_start, q_len, kv_start, reinterpret_cast<__nv_bfloat16*>(out),
+                                          (long long)n_heads * 128, 0, kv_rows, batch, n_kv_heads, n_heads / n_kv_heads, max_tokens,
+                                          min_len, causal, scale, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int32_t vlaser_op_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, int32_t rows,

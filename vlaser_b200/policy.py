@@ -160,7 +160,8 @@ class PiZeroInference:
                          ("VLASER_EXPERT_STREAMS", "expert_streams"), ("VLASER_EXPERT_GEMV", "expert_gemv"),
                          ("VLASER_L2_PREFETCH", "l2_prefetch"), ("VLASER_SMALL_M_SPLIT", "small_m_split"),
                          ("VLASER_PAIR_MIN_TILES", "pair_min_tiles"), ("VLASER_PROP_STREAM", "prop_stream"),
-                         ("VLASER_DET_SPLITK", "det_splitk"), ("VLASER_VIT_TC", "vit_tc")):  # measurement switches
+                         ("VLASER_DET_SPLITK", "det_splitk"), ("VLASER_VIT_TC", "vit_tc"),
+                         ("VLASER_PREFILL_TC_LONG", "prefill_tc_long")):  # measurement switches
             if env in os.environ:
                 self._options[opt] = int(os.environ[env])
         self._create_handle()
