@@ -144,6 +144,8 @@ void vlaser_destroy(vlaser_t* h);
  * "l2_prefetch" (default 0, measured no gain: the RMSNorm launches of a denoise step issue bulk L2 prefetches of the expert weights the
  * next launches of the chain will read),
  * "expert_gemv" (default 1: at B = 1 the expert passes run on the weight-streaming single-observation kernel, csrc/expert_gemv.cu),
+ * "attn_small" (default 1: the denoise-step attention, group * H <= 32 query rows per (sample, kv head), on the kernel that splits
+ * the key blocks between its two warp pairs),
  * "prefill_tc_long" (default 1: prefixes of more than 256 tokens and the causal text prefill on the two-pass tcgen05 attention
  * kernel instead of the generic mma.sync one),
  * "decode_chunk" (default 128: keys per CTA of the split-KV decode-step attention of vlaser_generate; 0 = the generic kernel),
@@ -228,6 +230,7 @@ typedef struct vlaser_attn_args {
   int32_t uni_q_len, uni_kv_len, max_q_len, group, n_kv_heads, batch, head_dim;
   float scale;
   int32_t causal;  /* 1: query token t of a sample sees keys [0, kv_len - q_len + t] (text prefill of the chat VLM) */
+  int32_t small_rows; /* 1: with group * max_q_len <= 32 (head_dim 128) use the kernel that splits the key blocks between its warp pairs */
 } vlaser_attn_args;
 int32_t vlaser_op_attention(const vlaser_attn_args* a, void* stream);
 /* Decode-step attention of the chat VLM (one query row per sample over its K/V window, head_dim 128, GQA; HF Qwen2

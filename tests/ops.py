@@ -71,10 +71,11 @@ def rope_ref(x, cos, sin):
 
 def attention(q, k, v, out, head_dim, group, n_kv_heads, batch, scale, q_row_stride, kv_row_stride, kv_head_stride,
               out_row_stride, uni_q_len=0, uni_kv_len=0, max_q_len=0, q_start=None, q_len=None, kv_start=None,
-              kv_len=None, q2=None, q2_row_stride=0, out2=None, out2_row_stride=0, causal=0):
+              kv_len=None, q2=None, q2_row_stride=0, out2=None, out2_row_stride=0, causal=0, small_rows=0):
     lib = _lib.load()
     a = AttnArgs()
     a.causal = causal
+    a.small_rows = small_rows
     a.q, a.q_row_stride, a.q2, a.q2_row_stride = _p(q), q_row_stride, _p(q2), q2_row_stride
     a.k, a.v, a.kv_row_stride, a.kv_head_stride = _p(k), _p(v), kv_row_stride, kv_head_stride
     a.out, a.out_row_stride, a.out2, a.out2_row_stride = _p(out), out_row_stride, _p(out2), out2_row_stride

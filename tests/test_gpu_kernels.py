@@ -457,6 +457,29 @@ def test_attention_prefill_and_denoise():
             errs.append(ops.rel_err(outa[b * H:(b + 1) * H, h * hd:(h + 1) * hd], r))
     print(f"attention_denoise max rel={max(errs):.2e}")
     assert max(errs) < 1e-2
+    # the same step on the small-row kernel (key blocks split between the warp pairs): windows of 1, 2 and 3+ key blocks
+    for lens2 in (lens, [30, 64, 59], [200, 129, 250]):
+        kvoff2 = [sum(lens2[:b]) + b * (1 + H) for b in range(B)]
+        cap2 = sum(lens2) + B * (1 + H) + 3
+        kc2, vc2 = _rand(nkv, cap2, hd, seed=6), _rand(nkv, cap2, hd, seed=7)
+        kw = dict(max_q_len=H, q_start=i32([b * H for b in range(B)]), q_len=i32([H] * B), kv_start=i32(kvoff2),
+                  kv_len=i32([L + 1 + H for L in lens2]))
+        o_small, o_gen = torch.zeros_like(qa), torch.zeros_like(qa)
+        ops.attention(qa, kc2, vc2, o_small, hd, group, nkv, B, scale, nq * hd, hd, cap2 * hd, nq * hd, small_rows=1, **kw)
+        ops.attention(qa, kc2, vc2, o_gen, hd, group, nkv, B, scale, nq * hd, hd, cap2 * hd, nq * hd, **kw)
+        errs = []
+        for b in range(B):
+            Lk = lens2[b] + 1 + H
+            for h in range(nq):
+                g = h // group
+                r = _attn_ref(qa[b * H:(b + 1) * H, h * hd:(h + 1) * hd].float(), kc2[g, kvoff2[b]:kvoff2[b] + Lk].float(),
+                              vc2[g, kvoff2[b]:kvoff2[b] + Lk].float(), scale, Lk)
+                errs.append(ops.rel_err(o_small[b * H:(b + 1) * H, h * hd:(h + 1) * hd], r))
+        print(f"attention_denoise small-row kernel lens={lens2} max rel={max(errs):.2e}")
+        assert max(errs) < 1e-2 and ops.rel_err(o_small, o_gen.float()) < 1e-2
+        o_again = torch.zeros_like(qa)
+        ops.attention(qa, kc2, vc2, o_again, hd, group, nkv, B, scale, nq * hd, hd, cap2 * hd, nq * hd, small_rows=1, **kw)
+        assert torch.equal(o_small, o_again)
 
 
 def test_attention_causal():

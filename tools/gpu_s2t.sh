@@ -1,0 +1,5 @@
+#!/bin/bash
+OUT=gpurun_out/r02s2t
+mkdir -p $OUT
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > $OUT/bench_n2.json 2> $OUT/bench_n2.err; echo "bench n2 rc=$?"; cat $OUT/bench_n2.json | cut -c1-900; tail -3 $OUT/bench_n2.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > $OUT/bench_n2_ref.json 2> $OUT/bench_n2_ref.err; echo "bench n2 ref rc=$?"; cat $OUT/bench_n2_ref.json | cut -c1-400

@@ -56,7 +56,7 @@ class AttnArgs(C.Structure):
         ("q_start", C.c_void_p), ("q_len", C.c_void_p), ("kv_start", C.c_void_p), ("kv_len", C.c_void_p),
         ("uni_q_len", C.c_int32), ("uni_kv_len", C.c_int32), ("max_q_len", C.c_int32), ("group", C.c_int32),
         ("n_kv_heads", C.c_int32), ("batch", C.c_int32), ("head_dim", C.c_int32), ("scale", C.c_float),
-        ("causal", C.c_int32),
+        ("causal", C.c_int32), ("small_rows", C.c_int32),
     ]
 
 

@@ -429,6 +429,211 @@ int decode_attention_launch(const DecodeAttnParams& p, cudaStream_t stream) {
 
 namespace {
 
+// ------------------------------------------------------------------------------------------
+// Few query rows per (sample, kv head) -- the denoise steps: H action tokens x `group` heads = 24 rows of the 64-row tile of
+// the generic kernel, i.e. two of its four warps idle while the other two walk the key blocks one after the other (the
+// legacy mma.sync path costs ~2 us per 64-key block and warp). Here rows <= 32: warp w owns row tile (w & 1) and the key
+// blocks of parity (w >> 1), so both blocks of a 94-key window are multiplied at the same time; the two partial softmax
+// states of a row tile are merged through shared memory at the end (fixed order: bit-identical from call to call).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ATT_THREADS) attention_small_kernel(AttnParams p) {
+  constexpr int HD = 128, CH = HD / 8;
+  pdl_launch_dependents();
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* Qs = smem;                          // [32][HD]
+  uint8_t* Ks = Qs + 32 * HD * 2;              // [2][64][HD]
+  uint8_t* Vs = Ks + 2 * ATT_BN * HD * 2;      // [2][64][HD]
+  long long* tr = (blockIdx.x + blockIdx.y + blockIdx.z == 0 && threadIdx.x == 0) ? p.trace : nullptr;
+  trace_stamp(tr, 0);
+  const int b = blockIdx.z, kvh = blockIdx.y, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int rt = warp & 1, kg = warp >> 1;
+  const int q_len = p.q_len ? p.q_len[b] : p.uni_q_len;
+  const int q_start = p.q_len ? p.q_start[b] : b * p.uni_q_len;
+  const int kv_len = p.kv_len ? p.kv_len[b] : p.uni_kv_len;
+  const int kv_start = p.kv_len ? p.kv_start[b] : b * p.uni_kv_len;
+  const int group = p.group;
+  const int rows_total = group * q_len;  // <= 32
+  if (rows_total <= 0 || kv_len < p.min_kv_len) return;
+  const int n_blocks = (kv_len + ATT_BN - 1) / ATT_BN;
+  const __nv_bfloat16* kbase = p.k + (size_t)kvh * p.kv_head_stride + (size_t)kv_start * p.kv_row_stride;
+  const __nv_bfloat16* vbase = p.v + (size_t)kvh * p.kv_head_stride + (size_t)kv_start * p.kv_row_stride;
+  auto load_kv = [&](int blk, int buf) {
+    uint8_t* kd = Ks + buf * ATT_BN * HD * 2;
+    uint8_t* vd = Vs + buf * ATT_BN * HD * 2;
+    for (int i = tid; i < ATT_BN * CH; i += ATT_THREADS) {
+      const int row = i / CH, c = i - row * CH;
+      const int kr = blk * ATT_BN + row;
+      const bool ok = kr < kv_len;
+      const size_t off = (size_t)(ok ? kr : 0) * p.kv_row_stride + c * 8;
+      cp_async_16(kd + swz<HD>(row, c), kbase + off, ok);
+      cp_async_16(vd + swz<HD>(row, c), vbase + off, ok);
+    }
+  };
+  // block 0 lies entirely in the stable prefix: fetch it before waiting on the previous grid
+  const bool pre = p.stable_prefix && (kv_len - q_len >= ATT_BN);
+  if (pre) load_kv(0, 0);
+  pdl_wait();
+  trace_stamp(tr, 1);
+  for (int i = tid; i < 32 * CH; i += ATT_THREADS) {
+    const int row = i / CH, c = i - row * CH;
+    const bool ok = row < rows_total;
+    const int t = ok ? row / group : 0, hh = ok ? row - t * group : 0;
+    cp_async_16(Qs + swz<HD>(row, c), p.q + (size_t)(q_start + t) * p.q_row_stride + (size_t)(kvh * group + hh) * HD + c * 8, ok);
+  }
+  if (!pre) load_kv(0, 0);
+  if (n_blocks > 1) load_kv(1, 1);
+  cp_async_commit();
+
+  const int rlo = rt * 16 + (lane >> 2);
+  const bool warp_active = rt * 16 < rows_total;
+  const float sl2 = p.scale * 1.4426950408889634f;
+  float o[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  uint32_t qf[HD / 16][4];
+  const uint32_t qs_u = smem_u32(Qs);
+  for (int r2 = 0; r2 * 2 < n_blocks; ++r2) {  // rounds of two key blocks: buffer kg holds block 2 * r2 + kg
+    if (r2 > 0) {
+      __syncthreads();  // both buffers have been consumed
+      load_kv(2 * r2, 0);
+      if (2 * r2 + 1 < n_blocks) load_kv(2 * r2 + 1, 1);
+      cp_async_commit();
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    const int jb = 2 * r2 + kg;
+    if (warp_active && jb < n_blocks) {
+      if (r2 == 0) {
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const int mi = lane >> 3;
+          const int row = rt * 16 + (mi & 1) * 8 + (lane & 7);
+          ldmatrix_x4(qf[kk], qs_u + swz<HD>(row, kk * 2 + (mi >> 1)));
+        }
+      }
+      const uint32_t ks_u = smem_u32(Ks + kg * ATT_BN * HD * 2);
+      const uint32_t vs_u = smem_u32(Vs + kg * ATT_BN * HD * 2);
+      float sc[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk) {
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+          uint32_t kf[4];
+          const int mi = lane >> 3;
+          const int row = jp * 16 + (mi >> 1) * 8 + (lane & 7);
+          ldmatrix_x4(kf, ks_u + swz<HD>(row, kk * 2 + (mi & 1)));
+          mma_bf16_16816(sc[2 * jp], qf[kk], kf[0], kf[1]);
+          mma_bf16_16816(sc[2 * jp + 1], qf[kk], kf[2], kf[3]);
+        }
+      }
+      const int colbase = jb * ATT_BN + (lane & 3) * 2;
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = colbase + j * 8 + (e & 1);
+          const float val = (col < kv_len) ? sc[j][e] * sl2 : -INFINITY;
+          sc[j][e] = val;
+          mx[e >> 1] = fmaxf(mx[e >> 1], val);
+        }
+      }
+      float alpha[2], moff[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+        mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+        const float m_new = fmaxf(m_run[h], mx[h]);
+        moff[h] = (m_new == -INFINITY) ? 0.f : m_new;
+        alpha[h] = exp2f(m_run[h] - moff[h]);
+        m_run[h] = m_new;
+      }
+      float rs[2] = {0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float pv = exp2f(sc[j][e] - moff[e >> 1]);
+          sc[j][e] = pv;
+          rs[e >> 1] += pv;
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        rs[h] += __shfl_xor_sync(0xffffffffu, rs[h], 1);
+        rs[h] += __shfl_xor_sync(0xffffffffu, rs[h], 2);
+        l_run[h] = l_run[h] * alpha[h] + rs[h];
+      }
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) {
+        o[i][0] *= alpha[0];
+        o[i][1] *= alpha[0];
+        o[i][2] *= alpha[1];
+        o[i][3] *= alpha[1];
+      }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t pf[4];
+        pf[0] = pack_bf16(sc[2 * ks][0], sc[2 * ks][1]);
+        pf[1] = pack_bf16(sc[2 * ks][2], sc[2 * ks][3]);
+        pf[2] = pack_bf16(sc[2 * ks + 1][0], sc[2 * ks + 1][1]);
+        pf[3] = pack_bf16(sc[2 * ks + 1][2], sc[2 * ks + 1][3]);
+#pragma unroll
+        for (int dp = 0; dp < HD / 16; ++dp) {
+          uint32_t vf[4];
+          const int mi = lane >> 3;
+          const int row = ks * 16 + (mi & 1) * 8 + (lane & 7);
+          ldmatrix_x4_trans(vf, vs_u + swz<HD>(row, dp * 2 + (mi >> 1)));
+          mma_bf16_16816(o[2 * dp], pf, vf[0], vf[1]);
+          mma_bf16_16816(o[2 * dp + 1], pf, vf[2], vf[3]);
+        }
+      }
+    }
+  }
+  // ---- merge the two key-parity states of a row tile: warps 2, 3 hand (m, l, o) to warps 0, 1 through the K / V buffers
+  __syncthreads();
+  float* xch = reinterpret_cast<float*>(Ks);  // [2 row tiles][32 lanes][4 + 64]
+  if (kg == 1) {
+    float* w = xch + ((size_t)rt * 32 + lane) * 68;
+    w[0] = m_run[0], w[1] = m_run[1], w[2] = l_run[0], w[3] = l_run[1];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) *reinterpret_cast<float4*>(w + 4 + 4 * i) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+  }
+  __syncthreads();
+  if (kg == 1 || !warp_active) return;
+  const float* w = xch + ((size_t)rt * 32 + lane) * 68;
+  float a0[2], a1[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float m1 = w[h], l1 = w[2 + h];
+    const float M = fmaxf(m_run[h], m1);
+    const float mo = (M == -INFINITY) ? 0.f : M;
+    a0[h] = exp2f(m_run[h] - mo);
+    a1[h] = exp2f(m1 - mo);
+    l_run[h] = l_run[h] * a0[h] + l1 * a1[h];
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = rlo + h * 8;
+    if (r >= rows_total) continue;
+    const int t = r / group, hh = r - t * group;
+    const float inv = l_run[h] > 0.f ? 1.f / l_run[h] : 0.f;
+    __nv_bfloat16* dst = p.out + (size_t)(q_start + t) * p.out_row_stride + (size_t)(kvh * group + hh) * HD;
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      const float4 o1 = *reinterpret_cast<const float4*>(w + 4 + 4 * i);
+      const float x0 = o[i][2 * h] * a0[h] + (h ? o1.z : o1.x) * a1[h];
+      const float x1 = o[i][2 * h + 1] * a0[h] + (h ? o1.w : o1.y) * a1[h];
+      *reinterpret_cast<uint32_t*>(dst + i * 8 + (lane & 3) * 2) = pack_bf16(x0 * inv, x1 * inv);
+    }
+  }
+  trace_stamp(tr, 6);
+}
+
 template <int HD>
 int launch_hd(const AttnParams& p, cudaStream_t stream) {
   constexpr int SMEM = (ATT_BM + 4 * ATT_BN) * HD * 2;
@@ -438,6 +643,16 @@ int launch_hd(const AttnParams& p, cudaStream_t stream) {
   }
   const int rows_max = p.group * p.max_q_len;
   dim3 grid((rows_max + ATT_BM - 1) / ATT_BM, p.n_kv_heads, p.batch);
+  if constexpr (HD == 128) {
+    if (p.small_rows && rows_max <= 32 && !p.causal && p.q2 == nullptr) {  // the denoise steps: both warp pairs busy
+      constexpr int SSMEM = (32 + 4 * ATT_BN) * HD * 2;
+      static unsigned long long attr_devs_s = 0;
+      if (vl_first_on_device(attr_devs_s))
+        VL_CUDA_CHECK(cudaFuncSetAttribute(attention_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SSMEM));
+      VL_CUDA_CHECK(launch_kernel(attention_small_kernel, dim3(1, p.n_kv_heads, p.batch), dim3(ATT_THREADS), SSMEM, stream, p));
+      return 0;
+    }
+  }
   if (p.causal) {  // text prefill / decode of the chat VLM
     VL_CHECK(p.q2 == nullptr, "attention: the causal rule has no extra query row");
     static unsigned long long attr_devs_c = 0;

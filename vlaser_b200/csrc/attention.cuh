@@ -42,6 +42,8 @@ struct AttnParams {
   int stable_prefix = 0;
   int min_kv_len = 0;   // samples with fewer kv rows are skipped (they were handled by the tcgen05 prefill kernel)
   int causal = 0;       // 1: query token t of a sample sees keys [0, kv_len - q_len + t] (HF causal mask; no q2 row)
+  int small_rows = 0;   // 1: when group * max_q_len <= 32 (the denoise steps) use the kernel that splits the key blocks between
+                        // its two warp pairs (attention_small_kernel)
   long long* trace = nullptr;  // optional timeline record of this launch (common.cuh trace_stamp)
 };
 

@@ -206,6 +206,8 @@ struct Engine {
   std::string trace_names;
   static constexpr size_t TRACE_MAX = 8192;
   int prefill_tc = 1;          // 1: prefix-prefill attention on the tcgen05 kernel (samples of <= 256 valid tokens; attention_tc.cu)
+  int attn_small = 1;          // 1: the denoise-step attention (group * H <= 32 query rows) on the kernel that splits the key blocks
+                               // between its two warp pairs (attention_small_kernel)
   int prefill_tc_long = 1;     // 1: samples of more than 256 tokens (and the causal text prefill) on the two-pass tcgen05 kernel
   int gelu_warps = 16;         // epilogue warps of the pair kernel's exact-GELU variant (16 | 8)
   int pair_bn128 = 1;          // 1: 256 x 128 pair tiles for the one-row-tile split-K projections (see Run::gemm)
@@ -1464,6 +1466,7 @@ struct Run {
       ap.kv_start = e.pb.kvoff + ch.b0;
       ap.kv_len = e.pb.den_kv_len + ch.b0;
       ap.stable_prefix = 1;  // prefix + proprio K/V of this layer date from the prefill
+      ap.small_rows = e.attn_small;
       ap.max_q_len = e.H;
       ap.group = c.n_heads / c.n_kv_heads;
       ap.n_kv_heads = c.n_kv_heads;
@@ -1793,7 +1796,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc" || k == "fuse_tail" || k == "decode_chunk" || k == "prefill_tc_long") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc" || k == "fuse_tail" || k == "decode_chunk" || k == "prefill_tc_long" || k == "attn_small") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
@@ -1815,6 +1818,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
     else if (k == "prefill_tc") h->e.prefill_tc = (int)value;
     else if (k == "fuse_tail") h->e.fuse_tail = (int)value;
     else if (k == "prefill_tc_long") h->e.prefill_tc_long = (int)value;
+    else if (k == "attn_small") h->e.attn_small = (int)value;
     else if (k == "decode_chunk") h->e.dec_chunk = (value <= 0) ? 0 : std::min(256, std::max(64, (int)value / 64 * 64));
     else if (k == "exp_splits_o") h->e.xs_o = std::max(1, (int)value);
     else if (k == "exp_splits_down") h->e.xs_down = std::max(1, (int)value);
@@ -2250,6 +2254,7 @@ int32_t vlaser_op_attention(const vlaser_attn_args* a, void* stream) {
   p.batch = a->batch;
   p.scale = a->scale;
   p.causal = a->causal;
+  p.small_rows = a->small_rows;
   VL_CHECK(!(p.causal && p.q2), "attention: the causal rule has no extra query row");
   return attention_launch(p, a->head_dim, reinterpret_cast<cudaStream_t>(stream));
 }
