@@ -432,17 +432,21 @@ namespace {
 // ------------------------------------------------------------------------------------------
 // Few query rows per (sample, kv head) -- the denoise steps: H action tokens x `group` heads = 24 rows of the 64-row tile of
 // the generic kernel, i.e. two of its four warps idle while the other two walk the key blocks one after the other (the
-// legacy mma.sync path costs ~2 us per 64-key block and warp). Here rows <= 32: warp w owns row tile (w & 1) and the key
-// blocks of parity (w >> 1), so both blocks of a 94-key window are multiplied at the same time; the two partial softmax
-// states of a row tile are merged through shared memory at the end (fixed order: bit-identical from call to call).
+// legacy mma.sync path costs ~2 us per 64-key block and warp). Here rows <= 32 and 8 warps: warp w owns row tile (w & 1)
+// and, in every round of 128 keys, the 32 keys of group (w >> 1), so a 94-key window is multiplied in one round by six warps
+// at once; the partial softmax states of a row tile are merged through shared memory in a fixed order (bit-identical from
+// call to call).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ATT_THREADS) attention_small_kernel(AttnParams p) {
+constexpr int AS_THREADS = 256;
+constexpr int AS_ROUND = 128;  // keys per round: 4 key groups x 32
+
+__global__ void __launch_bounds__(AS_THREADS) attention_small_kernel(AttnParams p) {
   constexpr int HD = 128, CH = HD / 8;
   pdl_launch_dependents();
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* Qs = smem;                          // [32][HD]
-  uint8_t* Ks = Qs + 32 * HD * 2;              // [2][64][HD]
-  uint8_t* Vs = Ks + 2 * ATT_BN * HD * 2;      // [2][64][HD]
+  uint8_t* Ks = Qs + 32 * HD * 2;              // [128][HD]
+  uint8_t* Vs = Ks + AS_ROUND * HD * 2;        // [128][HD]
   long long* tr = (blockIdx.x + blockIdx.y + blockIdx.z == 0 && threadIdx.x == 0) ? p.trace : nullptr;
   trace_stamp(tr, 0);
   const int b = blockIdx.z, kvh = blockIdx.y, tid = threadIdx.x;
@@ -455,34 +459,31 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_small_kernel(AttnParams
   const int group = p.group;
   const int rows_total = group * q_len;  // <= 32
   if (rows_total <= 0 || kv_len < p.min_kv_len) return;
-  const int n_blocks = (kv_len + ATT_BN - 1) / ATT_BN;
+  const int n_rounds = (kv_len + AS_ROUND - 1) / AS_ROUND;
   const __nv_bfloat16* kbase = p.k + (size_t)kvh * p.kv_head_stride + (size_t)kv_start * p.kv_row_stride;
   const __nv_bfloat16* vbase = p.v + (size_t)kvh * p.kv_head_stride + (size_t)kv_start * p.kv_row_stride;
-  auto load_kv = [&](int blk, int buf) {
-    uint8_t* kd = Ks + buf * ATT_BN * HD * 2;
-    uint8_t* vd = Vs + buf * ATT_BN * HD * 2;
-    for (int i = tid; i < ATT_BN * CH; i += ATT_THREADS) {
+  // keys [k0 + r0, k0 + r1) of a round into rows [r0, r1) of the buffers
+  auto load_rows = [&](int k0, int r0, int r1) {
+    for (int i = tid + r0 * CH; i < r1 * CH; i += AS_THREADS) {
       const int row = i / CH, c = i - row * CH;
-      const int kr = blk * ATT_BN + row;
-      const bool ok = kr < kv_len;
-      const size_t off = (size_t)(ok ? kr : 0) * p.kv_row_stride + c * 8;
-      cp_async_16(kd + swz<HD>(row, c), kbase + off, ok);
-      cp_async_16(vd + swz<HD>(row, c), vbase + off, ok);
+      const bool ok = k0 + row < kv_len;
+      const size_t off = (size_t)(ok ? k0 + row : 0) * p.kv_row_stride + c * 8;
+      cp_async_16(Ks + swz<HD>(row, c), kbase + off, ok);
+      cp_async_16(Vs + swz<HD>(row, c), vbase + off, ok);
     }
   };
-  // block 0 lies entirely in the stable prefix: fetch it before waiting on the previous grid
-  const bool pre = p.stable_prefix && (kv_len - q_len >= ATT_BN);
-  if (pre) load_kv(0, 0);
+  // the first 64 keys lie in the stable prefix: fetch them before waiting on the previous grid
+  const bool pre = p.stable_prefix && (kv_len - q_len >= 64);
+  if (pre) load_rows(0, 0, 64);
   pdl_wait();
   trace_stamp(tr, 1);
-  for (int i = tid; i < 32 * CH; i += ATT_THREADS) {
+  for (int i = tid; i < 32 * CH; i += AS_THREADS) {
     const int row = i / CH, c = i - row * CH;
     const bool ok = row < rows_total;
     const int t = ok ? row / group : 0, hh = ok ? row - t * group : 0;
     cp_async_16(Qs + swz<HD>(row, c), p.q + (size_t)(q_start + t) * p.q_row_stride + (size_t)(kvh * group + hh) * HD + c * 8, ok);
   }
-  if (!pre) load_kv(0, 0);
-  if (n_blocks > 1) load_kv(1, 1);
+  load_rows(0, pre ? 64 : 0, AS_ROUND);
   cp_async_commit();
 
   const int rlo = rt * 16 + (lane >> 2);
@@ -493,18 +494,17 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_small_kernel(AttnParams
   for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   uint32_t qf[HD / 16][4];
-  const uint32_t qs_u = smem_u32(Qs);
-  for (int r2 = 0; r2 * 2 < n_blocks; ++r2) {  // rounds of two key blocks: buffer kg holds block 2 * r2 + kg
+  const uint32_t qs_u = smem_u32(Qs), ks_u = smem_u32(Ks), vs_u = smem_u32(Vs);
+  for (int r2 = 0; r2 < n_rounds; ++r2) {
     if (r2 > 0) {
-      __syncthreads();  // both buffers have been consumed
-      load_kv(2 * r2, 0);
-      if (2 * r2 + 1 < n_blocks) load_kv(2 * r2 + 1, 1);
+      __syncthreads();  // the buffers have been consumed
+      load_rows(r2 * AS_ROUND, 0, AS_ROUND);
       cp_async_commit();
     }
     cp_async_wait<0>();
     __syncthreads();
-    const int jb = 2 * r2 + kg;
-    if (warp_active && jb < n_blocks) {
+    const int key0 = r2 * AS_ROUND + kg * 32;  // this warp's 32 keys: buffer rows kg * 32 ..
+    if (warp_active && key0 < kv_len) {
       if (r2 == 0) {
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
@@ -513,27 +513,25 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_small_kernel(AttnParams
           ldmatrix_x4(qf[kk], qs_u + swz<HD>(row, kk * 2 + (mi >> 1)));
         }
       }
-      const uint32_t ks_u = smem_u32(Ks + kg * ATT_BN * HD * 2);
-      const uint32_t vs_u = smem_u32(Vs + kg * ATT_BN * HD * 2);
-      float sc[8][4];
+      float sc[4][4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+      for (int j = 0; j < 4; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
 #pragma unroll
       for (int kk = 0; kk < HD / 16; ++kk) {
 #pragma unroll
-        for (int jp = 0; jp < 4; ++jp) {
+        for (int jp = 0; jp < 2; ++jp) {
           uint32_t kf[4];
           const int mi = lane >> 3;
-          const int row = jp * 16 + (mi >> 1) * 8 + (lane & 7);
+          const int row = kg * 32 + jp * 16 + (mi >> 1) * 8 + (lane & 7);
           ldmatrix_x4(kf, ks_u + swz<HD>(row, kk * 2 + (mi & 1)));
           mma_bf16_16816(sc[2 * jp], qf[kk], kf[0], kf[1]);
           mma_bf16_16816(sc[2 * jp + 1], qf[kk], kf[2], kf[3]);
         }
       }
-      const int colbase = jb * ATT_BN + (lane & 3) * 2;
+      const int colbase = key0 + (lane & 3) * 2;
       float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int col = colbase + j * 8 + (e & 1);
@@ -554,7 +552,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_small_kernel(AttnParams
       }
       float rs[2] = {0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float pv = exp2f(sc[j][e] - moff[e >> 1]);
@@ -576,7 +574,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_small_kernel(AttnParams
         o[i][3] *= alpha[1];
       }
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
+      for (int ks = 0; ks < 2; ++ks) {
         uint32_t pf[4];
         pf[0] = pack_bf16(sc[2 * ks][0], sc[2 * ks][1]);
         pf[1] = pack_bf16(sc[2 * ks][2], sc[2 * ks][3]);
@@ -586,7 +584,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_small_kernel(AttnParams
         for (int dp = 0; dp < HD / 16; ++dp) {
           uint32_t vf[4];
           const int mi = lane >> 3;
-          const int row = ks * 16 + (mi & 1) * 8 + (lane & 7);
+          const int row = kg * 32 + ks * 16 + (mi & 1) * 8 + (lane & 7);
           ldmatrix_x4_trans(vf, vs_u + swz<HD>(row, dp * 2 + (mi >> 1)));
           mma_bf16_16816(o[2 * dp], pf, vf[0], vf[1]);
           mma_bf16_16816(o[2 * dp + 1], pf, vf[2], vf[3]);
@@ -594,27 +592,39 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_small_kernel(AttnParams
       }
     }
   }
-  // ---- merge the two key-parity states of a row tile: warps 2, 3 hand (m, l, o) to warps 0, 1 through the K / V buffers
+  // ---- merge the key-group states of a row tile: warps of groups 1..3 hand (m, l, o) to group 0 through the K / V buffers
   __syncthreads();
-  float* xch = reinterpret_cast<float*>(Ks);  // [2 row tiles][32 lanes][4 + 64]
-  if (kg == 1) {
-    float* w = xch + ((size_t)rt * 32 + lane) * 68;
+  float* xch = reinterpret_cast<float*>(Ks);  // [2 row tiles][3 groups][32 lanes][4 + 64]
+  if (kg > 0) {
+    float* w = xch + (((size_t)rt * 3 + (kg - 1)) * 32 + lane) * 68;
     w[0] = m_run[0], w[1] = m_run[1], w[2] = l_run[0], w[3] = l_run[1];
 #pragma unroll
     for (int i = 0; i < HD / 8; ++i) *reinterpret_cast<float4*>(w + 4 + 4 * i) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
   }
   __syncthreads();
-  if (kg == 1 || !warp_active) return;
-  const float* w = xch + ((size_t)rt * 32 + lane) * 68;
-  float a0[2], a1[2];
+  if (kg > 0 || !warp_active) return;
+#pragma unroll 1
+  for (int g2 = 0; g2 < 3; ++g2) {  // fixed order
+    const float* w = xch + (((size_t)rt * 3 + g2) * 32 + lane) * 68;
+    float a0[2], a1[2];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const float m1 = w[h], l1 = w[2 + h];
-    const float M = fmaxf(m_run[h], m1);
-    const float mo = (M == -INFINITY) ? 0.f : M;
-    a0[h] = exp2f(m_run[h] - mo);
-    a1[h] = exp2f(m1 - mo);
-    l_run[h] = l_run[h] * a0[h] + l1 * a1[h];
+    for (int h = 0; h < 2; ++h) {
+      const float m1 = w[h], l1 = w[2 + h];
+      const float M = fmaxf(m_run[h], m1);
+      const float mo = (M == -INFINITY) ? 0.f : M;
+      a0[h] = exp2f(m_run[h] - mo);
+      a1[h] = exp2f(m1 - mo);
+      l_run[h] = l_run[h] * a0[h] + l1 * a1[h];
+      m_run[h] = M;
+    }
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      const float4 o1 = *reinterpret_cast<const float4*>(w + 4 + 4 * i);
+      o[i][0] = o[i][0] * a0[0] + o1.x * a1[0];
+      o[i][1] = o[i][1] * a0[0] + o1.y * a1[0];
+      o[i][2] = o[i][2] * a0[1] + o1.z * a1[1];
+      o[i][3] = o[i][3] * a0[1] + o1.w * a1[1];
+    }
   }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -624,12 +634,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_small_kernel(AttnParams
     const float inv = l_run[h] > 0.f ? 1.f / l_run[h] : 0.f;
     __nv_bfloat16* dst = p.out + (size_t)(q_start + t) * p.out_row_stride + (size_t)(kvh * group + hh) * HD;
 #pragma unroll
-    for (int i = 0; i < HD / 8; ++i) {
-      const float4 o1 = *reinterpret_cast<const float4*>(w + 4 + 4 * i);
-      const float x0 = o[i][2 * h] * a0[h] + (h ? o1.z : o1.x) * a1[h];
-      const float x1 = o[i][2 * h + 1] * a0[h] + (h ? o1.w : o1.y) * a1[h];
-      *reinterpret_cast<uint32_t*>(dst + i * 8 + (lane & 3) * 2) = pack_bf16(x0 * inv, x1 * inv);
-    }
+    for (int i = 0; i < HD / 8; ++i)
+      *reinterpret_cast<uint32_t*>(dst + i * 8 + (lane & 3) * 2) = pack_bf16(o[i][2 * h] * inv, o[i][2 * h + 1] * inv);
   }
   trace_stamp(tr, 6);
 }
@@ -645,11 +651,11 @@ int launch_hd(const AttnParams& p, cudaStream_t stream) {
   dim3 grid((rows_max + ATT_BM - 1) / ATT_BM, p.n_kv_heads, p.batch);
   if constexpr (HD == 128) {
     if (p.small_rows && rows_max <= 32 && !p.causal && p.q2 == nullptr) {  // the denoise steps: both warp pairs busy
-      constexpr int SSMEM = (32 + 4 * ATT_BN) * HD * 2;
+      constexpr int SSMEM = (32 + 2 * AS_ROUND) * HD * 2;
       static unsigned long long attr_devs_s = 0;
       if (vl_first_on_device(attr_devs_s))
         VL_CUDA_CHECK(cudaFuncSetAttribute(attention_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SSMEM));
-      VL_CUDA_CHECK(launch_kernel(attention_small_kernel, dim3(1, p.n_kv_heads, p.batch), dim3(ATT_THREADS), SSMEM, stream, p));
+      VL_CUDA_CHECK(launch_kernel(attention_small_kernel, dim3(1, p.n_kv_heads, p.batch), dim3(AS_THREADS), SSMEM, stream, p));
       return 0;
     }
   }
