@@ -33,9 +33,10 @@ __global__ void __launch_bounds__(128) norm_kernel(float* __restrict__ x, const 
   trace_stamp(tr, 1);
   constexpr int W = VPL * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 4 + warp;
   const int nrows = rows_dev ? min(*rows_dev, rows) : rows;
-  if (row >= nrows) return;
+  // (a device-resident row count comes with a capped grid: the warps stride over the live rows instead of launching one
+  // warp per row of the capacity, most of which would only read the count and exit)
+  for (int row = blockIdx.x * 4 + warp; row < nrows; row += gridDim.x * 4) {
   float4 v[VPL];
   if constexpr (GATHER) {
     // row = (img, r2, c2) of the pixel-shuffled grid; source = 4 ViT tokens (CLS skipped)
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(128) norm_kernel(float* __restrict__ x, const 
     u.x = pack_bf16(y.x, y.y);
     u.y = pack_bf16(y.z, y.w);
     dst[e4] = u;
+  }
   }
   trace_stamp(tr, 6);
 }
@@ -201,7 +203,8 @@ int norm_dispatch(float* x, const float* gamma, const float* beta, __nv_bfloat16
   }
   VL_CHECK(width % 128 == 0 && width >= 128 && width <= 4096, "norm: width must be a multiple of 128, <= 4096");
   if (rows <= 0) return 0;
-  const int grid = (rows + 3) / 4;
+  // live rows in device memory (the packed prefix): `rows` is the capacity, a few times the live count
+  const int grid = rows_dev ? std::min((rows + 3) / 4, 8 * 148) : (rows + 3) / 4;
 #define VL_NORM_CASE(V)                                                                                          \
   case V:                                                                                                        \
     VL_CUDA_CHECK(launch_kernel(norm_kernel<V, RMS, GATHER>, dim3(grid), dim3(128), 0, stream, x, gamma, beta, out, rows, rows_dev, eps, g, C, pf, trace));       \
