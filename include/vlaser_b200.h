@@ -144,6 +144,8 @@ void vlaser_destroy(vlaser_t* h);
  * "l2_prefetch" (default 0, measured no gain: the RMSNorm launches of a denoise step issue bulk L2 prefetches of the expert weights the
  * next launches of the chain will read),
  * "expert_gemv" (default 1: at B = 1 the expert passes run on the weight-streaming single-observation kernel, csrc/expert_gemv.cu),
+ * "rn_small" (process-wide, default 1: the residual update + RMSNorm of narrow split-K streams -- the action expert -- with one
+ * thread per column instead of four split groups of threads; bit-identical residual stream),
  * "attn_small" (default 1: the denoise-step attention, group * H <= 32 query rows per (sample, kv head), on the kernel that splits
  * the key blocks between its two warp pairs),
  * "prefill_tc_long" (default 1: prefixes of more than 256 tokens and the causal text prefill on the two-pass tcgen05 attention

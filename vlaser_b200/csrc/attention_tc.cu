@@ -1102,6 +1102,15 @@ prefill_attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    // Nothing to do? (The common policy call: max_image_text_tokens allows long prefixes, but every sample of the batch fits
+    // the short kernel.) The lengths were written by the plan kernels at the start of the call -- every launch since has
+    // waited for its predecessor, so they are visible here without the dependent-launch wait -- and leaving before the
+    // barrier / TMEM set-up makes the empty launch a bare hop of the chain.
+    int any = 0;
+    for (int i = threadIdx.x; i < p.batch; i += PL_THREADS) any |= (p.q_len[i] >= p.min_len) ? 1 : 0;
+    if (!__syncthreads_or(any)) return;
+  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);

@@ -4,6 +4,9 @@
 
 namespace vlaser {
 
+static int g_resid_norm_small = 1;  // measurement switch (option "rn_small"): narrow split-K streams on resid_rmsnorm_small_kernel
+void set_resid_norm_small(int on) { g_resid_norm_small = on; }
+
 namespace {
 
 // ------------------------------------------------------------------------------------------
@@ -179,11 +182,83 @@ __global__ void __launch_bounds__(1024) resid_norm_kernel(float* __restrict__ x,
   trace_stamp(tr, 6);
 }
 
+// The same residual update + RMSNorm for narrow streams with few splits (the action expert: 768 columns, <= 12 partial
+// tiles): one CTA per row with ONE thread per float4 column -- all 13 loads of a thread in flight at once, no exchange of
+// group sums through shared memory, a block reduction over 6 warps instead of 24. The partial sums keep the association of
+// resid_norm_kernel (four interleaved split groups, each summed in ascending order, then added to x in group order), so the
+// residual stream is bit-identical; only the reduction tree of the sum of squares differs.
+__global__ void __launch_bounds__(256) resid_rmsnorm_small_kernel(float* __restrict__ x, const float* __restrict__ gamma,
+                                                                  __nv_bfloat16* __restrict__ out, int rows,
+                                                                  const int* __restrict__ rows_dev, int W, float eps,
+                                                                  const SplitKPartials sp, long long* trace) {
+  __shared__ float red[8];
+  pdl_launch_dependents();
+  long long* tr = (blockIdx.x == 0 && threadIdx.x == 0) ? trace : nullptr;
+  trace_stamp(tr, 0);
+  const int C4 = W >> 2, c = threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C4 && out) gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+  pdl_wait();
+  trace_stamp(tr, 1);
+  const int row = blockIdx.x;
+  const int nrows = rows_dev ? min(*rows_dev, rows) : rows;
+  if (row >= nrows) return;
+  const int S = sp.splits ? *sp.splits : 0;  // <= 12 on this path
+  const size_t off = (size_t)row * W + 4 * c;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C4) {
+    v = *reinterpret_cast<const float4*>(x + off);
+    float4 pv[12];
+#pragma unroll
+    for (int u = 0; u < 12; ++u) {
+      pv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (u < S) pv[u] = __ldcg(reinterpret_cast<const float4*>(sp.part + (size_t)u * sp.stride + off));
+    }
+    float4 acc[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 12; ++u) {
+      acc[u & 3].x += pv[u].x;
+      acc[u & 3].y += pv[u].y;
+      acc[u & 3].z += pv[u].z;
+      acc[u & 3].w += pv[u].w;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) v.x += acc[g].x, v.y += acc[g].y, v.z += acc[g].z, v.w += acc[g].w;
+    if (S > 0) *reinterpret_cast<float4*>(x + off) = v;
+  }
+  if (out == nullptr) return;
+  float q = warp_sum((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
+  if (lane == 0) red[warp] = q;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < nwarps; ++w) tot += red[w];
+  if (c < C4) {
+    const float rstd = rsqrtf(tot / (float)W + eps);
+    uint2 u;
+    u.x = pack_bf16(v.x * rstd * gm.x, v.y * rstd * gm.y);
+    u.y = pack_bf16(v.z * rstd * gm.z, v.w * rstd * gm.w);
+    *reinterpret_cast<uint2*>(out + off) = u;
+  }
+  trace_stamp(tr, 6);
+}
+
 template <bool RMS>
 int resid_norm_launch(float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows, const int* rows_dev,
                       int width, float eps, const SplitKPartials& sp, cudaStream_t stream, long long* trace) {
   VL_CHECK(width % 128 == 0 && width <= 4096, "resid_norm: width must be a multiple of 128, <= 4096");
   if (rows <= 0) return 0;
+  if constexpr (RMS) {
+    // narrow stream, few splits (sp.max_splits is the launch's cap): one thread per column, see the kernel
+    if (g_resid_norm_small && width <= 1024 && sp.max_splits > 0 && sp.max_splits <= 12) {
+      const int threads = (width / 4 + 31) / 32 * 32;
+      VL_CUDA_CHECK(launch_kernel(resid_rmsnorm_small_kernel, dim3(rows), dim3(threads), 0, stream, x, gamma, out, rows, rows_dev,
+                                  width, eps, sp, trace));
+      return 0;
+    }
+  }
   const int C4 = width / 4;
   const int G = std::max(1, std::min(4, 1024 / C4));
   const size_t smem = (size_t)(G - 1) * C4 * sizeof(float4) + 32 * sizeof(float);

@@ -22,7 +22,9 @@ struct SplitKPartials {
   const float* part = nullptr;
   long long stride = 0;        // floats between consecutive splits
   const int* splits = nullptr;
+  int max_splits = 0;          // host-side cap of *splits for this launch (0: unknown)
 };
+void set_resid_norm_small(int on);  // measurement switch, see elementwise.cu
 int layernorm_launch(float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows, int width,
                      float eps, ShuffleGather sg, cudaStream_t stream, const SplitKPartials* sp = nullptr);
 // x[row] += sum of the partials (no norm): for consumers of the residual stream that are not a plain norm launch

@@ -898,6 +898,7 @@ struct Run {
         max_splits = d.max_splits = std::min(max_splits, fit);
       }
     }
+    if (ep.part && pend[si()].x == reinterpret_cast<float*>(ep.out)) pend[si()].sp.max_splits = d.max_splits;  // final cap
     // tile order: with many more rows than weight rows a wave of pairs should share A tiles (n fastest); measured on
     // B200: ViT GEMMs and the LLM o/down projections gain, the wide-N LLM qkv/gate-up GEMMs prefer m fastest
     d.n_fast = (M_dev == nullptr) ? (M > w.N) : (w.N <= 1536);
@@ -1796,7 +1797,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc" || k == "fuse_tail" || k == "decode_chunk" || k == "prefill_tc_long" || k == "attn_small") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc" || k == "fuse_tail" || k == "decode_chunk" || k == "prefill_tc_long" || k == "attn_small" || k == "rn_small") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
@@ -1819,6 +1820,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
     else if (k == "fuse_tail") h->e.fuse_tail = (int)value;
     else if (k == "prefill_tc_long") h->e.prefill_tc_long = (int)value;
     else if (k == "attn_small") h->e.attn_small = (int)value;
+    else if (k == "rn_small") set_resid_norm_small((int)value);
     else if (k == "decode_chunk") h->e.dec_chunk = (value <= 0) ? 0 : std::min(256, std::max(64, (int)value / 64 * 64));
     else if (k == "exp_splits_o") h->e.xs_o = std::max(1, (int)value);
     else if (k == "exp_splits_down") h->e.xs_down = std::max(1, (int)value);
