@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256) resid_rmsnorm_small_kernel(float* __restr
   const int row = blockIdx.x;
   const int nrows = rows_dev ? min(*rows_dev, rows) : rows;
   if (row >= nrows) return;
-  const int S = sp.splits ? *sp.splits : 0;  // <= 12 on this path
+  const int S = sp.known_splits >= 0 ? sp.known_splits : (sp.splits ? *sp.splits : 0);  // <= 12 on this path
   const size_t off = (size_t)row * W + 4 * c;
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c < C4) {

@@ -23,6 +23,9 @@ struct SplitKPartials {
   long long stride = 0;        // floats between consecutive splits
   const int* splits = nullptr;
   int max_splits = 0;          // host-side cap of *splits for this launch (0: unknown)
+  int known_splits = -1;       // >= 0: the split count itself, derived on the host (static row count: gemm_pair_split_count);
+                               // the norm launch then issues its partial loads without first reading *splits (one L2 round
+                               // trip less on the dependent chain of the action expert)
 };
 void set_resid_norm_small(int on);  // measurement switch, see elementwise.cu
 int layernorm_launch(float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows, int width,

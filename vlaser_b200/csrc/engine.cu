@@ -212,6 +212,7 @@ struct Engine {
   int gelu_warps = 16;         // epilogue warps of the pair kernel's exact-GELU variant (16 | 8)
   int pair_bn128 = 1;          // 1: 256 x 128 pair tiles for the one-row-tile split-K projections (see Run::gemm)
   int den_chains = 1;          // sub-batch chains of the denoise steps (1 | 2), see Run::denoise_all
+  int known_splits = 1;        // 1: norm launches behind a static-M split-K projection get the split count from the host
   int fuse_tail = 0;           // 1: the o / down projections of the action expert at one 256-row tile finish the residual update +
                                // the following RMSNorm themselves behind an in-kernel grid barrier (EpiParams::tail_ctr): two of
                                // the seven dependent launches of an expert layer disappear. Bit-identical actions; measured at
@@ -898,7 +899,12 @@ struct Run {
         max_splits = d.max_splits = std::min(max_splits, fit);
       }
     }
-    if (ep.part && pend[si()].x == reinterpret_cast<float*>(ep.out)) pend[si()].sp.max_splits = d.max_splits;  // final cap
+    if (ep.part && pend[si()].x == reinterpret_cast<float*>(ep.out)) {
+      pend[si()].sp.max_splits = d.max_splits;  // final cap
+      // static row count on the pair kernel's TMA epilogue: the count itself is known here
+      if (d.pair && pair_split && M_dev == nullptr && e.tma_epi && out_tm != nullptr && e.known_splits)
+        pend[si()].sp.known_splits = gemm_pair_split_count(d, true);
+    }
     // tile order: with many more rows than weight rows a wave of pairs should share A tiles (n fastest); measured on
     // B200: ViT GEMMs and the LLM o/down projections gain, the wide-N LLM qkv/gate-up GEMMs prefer m fastest
     d.n_fast = (M_dev == nullptr) ? (M > w.N) : (w.N <= 1536);
@@ -1797,7 +1803,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc" || k == "fuse_tail" || k == "decode_chunk" || k == "prefill_tc_long" || k == "attn_small" || k == "rn_small") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc" || k == "fuse_tail" || k == "decode_chunk" || k == "prefill_tc_long" || k == "attn_small" || k == "rn_small" || k == "known_splits") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
@@ -1820,6 +1826,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
     else if (k == "fuse_tail") h->e.fuse_tail = (int)value;
     else if (k == "prefill_tc_long") h->e.prefill_tc_long = (int)value;
     else if (k == "attn_small") h->e.attn_small = (int)value;
+    else if (k == "known_splits") h->e.known_splits = (int)value;
     else if (k == "rn_small") set_resid_norm_small((int)value);
     else if (k == "decode_chunk") h->e.dec_chunk = (value <= 0) ? 0 : std::min(256, std::max(64, (int)value / 64 * 64));
     else if (k == "exp_splits_o") h->e.xs_o = std::max(1, (int)value);

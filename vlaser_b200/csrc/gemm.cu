@@ -29,8 +29,9 @@ struct GemmCfg {
   static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages
-  // the q|k|v epilogue transposes its unit through one 32-row x 128-byte tile per epilogue warp; other epilogues need none
-  static constexpr uint32_t epi_stage_bytes(int epi) { return epi == EPI_QKV_ROPE ? EPI_WARPS * 4096 : 0; }
+  // the q|k|v epilogue keeps two 32-row x 128-byte tiles per epilogue warp (the unit's RoPE factors, fetched while the
+  // mainloop runs; the first one then transposes the rotated unit for the stores); other epilogues: none
+  static constexpr uint32_t epi_stage_bytes(int epi) { return epi == EPI_QKV_ROPE ? EPI_WARPS * 8192 : 0; }
   static constexpr uint32_t smem_bytes(int stages, int epi) {
     return stages * STAGE_BYTES + epi_stage_bytes(epi) + 1024 /*align slack*/ + 256 /*barriers*/;
   }
@@ -265,42 +266,85 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       constexpr bool ROPE_PRE = EPI == EPI_QKV_ROPE && BLOCK_N == 128 && EPI_WARPS == 8;
       RopeOperands ro;
       int rope_pos = 0;
+      float bias_v = 0.f, bias_w = 0.f;
       if constexpr (ROPE_PRE) {
-        // the row's position id and KV-cache row are fetched while the mainloop runs; the 64 RoPE factors only once the
-        // accumulator is there, beside the TMEM loads (held across the wait they spill: 64 registers per thread)
+        // Everything of this unit that does not depend on the accumulator is fetched while the mainloop runs: the row's
+        // position id and KV-cache row (registers), the tile's bias and the unit's 2 x 32 RoPE factors per row (shared
+        // memory: held in registers across the wait they spill). The factor rows are read in the transposed domain --
+        // 8 lanes share a row, 128-byte runs -- instead of 32 scattered 16-byte pieces per instruction behind the
+        // accumulator (in-situ stamps: that epilogue took 3.8 us of the launch's 8, profiles/r02s2y).
+        uint8_t* cs_tile = epi_stage + (warp - 2) * 8192;
+        uint8_t* sn_tile = cs_tile + 4096;
         if (row_ok) {
           rope_pos = __ldg(ep.row_pos + row);
           ro.kvrow = __ldg(ep.row_kvrow + row);
         }
-        if (ep.bias) {  // this unit's 64 bias values into the head of the warp's staging tile (cold in L2: a DRAM round trip)
-          float* bias_s = reinterpret_cast<float*>(epi_stage + (warp - 2) * 4096);
-          bias_s[lane] = __ldg(ep.bias + n0 + half * 32 + lane);
-          bias_s[32 + lane] = __ldg(ep.bias + n0 + half * 32 + 64 + lane);
-          __syncwarp();
+        if (ep.bias) {  // lane j keeps bias[j] of both chunks (cold in L2: a DRAM round trip); broadcast by shuffle below
+          bias_v = __ldg(ep.bias + n0 + half * 32 + lane);
+          bias_w = __ldg(ep.bias + n0 + half * 32 + 64 + lane);
         }
+        const bool rot = (n0 >> 7) < ep.n_q_heads + ep.n_kv_heads;
+        if (rot) {
+          const int ch = lane & 7;
+          float4 c4[8], s4[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + (lane >> 3);
+            const int p = __shfl_sync(0xffffffffu, rope_pos, r);
+            c4[it] = __ldg(reinterpret_cast<const float4*>(ep.cos_tab + (size_t)p * 64 + half * 32 + 4 * ch));
+            s4[it] = __ldg(reinterpret_cast<const float4*>(ep.sin_tab + (size_t)p * 64 + half * 32 + 4 * ch));
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + (lane >> 3);
+            const int sw = r * 128 + ((ch ^ (r & 7)) << 4);
+            *reinterpret_cast<float4*>(cs_tile + sw) = c4[it];
+            *reinterpret_cast<float4*>(sn_tile + sw) = s4[it];
+          }
+        }
+        __syncwarp();
       }
       {
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         if (t == (int)blockIdx.x) trace_stamp(tr, 4);
         if constexpr (ROPE_PRE) {
+          uint8_t* buf = epi_stage + (warp - 2) * 8192;  // factor tile, then the transposition tile of the stores
           uint32_t r0[32], r1[32];
           tmem_ld_32x32(taddr + half * 32, r0);
           tmem_ld_32x32(taddr + half * 32 + 64, r1);
           const int col0 = n0 + half * 32;
-          rope_factors(ep, rope_pos, row_ok, col0, ro);
+          if ((n0 >> 7) < ep.n_q_heads + ep.n_kv_heads) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const int sw = lane * 128 + ((c ^ (lane & 7)) << 4);
+              const float4 cc = *reinterpret_cast<const float4*>(buf + sw);
+              const float4 sn = *reinterpret_cast<const float4*>(buf + 4096 + sw);
+              ro.cs[4 * c] = cc.x, ro.cs[4 * c + 1] = cc.y, ro.cs[4 * c + 2] = cc.z, ro.cs[4 * c + 3] = cc.w;
+              ro.sn[4 * c] = sn.x, ro.sn[4 * c + 1] = sn.y, ro.sn[4 * c + 2] = sn.z, ro.sn[4 * c + 3] = sn.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ro.cs[j] = 1.f, ro.sn[j] = 0.f;
+          }
           tmem_ld_wait();
           float v[32], w[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            v[j] = __uint_as_float(r0[j]) * rstd;
-            w[j] = __uint_as_float(r1[j]) * rstd;
+            v[j] = __uint_as_float(r0[j]) * rstd + __shfl_sync(0xffffffffu, bias_v, j);
+            w[j] = __uint_as_float(r1[j]) * rstd + __shfl_sync(0xffffffffu, bias_w, j);
           }
           // Transpose the unit through this warp's 4 KB swizzled staging tile so that every store instruction writes
           // whole 64-byte runs (4 rows x 2 runs) instead of 32 scattered 16-byte pieces
-          uint8_t* buf = epi_stage + (warp - 2) * 4096;
-          rope_rotate(ep, col0, v, w, ro, reinterpret_cast<const float*>(buf));
-          __syncwarp();  // every lane has read the bias before the tile is overwritten
+          if ((n0 >> 7) < ep.n_q_heads + ep.n_kv_heads) {  // q or k head: x*cos + rot(x)*sin (rope_rotate)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float a = v[j], b = w[j];
+              v[j] = a * ro.cs[j] - b * ro.sn[j];
+              w[j] = b * ro.cs[j] + a * ro.sn[j];
+            }
+          }
+          __syncwarp();  // every lane has read its factors before the tile is overwritten
           stage_row_bf16(buf, lane, 0, v);
           stage_row_bf16(buf, lane, 4, w);
           __nv_bfloat16* my_dst = row_ok ? rope_dst(ep, row, col0, ro) : nullptr;
@@ -551,9 +595,13 @@ constexpr uint32_t PAIR_A_BYTES = BLOCK_M * BLOCK_K * 2;           // this CTA's
 constexpr uint32_t PAIR_B_BYTES = (PAIR_BLOCK_N / 2) * BLOCK_K * 2;  // this CTA's half of the W tile
 constexpr uint32_t PAIR_STAGE_BYTES = PAIR_A_BYTES + PAIR_B_BYTES;
 // smem budget (227 KB): one 32-row x 128-byte output staging tile per epilogue warp + as many ring stages as fit
-constexpr int pair_stages(int nw) { return nw == 16 ? 5 : 6; }
-constexpr uint32_t pair_out_bytes(int nw) { return nw * 4096; }
-constexpr uint32_t pair_smem_bytes(int nw) { return pair_stages(nw) * PAIR_STAGE_BYTES + pair_out_bytes(nw) + 1024 + 256; }
+// (the q|k|v + RoPE epilogue transposes a unit as fp32 -- 32 rows x 256 bytes per warp -- and gives one ring stage for it)
+constexpr int pair_stages(int nw, int epi) { return (nw == 16 || epi == EPI_QKV_ROPE) ? 5 : 6; }
+constexpr uint32_t pair_warp_stage_bytes(int epi) { return epi == EPI_QKV_ROPE ? 8192 : 4096; }
+constexpr uint32_t pair_out_bytes(int nw, int epi) { return nw * pair_warp_stage_bytes(epi); }
+constexpr uint32_t pair_smem_bytes(int nw, int epi) {
+  return pair_stages(nw, epi) * PAIR_STAGE_BYTES + pair_out_bytes(nw, epi) + 1024 + 256;
+}
 
 // tile order of the persistent loop: m fastest (the pairs of a wave share one W tile) or n fastest (share one A tile)
 __device__ __forceinline__ void pair_tile(int t, int m_tiles, int n_tiles, int n_fast, int& m_idx, int& n_idx) {
@@ -661,6 +709,107 @@ __device__ __forceinline__ void pair_tail_resid_norm(const EpiParams& ep, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// q|k|v + RoPE epilogue of the pair kernel (256-column tiles, 8 epilogue warps): a warp owns 32 rows x one head (128
+// columns) = two units {x[i0..i0+31], x[i0+64..i0+95]}, i0 in {0, 32}. The row-per-lane form (epilogue_tile) issues
+// every RoPE-factor load and every q / KV-cache store as 32 scattered 16-byte pieces (32 L1 wavefronts per instruction,
+// the factor table missing in the 20 KB of L1 this kernel leaves): 19 us per tile, three times the tile's mainloop, so the
+// LLM-prefill q|k|v projection ran at 40 % of the tensor roofline. Here a unit is transposed as fp32 through the warp's
+// 8 KB swizzled tile; in the transposed domain 8 lanes share a row: factor loads are 128-byte runs, stores 64-byte runs,
+// bias / rotation in fp32 exactly as before. The accumulator stage is handed back once the second unit is staged.
+// ------------------------------------------------------------------------------------------
+template <class Release>
+__device__ __forceinline__ void epilogue_rope_pair(const EpiParams& ep, uint8_t* tile, uint32_t taddr, int lane, int row,
+                                                   bool row_ok, int col_head, float rstd, Release&& release) {
+  const int head = col_head >> 7;
+  const bool is_q = head < ep.n_q_heads;
+  const bool is_k = !is_q && head < ep.n_q_heads + ep.n_kv_heads;
+  const bool rot = is_q || is_k;
+  const int ch = lane & 7, rsub = lane >> 3;
+  // per-row operands (this call's plan: read after the dependent-launch wait the caller has passed)
+  int pos = 0;
+  unsigned long long dst_bits = 0;
+  if (row_ok) {
+    if (rot) pos = __ldg(ep.row_pos + row);
+    __nv_bfloat16* dst;
+    if (is_q) {
+      dst = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + head * 128;
+    } else {
+      const int kvrow = __ldg(ep.row_kvrow + row);
+      const int kvh = is_k ? head - ep.n_q_heads : head - ep.n_q_heads - ep.n_kv_heads;
+      dst = (is_k ? ep.k_cache : ep.v_cache) + (size_t)kvh * ep.kv_head_stride + (size_t)kvrow * 128;
+    }
+    dst_bits = reinterpret_cast<unsigned long long>(dst);
+  }
+#pragma unroll 1
+  for (int u = 0; u < 2; ++u) {
+    const int i0 = u * 32;
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bw = bv;
+    if (ep.bias) {
+      bv = __ldg(reinterpret_cast<const float4*>(ep.bias + col_head + i0 + 4 * ch));
+      bw = __ldg(reinterpret_cast<const float4*>(ep.bias + col_head + i0 + 64 + 4 * ch));
+    }
+    {
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(taddr + i0, r0);
+      tmem_ld_32x32(taddr + i0 + 64, r1);
+      tmem_ld_wait();
+      if (u == 1) release();
+      uint8_t* rowp = tile + lane * 256;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int sw = (c ^ (lane & 7)) << 4;
+        *reinterpret_cast<float4*>(rowp + sw) =
+            make_float4(__uint_as_float(r0[4 * c]) * rstd, __uint_as_float(r0[4 * c + 1]) * rstd,
+                        __uint_as_float(r0[4 * c + 2]) * rstd, __uint_as_float(r0[4 * c + 3]) * rstd);
+        *reinterpret_cast<float4*>(rowp + 128 + sw) =
+            make_float4(__uint_as_float(r1[4 * c]) * rstd, __uint_as_float(r1[4 * c + 1]) * rstd,
+                        __uint_as_float(r1[4 * c + 2]) * rstd, __uint_as_float(r1[4 * c + 3]) * rstd);
+      }
+    }
+    __syncwarp();
+    // transposed domain: lane (rsub, ch) finishes pairs 4 ch .. 4 ch + 3 of rows it * 4 + rsub
+#pragma unroll 1
+    for (int hb = 0; hb < 2; ++hb) {  // two batches of four rows: the factor loads of a batch are in flight together
+      float4 cs[4], sn[4];
+      unsigned long long db[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = (hb * 4 + i) * 4 + rsub;
+        db[i] = __shfl_sync(0xffffffffu, dst_bits, r);
+        const int p = __shfl_sync(0xffffffffu, pos, r);
+        if (rot) {
+          cs[i] = __ldg(reinterpret_cast<const float4*>(ep.cos_tab + (size_t)p * 64 + i0 + 4 * ch));
+          sn[i] = __ldg(reinterpret_cast<const float4*>(ep.sin_tab + (size_t)p * 64 + i0 + 4 * ch));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = (hb * 4 + i) * 4 + rsub;
+        const int sw = (ch ^ (r & 7)) << 4;
+        float4 a = *reinterpret_cast<const float4*>(tile + r * 256 + sw);
+        float4 b = *reinterpret_cast<const float4*>(tile + r * 256 + 128 + sw);
+        a.x += bv.x, a.y += bv.y, a.z += bv.z, a.w += bv.w;
+        b.x += bw.x, b.y += bw.y, b.z += bw.z, b.w += bw.w;
+        if (rot) {  // x*cos + rot(x)*sin, rot(x)[i] = -x[i+64], rot(x)[i+64] = x[i]
+          const float4 c = cs[i], s = sn[i];
+          const float4 a0 = a, b0 = b;
+          a.x = a0.x * c.x - b0.x * s.x, a.y = a0.y * c.y - b0.y * s.y;
+          a.z = a0.z * c.z - b0.z * s.z, a.w = a0.w * c.w - b0.w * s.w;
+          b.x = b0.x * c.x + a0.x * s.x, b.y = b0.y * c.y + a0.y * s.y;
+          b.z = b0.z * c.z + a0.z * s.z, b.w = b0.w * c.w + a0.w * s.w;
+        }
+        if (db[i]) {
+          __nv_bfloat16* d0 = reinterpret_cast<__nv_bfloat16*>(db[i]) + i0 + 4 * ch;
+          *reinterpret_cast<uint2*>(d0) = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
+          *reinterpret_cast<uint2*>(d0 + 64) = make_uint2(pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+        }
+      }
+    }
+    __syncwarp();  // the tile is free for the next unit
+  }
+}
+
 template <int EPI>
 constexpr int pair_epi_warps() { return EPI == EPI_GELU_BF16 ? 16 : 8; }  // the exact-GELU epilogue is issue-bound at 8
 
@@ -669,7 +818,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * NW, 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, GemmDims d,
                          EpiParams ep) {
-  constexpr int STAGES = pair_stages(NW);
+  constexpr int STAGES = pair_stages(NW, EPI);
   // (BN = 128: the ring keeps its 32 KB slots, the W half of a slot is simply half full)
   constexpr uint32_t STAGE_TX = 2 * (PAIR_A_BYTES + (BN / 2) * BLOCK_K * 2);  // bytes both CTAs land per stage
   extern __shared__ uint8_t smem_raw[];
@@ -677,7 +826,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint8_t* out_stage = smem + STAGES * PAIR_STAGE_BYTES;  // [NW][NBUF][4096], 1024-byte aligned
   constexpr int PARTS = NW / 4;                           // column parts per TMEM lane quarter
   constexpr int NBUF = 1;                                 // staging tiles per epilogue warp
-  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + pair_out_bytes(NW));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + pair_out_bytes(NW, EPI));
   uint64_t* full_bar = bars;                          // [STAGES]   used in the leader only
   uint64_t* empty_bar = bars + MAX_STAGES;            // [STAGES]   one set per CTA
   uint64_t* tfull_bar = bars + 2 * MAX_STAGES;        // [2]        one set per CTA
@@ -729,13 +878,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int k_blocks = d.K / BLOCK_K;
   const int base = m_tiles * n_tiles;
   // split-K (residual epilogue through TMA reduce-add / partial stores only): partial sums meet in L2 or in the workspace
-  int splits = 1;
-  if (EPI == EPI_RESID_F32 && d.max_splits > 1 && d.tma_out && base > 0) {
-    splits = min(min(d.max_splits, n_pairs / base), k_blocks / 2);
-    if (splits < 1) splits = 1;
-  }
+  const int splits = (EPI == EPI_RESID_F32 && d.tma_out) ? pair_split_count(base, n_pairs, k_blocks, d.max_splits) : 1;
   const int kb_per_split = (k_blocks + splits - 1) / splits;
-  splits = (k_blocks + kb_per_split - 1) / kb_per_split;
   const int total = base * splits;
   if constexpr (EPI == EPI_RESID_F32) {
     if (ep.part_splits && blockIdx.x == 0 && threadIdx.x == 64) {
@@ -850,7 +994,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const uint32_t tempty0 = mapa_u32(smem_u32(tempty_bar), 0);
-    uint8_t* wbuf = out_stage + (warp - 2) * (NBUF * 4096);
+    uint8_t* wbuf = out_stage + (warp - 2) * (NBUF * (int)pair_warp_stage_bytes(EPI));
     uint32_t out_par = 0;
     int as = 0;
     uint32_t aphase = 0;
@@ -885,7 +1029,22 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             done = true;
           }
         }
+        bool released = false;
+        if constexpr (EPI == EPI_QKV_ROPE && BN == 256 && NW == 8) {
+          epilogue_rope_pair(ep, wbuf, taddr + half * 128, lane, row, row_ok, n0 + half * 128, rstd, [&]() {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty0 + as * 8);
+          });
+          done = released = true;
+        }
         if (!done) epilogue_tile<BN, EPI, PARTS>(ep, d.N, taddr, half, row, row_ok, n0, true, false, rstd, ss);
+        if (released) {
+          if (t == pair) trace_stamp(tr, 12);
+          as ^= 1;
+          if (as == 0) aphase ^= 1;
+          continue;
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -1011,7 +1170,7 @@ int launch_pair_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   static unsigned long long attr_devs = 0;  // devices this kernel's attributes were set on
   auto kern = gemm_tcgen05_pair_kernel<EPI, NW, BN>;
   if (vl_first_on_device(attr_devs)) {
-    VL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes(NW)));
+    VL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes(NW, EPI)));
   }
   long long tiles = (long long)((d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (d.N / BN);
   if (EPI == EPI_RESID_F32 && d.max_splits > 1) {
@@ -1020,7 +1179,7 @@ int launch_pair_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   }
   const int pairs = (int)std::min<long long>(tiles, gemm_num_sms() / 2);
   // __cluster_dims__(2,1,1) is part of the kernel: a plain launch (with the optional PDL attribute) suffices
-  VL_CUDA_CHECK(launch_kernel(kern, dim3(2 * pairs), dim3(64 + 32 * NW), pair_smem_bytes(NW), stream, tmA, tmB, tc, tp, d, ep));
+  VL_CUDA_CHECK(launch_kernel(kern, dim3(2 * pairs), dim3(64 + 32 * NW), pair_smem_bytes(NW, EPI), stream, tmA, tmB, tc, tp, d, ep));
   return 0;
 }
 
@@ -1054,6 +1213,16 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap*
 }
 
 }  // namespace
+
+int gemm_pair_split_count(const GemmDims& d, bool with_partials) {
+  const int bn = d.pair_bn;
+  const int base = ((d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (d.N / bn);
+  long long tiles = base;
+  if (d.max_splits > 1) tiles *= d.max_splits;
+  const int n_pairs = (int)std::min<long long>(tiles, gemm_num_sms() / 2);  // launch_pair_bn
+  const int splits = pair_split_count(base, n_pairs, d.K / BLOCK_K, d.max_splits);
+  return (splits > 1 && with_partials) ? splits : 0;
+}
 
 int gemm_num_sms() {
   static int sms[64] = {0};  // per device ordinal

@@ -76,6 +76,19 @@ struct EpiParams {
 };
 constexpr int GEMM_ERR_TAIL_BARRIER = 0x7ffffff2;
 
+// K splits of the pair kernel: as many as the idle pairs allow, at least two k-blocks each, evened out
+__host__ __device__ inline int pair_split_count(int base, int n_pairs, int k_blocks, int max_splits) {
+  int splits = 1;
+  if (max_splits > 1 && base > 0) {
+    splits = n_pairs / base;
+    if (splits > max_splits) splits = max_splits;
+    if (splits > k_blocks / 2) splits = k_blocks / 2;
+    if (splits < 1) splits = 1;
+  }
+  const int kb_per_split = (k_blocks + splits - 1) / splits;
+  return (k_blocks + kb_per_split - 1) / kb_per_split;
+}
+
 struct GemmDims {
   int M = 0, N = 0, K = 0;       // K % 64 == 0, N % block_n == 0
   const int* M_dev = nullptr;    // optional: live row count in device memory (M is then the capacity)
@@ -106,5 +119,9 @@ int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDims& 
 int gemm_launch_simt(const __nv_bfloat16* A, const __nv_bfloat16* W, const GemmDims& d, const EpiParams& ep, int epi,
                      cudaStream_t stream);
 int gemm_num_sms();
+// Split count a CTA-pair launch (d.pair, EPI_RESID_F32, TMA epilogue) with a STATIC row count d.M will use and report through
+// EpiParams::part_splits (0: one split, `out` updated directly) -- the arithmetic of the kernel, for callers that want
+// the count at launch time.
+int gemm_pair_split_count(const GemmDims& d, bool with_partials);
 
 }  // namespace vlaser
