@@ -27,9 +27,10 @@ def gemm(A, W, epi, block_n=128, simt=False, out=None, ldo=None, bias=None, scal
          partial=None, partial_stride=0, partial_splits=None):
     lib = _lib.load()
     tma_out = False
-    if block_n in (512, 513, 515, 517):  # test shorthand for the CTA-pair kernel; 513 = TMA epilogue, 515 = + n-fastest tiles,
-        # 517 = TMA epilogue with 256 x 128 tiles (residual epilogue)
-        block_n, pair, tma_out = 256, {515: 3, 517: 5}.get(block_n, 1), block_n >= 513
+    if block_n in (512, 513, 515, 517, 521, 525):  # test shorthand for the CTA-pair kernel; 513 = TMA epilogue, 515 = + n-fastest
+        # tiles, 517 = TMA epilogue with 256 x 128 tiles (residual epilogue); 521 / 525 = the half-SM variant (one tile per CTA
+        # pair, static M) with 256- / 128-column tiles
+        block_n, pair, tma_out = 256, {515: 3, 517: 5, 521: 9, 525: 13}.get(block_n, 1), block_n >= 513
     a = GemmArgs()
     a.A, a.W = _p(A), _p(W)
     a.M, a.K = A.shape

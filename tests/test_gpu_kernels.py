@@ -174,6 +174,53 @@ def test_gemm_dynamic_m(name, bn, simt):
     assert torch.all(out[lim:] == 7.0)
 
 
+@pytest.mark.parametrize("M,N,K,splits", [(256, 768, 8960, 12), (256, 768, 1536, 12), (200, 768, 1536, 12), (130, 1024, 4096, 9)])
+def test_gemm_half_sm_resid_partials(M, N, K, splits):
+    """Half-SM variant of the pair kernel (two CTAs fit on an SM: 4 epilogue warps, packed ring, one accumulator stage,
+    staging in the idle ring), residual epilogue with deterministic split-K partials at one tile per CTA pair: same
+    numbers as the full-SM kernel with the same split count, bit-identical from call to call."""
+    A, W = _rand(M, K), _rand(N, K, scale=0.05)
+    bias = torch.randn(N, device=DEV)
+    scale = torch.rand(N, device=DEV) + 0.5
+    x0 = torch.randn(M, N, device=DEV)
+    rows_p = (M + 255) // 256 * 256
+    ref = x0 + (_ref_mm(A, W) + bias) * scale
+    res = {}
+    for bn in (525, 517):
+        part = torch.full((splits, rows_p, N), float("nan"), device=DEV)
+        nsp = torch.full((1,), -1, dtype=torch.int32, device=DEV)
+        outs = []
+        for rep in range(2):
+            x = x0.clone()
+            ops.gemm(A, W, EPI_RESID_F32, bn, False, out=x, bias=bias, scale=scale, max_splits=splits, partial=part,
+                     partial_stride=rows_p * N, partial_splits=nsp)
+            assert 2 <= int(nsp.item()) <= splits
+            assert torch.equal(x, x0)
+            ops.splitk_reduce(x, part, rows_p * N, nsp)
+            outs.append(x)
+        assert torch.equal(outs[0], outs[1])
+        assert ops.rel_err(outs[0], ref) < 1e-5
+        res[bn] = (outs[0], int(nsp.item()))
+    assert res[525][1] == res[517][1]
+    assert torch.equal(res[525][0], res[517][0]), "same splits, same association: the two variants agree bit for bit"
+
+
+@pytest.mark.parametrize("M,F,K", [(256, 8960, 768), (256, 512, 256), (140, 2816, 768)])
+def test_gemm_half_sm_swiglu(M, F, K):
+    """Half-SM variant, SwiGLU epilogue (the gate/up launch of a denoise step: N = 2 F accumulator columns, one 256 x 256
+    tile per CTA pair): equal to the full-SM pair kernel bit for bit."""
+    A = _rand(M, K)
+    gate, up = _rand(F, K, scale=0.1, seed=1), _rand(F, K, scale=0.1, seed=2)
+    W = ops.interleave_gate_up(gate, up)
+    out = torch.empty(M, F, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(A, W, EPI_SWIGLU_BF16, 521, False, out=out)
+    ref = torch.nn.functional.silu(_ref_mm(A, gate)) * _ref_mm(A, up)
+    assert ops.rel_err(out, ref) < BF16_TOL
+    out2 = torch.empty(M, F, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(A, W, EPI_SWIGLU_BF16, 513, False, out=out2)
+    assert torch.equal(out, out2)
+
+
 @pytest.mark.parametrize("name,bn,simt", VARIANTS)
 def test_gemm_swiglu(name, bn, simt):
     M, F, K = 500, 512, 256

@@ -64,8 +64,11 @@ def show(sel, title):
     print(f"{'launch':22s} " + " ".join(f"{s:>10s}" for s in SLOTS))
     for r in sel:
         vals = " ".join(f"{(float(v) - t0) / 1e3:10.2f}" if v > 0 else f"{'-':>10s}" for v in r["t"][:7])
-        fine = " ".join(f"{(float(v) - t0) / 1e3:.2f}" for v in r["t"][8:16] if v > 0)
-        print(f"{(r['kind'] + ' L' + str(r['layer'])):22s} {vals}" + (f"   fine: {fine}" if fine else ""))
+        fine = " ".join(f"{(float(v) - t0) / 1e3:.2f}" for v in r["t"][8:14] if v > 0)
+        allc = " ".join(f"{n} {(float(r['t'][i]) - t0) / 1e3:.2f}" for n, i in (("entry<=", 14), ("ready<=", 15), ("exit<=", 7))
+                        if r["t"][i] > 0)
+        print(f"{(r['kind'] + ' L' + str(r['layer'])):22s} {vals}" + (f"   all CTAs: {allc}" if allc else "")
+              + (f"   fine: {fine}" if fine else ""))
 
 
 stage, sstep, slayer = a.show.split(":")

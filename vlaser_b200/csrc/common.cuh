@@ -82,6 +82,16 @@ __device__ __forceinline__ void trace_stamp(long long* t, int slot) {
   }
 }
 
+// Stamps over ALL CTAs of a launch (thread 0 of each): slot 14 latest entry, 15 latest arrival at the dependent-launch
+// wait (prologue done), 7 latest exit -- block 0 is not the straggler when the launch needs SMs the previous one still holds.
+__device__ __forceinline__ void trace_max(long long* t, int slot) {
+  if (t) {
+    long long now;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+    atomicMax(reinterpret_cast<unsigned long long*>(t + slot), (unsigned long long)now);
+  }
+}
+
 // ---------------------------------------------------------------- small device utilities
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

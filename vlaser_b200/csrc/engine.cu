@@ -212,6 +212,13 @@ struct Engine {
   int gelu_warps = 16;         // epilogue warps of the pair kernel's exact-GELU variant (16 | 8)
   int pair_bn128 = 1;          // 1: 256 x 128 pair tiles for the one-row-tile split-K projections (see Run::gemm)
   int den_chains = 1;          // sub-batch chains of the denoise steps (1 | 2), see Run::denoise_all
+  int half_sm = 0;             // 1: one-tile-per-CTA pair launches at a static M <= 256 on the half-SM variant of the pair kernel
+                               // (two CTAs per SM, so the next launch of the denoise chain is resident and through its prologue
+                               // while the current one runs). Measured (profiles/r02s3f): the late-entry stragglers of the o /
+                               // gate-up / down launches disappear, but a 3-stage ring does not cover the HBM latency of the
+                               // gate/up weights (mainloop 4.3 -> 8.4 us), 4 epilogue warps issue the partial-tile TMA stores in
+                               // twice the time, and the denoise attention capped at 128 registers to make room loses 1.8 us:
+                               // 38.9 vs 37.7 ms per call. Off.
   int known_splits = 1;        // 1: norm launches behind a static-M split-K projection get the split count from the host
   int fuse_tail = 0;           // 1: the o / down projections of the action expert at one 256-row tile finish the residual update +
                                // the following RMSNorm themselves behind an in-kernel grid barrier (EpiParams::tail_ctr): two of
@@ -941,6 +948,15 @@ struct Run {
       pend[si()] = Pending();  // the projection itself finishes the residual update
       tail_done[si()].x = reinterpret_cast<const float*>(ep.out);
       tail_done[si()].gamma = offer.gamma;
+    }
+    // one tile per CTA pair at a static row count (the o / gate-up / down launches of a denoise step): the half-SM variant,
+    // whose CTAs become resident and run their prologue while the previous launch of the chain still holds the SMs
+    if (e.half_sm && d.pair && M_dev == nullptr && M <= 256 && out_tm != nullptr && e.tma_epi && !ep.a_next && !ep.row_ss &&
+        !ep.tail_ctr) {
+      const long long t = (long long)(w.N / d.pair_bn) * (epi == EPI_RESID_F32 ? std::max(1, d.max_splits) : 1);
+      if (((epi == EPI_RESID_F32 && d.pair_bn == 128) || (epi == EPI_SWIGLU_BF16 && d.pair_bn == 256)) &&
+          t <= gemm_num_sms() / 2)
+        d.half_sm = 1;
     }
     const CUtensorMap& wtm = (d.pair && d.pair_bn == 128) ? w.tm64 : (bn == 256 ? w.tm256 : w.tm128);
     const int rc = gemm_launch(a.tm, wtm, d, ep, bn, epi, st, e.tma_epi ? out_tm : nullptr, part_tm);
@@ -1803,7 +1819,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc" || k == "fuse_tail" || k == "decode_chunk" || k == "prefill_tc_long" || k == "attn_small" || k == "rn_small" || k == "known_splits") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc" || k == "fuse_tail" || k == "decode_chunk" || k == "prefill_tc_long" || k == "attn_small" || k == "rn_small" || k == "known_splits" || k == "half_sm") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
@@ -1827,6 +1843,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
     else if (k == "prefill_tc_long") h->e.prefill_tc_long = (int)value;
     else if (k == "attn_small") h->e.attn_small = (int)value;
     else if (k == "known_splits") h->e.known_splits = (int)value;
+    else if (k == "half_sm") h->e.half_sm = (int)value;
     else if (k == "rn_small") set_resid_norm_small((int)value);
     else if (k == "decode_chunk") h->e.dec_chunk = (value <= 0) ? 0 : std::min(256, std::max(64, (int)value / 64 * 64));
     else if (k == "exp_splits_o") h->e.xs_o = std::max(1, (int)value);
@@ -2216,6 +2233,7 @@ int32_t vlaser_op_gemm(const vlaser_gemm_args* a, void* stream) {
   d.pair = a->pair & 1;
   d.n_fast = (a->pair >> 1) & 1;
   d.pair_bn = (a->pair & 4) ? 128 : 256;
+  d.half_sm = (a->pair >> 3) & 1;
   if (a->simt)
     return gemm_launch_simt(reinterpret_cast<const __nv_bfloat16*>(a->A), reinterpret_cast<const __nv_bfloat16*>(a->W),
                             d, ep, a->epi, st);

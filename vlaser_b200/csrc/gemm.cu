@@ -104,6 +104,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     trace_stamp(tr, 0);
+    trace_max(d.trace, 14);
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
@@ -173,6 +174,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           ++npre;
           advance();
         }
+        trace_max(d.trace, 15);
         pdl_wait();
         trace_stamp(tr, 1);
         for (int i = 0; i < npre; ++i)
@@ -433,6 +435,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   if (warp == 2) trace_stamp(tr, 6);
+  if (threadIdx.x == 0) trace_max(d.trace, 7);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -528,8 +531,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiParams& ep, const CUt
       trace_stamp(tr, 11);
     }
   } else if constexpr (EPI == EPI_SWIGLU_BF16) {
-    static_assert(PARTS == 2, "SwiGLU TMA epilogue: 8 epilogue warps");
     constexpr int U = BN / 128 / PARTS;  // 128 accumulator columns -> 64 outputs -> one 128-byte row
+    static_assert(U >= 1, "SwiGLU TMA epilogue: at least 128 accumulator columns per warp");
 #pragma unroll 1
     for (int u = half * U; u < (half + 1) * U; ++u) {
       uint8_t* b = acquire();
@@ -600,8 +603,24 @@ constexpr int pair_stages(int nw, int epi) { return (nw == 16 || epi == EPI_QKV_
 constexpr uint32_t pair_warp_stage_bytes(int epi) { return epi == EPI_QKV_ROPE ? 8192 : 4096; }
 constexpr uint32_t pair_out_bytes(int nw, int epi) { return nw * pair_warp_stage_bytes(epi); }
 constexpr uint32_t pair_smem_bytes(int nw, int epi) {
-  return pair_stages(nw, epi) * PAIR_STAGE_BYTES + pair_out_bytes(nw, epi) + 1024 + 256;
+  // (no alignment slack: the kernel declares its dynamic shared memory 1024-byte aligned and has no static shared memory.
+  // 229,632 bytes at 6 stages + the 1 KB the system reserves per CTA leave 2.8 KB of the SM: the two row-per-CTA norm CTAs
+  // an SM gets between the launches of the denoise chain fit beside a CTA of this kernel -- with the slack only one did, the
+  // second had to wait for the projection to finish, and with it the launch of everything behind the norm)
+  return pair_stages(nw, epi) * PAIR_STAGE_BYTES + pair_out_bytes(nw, epi) + 256;
 }
+// ---- half-SM variant (template parameter HALF): the launches of the action expert's denoise chain. Every CTA of such a
+// launch owns ONE tile, and the launch is one hop of a latency-bound chain of ~2500 dependent launches. A CTA that
+// needs a whole SM (225 KB of shared memory, 320 threads x 168 registers) cannot enter until a CTA of the previous launch
+// has left its SM, and only then starts its ~2.8 us prologue (barriers, TMEM, cluster sync, weight prefetch): the in-situ
+// stamps over all CTAs (profiles/r02s3e) put that prologue on the critical path of the o / gate-up / down launches,
+// 2 - 2.8 us each. The half-SM variant fits twice on an SM -- 4 epilogue warps (192 threads), a short ring (the K loop of a
+// CTA is 2 - 12 k-blocks), no dedicated staging tiles (the epilogue stages in the idle ring), ONE accumulator stage
+// (BN TMEM columns) -- so the next launch's CTAs are resident, initialised and have their weights in flight while the
+// current launch still runs.
+constexpr int pair_half_stages(int bn) { return bn == 128 ? 4 : 3; }
+constexpr uint32_t pair_half_slot_bytes(int bn) { return PAIR_A_BYTES + (bn / 2) * BLOCK_K * 2; }  // 24 KB | 32 KB
+constexpr uint32_t pair_half_smem_bytes(int bn) { return pair_half_stages(bn) * pair_half_slot_bytes(bn) + 256; }
 
 // tile order of the persistent loop: m fastest (the pairs of a wave share one W tile) or n fastest (share one A tile)
 __device__ __forceinline__ void pair_tile(int t, int m_tiles, int n_tiles, int n_fast, int& m_idx, int& n_idx) {
@@ -617,8 +636,7 @@ __device__ __forceinline__ void pair_tile(int t, int m_tiles, int n_tiles, int n
 // Fused tail of a split-K residual projection (see EpiParams::tail_ctr): in-kernel grid barrier, then this CTA's share of
 // the residual update + RMSNorm rows. Called by every thread of every CTA after the CTA-wide (cluster-wide) barrier that
 // follows the completion of its TMA stores. N <= 1024 columns (one float4 per thread of the first N / 4 threads).
-__device__ __forceinline__ void pair_tail_resid_norm(const EpiParams& ep, const GemmDims& d, int M, int S) {
-  __shared__ float tail_red[32];
+__device__ __forceinline__ void pair_tail_resid_norm(const EpiParams& ep, const GemmDims& d, int M, int S, float* tail_red) {
   if (threadIdx.x == 0) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ep.tail_ctr) : "memory");
     unsigned int v;
@@ -813,20 +831,23 @@ __device__ __forceinline__ void epilogue_rope_pair(const EpiParams& ep, uint8_t*
 template <int EPI>
 constexpr int pair_epi_warps() { return EPI == EPI_GELU_BF16 ? 16 : 8; }  // the exact-GELU epilogue is issue-bound at 8
 
-template <int EPI, int NW, int BN = PAIR_BLOCK_N>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * NW, 1)
+template <int EPI, int NW, int BN = PAIR_BLOCK_N, bool HALF = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * NW, HALF ? 2 : 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, GemmDims d,
                          EpiParams ep) {
-  constexpr int STAGES = pair_stages(NW, EPI);
-  // (BN = 128: the ring keeps its 32 KB slots, the W half of a slot is simply half full)
+  static_assert(!HALF || (NW == 4 && (EPI == EPI_RESID_F32 || EPI == EPI_SWIGLU_BF16)), "half-SM variant: 4 epilogue warps");
+  constexpr int STAGES = HALF ? pair_half_stages(BN) : pair_stages(NW, EPI);
+  // (BN = 128: the ring keeps its 32 KB slots, the W half of a slot is simply half full; the half-SM variant packs them)
+  constexpr uint32_t SLOT = HALF ? pair_half_slot_bytes(BN) : PAIR_STAGE_BYTES;
+  constexpr int ACC = HALF ? 1 : 2;                                           // accumulator stages in TMEM
   constexpr uint32_t STAGE_TX = 2 * (PAIR_A_BYTES + (BN / 2) * BLOCK_K * 2);  // bytes both CTAs land per stage
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* out_stage = smem + STAGES * PAIR_STAGE_BYTES;  // [NW][NBUF][4096], 1024-byte aligned
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;  // 1024-byte aligned by declaration (128B-swizzle atoms); the kernel has no static shared memory
+  uint8_t* out_stage = smem + STAGES * SLOT;  // [NW][NBUF][4096], 1024-byte aligned (half-SM variant: none)
   constexpr int PARTS = NW / 4;                           // column parts per TMEM lane quarter
   constexpr int NBUF = 1;                                 // staging tiles per epilogue warp
-  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + pair_out_bytes(NW, EPI));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + (HALF ? 0u : pair_out_bytes(NW, EPI)));
   uint64_t* full_bar = bars;                          // [STAGES]   used in the leader only
   uint64_t* empty_bar = bars + MAX_STAGES;            // [STAGES]   one set per CTA
   uint64_t* tfull_bar = bars + 2 * MAX_STAGES;        // [2]        one set per CTA
@@ -843,6 +864,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   if (warp == 0 && lane == 0) {
     trace_stamp(tr, 0);
+    trace_max(d.trace, 14);
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (d.tma_out) tma_prefetch_desc(&tmC);
@@ -857,15 +879,22 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     fence_barrier_init();
   }
+  // Both CTAs' barriers are initialised before any remote arrive / multicast commit. The TMEM allocation comes AFTER this
+  // sync: the producer does not need it, and its first ring fill (the weights) is what a CTA that could only enter when the
+  // previous launch of a dependent chain left its SM is waited for (prologue stamps over all CTAs, profiles/r02s3g: barriers
+  // 0.3 us, TMEM 1.0, cluster sync 1.5, weights issued 2.9 - 3.8 us after entry with the allocation in front of the sync)
+  cluster_sync_all();
+  pdl_launch_dependents();
   if (warp == 1) {
-    tmem_alloc_pair(tmem_slot, 2 * BN);
+    tmem_alloc_pair(tmem_slot, ACC * BN);
     tmem_relinquish_pair();
   }
-  tc_fence_before();
-  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_launch_dependents();
+  if (warp != 0) {  // the MMA and epilogue warps meet on the TMEM address; the producer is already filling the ring
+    tc_fence_before();
+    asm volatile("bar.sync 2, %0;" ::"n"(32 * (NW + 1)) : "memory");
+    tc_fence_after();
+  }
+  const uint32_t tmem_base = warp != 0 ? *tmem_slot : 0u;
   // A device-resident row count belongs to this call's plan: it is read after the dependent-launch wait. With a static
   // M only the threads that touch activations wait (producer: after its weight prefetch; epilogue warps).
   int M = d.M;
@@ -923,14 +952,15 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           pre_kb[npre] = kb;
           pre_row[npre] = row_a;
           if (leader) mbar_arrive_expect_tx(&full_bar[npre], STAGE_TX);
-          tma_load_2d_pair(smem + npre * PAIR_STAGE_BYTES + PAIR_A_BYTES, &tmB, full0 + npre * 8, kb * BLOCK_K, row_b);
+          tma_load_2d_pair(smem + npre * SLOT + PAIR_A_BYTES, &tmB, full0 + npre * 8, kb * BLOCK_K, row_b);
           ++npre;
           advance();
         }
+        trace_max(d.trace, 15);
         pdl_wait();
         trace_stamp(tr, 1);
         for (int i = 0; i < npre; ++i)
-          tma_load_2d_pair(smem + i * PAIR_STAGE_BYTES, &tmA, full0 + i * 8, pre_kb[i] * BLOCK_K, pre_row[i]);
+          tma_load_2d_pair(smem + i * SLOT, &tmA, full0 + i * 8, pre_kb[i] * BLOCK_K, pre_row[i]);
         stage = npre;
         if (stage == STAGES) {
           stage = 0;
@@ -941,7 +971,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
       while (have) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * PAIR_STAGE_BYTES;
+        uint8_t* sa = smem + stage * SLOT;
         if (leader) mbar_arrive_expect_tx(&full_bar[stage], STAGE_TX);
         tma_load_2d_pair(sa, &tmA, full0 + stage * 8, kb * BLOCK_K, row_a);
         tma_load_2d_pair(sa + PAIR_A_BYTES, &tmB, full0 + stage * 8, kb * BLOCK_K, row_b);
@@ -970,7 +1000,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (t == pair && kb == kb0) trace_stamp(tr, 2);
-          const uint32_t sa = smem_u32(smem + stage * PAIR_STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + stage * SLOT);
           const uint64_t da = make_umma_desc_sw128(sa);
           const uint64_t db = make_umma_desc_sw128(sa + PAIR_A_BYTES);
 #pragma unroll
@@ -984,7 +1014,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         umma_commit_pair(&tfull_bar[as], 0x3);  // accumulators (both CTAs' TMEM) ready
         trace_stamp(tr, 3);
-        as ^= 1;
+        if (ACC == 2) as ^= 1;
         if (as == 0) aphase ^= 1;
       }
     }
@@ -994,7 +1024,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const uint32_t tempty0 = mapa_u32(smem_u32(tempty_bar), 0);
-    uint8_t* wbuf = out_stage + (warp - 2) * (NBUF * (int)pair_warp_stage_bytes(EPI));
+    // (half-SM variant: one tile per CTA, so the operand ring is idle whenever the epilogue runs -- it stages there)
+    uint8_t* wbuf = HALF ? smem + (warp - 2) * 4096 : out_stage + (warp - 2) * (NBUF * (int)pair_warp_stage_bytes(EPI));
     uint32_t out_par = 0;
     int as = 0;
     uint32_t aphase = 0;
@@ -1022,7 +1053,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             // last tile of this pair: the operand ring (STAGES x 32 KB) is idle once the accumulator is complete
             uint8_t* ring = nullptr;
             if (EPI == EPI_RESID_F32 && t + n_pairs >= total &&
-                (BN / 32 / PARTS) * 4096 * NW <= STAGES * (int)PAIR_STAGE_BYTES)
+                (BN / 32 / PARTS) * 4096 * NW <= STAGES * (int)SLOT)
               ring = smem + (warp - 2) * ((BN / 32 / PARTS) * 4096);
             epilogue_tile_tma<BN, EPI, PARTS, NBUF>(ep, &tmC, wbuf, out_par, taddr, half, lane, row - lane, n0, rstd,
                                                     split == 0, &tmP, part_row0, ring, t == pair ? tr : nullptr);
@@ -1041,7 +1072,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (!done) epilogue_tile<BN, EPI, PARTS>(ep, d.N, taddr, half, row, row_ok, n0, true, false, rstd, ss);
         if (released) {
           if (t == pair) trace_stamp(tr, 12);
-          as ^= 1;
+          if (ACC == 2) as ^= 1;
           if (as == 0) aphase ^= 1;
           continue;
         }
@@ -1051,7 +1082,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if (t == pair) trace_stamp(tr, 12);
       if (lane == 0) mbar_arrive_cluster(tempty0 + as * 8);  // the leader's MMA thread owns both accumulators
       if (t == pair) trace_stamp(tr, 13);
-      as ^= 1;
+      if (ACC == 2) as ^= 1;
       if (as == 0) aphase ^= 1;
       if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_STORE_F32) {
         if (ep.a_next) {
@@ -1070,10 +1101,11 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   // neither CTA may exit (or free TMEM) while its peer can still signal its barriers or read its smem
   tc_fence_before();
   cluster_sync_all();
-  if (warp == 1) tmem_dealloc_pair(tmem_base, 2 * BN);
+  if (warp == 1) tmem_dealloc_pair(tmem_base, ACC * BN);
   if (warp == 2) trace_stamp(tr, 6);
+  if (threadIdx.x == 0) trace_max(d.trace, 7);
   if constexpr (EPI == EPI_RESID_F32 && BN == 128) {
-    if (ep.tail_ctr) pair_tail_resid_norm(ep, d, M, (splits > 1 && ep.part) ? splits : 0);
+    if (ep.tail_ctr) pair_tail_resid_norm(ep, d, M, (splits > 1 && ep.part) ? splits : 0, reinterpret_cast<float*>(smem));
   }
 }
 
@@ -1164,13 +1196,14 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDims d, const
   return 0;
 }
 
-template <int EPI, int BN, int NW = pair_epi_warps<EPI>()>
+template <int EPI, int BN, int NW = pair_epi_warps<EPI>(), bool HALF = false>
 int launch_pair_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tc, const CUtensorMap& tp, const GemmDims& d,
                    const EpiParams& ep, cudaStream_t stream) {
   static unsigned long long attr_devs = 0;  // devices this kernel's attributes were set on
-  auto kern = gemm_tcgen05_pair_kernel<EPI, NW, BN>;
+  auto kern = gemm_tcgen05_pair_kernel<EPI, NW, BN, HALF>;
+  constexpr uint32_t smem_bytes = HALF ? pair_half_smem_bytes(BN) : pair_smem_bytes(NW, EPI);
   if (vl_first_on_device(attr_devs)) {
-    VL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes(NW, EPI)));
+    VL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   }
   long long tiles = (long long)((d.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (d.N / BN);
   if (EPI == EPI_RESID_F32 && d.max_splits > 1) {
@@ -1179,7 +1212,11 @@ int launch_pair_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   }
   const int pairs = (int)std::min<long long>(tiles, gemm_num_sms() / 2);
   // __cluster_dims__(2,1,1) is part of the kernel: a plain launch (with the optional PDL attribute) suffices
-  VL_CUDA_CHECK(launch_kernel(kern, dim3(2 * pairs), dim3(64 + 32 * NW), pair_smem_bytes(NW, EPI), stream, tmA, tmB, tc, tp, d, ep));
+  if (HALF) {
+    VL_CHECK(d.tma_out && !d.M_dev && tiles <= gemm_num_sms() / 2 && !ep.tail_ctr && !ep.row_ss,
+             "gemm: the half-SM pair kernel takes static-M launches of at most one tile per CTA pair through the TMA epilogue");
+  }
+  VL_CUDA_CHECK(launch_kernel(kern, dim3(2 * pairs), dim3(64 + 32 * NW), smem_bytes, stream, tmA, tmB, tc, tp, d, ep));
   return 0;
 }
 
@@ -1191,8 +1228,13 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   VL_CHECK(!(EPI == EPI_RESID_F32 && ep.part) || tmP != nullptr, "gemm: pair kernel with split-K partials needs the workspace tensor map");
   const CUtensorMap& tp = tmP ? *tmP : tmA;
   if constexpr (EPI == EPI_RESID_F32) {
+    if (d.pair_bn == 128 && d.half_sm) return launch_pair_bn<EPI, 128, 4, true>(tmA, tmB, tc, tp, d, ep, stream);
     if (d.pair_bn == 128) return launch_pair_bn<EPI, 128>(tmA, tmB, tc, tp, d, ep, stream);
   }
+  if constexpr (EPI == EPI_SWIGLU_BF16) {
+    if (d.pair_bn == 256 && d.half_sm) return launch_pair_bn<EPI, PAIR_BLOCK_N, 4, true>(tmA, tmB, tc, tp, d, ep, stream);
+  }
+  VL_CHECK(!d.half_sm, "gemm: the half-SM pair kernel exists for the residual (128-column tiles) and SwiGLU epilogues");
   VL_CHECK(d.pair_bn == 256, "gemm: 128-column pair tiles exist for the residual epilogue only");
   if constexpr (EPI == EPI_GELU_BF16) {
     if (d.gelu_warps == 8) return launch_pair_bn<EPI, PAIR_BLOCK_N, 8>(tmA, tmB, tc, tp, d, ep, stream);

@@ -97,6 +97,7 @@ struct GemmDims {
   int pair = 0;                  // 1: CTA-pair kernel (cta_group::2, 256x256 tile per pair; W map with 128-row boxes)
   int pair_bn = 256;             // pair kernel tile width: 256, or 128 (residual epilogue only; W map with 64-row boxes): half the
                                  // output bytes per CTA and twice the CTAs for the one-row-tile split-K projections
+  int half_sm = 0;               // pair kernel: 1 = the half-SM variant (static M, one tile per CTA pair; see gemm.cu)
   int gelu_warps = 16;           // pair kernel, exact-GELU epilogue: epilogue warps (16, or 8 with one more ring stage)
   int n_fast = 0;                // pair kernel tile order: 0 = m fastest, 1 = n fastest
   int tma_out = 0;               // set by the launcher: epilogue leaves through the output tensor map
