@@ -219,6 +219,9 @@ typedef struct vlaser_gemm_args {
   float* partial;
   int64_t partial_stride;
   int32_t* partial_splits;
+  /* > 0 (pair kernel): ss_next / row_ss are [M, ss_slots] partial sums of squares, one slot per (256-column tile, column
+   * half) of the producer, plain stores, added in slot order by the consumer (csrc/gemm.cuh EpiParams::ss_slots) */
+  int32_t ss_slots;
 } vlaser_gemm_args;
 int32_t vlaser_op_gemm(const vlaser_gemm_args* a, void* stream);
 

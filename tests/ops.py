@@ -24,7 +24,7 @@ def gemm(A, W, epi, block_n=128, simt=False, out=None, ldo=None, bias=None, scal
          row_map=None, row_pos=None, row_kvrow=None, cos_tab=None, sin_tab=None, k_cache=None, v_cache=None,
          kv_head_stride=0, n_q_heads=0, n_kv_heads=0, pos_emb=None, patches=0, gamma_next=None, a_next=None,
          ss_next=None, tile_counters=None, row_ss=None, inv_width=0.0, eps=0.0, stages=0, pair=False,
-         partial=None, partial_stride=0, partial_splits=None):
+         partial=None, partial_stride=0, partial_splits=None, ss_slots=0):
     lib = _lib.load()
     tma_out = False
     if block_n in (512, 513, 515, 517, 521, 525):  # test shorthand for the CTA-pair kernel; 513 = TMA epilogue, 515 = + n-fastest
@@ -48,6 +48,7 @@ def gemm(A, W, epi, block_n=128, simt=False, out=None, ldo=None, bias=None, scal
     a.row_ss, a.inv_width, a.eps, a.stages = _p(row_ss), inv_width, eps, stages
     a.pair, a.tma_out = int(pair), int(tma_out)
     a.partial, a.partial_stride, a.partial_splits = _p(partial), partial_stride, _p(partial_splits)
+    a.ss_slots = ss_slots
     _lib.check(lib.vlaser_op_gemm(C.byref(a), _stream()), "op_gemm")
     return out
 

@@ -115,6 +115,42 @@ def test_gemm_fused_rmsnorm_chain(name, simt, splits, M):
     assert err < 1.5 * BF16_TOL
 
 
+@pytest.mark.parametrize("M,N,K,F", [(700, 1536, 512, 512), (256, 768, 1024, 256), (5570, 1536, 1536, 1024)])
+def test_gemm_pair_fused_rmsnorm_chain_slots(M, N, K, F):
+    """Large-M form of the fused RMSNorm chain on the CTA-pair kernel (the LLM prefill): the residual projection reads
+    x, writes x_new, bf16(x_new * gamma) and one partial sum of squares per (256-column tile, column half) with plain
+    stores; the consumer (gate/up with SwiGLU) adds the slots in order and scales its accumulator rows by rstd.
+    Together == RMSNorm between the two GEMMs (HF Qwen2RMSNorm, joint_model.py:166,209); bit-identical from call to call."""
+    eps = 1e-6
+    A, W = _rand(M, K), _rand(N, K, scale=0.05)
+    bias = _rand(N, dtype=torch.float32, seed=7)
+    x0 = _rand(M, N, dtype=torch.float32, seed=9)
+    gamma = 1.0 + 0.1 * _rand(N, dtype=torch.float32, seed=10)
+    slots = N // 128
+    gate, up = _rand(F, N, scale=0.1, seed=1), _rand(F, N, scale=0.1, seed=2)
+    runs = []
+    for rep in range(2):
+        x = x0.clone()
+        a_next = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+        ss = torch.full((M, slots), float("nan"), dtype=torch.float32, device=DEV)
+        ops.gemm(A, W, EPI_RESID_F32, 513, False, out=x, bias=bias, gamma_next=gamma, a_next=a_next, ss_next=ss, ss_slots=slots)
+        x_ref = x0 + _ref_mm(A, W) + bias
+        assert ops.rel_err(x, x_ref) < 1e-5
+        assert ops.rel_err(ss.sum(-1), (x_ref * x_ref).sum(-1)) < 1e-5
+        assert ops.rel_err(a_next, x_ref * gamma) < BF16_TOL
+        out = torch.empty(M, F, dtype=torch.bfloat16, device=DEV)
+        ops.gemm(a_next, ops.interleave_gate_up(gate, up), EPI_SWIGLU_BF16, 513, False, out=out, row_ss=ss,
+                 inv_width=1.0 / N, eps=eps, ss_slots=slots)
+        xn = x_ref * torch.rsqrt((x_ref * x_ref).mean(-1, keepdim=True) + eps) * gamma
+        ref = torch.nn.functional.silu(xn @ gate.float().t()) * (xn @ up.float().t())
+        err = ops.rel_err(out, ref)
+        print(f"pair fused_rmsnorm_chain M={M} N={N}: rel={err:.2e}")
+        assert err < 1.5 * BF16_TOL
+        runs.append((x, ss, a_next, out))
+    for a, b in zip(runs[0], runs[1]):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("bn", [128, 513, 517])
 @pytest.mark.parametrize("M,N,K", [(256, 768, 8960), (64, 768, 1536), (257, 1024, 4096), (200, 1536, 1536)])
 def test_gemm_splitk_partials_deterministic(bn, M, N, K):

@@ -206,6 +206,39 @@ def _rows(inp, idx):
 
 
 @pytest.mark.skipif(os.environ.get("VLASER_SKIP_FULL", "0") == "1", reason="full-size parity skipped by env")
+@pytest.mark.parametrize("opt", ["fuse_norm_llm", "half_sm"])
+def test_full_size_optional_schedules_vs_oracle(opt, capsys):
+    """Schedules that are measured but off by default, at full size and a batch large enough to take them (B = 16: the
+    LLM prefill on the CTA-pair kernel, 64 action rows... the o / gate-up / down launches of a denoise step at one tile per
+    CTA pair): `fuse_norm_llm` (RMSNorm of the LLM prefill fused across the GEMM chain, transposed read-modify-write
+    epilogue + per-row partial sums of squares) and `half_sm` (half-SM variant of the pair kernel). Same bar as the
+    default schedule: <= 1e-2 against the fp32 oracle pre- and post-clamp, bit-identical from call to call."""
+    from vlaser_b200.config import PRESETS
+    cfg = PRESETS["vlaser_2b_bridge"]().with_(final_action_clip_value=None)
+    sd = random_state_dict(cfg, 0)
+    B = 64 if opt == "half_sm" else 16
+    inp = make_inputs(cfg, B, 7)
+    for k in ("pixel_values", "proprios", "noise"):
+        inp[k] = inp[k].bfloat16().float()
+    base = _run(_policy(cfg, sd, B), inp)
+    pol = _policy(cfg, sd, B, **{opt: 1})
+    got = _run(pol, inp)
+    assert torch.equal(_run(pol, inp), got), "repeated calls must agree bit for bit"
+    rows = [0, B // 2 - 1, B - 1]
+    ref = O.infer_action(cfg, sd, **{k: v for k, v in _rows(inp, rows).items()})
+    worst = 0.0
+    for i, b in enumerate(rows):
+        worst = max(worst, max_err(got[b], ref[i]), max_err(got[b].clamp(-1, 1), ref[i].clamp(-1, 1)))
+    with capsys.disabled():
+        print(f"\n[{opt}=1, B={B}] max-abs vs fp32 oracle {worst:.3e}; vs the default schedule {max_err(got, base):.3e}")
+    assert worst <= ACTION_TOL
+    if opt == "half_sm":
+        assert torch.equal(got, base), "same splits, same summation order: the half-SM kernels change no bit"
+    else:
+        assert not torch.equal(got, base), "the fused chain rounds the operand before the row scale: the option did not take"
+
+
+@pytest.mark.skipif(os.environ.get("VLASER_SKIP_FULL", "0") == "1", reason="full-size parity skipped by env")
 @pytest.mark.parametrize("preset,B", [("vlaser_2b_bridge", 64), ("vlaser_2b_fractal", 64), ("vlaser_2b_bridge", 128)])
 def test_full_size_b64_default_schedule_vs_oracle(preset, B, capsys):
     """The benched configuration itself (BASELINE configs[1] / [2] shapes: full-size 2B, B = 64, every option at its

@@ -44,7 +44,7 @@ class GemmArgs(C.Structure):
         ("gamma_next", C.c_void_p), ("a_next", C.c_void_p), ("lda_next", C.c_int32), ("ss_next", C.c_void_p),
         ("tile_counters", C.c_void_p), ("row_ss", C.c_void_p), ("inv_width", C.c_float), ("eps", C.c_float),
         ("stages", C.c_int32), ("pair", C.c_int32), ("tma_out", C.c_int32),
-        ("partial", C.c_void_p), ("partial_stride", C.c_int64), ("partial_splits", C.c_void_p),
+        ("partial", C.c_void_p), ("partial_stride", C.c_int64), ("partial_splits", C.c_void_p), ("ss_slots", C.c_int32),
     ]
 
 

@@ -130,6 +130,10 @@ struct Engine {
   // squares slot per norm site [(steps+1)][2*layers+1][ss_rows], zeroed once per call; split-K tile counters
   float* ss = nullptr;
   int ss_rows = 0;
+  // LLM prefill with RMSNorm fused across the GEMM chain (option fuse_norm_llm): row sums of squares of the prefix stream
+  // as partial sums per (256-column tile, column half) of the producing projection, [2 sites][rows][hidden / 128]
+  float* llm_ss = nullptr;
+  int llm_ss_slots = 0;
   size_t ss_floats = 0;
   int* tile_ctr = nullptr;
   // persistent expert-stream kernel (expert.cu): per-layer operand table and one grid-barrier counter per pass
@@ -219,6 +223,13 @@ struct Engine {
                                // gate/up weights (mainloop 4.3 -> 8.4 us), 4 epilogue warps issue the partial-tile TMA stores in
                                // twice the time, and the denoise attention capped at 128 registers to make room loses 1.8 us:
                                // 38.9 vs 37.7 ms per call. Off.
+  int fuse_norm_llm = 0;       // 1: LLM prefill at large M (all four projections on the CTA-pair kernel): the o / down projections
+                               // write the next GEMM's operand bf16(x * gamma) and the row sums of squares themselves, the q|k|v /
+                               // gate-up epilogues scale their accumulator rows by rstd -- the 2 RMSNorm launches per layer go.
+                               // Measured at B = 64 (profiles/r02s3j): the 55 norm launches (0.57 ms) disappear, but the read-
+                               // modify-write epilogue of the last tile is 12 us against 3-5 for the L2-side reduce-add (o + 7 us,
+                               // down + 6.6 us per launch) and the gate/up tile loop slows from 7.98 to 8.67 us per tile with the
+                               // per-row statistics loads: 25.4 vs 24.7 ms for ViT + prefill, 37.9 vs 37.1 ms per call. Off.
   int known_splits = 1;        // 1: norm launches behind a static-M split-K projection get the split count from the host
   int fuse_tail = 0;           // 1: the o / down projections of the action expert at one 256-row tile finish the residual update +
                                // the following RMSNorm themselves behind an in-kernel grid barrier (EpiParams::tail_ctr): two of
@@ -495,6 +506,8 @@ int engine_build(Engine& e) {
   e.ss_rows = std::max(arow, e.Bc);
   e.ss_floats = (size_t)(c.num_inference_steps + 1) * (2 * c.layers + 1) * e.ss_rows;
   VL_TRY(e.alloc(&e.ss, e.ss_floats));
+  e.llm_ss_slots = c.hidden / 128;
+  VL_TRY(e.alloc(&e.llm_ss, (size_t)2 * e.Bc * e.S * e.llm_ss_slots));
   VL_TRY(e.alloc(&e.tile_ctr, 4096));
   VL_TRY(e.alloc(&e.trace, Engine::TRACE_MAX * 16));
   {
@@ -1096,7 +1109,12 @@ struct Run {
   int block_pre(LlmLayer& L, float* x, Act& xn, bf16* qout, int M, const int* M_dev, int hid, const int* pos,
                 const int* kvrow, int layer, const L2Prefetch* pf = nullptr) {
     tr_layer = layer;
-    if (take_tail(x, L.ln_in)) {
+    EpiParams qe = rope_ep(qout, L.bqkv, pos, kvrow, layer);
+    if (llm_fused_in && x == e.xv) {
+      // fused chain: the down projection of the previous layer left bf16(x * ln_in) in xn and the row sums of squares in
+      // site 1; the q|k|v epilogue scales its accumulator rows by rstd
+      llm_consumer(qe, 1, hid);
+    } else if (take_tail(x, L.ln_in)) {
       // the down projection of the previous layer already left RMSNorm(x) * ln_in in xn
     } else if (!(abl & 1)) {
       SplitKPartials spt;
@@ -1105,7 +1123,23 @@ struct Run {
     }
     if (abl & 2) return 0;
     tr_name = "qkv";
-    return gemm(xn, L.qkv, M, M_dev, EPI_QKV_ROPE, rope_ep(qout, L.bqkv, pos, kvrow, layer));
+    return gemm(xn, L.qkv, M, M_dev, EPI_QKV_ROPE, qe);
+  }
+  // ---- LLM prefill, RMSNorm fused across the GEMM chain (see Engine::fuse_norm_llm)
+  bool llm_fused = false;     // this prefill runs fused (set by prefill())
+  bool llm_fused_in = false;  // xn / site 1 hold the operand and statistics of the coming q|k|v projection
+  void llm_consumer(EpiParams& ep, int site, int hid) {
+    ep.row_ss = e.llm_ss + (size_t)site * e.Bc * e.S * e.llm_ss_slots;
+    ep.ss_slots = e.llm_ss_slots;
+    ep.inv_width = 1.0f / (float)hid;
+    ep.eps = e.c.rms_eps;
+  }
+  void llm_producer(EpiParams& ep, Act& xn, const float* gamma, int site, int hid) {
+    ep.a_next = xn.p;
+    ep.lda_next = hid;
+    ep.gamma_next = gamma;
+    ep.ss_next = e.llm_ss + (size_t)site * e.Bc * e.S * e.llm_ss_slots;
+    ep.ss_slots = e.llm_ss_slots;
   }
   int block_post(LlmLayer& L, float* x, Act& xn, Act& ao, Act& act, int M, const int* M_dev, int hid, int mlp,
                  int splits, const CUtensorMap* x_otm = nullptr, const L2Prefetch* pf = nullptr,
@@ -1114,6 +1148,23 @@ struct Run {
     eo.out = x;
     eo.ldo = hid;
     tr_name = "o";
+    const bool fused = llm_fused && M_dev != nullptr && x == e.xv;
+    if (fused) {
+      EpiParams ef = eo;
+      llm_producer(ef, xn, L.ln_post, 0, hid);
+      VL_TRY(gemm(ao, L.o, M, M_dev, EPI_RESID_F32, ef, 1, 0, x_otm));
+      EpiParams eg;
+      eg.out = act.p;
+      eg.ldo = mlp;
+      llm_consumer(eg, 0, hid);
+      tr_name = "gate_up";
+      VL_TRY(gemm(xn, L.gu, M, M_dev, EPI_SWIGLU_BF16, eg, 1, 0, &act.otm));
+      tr_name = "down";
+      EpiParams ed = eo;
+      if (next_gamma) llm_producer(ed, xn, next_gamma, 1, hid);
+      llm_fused_in = next_gamma != nullptr;
+      return gemm(act, L.down, M, M_dev, EPI_RESID_F32, ed, 1, 0, x_otm);
+    }
     if (!abl) tail_offer.gamma = L.ln_post, tail_offer.out = xn.p;
     if (!(abl & 8)) VL_TRY(gemm(ao, L.o, M, M_dev, EPI_RESID_F32, eo, splits > 1 ? std::min(splits, e.xs_o) : 1, 0, x_otm));
     if (take_tail(x, L.ln_post)) {
@@ -1303,6 +1354,11 @@ struct Run {
       VL_CUDA_CHECK(cudaEventRecord(e.side_events[c.layers], main_st));        // fork: xp (proprio encoder) is ready
       VL_CUDA_CHECK(cudaStreamWaitEvent(e.side_stream, e.side_events[c.layers], 0));
     }
+    // RMSNorm fused across the GEMM chain of the prefix stream: only when all four projections run on the CTA-pair kernel
+    // through its TMA / transposed epilogues (the o projection has the fewest tiles)
+    llm_fused = e.fuse_norm_llm && !e.simt && e.pair_gemm && e.tma_epi && !abl && c.hidden % 256 == 0 &&
+                (long long)((cap + 255) / 256) * (c.hidden / 256) >= e.pair_min_tiles;
+    llm_fused_in = false;
     for (int li = 0; li < c.layers; ++li) {
       VL_TRY(block_pre(e.llm[li], e.xv, e.xn, e.q, cap, e.pb.m_tot, c.hidden, e.pb.row_pos, e.pb.row_kvrow, li));
       if (side) {
@@ -1361,7 +1417,8 @@ struct Run {
         VL_TRY(attention_launch(ap, 128, st));
         e.launches++;
       }
-      VL_TRY(block_post(e.llm[li], e.xv, e.xn, e.ao, e.act, cap, e.pb.m_tot, c.hidden, e.mlp_p, 1, &e.xv_otm));
+      VL_TRY(block_post(e.llm[li], e.xv, e.xn, e.ao, e.act, cap, e.pb.m_tot, c.hidden, e.mlp_p, 1, &e.xv_otm, nullptr,
+                        llm_fused ? e.llm[li + 1].ln_in : nullptr));
       if (mega() || side) continue;
       if (e.fuse_norm) VL_TRY(exp_post(li, e.xp, e.xpn, e.aop, e.actp, B, 0, false));
       else VL_TRY(block_post(e.exp[li], e.xp, e.xpn, e.aop, e.actp, B, nullptr, c.hidden_e, e.mlp_e_p, 32, &e.xp_otm));
@@ -1819,7 +1876,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc" || k == "fuse_tail" || k == "decode_chunk" || k == "prefill_tc_long" || k == "attn_small" || k == "rn_small" || k == "known_splits" || k == "half_sm") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc" || k == "fuse_tail" || k == "decode_chunk" || k == "prefill_tc_long" || k == "attn_small" || k == "rn_small" || k == "known_splits" || k == "half_sm" || k == "fuse_norm_llm") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
@@ -1844,6 +1901,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
     else if (k == "attn_small") h->e.attn_small = (int)value;
     else if (k == "known_splits") h->e.known_splits = (int)value;
     else if (k == "half_sm") h->e.half_sm = (int)value;
+    else if (k == "fuse_norm_llm") h->e.fuse_norm_llm = (int)value;
     else if (k == "rn_small") set_resid_norm_small((int)value);
     else if (k == "decode_chunk") h->e.dec_chunk = (value <= 0) ? 0 : std::min(256, std::max(64, (int)value / 64 * 64));
     else if (k == "exp_splits_o") h->e.xs_o = std::max(1, (int)value);
@@ -2229,6 +2287,7 @@ int32_t vlaser_op_gemm(const vlaser_gemm_args* a, void* stream) {
   ep.part = a->partial;
   ep.part_stride = a->partial_stride;
   ep.part_splits = a->partial_splits;
+  ep.ss_slots = a->ss_slots;
   d.stages = a->stages;
   d.pair = a->pair & 1;
   d.n_fast = (a->pair >> 1) & 1;

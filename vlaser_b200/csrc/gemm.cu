@@ -828,6 +828,74 @@ __device__ __forceinline__ void epilogue_rope_pair(const EpiParams& ep, uint8_t*
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Residual epilogue of the pair kernel that also produces the NEXT GEMM's operand (RMSNorm fused across the GEMM chain at
+// large M: the o / down projections of the LLM prefill). The TMA reduce-add epilogue never sees x_new = x_old + acc -- the
+// add happens at L2 --, so the norm needed a launch of its own that read x_new back (34 MB) and wrote bf16 (17 MB): 55
+// launches of ~10 us per call. Here a warp's 32 rows x 128 columns go through its 4 KB tile one 32-column chunk at a time:
+// accumulator rows in (row per lane), then in the transposed domain (8 lanes share a row, 128-byte runs) x_old is read
+// (the loads are issued before the accumulator chunk is fetched), x_new and bf16(x_new * gamma_next) are written, and the
+// squares are summed per row; the row's sum over this warp's 128 columns goes to ITS slot of ss_next[row][ss_slots]
+// (plain store; the consumer adds the slots in order: bit-reproducible, unlike an atomicAdd per tile).
+// ------------------------------------------------------------------------------------------
+template <int BN, int PARTS, class Release>
+__device__ __forceinline__ void epilogue_resid_rmw_pair(const EpiParams& ep, uint8_t* tile, uint32_t taddr, int half,
+                                                        int lane, int row0, int M, int n0, Release&& release) {
+  constexpr int U = BN / 32 / PARTS;
+  const int ch = lane & 7, rsub = lane >> 3;
+  float* x = reinterpret_cast<float*>(ep.out);
+  float ssum[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) ssum[it] = 0.f;
+#pragma unroll 1
+  for (int c = half * U; c < (half + 1) * U; ++c) {
+    const int col = n0 + c * 32 + 4 * ch;
+    float4 xo[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = row0 + it * 4 + rsub;
+      xo[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < M) xo[it] = __ldcg(reinterpret_cast<const float4*>(x + (size_t)r * ep.ldo + col));
+    }
+    float4 bs = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (ep.bias) bs = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+    if (ep.scale) sc = __ldg(reinterpret_cast<const float4*>(ep.scale + col));
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(ep.gamma_next + col));
+    {
+      float v[32];
+      load_acc32(taddr + c * 32, v);
+      if (c == (half + 1) * U - 1) release();
+      stage_row_f32(tile, lane, v);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rl = it * 4 + rsub, r = row0 + rl;
+      float4 v = *reinterpret_cast<const float4*>(tile + rl * 128 + ((ch ^ (rl & 7)) << 4));
+      v.x = (v.x + bs.x) * sc.x, v.y = (v.y + bs.y) * sc.y, v.z = (v.z + bs.z) * sc.z, v.w = (v.w + bs.w) * sc.w;
+      float4 xn = xo[it];
+      xn.x += v.x, xn.y += v.y, xn.z += v.z, xn.w += v.w;
+      if (r < M) {
+        *reinterpret_cast<float4*>(x + (size_t)r * ep.ldo + col) = xn;
+        *reinterpret_cast<uint2*>(ep.a_next + (size_t)r * ep.lda_next + col) =
+            make_uint2(pack_bf16(xn.x * gm.x, xn.y * gm.y), pack_bf16(xn.z * gm.z, xn.w * gm.w));
+        ssum[it] += (xn.x * xn.x + xn.y * xn.y) + (xn.z * xn.z + xn.w * xn.w);
+      }
+    }
+    __syncwarp();
+  }
+  const int slot = (n0 / BN) * PARTS + half;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    float s = ssum[it];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    const int r = row0 + it * 4 + rsub;
+    if (ch == 0 && r < M) ep.ss_next[(size_t)r * ep.ss_slots + slot] = s;
+  }
+}
+
 template <int EPI>
 constexpr int pair_epi_warps() { return EPI == EPI_GELU_BF16 ? 16 : 8; }  // the exact-GELU epilogue is issue-bound at 8
 
@@ -1039,7 +1107,16 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
       const int n0 = n_idx * BN;
       float rstd = 1.f;
-      if (ep.row_ss && row_ok) rstd = rsqrtf(__ldcg(ep.row_ss + row) * ep.inv_width + ep.eps);
+      if (ep.row_ss && row_ok) {
+        float sq;
+        if (ep.ss_slots > 0) {  // partial sums of the producer's column halves, added in slot order
+          sq = 0.f;
+          for (int j = 0; j < ep.ss_slots; ++j) sq += __ldcg(ep.row_ss + (size_t)row * ep.ss_slots + j);
+        } else {
+          sq = __ldcg(ep.row_ss + row);
+        }
+        rstd = rsqrtf(sq * ep.inv_width + ep.eps);
+      }
       float ss = 0.f;
       int part_row0 = -1;
       if (EPI == EPI_RESID_F32 && splits > 1 && ep.part) part_row0 = split * (int)(ep.part_stride / ep.ldo) + (row - lane);
@@ -1068,6 +1145,16 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (lane == 0) mbar_arrive_cluster(tempty0 + as * 8);
           });
           done = released = true;
+        }
+        if constexpr (EPI == EPI_RESID_F32 && BN == 256 && !HALF) {
+          if (!done && ep.a_next && ep.ss_slots > 0) {
+            epilogue_resid_rmw_pair<BN, PARTS>(ep, wbuf, taddr, half, lane, row - lane, M, n0, [&]() {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(tempty0 + as * 8);
+            });
+            done = released = true;
+          }
         }
         if (!done) epilogue_tile<BN, EPI, PARTS>(ep, d.N, taddr, half, row, row_ok, n0, true, false, rstd, ss);
         if (released) {

@@ -51,6 +51,11 @@ struct EpiParams {
   float* ss_next = nullptr;            // [M], zeroed by the caller
   int* tile_counters = nullptr;        // [m_tiles*n_tiles] zero-initialised, self-resetting (split-K only)
   // consumer side (any epilogue): acc is multiplied by rstd[m] before bias / activation.
+  // ss_slots > 0 (CTA-pair kernel, large M: the LLM prefill): the sum of squares of a row is kept as ss_slots partial sums,
+  // one per (256-column tile, column half) of the producing GEMM, written with plain stores by the producer's transposed
+  // read-modify-write epilogue (epilogue_resid_rmw_pair) and added in slot order by the consumer: no atomics, bit-
+  // reproducible. ss_next / row_ss then point at [M][ss_slots].
+  int ss_slots = 0;
   const float* row_ss = nullptr;       // [M] sum of squares of the un-normalised row
   float inv_width = 0.f;               // 1 / hidden width of the normalised row
   float eps = 0.f;
