@@ -16,6 +16,7 @@ ap.add_argument("--only", default="")
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--bn", type=int, default=0, help="force block_n (0 = engine heuristic)")
+ap.add_argument("--epi", type=int, default=-1, help="override the epilogue of bf16-output shapes (0 store, 1 GELU, 2 SiLU): what an epilogue costs")
 ap.add_argument("--pair", type=int, default=1, help="0 single-CTA kernels, 1 CTA-pair kernel + TMA epilogue, 2 pair w/o TMA epilogue")
 a = ap.parse_args()
 B = a.batch
@@ -39,6 +40,8 @@ rows = []
 for name, M, N, K, epi, cnt, splits in SHAPES:
     if a.only and a.only != name:
         continue
+    if a.epi >= 0 and epi in (EPI_STORE_BF16, EPI_GELU_BF16, EPI_SILU_BF16):
+        epi = a.epi
     A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
     W = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
     kw = {}

@@ -130,6 +130,55 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float t = ex2_approx(x * p);           // e^(-2 q(x)); +inf for very negative x -> y = -0
   return __fdividef(x, 1.0f + t);
 }
+// The same function on two elements with the packed FP32 instructions of sm_100 (FMUL2 / FFMA2 / FADD2): 8 FP32 issue
+// slots + 4 MUFU per PAIR instead of 7 + 2 per element. The exact-GELU epilogue of the ViT fc1 GEMM is bound by the issue
+// slots of its epilogue warps, not by MUFU (same tile with SiLU, 2 MUFU + 3 FP32 per element: 96 us; with the scalar form
+// above: 113 us; profiles/r02s3l_fc1_epilogue_cost.txt). Same operations in the same order per element as gelu_erf_fast.
+__device__ __forceinline__ unsigned long long f32x2_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f32x2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long f32x2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// (a, b) <- gelu(a + ba), gelu(b + bb)
+__device__ __forceinline__ void gelu_erf_fast2(float& a, float& b, float ba, float bb) {
+  const unsigned long long x = f32x2_add(f32x2_pack(a, b), f32x2_pack(ba, bb));
+  const unsigned long long sq = f32x2_mul(x, x);
+  float s0, s1;
+  f32x2_unpack(sq, s0, s1);
+  const unsigned long long x2 = f32x2_pack(fminf(s0, 64.0f), fminf(s1, 64.0f));
+  unsigned long long p = f32x2_fma(f32x2_pack(0.0010142630897462368f, 0.0010142630897462368f), x2,
+                                   f32x2_pack(-0.10677572339773178f, -0.10677572339773178f));
+  p = f32x2_fma(p, x2, f32x2_pack(-2.3011212348937988f, -2.3011212348937988f));
+  float e0, e1;
+  f32x2_unpack(f32x2_mul(x, p), e0, e1);
+  const unsigned long long den = f32x2_add(f32x2_pack(ex2_approx(e0), ex2_approx(e1)), f32x2_pack(1.0f, 1.0f));
+  float d0, d1;
+  f32x2_unpack(den, d0, d1);
+  f32x2_unpack(f32x2_mul(x, f32x2_pack(rcp_approx(d0), rcp_approx(d1))), a, b);  // +inf denominators give -0 / +0
+}
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ bool elect_one() {

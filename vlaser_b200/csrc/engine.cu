@@ -213,7 +213,9 @@ struct Engine {
   int attn_small = 1;          // 1: the denoise-step attention (group * H <= 32 query rows) on the kernel that splits the key blocks
                                // between its two warp pairs (attention_small_kernel)
   int prefill_tc_long = 1;     // 1: samples of more than 256 tokens (and the causal text prefill) on the two-pass tcgen05 kernel
-  int gelu_warps = 16;         // epilogue warps of the pair kernel's exact-GELU variant (16 | 8)
+  int gelu_warps = 8;          // epilogue warps of the pair kernel's exact-GELU variant (8 with a 6-stage ring | 16 with 5 stages).
+                               // With the packed-FP32 GELU (gelu_erf_fast2) 8 warps win: ViT 11.50 vs 11.62 ms sustained
+                               // (profiles/r02s3n); with the scalar form the two were equal
   int pair_bn128 = 1;          // 1: 256 x 128 pair tiles for the one-row-tile split-K projections (see Run::gemm)
   int den_chains = 1;          // sub-batch chains of the denoise steps (1 | 2), see Run::denoise_all
   int half_sm = 0;             // 1: one-tile-per-CTA pair launches at a static M <= 256 on the half-SM variant of the pair kernel

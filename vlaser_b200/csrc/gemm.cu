@@ -564,10 +564,18 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiParams& ep, const CUt
         float v[32];
         load_acc32(taddr + u * 64 + q * 32, v);
         scale_rows(v);
-        if (ep.bias) add_vec32(v, ep.bias + col0);
         if constexpr (EPI == EPI_GELU_BF16) {
+          // bias + exact GELU on pairs (packed FP32 instructions, see gelu_erf_fast2)
+          const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+          for (int i = 0; i < 8; ++i) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ep.bias) b = __ldg(b4 + i);
+            gelu_erf_fast2(v[4 * i], v[4 * i + 1], b.x, b.y);
+            gelu_erf_fast2(v[4 * i + 2], v[4 * i + 3], b.z, b.w);
+          }
+        } else {
+          if (ep.bias) add_vec32(v, ep.bias + col0);
         }
         if constexpr (EPI == EPI_SILU_BF16) {
 #pragma unroll
