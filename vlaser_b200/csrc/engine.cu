@@ -228,10 +228,12 @@ struct Engine {
   int fuse_norm_llm = 0;       // 1: LLM prefill at large M (all four projections on the CTA-pair kernel): the o / down projections
                                // write the next GEMM's operand bf16(x * gamma) and the row sums of squares themselves, the q|k|v /
                                // gate-up epilogues scale their accumulator rows by rstd -- the 2 RMSNorm launches per layer go.
-                               // Measured at B = 64 (profiles/r02s3j): the 55 norm launches (0.57 ms) disappear, but the read-
-                               // modify-write epilogue of the last tile is 12 us against 3-5 for the L2-side reduce-add (o + 7 us,
-                               // down + 6.6 us per launch) and the gate/up tile loop slows from 7.98 to 8.67 us per tile with the
-                               // per-row statistics loads: 25.4 vs 24.7 ms for ViT + prefill, 37.9 vs 37.1 ms per call. Off.
+                               // Measured at B = 64 (profiles/r02s3j, r02s3o: both schedules traced in one run): the 55 norm
+                               // launches (21.7 us per layer) disappear, but every GEMM around them gets slower -- o + 9.4 us and
+                               // down + 5.6 us (the read-modify-write epilogue of the last tile is 12 us against 3-5 for the L2-side
+                               // reduce-add), gate/up + 10 us and q|k|v + 3.7 us (row statistics + row scale in epilogues that
+                               // already pace their tile loops) -- 36.6 us per layer: 25.4 vs 24.7 ms for ViT + prefill sustained,
+                               // 37.9 vs 37.1 ms per call. Off.
   int known_splits = 1;        // 1: norm launches behind a static-M split-K projection get the split count from the host
   int fuse_tail = 0;           // 1: the o / down projections of the action expert at one 256-row tile finish the residual update +
                                // the following RMSNorm themselves behind an in-kernel grid barrier (EpiParams::tail_ctr): two of
