@@ -31,6 +31,9 @@ SHAPES = [  # name, M, N, K, epi, count per call, max_splits
     ("act_qkv", MA, 2048, 768, EPI_QKV_ROPE, 280, 1), ("act_o", MA, 768, 1536, EPI_RESID_F32, 280, 32),
     ("act_gu", MA, 17920, 768, EPI_SWIGLU_BF16, 280, 1), ("act_down", MA, 768, 8960, EPI_RESID_F32, 280, 32),
     ("act_enc", MA, 768, 768, EPI_SILU_BF16, 20, 1),
+    # the same large shapes behind the plain bf16 store: what the fused epilogue costs (not part of a call: count 0)
+    ("llm_gu_st", MP, 17920, 1536, EPI_STORE_BF16, 0, 1), ("llm_qkv_st", MP, 2048, 1536, EPI_STORE_BF16, 0, 1),
+    ("fc2_st", MV, 1024, 4096, EPI_STORE_BF16, 0, 1), ("llm_down_st", MP, 1536, 8960, EPI_STORE_BF16, 0, 1),
 ]
 dev = "cuda"
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -82,5 +85,5 @@ for name, M, N, K, epi, cnt, splits in SHAPES:
     total += t * cnt
     rows.append((name, M, N, K, bn, t, tf, gbs, cnt, t * cnt))
 for r in rows:
-    print("%-9s M=%6d N=%6d K=%5d bn=%3d  %8.3f ms  %7.1f TF/s  %7.0f GB/s(in)  x%3d = %7.2f ms (%4.1f%%)" % (*r, 100 * r[-1] / total))
+    print("%-11s M=%6d N=%6d K=%5d bn=%3d  %8.3f ms  %7.1f TF/s  %7.0f GB/s(in)  x%3d = %7.2f ms (%4.1f%%)" % (*r, 100 * r[-1] / max(total, 1e-9)))
 print("total GEMM ms per call (cold L2): %.2f" % total)
