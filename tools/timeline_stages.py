@@ -57,7 +57,10 @@ for title, sel in (("ViT", [r for r in recs if r["kind"].startswith("vit") and r
     print(f"{'launch':26s} " + " ".join(f"{s:>10s}" for s in SLOTS))
     for r in sel:
         vals = " ".join(f"{(float(v) - t0) / 1e3:10.2f}" if v > 0 else f"{'-':>10s}" for v in r["t"][:7])
-        print(f"{(r['kind'] + ' L' + str(r['layer']) + (' [side]' if r['side'] else '')):26s} {vals}")
+        fine = ""
+        if r["kind"] == "attention_tc":  # kernel-specific stamps 8..15: first two tiles of softmax group 0
+            fine = "   tile0 p/o/read/stored, tile2 ...: " + " ".join(f"{(float(v) - t0) / 1e3:.2f}" for v in r["t"][8:16] if v > 0)
+        print(f"{(r['kind'] + ' L' + str(r['layer']) + (' [side]' if r['side'] else '')):26s} {vals}{fine}")
 main = [r for r in recs if not r["side"] and r["t"][1] > 0]
 cost = defaultdict(list)
 for r, nx in zip(main[:-1], main[1:]):

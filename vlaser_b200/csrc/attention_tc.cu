@@ -821,32 +821,37 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    // The whole warp walks the items; lane 0 waits and arms the barriers, then one lane per box issues the loads -- the
+    // 4 x ceil(L / 32) K / V boxes + 2 query boxes of an item took one thread 3.8 us (0.27 us per issue, in-situ stamps
+    // profiles/r02s3q), in front of the first score tile of a CTA that owns exactly one item
+    {
       int ic = 0, tcn = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         PT_ITEM(item)
         const int nblk = (L + 31) >> 5;
         const int krow = (int)(p.kv_layer_row0 + (long long)g * p.kv_rows) + p.kv_start[b];
-        mbar_wait(kv_empty, (ic & 1) ^ 1);
-        mbar_arrive_expect_tx(kv_full, (uint32_t)(4 * nblk * 4096));
-        for (int j = 0; j < nblk; ++j) {
-          tma_load_2d(Ks + j * 4096, &tmK, kv_full, 0, krow + j * 32);
-          tma_load_2d(Ks + PT_HALF_BYTES + j * 4096, &tmK, kv_full, 64, krow + j * 32);
+        if (lane == 0) {
+          mbar_wait(kv_empty, (ic & 1) ^ 1);
+          mbar_arrive_expect_tx(kv_full, (uint32_t)(4 * nblk * 4096));
         }
-        for (int j = 0; j < nblk; ++j) {
-          tma_load_2d(Vs + j * 4096, &tmV, kv_full, 0, krow + j * 32);
-          tma_load_2d(Vs + PT_HALF_BYTES + j * 4096, &tmV, kv_full, 64, krow + j * 32);
+        __syncwarp();
+        if (lane < 4 * nblk) {  // lane = 4 j + {K lo, K hi, V lo, V hi}
+          const int j = lane >> 2, hi = lane & 1, isv = (lane >> 1) & 1;
+          tma_load_2d((isv ? Vs : Ks) + hi * PT_HALF_BYTES + j * 4096, isv ? &tmV : &tmK, kv_full, hi * 64, krow + j * 32);
         }
         ++ic;
         const int q0 = p.q_start[b];
         for (int ti = 0; ti < n_tiles; ++ti, ++tcn) {
           const int t = sp + ti * tsplit;
           const int slot = tcn % PT_QSLOTS;
-          mbar_wait(&q_empty[slot], ((tcn / PT_QSLOTS) & 1) ^ 1);
           uint8_t* qd = Qs + slot * PT_Q_BYTES;
-          mbar_arrive_expect_tx(&q_full[slot], (uint32_t)(2 * rows_tile * 128));
-          tma_load_3d(qd, &tmQ, &q_full[slot], 0, g * group, q0 + t * TOK);
-          tma_load_3d(qd + VT_TILE_BYTES, &tmQ, &q_full[slot], 64, g * group, q0 + t * TOK);
+          if (lane == 0) {
+            mbar_wait(&q_empty[slot], ((tcn / PT_QSLOTS) & 1) ^ 1);
+            mbar_arrive_expect_tx(&q_full[slot], (uint32_t)(2 * rows_tile * 128));
+          }
+          __syncwarp();
+          if (lane < 2) tma_load_3d(qd + lane * VT_TILE_BYTES, &tmQ, &q_full[slot], lane * 64, g * group, q0 + t * TOK);
+          if (tcn == 0) trace_stamp(tr, 2);  // K / V and the first query tile are on their way
         }
       }
     }
@@ -863,6 +868,7 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         const uint32_t idesc_s = make_idesc_bf16(128, Lp);
         mbar_wait(kv_full, ic & 1);
         tc_fence_after();
+        if (ic == 0) trace_stamp(tr, 3);  // K / V landed
         auto issue_s = [&](int tc_i) {
           const int slot = tc_i & 1, qs = tc_i % PT_QSLOTS;
           const uint32_t ph = (tc_i >> 1) & 1;
@@ -997,9 +1003,12 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[grp]);
+        long long* trg = (warp == 2 && tc_i <= 2) ? tr : nullptr;  // group 0: its first two tiles
+        trace_stamp(trg, tc_i == 0 ? 8 : 12);    // probabilities written
         const float inv = 1.f / sum;
         mbar_wait(&o_full[grp], ph);
         tc_fence_after();
+        trace_stamp(trg, tc_i == 0 ? 9 : 13);    // O = P V complete
         // ---- O / sum -> bf16 -> this row of the transposition tile (the query slot is dead: S is complete)
 #pragma unroll 1
         for (int c0 = 0; c0 < 4; c0 += 2) {
@@ -1024,6 +1033,7 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[grp]);  // the slot's TMEM columns may take the group's next scores
+        trace_stamp(trg, tc_i == 0 ? 10 : 14);   // O read out of TMEM
         // ---- row-contiguous stores: 16 lanes x 16 B = one 256-byte row, two rows per instruction
         const unsigned ok_mask = __ballot_sync(0xffffffffu, row_ok);
 #pragma unroll 1
@@ -1039,6 +1049,7 @@ prefill_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         (void)tok;
         (void)hh;
         named_bar_sync(1 + grp, 128);  // every warp of the group has read its rows out of the slot
+        trace_stamp(trg, tc_i == 0 ? 11 : 15);   // tile stored
         if (gtid == 0) mbar_arrive(&q_empty[tc_i % PT_QSLOTS]);
       }
       tcn += n_tiles;

@@ -138,7 +138,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    // (first ring fill: one lane per stage, see the pair kernel; steady state: lane 0)
+    {
       int stage = 0;
       uint32_t phase = 0;
       int t = blockIdx.x;
@@ -162,41 +163,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (!d.M_dev) {
         // Weights do not depend on the previous kernel: fill the ring's B halves before the PDL wait,
         // then add the A halves (activations written by the previous kernel) after it.
-        int pre_n[MAX_STAGES], pre_m[MAX_STAGES], pre_kb[MAX_STAGES];
+        int my_n = 0, my_m = 0, my_kb = 0;
+        bool mine = false;
         int npre = 0;
         while (have && npre < STAGES) {
-          pre_n[npre] = tc.n_idx;
-          pre_m[npre] = tc.m_idx;
-          pre_kb[npre] = kb;
-          uint8_t* sa = smem + npre * Cfg::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[npre], Cfg::STAGE_BYTES);
-          tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[npre], kb * BLOCK_K, tc.n_idx * BLOCK_N);
+          if (lane == npre) mine = true, my_n = tc.n_idx, my_m = tc.m_idx, my_kb = kb;
           ++npre;
           advance();
         }
-        trace_max(d.trace, 15);
+        if (mine) {
+          mbar_arrive_expect_tx(&full_bar[lane], Cfg::STAGE_BYTES);
+          tma_load_2d(smem + lane * Cfg::STAGE_BYTES + Cfg::A_BYTES, &tmB, &full_bar[lane], my_kb * BLOCK_K, my_n * BLOCK_N);
+        }
+        if (lane == 0) trace_max(d.trace, 15);
         pdl_wait();
         trace_stamp(tr, 1);
-        for (int i = 0; i < npre; ++i)
-          tma_load_2d(smem + i * Cfg::STAGE_BYTES, &tmA, &full_bar[i], pre_kb[i] * BLOCK_K, pre_m[i] * BLOCK_M);
-        (void)pre_n;
+        if (mine) tma_load_2d(smem + lane * Cfg::STAGE_BYTES, &tmA, &full_bar[lane], my_kb * BLOCK_K, my_m * BLOCK_M);
         stage = npre;
         if (stage == STAGES) {
           stage = 0;
           phase = 1;
         }
       }
-      while (have) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-        tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, tc.m_idx * BLOCK_M);
-        tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, tc.n_idx * BLOCK_N);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+      if (lane == 0) {
+        while (have) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, tc.m_idx * BLOCK_M);
+          tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, tc.n_idx * BLOCK_N);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+          advance();
         }
-        advance();
       }
     }
   } else if (warp == 1) {
@@ -995,7 +996,11 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) ================================
-    if (lane == 0) {
+    // The whole warp walks the (tile, k-block) cursor; the FIRST ring fill is issued by one lane per stage -- a TMA issue
+    // costs a thread 0.25 - 0.35 us at the head of a launch (prologue stamps, profiles/r02s3g: six stages took 1.4 - 2.2 us
+    // from one thread), and a CTA of the denoise chain that could only enter when the previous launch left its SM is
+    // waited for exactly there. The steady state stays with lane 0.
+    {
       const uint32_t full0 = mapa_u32(smem_u32(full_bar), 0);  // the leader's full barriers
       int stage = 0;
       uint32_t phase = 0;
@@ -1022,21 +1027,22 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if (!d.M_dev) {
         // Weights do not depend on the previous kernel: the W halves of the first ring fill go out before the
         // dependent-launch wait, the A halves (activations written by the previous kernel) after it.
-        int pre_kb[PAIR_MAX_STAGES], pre_row[PAIR_MAX_STAGES];
+        int my_kb = 0, my_row_a = 0, my_row_b = 0;
+        bool mine = false;
         int npre = 0;
         while (have && npre < STAGES) {
-          pre_kb[npre] = kb;
-          pre_row[npre] = row_a;
-          if (leader) mbar_arrive_expect_tx(&full_bar[npre], STAGE_TX);
-          tma_load_2d_pair(smem + npre * SLOT + PAIR_A_BYTES, &tmB, full0 + npre * 8, kb * BLOCK_K, row_b);
+          if (lane == npre) mine = true, my_kb = kb, my_row_a = row_a, my_row_b = row_b;
           ++npre;
           advance();
         }
-        trace_max(d.trace, 15);
+        if (mine) {
+          if (leader) mbar_arrive_expect_tx(&full_bar[lane], STAGE_TX);
+          tma_load_2d_pair(smem + lane * SLOT + PAIR_A_BYTES, &tmB, full0 + lane * 8, my_kb * BLOCK_K, my_row_b);
+        }
+        if (lane == 0) trace_max(d.trace, 15);
         pdl_wait();
         trace_stamp(tr, 1);
-        for (int i = 0; i < npre; ++i)
-          tma_load_2d_pair(smem + i * SLOT, &tmA, full0 + i * 8, pre_kb[i] * BLOCK_K, pre_row[i]);
+        if (mine) tma_load_2d_pair(smem + lane * SLOT, &tmA, full0 + lane * 8, my_kb * BLOCK_K, my_row_a);
         stage = npre;
         if (stage == STAGES) {
           stage = 0;
@@ -1045,17 +1051,21 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       } else {
         trace_stamp(tr, 1);
       }
-      while (have) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * SLOT;
-        if (leader) mbar_arrive_expect_tx(&full_bar[stage], STAGE_TX);
-        tma_load_2d_pair(sa, &tmA, full0 + stage * 8, kb * BLOCK_K, row_a);
-        tma_load_2d_pair(sa + PAIR_A_BYTES, &tmB, full0 + stage * 8, kb * BLOCK_K, row_b);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+      if (lane < 2) {
+        // steady state: lane 0 loads the A half, lane 1 the W half of a stage -- ONE instruction with two active lanes
+        // instead of two issues in a row from one thread
+        const CUtensorMap* my_map = lane ? &tmB : &tmA;
+        const uint32_t my_off = lane ? PAIR_A_BYTES : 0u;
+        while (have) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader && lane == 0) mbar_arrive_expect_tx(&full_bar[stage], STAGE_TX);
+          tma_load_2d_pair(smem + stage * SLOT + my_off, my_map, full0 + stage * 8, kb * BLOCK_K, lane ? row_b : row_a);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+          advance();
         }
-        advance();
       }
     }
   } else if (warp == 1) {
