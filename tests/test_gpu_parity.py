@@ -206,6 +206,26 @@ def _rows(inp, idx):
 
 
 @pytest.mark.skipif(os.environ.get("VLASER_SKIP_FULL", "0") == "1", reason="full-size parity skipped by env")
+def test_ln_overlap_changes_no_bit():
+    """Option ln_overlap (default on): the LayerNorm launches of the ViT run under the residual GEMM in front of them,
+    released row block by row block through completion counters instead of waiting for the GEMM to finish. Same kernels,
+    same arithmetic: the actions equal the serial schedule bit for bit (full-size 2B, B = 16: the ViT GEMMs take the
+    CTA-pair kernel that reports the blocks), from call to call as well."""
+    from vlaser_b200.config import PRESETS
+    cfg = PRESETS["vlaser_2b_bridge"]()
+    sd = random_state_dict(cfg, 0)
+    B = 16
+    inp = make_inputs(cfg, B, 11)
+    on = _policy(cfg, sd, B)
+    a1 = _run(on, inp, dtype=torch.bfloat16)
+    a2 = _run(on, inp, dtype=torch.bfloat16)
+    off = _policy(cfg, sd, B, ln_overlap=0)
+    a0 = _run(off, inp, dtype=torch.bfloat16)
+    assert torch.equal(a1, a2) and torch.equal(a1, a0)
+    assert torch.isfinite(a1).all()
+
+
+@pytest.mark.skipif(os.environ.get("VLASER_SKIP_FULL", "0") == "1", reason="full-size parity skipped by env")
 @pytest.mark.parametrize("opt", ["fuse_norm_llm", "half_sm"])
 def test_full_size_optional_schedules_vs_oracle(opt, capsys):
     """Schedules that are measured but off by default, at full size and a batch large enough to take them (B = 16: the

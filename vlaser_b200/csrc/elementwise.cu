@@ -16,7 +16,8 @@ template <int VPL, bool RMS, bool GATHER>
 __global__ void __launch_bounds__(128) norm_kernel(float* __restrict__ x, const float* __restrict__ gamma,
                                                    const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                                    int rows, const int* __restrict__ rows_dev, float eps, int g,
-                                                   int C, const L2Prefetch pf, long long* trace) {
+                                                   int C, const L2Prefetch pf, long long* trace,
+                                                   const RowBlocksReady ready = RowBlocksReady()) {
   pdl_launch_dependents();
   long long* tr = (blockIdx.x == 0 && threadIdx.x == 0) ? trace : nullptr;
   trace_stamp(tr, 0);
@@ -32,7 +33,7 @@ __global__ void __launch_bounds__(128) norm_kernel(float* __restrict__ x, const 
       }
     }
   }
-  pdl_wait();
+  if (ready.ctr == nullptr) pdl_wait();  // (with `ready` the rows are released block by block, see RowBlocksReady)
   trace_stamp(tr, 1);
   constexpr int W = VPL * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -40,6 +41,24 @@ __global__ void __launch_bounds__(128) norm_kernel(float* __restrict__ x, const 
   // (a device-resident row count comes with a capped grid: the warps stride over the live rows instead of launching one
   // warp per row of the capacity, most of which would only read the count and exit)
   for (int row = blockIdx.x * 4 + warp; row < nrows; row += gridDim.x * 4) {
+  if (ready.ctr) {
+    if (lane == 0) {
+      const int* c = ready.ctr + (row >> 8);
+      int v;
+      long long t0 = 0;
+      while (true) {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+        if (v >= ready.expect) break;
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > 2000000000LL) {  // the producer never reported this block: flag the call, go on
+          if (ready.err) atomicExch(ready.err, NORM_ERR_READY_TIMEOUT);
+          break;
+        }
+        __nanosleep(100);
+      }
+    }
+    __syncwarp();
+  }
   float4 v[VPL];
   if constexpr (GATHER) {
     // row = (img, r2, c2) of the pixel-shuffled grid; source = 4 ViT tokens (CLS skipped)
@@ -271,7 +290,8 @@ template <bool RMS, bool GATHER>
 int norm_dispatch(float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows,
                   const int* rows_dev, int width, float eps, int g, int C, cudaStream_t stream,
                   const L2Prefetch& pf = L2Prefetch(), long long* trace = nullptr,
-                  const SplitKPartials& sp = SplitKPartials()) {
+                  const SplitKPartials& sp = SplitKPartials(), const RowBlocksReady& ready = RowBlocksReady()) {
+  VL_CHECK(!ready.ctr || (!GATHER && !sp.part && !rows_dev), "norm: row-block release needs the plain kernel at a static row count");
   VL_CHECK(!(GATHER && sp.part), "norm: the pixel-shuffle gather variant does not take split-K partials");
   if constexpr (!GATHER) {
     if (sp.part) return resid_norm_launch<RMS>(x, gamma, beta, out, rows, rows_dev, width, eps, sp, stream, trace);
@@ -282,7 +302,7 @@ int norm_dispatch(float* x, const float* gamma, const float* beta, __nv_bfloat16
   const int grid = rows_dev ? std::min((rows + 3) / 4, 8 * 148) : (rows + 3) / 4;
 #define VL_NORM_CASE(V)                                                                                          \
   case V:                                                                                                        \
-    VL_CUDA_CHECK(launch_kernel(norm_kernel<V, RMS, GATHER>, dim3(grid), dim3(128), 0, stream, x, gamma, beta, out, rows, rows_dev, eps, g, C, pf, trace));       \
+    VL_CUDA_CHECK(launch_kernel(norm_kernel<V, RMS, GATHER>, dim3(grid), dim3(128), 0, stream, x, gamma, beta, out, rows, rows_dev, eps, g, C, pf, trace, ready)); \
     break;
   switch (width / 128) {
     VL_NORM_CASE(1) VL_NORM_CASE(2) VL_NORM_CASE(3) VL_NORM_CASE(4) VL_NORM_CASE(6) VL_NORM_CASE(8)
@@ -759,14 +779,14 @@ __global__ void __launch_bounds__(256) decode_advance_kernel(TextGenBuffers g, c
 
 // ==========================================================================================
 int layernorm_launch(float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows, int width,
-                     float eps, ShuffleGather sg, cudaStream_t stream, const SplitKPartials* sp) {
+                     float eps, ShuffleGather sg, cudaStream_t stream, const SplitKPartials* sp, const RowBlocksReady* ready) {
   if (sg.grid > 0) {
     VL_CHECK(width == 4 * sg.channels && sg.channels % 4 == 0 && sg.grid % 2 == 0, "layernorm gather: bad shape");
     VL_CHECK(!sp || !sp->part, "layernorm gather: reduce the split-K partials first (splitk_reduce_launch)");
     return norm_dispatch<false, true>(x, gamma, beta, out, rows, nullptr, width, eps, sg.grid, sg.channels, stream);
   }
   return norm_dispatch<false, false>(x, gamma, beta, out, rows, nullptr, width, eps, 0, 0, stream, L2Prefetch(), nullptr,
-                                     sp ? *sp : SplitKPartials());
+                                     sp ? *sp : SplitKPartials(), ready ? *ready : RowBlocksReady());
 }
 
 int rmsnorm_launch(float* x, const float* gamma, __nv_bfloat16* out, int rows, const int* rows_dev, int width,

@@ -28,8 +28,19 @@ struct SplitKPartials {
                                // trip less on the dependent chain of the action expert)
 };
 void set_resid_norm_small(int on);  // measurement switch, see elementwise.cu
+// `ready` (optional, plain LayerNorm of a static row count only): row-block completion counters of the residual GEMM this
+// launch is the programmatic dependent of (EpiParams::done_ctr). The kernel then does NOT wait for the GEMM to finish: the
+// warp of a row waits until ready[row / 256] has reached `ready_expect` and normalises the row while the GEMM is still
+// working on later row blocks.
+struct RowBlocksReady {
+  const int* ctr = nullptr;
+  int expect = 0;
+  int* err = nullptr;  // receives NORM_ERR_READY_TIMEOUT if a counter never arrives (~1 s)
+};
+constexpr int NORM_ERR_READY_TIMEOUT = 0x7ffffff3;
 int layernorm_launch(float* x, const float* gamma, const float* beta, __nv_bfloat16* out, int rows, int width,
-                     float eps, ShuffleGather sg, cudaStream_t stream, const SplitKPartials* sp = nullptr);
+                     float eps, ShuffleGather sg, cudaStream_t stream, const SplitKPartials* sp = nullptr,
+                     const RowBlocksReady* ready = nullptr);
 // x[row] += sum of the partials (no norm): for consumers of the residual stream that are not a plain norm launch
 int splitk_reduce_launch(float* x, int rows, const int* rows_dev, int width, const SplitKPartials& sp, cudaStream_t stream);
 // Optional HBM -> L2 prefetch riding on a norm launch: before its dependent-launch wait, thread 0 of every CTA issues

@@ -134,6 +134,10 @@ struct Engine {
   // as partial sums per (256-column tile, column half) of the producing projection, [2 sites][rows][hidden / 128]
   float* llm_ss = nullptr;
   int llm_ss_slots = 0;
+  // ViT LayerNorm launches under the residual GEMM in front of them (option ln_overlap): row-block completion counters,
+  // [2 * vit_layers][ceil(rows / 256)], zeroed at the start of a call
+  int* ln_ctr = nullptr;
+  int ln_ctr_blocks = 0;
   size_t ss_floats = 0;
   int* tile_ctr = nullptr;
   // persistent expert-stream kernel (expert.cu): per-layer operand table and one grid-barrier counter per pass
@@ -234,6 +238,9 @@ struct Engine {
                                // reduce-add), gate/up + 10 us and q|k|v + 3.7 us (row statistics + row scale in epilogues that
                                // already pace their tile loops) -- 36.6 us per layer: 25.4 vs 24.7 ms for ViT + prefill sustained,
                                // 37.9 vs 37.1 ms per call. Off.
+  int ln_overlap = 1;          // 1: the LayerNorm launches of the ViT run UNDER the residual GEMM (proj / fc2) in front of them: the
+                               // GEMM's epilogue warps report finished 256-row blocks (EpiParams::done_ctr), the norm launch --
+                               // the GEMM's programmatic dependent -- does not wait for the GEMM but for the block of each row
   int known_splits = 1;        // 1: norm launches behind a static-M split-K projection get the split count from the host
   int fuse_tail = 0;           // 1: the o / down projections of the action expert at one 256-row tile finish the residual update +
                                // the following RMSNorm themselves behind an in-kernel grid barrier (EpiParams::tail_ctr): two of
@@ -510,6 +517,8 @@ int engine_build(Engine& e) {
   e.ss_rows = std::max(arow, e.Bc);
   e.ss_floats = (size_t)(c.num_inference_steps + 1) * (2 * c.layers + 1) * e.ss_rows;
   VL_TRY(e.alloc(&e.ss, e.ss_floats));
+  e.ln_ctr_blocks = (e.Bc * e.n_img * (e.P + 1) + 255) / 256;
+  VL_TRY(e.alloc(&e.ln_ctr, (size_t)2 * c.vit_layers * e.ln_ctr_blocks));
   e.llm_ss_slots = c.hidden / 128;
   VL_TRY(e.alloc(&e.llm_ss, (size_t)2 * e.Bc * e.S * e.llm_ss_slots));
   VL_TRY(e.alloc(&e.tile_ctr, 4096));
@@ -801,6 +810,7 @@ struct Run {
   }
   const char* tr_name = "gemm";
   int tr_layer = -1;
+  bool gemm_reports_blocks = false;  // the last gemm() bumps its EpiParams::done_ctr (see Engine::ln_overlap)
 
   // ---- deterministic split-K bookkeeping: the partials a split-K residual projection left for the next reader of x
   struct Pending {
@@ -975,6 +985,11 @@ struct Run {
           t <= gemm_num_sms() / 2)
         d.half_sm = 1;
     }
+    // row-block completion counters: only the one-split residual epilogue of the pair kernel through TMA reports them
+    if (ep.done_ctr && !(d.pair && d.pair_bn == 256 && !d.half_sm && epi == EPI_RESID_F32 && d.max_splits <= 1 && out_tm != nullptr &&
+                         e.tma_epi && !ep.a_next && !ep.tail_ctr && M_dev == nullptr))
+      ep.done_ctr = nullptr;
+    gemm_reports_blocks = ep.done_ctr != nullptr;
     const CUtensorMap& wtm = (d.pair && d.pair_bn == 128) ? w.tm64 : (bn == 256 ? w.tm256 : w.tm128);
     const int rc = gemm_launch(a.tm, wtm, d, ep, bn, epi, st, e.tma_epi ? out_tm : nullptr, part_tm);
     if (prof) {
@@ -1002,6 +1017,17 @@ struct Run {
     return ep;
   }
 
+  // the norm launch behind a residual GEMM that reports its row blocks: arrivals per 256-row block = (N / 256) column
+  // tiles x 2 CTAs x 8 epilogue warps
+  RowBlocksReady ln_ready;
+  void note_blocks(const int* ctr, int width) {
+    ln_ready = RowBlocksReady();
+    if (ctr && gemm_reports_blocks) {
+      ln_ready.ctr = ctr;
+      ln_ready.expect = (width / 256) * 2 * 8;
+      ln_ready.err = e.pb.bad_id;
+    }
+  }
   int vit() {
     const vlaser_cfg& c = e.c;
     const int d = c.vit_hidden, f = c.vit_mlp;
@@ -1021,7 +1047,10 @@ struct Run {
       VitLayer& L = e.vit[i];
       tr_layer = i;
       SplitKPartials spt;
-      VL_TRY(layernorm_launch(e.vx, L.n1w, L.n1b, e.vn.p, rows, d, c.vit_eps, ShuffleGather{}, st, take(e.vx, spt)));
+      // (i > 0: under the fc2 GEMM of the previous layer when that launch reports its row blocks)
+      VL_TRY(layernorm_launch(e.vx, L.n1w, L.n1b, e.vn.p, rows, d, c.vit_eps, ShuffleGather{}, st, take(e.vx, spt),
+                              ln_ready.ctr ? &ln_ready : nullptr));
+      ln_ready = RowBlocksReady();
       EpiParams e1;
       e1.out = e.vqkv;
       e1.ldo = 3 * d;
@@ -1055,8 +1084,12 @@ struct Run {
       e2.bias = L.bproj;
       e2.scale = L.ls1;
       tr_name = "vit_proj";
+      if (e.ln_overlap && !e.simt) e2.done_ctr = e.ln_ctr + (size_t)(2 * i) * e.ln_ctr_blocks;
       VL_TRY(gemm(e.vattn, L.proj, rows, nullptr, EPI_RESID_F32, e2, 1, 0, &e.vx_otm));
-      VL_TRY(layernorm_launch(e.vx, L.n2w, L.n2b, e.vn.p, rows, d, c.vit_eps, ShuffleGather{}, st, take(e.vx, spt)));
+      note_blocks(e2.done_ctr, d);
+      VL_TRY(layernorm_launch(e.vx, L.n2w, L.n2b, e.vn.p, rows, d, c.vit_eps, ShuffleGather{}, st, take(e.vx, spt),
+                              ln_ready.ctr ? &ln_ready : nullptr));
+      ln_ready = RowBlocksReady();
       EpiParams e3;
       e3.out = e.vmlp.p;
       e3.ldo = f;
@@ -1069,7 +1102,9 @@ struct Run {
       e4.bias = L.bfc2;
       e4.scale = L.ls2;
       tr_name = "vit_fc2";
+      if (e.ln_overlap && !e.simt && i + 1 < c.vit_layers) e4.done_ctr = e.ln_ctr + (size_t)(2 * i + 1) * e.ln_ctr_blocks;
       VL_TRY(gemm(e.vmlp, L.fc2, rows, nullptr, EPI_RESID_F32, e4, 1, 0, &e.vx_otm));
+      note_blocks(e4.done_ctr, d);
       e.launches += 3;
     }
     return flush();  // the last fc2 of a small batch may have left split-K partials
@@ -1738,6 +1773,7 @@ struct Run {
   int all(bool has_valid) {
     const vlaser_cfg& c = e.c;
     VL_CUDA_CHECK(cudaMemsetAsync(e.tail_ctrs, 0, sizeof(unsigned int) * Engine::TAIL_CTRS, st));  // fused-tail barriers
+    if (e.ln_overlap) VL_CUDA_CHECK(cudaMemsetAsync(e.ln_ctr, 0, sizeof(int) * (size_t)2 * c.vit_layers * e.ln_ctr_blocks, st));
     e.tail_used = 0;
     if (e.mode == 3) return text_decode();
     if (e.mode == 2) {
@@ -1880,7 +1916,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
   else if (k == "stop_after") h->e.stop_after = (int)value;
   else if (k == "simt_gemm") h->e.simt = (int)value;
   else if (k == "pdl" || k == "exp_stages" || k == "fuse_norm" || k == "pair_gemm" || k == "tma_epi" ||
-           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc" || k == "fuse_tail" || k == "decode_chunk" || k == "prefill_tc_long" || k == "attn_small" || k == "rn_small" || k == "known_splits" || k == "half_sm" || k == "fuse_norm_llm") {
+           k == "pair_min_tiles" || k == "expert_mega" || k == "expert_streams" || k == "expert_gemv" || k == "l2_prefetch" || k == "small_m_split" || k == "prop_stream" || k == "expert_timing" || k == "expert_flags" || k == "ablate" || k == "trace" || k == "det_splitk" || k == "vit_tc" || k == "exp_splits_o" || k == "exp_splits_down" || k == "den_chains" || k == "pair_bn128" || k == "gelu_warps" || k == "prefill_tc" || k == "fuse_tail" || k == "decode_chunk" || k == "prefill_tc_long" || k == "attn_small" || k == "rn_small" || k == "known_splits" || k == "half_sm" || k == "fuse_norm_llm" || k == "ln_overlap") {
     // schedule-shaping options: captured graphs are stale afterwards
     if (k == "pdl") g_pdl_mode = (int)value;
     else if (k == "fuse_norm") h->e.fuse_norm = (int)value;
@@ -1906,6 +1942,7 @@ int32_t vlaser_set_option(vlaser_t* h, const char* key, int64_t value) {
     else if (k == "known_splits") h->e.known_splits = (int)value;
     else if (k == "half_sm") h->e.half_sm = (int)value;
     else if (k == "fuse_norm_llm") h->e.fuse_norm_llm = (int)value;
+    else if (k == "ln_overlap") h->e.ln_overlap = (int)value;
     else if (k == "rn_small") set_resid_norm_small((int)value);
     else if (k == "decode_chunk") h->e.dec_chunk = (value <= 0) ? 0 : std::min(256, std::max(64, (int)value / 64 * 64));
     else if (k == "exp_splits_o") h->e.xs_o = std::max(1, (int)value);
@@ -1957,6 +1994,11 @@ int32_t vlaser_infer_action(vlaser_t* h, const int64_t* input_ids, const void* p
     const int bad = *host_bad - 1;
     *host_bad = 0;
     cudaMemsetAsync(e.pb.bad_id, 0, sizeof(int), st);
+    if (bad + 1 == NORM_ERR_READY_TIMEOUT) {
+      set_last_error("infer_action: a norm launch waited ~1 s for a row block its residual GEMM never reported (option ln_overlap) "
+                     "in an earlier call; the actions of that call are invalid");
+      return -5;
+    }
     if (bad + 1 == EXPERT_ERR_BARRIER) {
       set_last_error("infer_action: a grid barrier of the persistent expert kernel timed out in an earlier call (a CTA of its grid "
                      "was not resident); the actions of that call are invalid");
@@ -2120,6 +2162,11 @@ int32_t vlaser_infer_action_host(vlaser_t* h, const int64_t* input_ids, const vo
   if (*p_bad != 0) {
     const int bad = *p_bad - 1;
     cudaMemsetAsync(e.pb.bad_id, 0, sizeof(int), st);
+    if (*p_bad == NORM_ERR_READY_TIMEOUT) {
+      set_last_error("infer_action: a norm launch waited ~1 s for a row block its residual GEMM never reported (option ln_overlap); "
+                     "the actions are invalid");
+      return -5;
+    }
     if (*p_bad == EXPERT_ERR_BARRIER) {
       set_last_error("infer_action: a grid barrier of the persistent expert kernel timed out (a CTA of its grid was not resident); "
                      "the actions are invalid");

@@ -1116,6 +1116,19 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     int as = 0;
     uint32_t aphase = 0;
     if (warp != 2) tr = nullptr;
+    int pend_m = -1;  // row block whose reduce-adds this warp has issued but not yet reported (EpiParams::done_ctr)
+    auto report_done = [&]() {
+      if constexpr (EPI == EPI_RESID_F32) {
+        if (ep.done_ctr && pend_m >= 0) {
+          if (lane == 0) {
+            bulk_wait<0>();        // the warp's reduce-adds have been performed ...
+            fence_proxy_async();   // ... and are ordered (async proxy -> generic) before the release below
+            asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ep.done_ctr + pend_m) : "memory");
+          }
+          pend_m = -1;
+        }
+      }
+    };
     for (int t = pair; t < total; t += n_pairs) {
       int n_idx, m_idx;
       const int split = t / base;
@@ -1142,6 +1155,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         if (t == pair) trace_stamp(tr, 4);
+        report_done();  // the previous tile's stores have had this tile's mainloop to land
         bool done = false;
         if constexpr (epi_has_tma_out<EPI>()) {
           if (d.tma_out) {
@@ -1153,6 +1167,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             epilogue_tile_tma<BN, EPI, PARTS, NBUF>(ep, &tmC, wbuf, out_par, taddr, half, lane, row - lane, n0, rstd,
                                                     split == 0, &tmP, part_row0, ring, t == pair ? tr : nullptr);
             done = true;
+            pend_m = m_idx;
           }
         }
         bool released = false;
@@ -1196,10 +1211,14 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
       }
     }
+    report_done();  // the last tile of this warp
   }
 
   if (warp == 2) trace_stamp(tr, 5);
   if (warp >= 2 && lane == 0) bulk_wait<0>();  // this warp's TMA stores have landed
+  if constexpr (EPI == EPI_RESID_F32) {
+    // (the last tile of an epilogue warp; `pend_m` lives in the epilogue branch above, so the report is made there)
+  }
   if constexpr (EPI == EPI_RESID_F32 && BN == 128) {
     if (ep.tail_ctr) fence_proxy_async();  // ... and are ordered before the release below (async proxy -> generic)
   }
@@ -1317,6 +1336,8 @@ int launch_pair_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   }
   const int pairs = (int)std::min<long long>(tiles, gemm_num_sms() / 2);
   // __cluster_dims__(2,1,1) is part of the kernel: a plain launch (with the optional PDL attribute) suffices
+  VL_CHECK(!ep.done_ctr || (EPI == EPI_RESID_F32 && d.tma_out && d.max_splits <= 1 && !HALF && !ep.tail_ctr),
+           "gemm: row-block completion counters need the one-split residual epilogue of the pair kernel through TMA");
   if (HALF) {
     VL_CHECK(d.tma_out && !d.M_dev && tiles <= gemm_num_sms() / 2 && !ep.tail_ctr && !ep.row_ss,
              "gemm: the half-SM pair kernel takes static-M launches of at most one tile per CTA pair through the TMA epilogue");
@@ -1433,6 +1454,7 @@ int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDims& 
            "gemm: pair mode needs the W map with pair_bn / 2 row boxes, N % pair_bn == 0");
   VL_CHECK(d.N % block_n == 0, "gemm: N must be a multiple of block_n");
   VL_CHECK(ep.out != nullptr, "gemm: null output");
+  VL_CHECK(!ep.done_ctr || d.pair, "gemm: row-block completion counters exist in the pair kernel only");
   VL_CHECK(!ep.a_next || (ep.gamma_next && ep.ss_next && ep.lda_next > 0), "gemm: incomplete fused-norm outputs");
   VL_CHECK(!(ep.a_next && epi == EPI_RESID_F32 && d.max_splits > 1) || ep.tile_counters,
            "gemm: split-K with fused-norm outputs needs tile counters");

@@ -73,6 +73,11 @@ struct EpiParams {
   // launch are resident: one per SM, at most gemm_num_sms() of them) and then finishes rows blockIdx.x, + gridDim.x, ...:
   // out[row] += partials in split order (the same association as resid_norm_kernel), then RMSNorm(out[row]) * tail_gamma
   // -> tail_out (bf16) -- the work of the norm launch that would follow, without its hop.
+  // ---- row-block completion counters (pair kernel, EPI_RESID_F32 through the TMA reduce-add epilogue, one split): every
+  // epilogue warp, once the reduce-adds of a tile have landed, bumps done_ctr[m_idx] (release, gpu scope); a 256-row block
+  // is complete at (N / 256) * 2 * epilogue-warps arrivals. A norm launch behind this GEMM -- its programmatic dependent --
+  // then works under the GEMM, row block by row block, instead of behind it (norm_kernel `ready`).
+  int* done_ctr = nullptr;             // [ceil(M / 256)], zero on entry
   unsigned int* tail_ctr = nullptr;    // arrival counter of this launch, zero on entry
   const float* tail_gamma = nullptr;   // [N] gain of the following RMSNorm
   __nv_bfloat16* tail_out = nullptr;   // [M, ldo]
